@@ -1,0 +1,153 @@
+/*
+ * nrm_b200.h -- C ABI of libnrm_b200.so: the B200 (sm_100a) hot path of the EB-NeRD
+ * news recommender (ChuhanZhou/News_Recommendation_Model).
+ *
+ * The reference has no FFI: its hot path is Python calling torch.nn modules.  The
+ * entry points below are what a binding for that path binds, one per reference call
+ * site; every one takes plain device pointers and sizes, allocates nothing, never
+ * synchronises, and enqueues all of its work on `stream`.
+ *
+ *   reference call (file:line)                               entry point
+ *   ------------------------------------------------------   -------------------------
+ *   UserModel.forward         models/user_model.py:27-35      nrm_forward
+ *     UserInvariantInterestModel.forward
+ *                 models/user_invariant_interest_model.py:73-88   (inside nrm_forward)
+ *     PointwiseAttentionExpanded.forward
+ *                 models/attention_model.py:52-97             (inside nrm_forward)
+ *     UserInstantInterestModel.forward
+ *                 models/user_instant_interest_model.py:20-23 (inside nrm_forward)
+ *   UserModel.loss            models/user_model.py:37-43      nrm_loss_forward
+ *   loss.backward()           train.py:73                     nrm_loss_backward, nrm_backward
+ *   optimizer.step()          train.py:48,74                  nrm_adam_step
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless named host_*; `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success or a negative NRM_E* code; nrm_last_error()
+ *     returns a thread-local description of the last failure;
+ *   - feature tensors are the reference's packed float64 rows
+ *       x_history [B,H,80], x_target [B,C,78], x_global [B,C,3]
+ *     (models/user_invariant_interest_model.py:14-22); x_target / x_global may be
+ *     column-trimmed views as produced by test.py:53-54, hence the batch strides
+ *     (in elements); rows inside one impression are contiguous;
+ *   - parameters live in ONE flat float32 buffer whose layout is given by the
+ *     nrm_layout_* functions (state_dict order of the reference, 16-byte aligned
+ *     entries, `delta` last); gradients use the same layout;
+ *   - `precision`: 0 = fp32 (FFMA everywhere), 1 = bf16 tensor-core tiles with fp32
+ *     accumulation for the pairwise attention GEMMs (everything else stays fp32).
+ */
+#ifndef NRM_B200_H
+#define NRM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRM_OK            0
+#define NRM_EINVAL       -1   /* bad argument (null pointer, non-positive size, ...) */
+#define NRM_EWORKSPACE   -2   /* workspace too small or misaligned                    */
+#define NRM_ECUDA        -3   /* a CUDA runtime call or kernel launch failed          */
+#define NRM_EUNSUPPORTED -4   /* configuration not built into this library           */
+
+#define NRM_PRECISION_FP32 0
+#define NRM_PRECISION_BF16 1
+
+/* `mode` bit flags of the forward/backward entry points */
+#define NRM_MODE_BN_BATCH_STATS 1   /* module.training: BatchNorm uses (and records) batch statistics */
+#define NRM_MODE_KEEP_FOR_BWD   2   /* keep activations / sort keys in the workspace for nrm_backward  */
+#define NRM_MODE_EVAL           0
+#define NRM_MODE_TRAIN          3
+
+int         nrm_version(void);
+const char* nrm_last_error(void);
+
+/* ---- flat parameter layout (reference state_dict order) ---- */
+int         nrm_layout_entries(void);                 /* trainable tensors incl. delta     */
+const char* nrm_layout_name(int i);                   /* reference state_dict key          */
+long long   nrm_layout_offset(int i);                 /* offset in floats                  */
+long long   nrm_layout_numel(int i);                  /* element count (-1: delta, runtime)*/
+long long   nrm_layout_fixed_floats(void);            /* floats before delta (16B padded)  */
+
+/* ---- workspace ------------------------------------------------------------------- */
+/* Bytes of scratch nrm_forward/nrm_backward need for one (B,H,C) batch.  With
+ * NRM_MODE_KEEP_FOR_BWD in `mode` it is sized for forward + backward (activations are kept
+ * between the two calls). */
+size_t nrm_workspace_bytes(int B, int H, int C, int mode);
+
+/* ---- UserModel.forward (user_model.py:27-35) ------------------------------------- */
+/* mode & NRM_MODE_BN_BATCH_STATS: BatchNorm uses batch statistics, updates
+ * bn_running_mean/var (momentum 0.1, unbiased variance) and increments
+ * *bn_num_batches_tracked; otherwise it uses the running statistics (module.eval()).
+ * mode & NRM_MODE_KEEP_FOR_BWD: keeps what nrm_backward needs in `workspace`.
+ * logits: [B,C] float32. */
+int nrm_forward(const double* x_history, const double* x_target, long long x_target_batch_stride,
+                const double* x_global, long long x_global_batch_stride,
+                int B, int H, int C,
+                const float* params, float* bn_running_mean, float* bn_running_var,
+                long long* bn_num_batches_tracked,
+                int mode, int precision,
+                float* logits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Two-phase variant for synchronised BatchNorm across data-parallel ranks:
+ * nrm_forward_encoder writes e_concat and bn_sums[2][264] (double: column sums and sums
+ * of squares over this rank's B*C rows, may be null to keep them in the workspace only);
+ * the caller all-reduces bn_sums and calls nrm_forward_head with the GLOBAL row count
+ * (bn_sums null / bn_global_rows 0 = use this rank's own statistics). */
+int nrm_forward_encoder(const double* x_history, const double* x_target, long long x_target_batch_stride,
+                        const double* x_global, long long x_global_batch_stride,
+                        int B, int H, int C, const float* params, int mode, int precision,
+                        double* bn_sums, void* workspace, size_t workspace_bytes, void* stream);
+int nrm_forward_head(int B, int H, int C, const float* params, float* bn_running_mean, float* bn_running_var,
+                     long long* bn_num_batches_tracked, int mode,
+                     const double* bn_sums, long long bn_global_rows,
+                     float* logits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- backward of UserModel.forward (loss.backward(), train.py:73) ---------------- */
+/* dlogits [B,C] float32.  Writes the gradient of every trainable tensor except `delta`
+ * into `grads` (flat layout, overwritten, not accumulated).  Must follow an
+ * nrm_forward(mode & NRM_MODE_KEEP_FOR_BWD) on the same inputs and workspace.
+ * Two-phase variant for synchronised BatchNorm: nrm_backward_head stops after writing
+ * bn_bwd_sums[2][264] (double: column sums of dL/dxhat and dL/dxhat*xhat); the caller
+ * all-reduces them and calls nrm_backward_encoder. */
+int nrm_backward(const double* x_history, const double* x_target, long long x_target_batch_stride,
+                 const double* x_global, long long x_global_batch_stride,
+                 int B, int H, int C, const float* params, int mode, int precision,
+                 const float* dlogits, float* grads,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int nrm_backward_head(int B, int H, int C, const float* params, const float* dlogits, float* grads,
+                      double* bn_bwd_sums, void* workspace, size_t workspace_bytes, void* stream);
+int nrm_backward_encoder(const double* x_history, const double* x_target, long long x_target_batch_stride,
+                         const double* x_global, long long x_global_batch_stride,
+                         int B, int H, int C, const float* params, int mode, int precision,
+                         const double* bn_bwd_sums, long long bn_global_rows, float* grads,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- UserModel.loss (user_model.py:37-43) ---------------------------------------- */
+/* loss = (1-alpha) BCE(softmax(out), y) + alpha BCE(softmax(out + delta[id]), y), mean
+ * over B*C, log clamped at -100 (nn.BCELoss).  Writes *loss (float32) and keeps the unit
+ * gradients in `scratch` (>= nrm_loss_scratch_bytes(B,C)). */
+size_t nrm_loss_scratch_bytes(int B, int C);
+int nrm_loss_forward(const float* logits, const float* delta, const long long* user_id,
+                     const double* label, int B, int C, float alpha,
+                     float* loss, void* scratch, size_t scratch_bytes, void* stream);
+/* grad_loss: device scalar dL/dloss.  dlogits [B,C]; ddelta: dense [delta_numel],
+ * overwritten (zeros + per-user sums, duplicates combined in batch order). */
+int nrm_loss_backward(const long long* user_id, int B, int C, const float* grad_loss,
+                      float* dlogits, float* ddelta, long long delta_numel,
+                      const void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- torch.optim.Adam single step, coupled L2 (train.py:48,74) -------------------- */
+/* g' = g + wd p; m = lerp(m, g', 1-b1); v = b2 v + (1-b2) g'^2;
+ * p -= (lr / (1-b1^step)) * m / (sqrt(v)/sqrt(1-b2^step) + eps).  n floats, in place.
+ * grad_scale multiplies g first (1/world_size for a summed data-parallel gradient). */
+int nrm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay,
+                  long long step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRM_B200_H */

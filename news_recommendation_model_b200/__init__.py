@@ -1,0 +1,9 @@
+"""B200-native (sm_100a) hot path of the EB-NeRD news recommender: the reference's
+`models/` nn.Module surface computed by hand-written CUDA kernels behind a C ABI."""
+from .models import (MLP, PointwiseAttention, PointwiseAttentionExpanded, UserInstantInterestModel,
+                     UserInvariantInterestModel, UserModel)
+from .optim import FusedAdam
+from ._lib import NrmError, build
+
+__all__ = ['MLP', 'PointwiseAttention', 'PointwiseAttentionExpanded', 'UserInstantInterestModel',
+           'UserInvariantInterestModel', 'UserModel', 'FusedAdam', 'NrmError', 'build']

@@ -1,0 +1,295 @@
+// C ABI of libnrm_b200 (include/nrm_b200.h): argument checking, workspace carving and
+// the kernel sequence of UserModel.forward / its backward.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "nrm_kernels.cuh"
+#include "nrm_gemm.cuh"
+
+namespace nrm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return NRM_ECUDA;
+}
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = 148;
+  }
+  return n;
+}
+
+struct LayoutEntry { const char* name; long long offset; long long numel; };
+#define II "invariant_interest_model."
+static const LayoutEntry kLayout[] = {
+    {II "category_embedding.0.weight", P_CAT, NCAT * 32},
+    {II "sentiment_embedding.0.weight", P_SENT_W, 16 * 3},
+    {II "sentiment_embedding.0.bias", P_SENT_B, 16},
+    {II "type_embedding.0.weight", P_TYPE, NTYPE * 8},
+    {II "w1.weight", P_W1_W, 64 * XIN},
+    {II "w1.bias", P_W1_B, 64},
+    {II "year_embedding.0.weight", P_YEAR, NYEAR * 8},
+    {II "month_embedding.0.weight", P_MONTH, NMONTH * 8},
+    {II "day_embedding.0.weight", P_DAY, NDAY * 8},
+    {II "hour_embedding.0.weight", P_HOUR, NHOUR * 8},
+    {II "label_attention.mlp.fc1.weight", P_LA_FC1_W, 64 * 256},
+    {II "label_attention.mlp.fc1.bias", P_LA_FC1_B, 64},
+    {II "label_attention.mlp.fc2.weight", P_LA_FC2_W, 64},
+    {II "label_attention.mlp.fc2.bias", P_LA_FC2_B, 1},
+    {II "text_img_attention.mlp.fc1.weight", P_TI_FC1_W, 64 * 256},
+    {II "text_img_attention.mlp.fc1.bias", P_TI_FC1_B, 64},
+    {II "text_img_attention.mlp.fc2.weight", P_TI_FC2_W, 64},
+    {II "text_img_attention.mlp.fc2.bias", P_TI_FC2_B, 1},
+    {"instant_interest_model.out_fc.0.weight", P_INST_W, 8 * 3},
+    {"instant_interest_model.out_fc.0.bias", P_INST_B, 8},
+    {"bn.weight", P_BN_W, E},
+    {"bn.bias", P_BN_B, E},
+    {"gate.fc1.weight", P_GATE_FC1_W, HID * E},
+    {"gate.fc1.bias", P_GATE_FC1_B, HID},
+    {"gate.fc2.weight", P_GATE_FC2_W, E * HID},
+    {"gate.fc2.bias", P_GATE_FC2_B, E},
+    {"mlp.fc1.weight", P_MLP_FC1_W, HID * E},
+    {"mlp.fc1.bias", P_MLP_FC1_B, HID},
+    {"mlp.fc2.weight", P_MLP_FC2_W, E * HID},
+    {"mlp.fc2.bias", P_MLP_FC2_B, E},
+    {"out_mlp.fc1.weight", P_OUT_FC1_W, HID * E},
+    {"out_mlp.fc1.bias", P_OUT_FC1_B, HID},
+    {"out_mlp.fc2.weight", P_OUT_FC2_W, HID},
+    {"out_mlp.fc2.bias", P_OUT_FC2_B, 1},
+    {"delta", P_DELTA, -1},
+};
+#undef II
+constexpr int kLayoutEntries = sizeof(kLayout) / sizeof(kLayout[0]);
+
+size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) {
+  const bool training = (mode & NRM_MODE_KEEP_FOR_BWD) != 0;   // backward buffers wanted
+  memset(&w, 0, sizeof(w));
+  w.B = B; w.H = H; w.C = C;
+  w.NH = (long long)B * H; w.R = (long long)B * C; w.N = w.NH + w.R;
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> void* {
+    void* p = base ? (char*)base + off : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  const size_t f = sizeof(float);
+  const size_t NH = (size_t)w.NH, R = (size_t)w.R, N = (size_t)w.N;
+  w.xin_h = (float*)take(f * NH * XIN);
+  w.xh = (float*)take(f * NH * 64);
+  w.e = (float*)take(f * R * E);
+  w.mean = (float*)take(f * E);
+  w.rstd = (float*)take(f * E);
+  w.bn_sums = (double*)take(sizeof(double) * 2 * E);
+  w.stat_part = (double*)take(sizeof(double) * STAT_BLOCKS * 2 * E);
+  w.z = (float*)take(f * R * E);
+  w.a1 = (float*)take(f * R * HID); w.u1 = (float*)take(f * R * HID);
+  w.gate = (float*)take(f * R * E);
+  w.x = (float*)take(f * R * E);
+  w.a2 = (float*)take(f * R * HID); w.u2 = (float*)take(f * R * HID);
+  w.y = (float*)take(f * R * E);
+  w.a3 = (float*)take(f * R * HID); w.u3 = (float*)take(f * R * HID);
+  if (training) {
+    w.da3 = (float*)take(f * R * HID); w.da2 = (float*)take(f * R * HID); w.da1 = (float*)take(f * R * HID);
+    w.dy = (float*)take(f * R * E);
+    w.dgate = (float*)take(f * R * E);
+    w.de = (float*)take(f * R * E);
+    w.dz = (float*)take(f * R * E);
+    w.bn_bwd_sums = (double*)take(sizeof(double) * 2 * E);
+    w.gt = (float*)take(f * 2 * R * 64);
+    w.dxh = (float*)take(f * NH * 64);
+    w.dxt = (float*)take(f * R * 64);
+    w.dxin_h = (float*)take(f * NH * XIN);
+    w.att_part = (float*)take(f * 2 * ATT_BWD_CTAS_MAX * ATT_PARTIAL);
+    w.splitk = (float*)take(f * 32 * (size_t)(HID * E));      // >= WGRAD_SPLITS x largest weight, >= 32 x 64x64
+    w.small_part = (float*)take(f * 128 * E);
+    const size_t n32 = N * 6, n8 = N * 5;
+    const size_t c32 = (n32 + SORT_CHUNK - 1) / SORT_CHUNK, c8 = (n8 + SORT_CHUNK - 1) / SORT_CHUNK;
+    const size_t g32 = n32 / SEG_GROUP + NKEY32 + 1, g8 = n8 / SEG_GROUP + NKEY8 + 1;
+    w.keys32 = (int*)take(sizeof(int) * n32); w.keys8 = (int*)take(sizeof(int) * n8);
+    w.perm32 = (int*)take(sizeof(int) * n32); w.perm8 = (int*)take(sizeof(int) * n8);
+    w.chunk_hist32 = (int*)take(sizeof(int) * c32 * NKEY32); w.chunk_hist8 = (int*)take(sizeof(int) * c8 * NKEY8);
+    w.seg32 = (int*)take(sizeof(int) * 2 * (NKEY32 + 1)); w.seg8 = (int*)take(sizeof(int) * 2 * (NKEY8 + 1));
+    w.gkey32 = (int*)take(sizeof(int) * g32); w.gkey8 = (int*)take(sizeof(int) * g8);
+    w.gpart32 = (float*)take(f * g32 * 32); w.gpart8 = (float*)take(f * g8 * 8);
+  }
+  w.bytes = off;
+  return off;
+}
+
+static int check_shape(const char* fn, int B, int H, int C) {
+  if (B <= 0 || H <= 0 || C <= 0) { set_error("%s: B, H, C must be positive (got %d, %d, %d)", fn, B, H, C); return NRM_EINVAL; }
+  if (((long long)B * H + (long long)B * C) * 6 >= (1LL << 31)) { set_error("%s: batch too large for 32-bit entry ids", fn); return NRM_EINVAL; }
+  return NRM_OK;
+}
+static int get_workspace(const char* fn, Workspace& w, void* ws, size_t ws_bytes, int B, int H, int C, int mode) {
+  if (ws == nullptr || ((uintptr_t)ws & 255) != 0) { set_error("%s: workspace must be non-null and 256-byte aligned", fn); return NRM_EWORKSPACE; }
+  const size_t need = carve_workspace(w, ws, B, H, C, mode);
+  if (need > ws_bytes) { set_error("%s: workspace too small (%zu < %zu bytes)", fn, ws_bytes, need); return NRM_EWORKSPACE; }
+  return NRM_OK;
+}
+
+static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, int mode, int precision, cudaStream_t s) {
+  NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s));
+  // xh = w1(xin_h)   (user_invariant_interest_model.py:78)
+  GemmArgs g{};
+  g.M = (int)w.NH; g.N = 64; g.K = XIN;
+  g.A = w.xin_h; g.sam = XIN; g.sak = 1;
+  g.B = P + P_W1_W; g.sbk = 1; g.sbn = XIN;
+  g.C = w.xh; g.scm = 64; g.scn = 1;
+  g.bias = P + P_W1_B;
+  const int rc = launch_gemm<EPI_BIAS>(g, 1, s);
+  if (rc < 0) return rc;
+  NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s));
+  NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s));
+  return NRM_OK;
+}
+
+static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, int precision, float* G, cudaStream_t s) {
+  NRM_TRY(launch_attention_backward(in, P, w, 0, precision, s));
+  NRM_TRY(launch_attention_finish(P, w, 0, G, s));
+  NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s));
+  NRM_TRY(launch_attention_finish(P, w, 1, G, s));
+  // w1: dW = dxh^T xin_h, db = colsum(dxh), dxin_h = dxh W1
+  {
+    GemmArgs g{};
+    g.M = 64; g.N = XIN; g.K = (int)w.NH;
+    g.A = w.dxh; g.sam = 1; g.sak = 64;
+    g.B = w.xin_h; g.sbk = XIN; g.sbn = 1;
+    g.C = w.splitk; g.scm = XIN; g.scn = 1;
+    g.split_stride = 64 * XIN;
+    const int nsplit = launch_gemm<EPI_NONE>(g, 32, s);
+    if (nsplit < 0) return nsplit;
+    reduce_splits_kernel<<<(64 * XIN + 255) / 256, 256, 0, s>>>(w.splitk, nsplit, 64 * XIN, G + P_W1_W, 64 * XIN);
+    NRM_LAUNCH_CHECK("reduce_splits_kernel(w1)");
+    const int rp = (int)((w.NH + STAT_BLOCKS - 1) / STAT_BLOCKS);
+    const int nch = (int)((w.NH + rp - 1) / rp);
+    colsum_partial_kernel<<<dim3(1, nch), 64, 0, s>>>(w.dxh, 64, w.NH, 64, rp, w.small_part);
+    NRM_LAUNCH_CHECK("colsum_partial_kernel(dxh)");
+    reduce_splits_kernel<<<1, 256, 0, s>>>(w.small_part, nch, 64, G + P_W1_B, 64);
+    NRM_LAUNCH_CHECK("reduce_splits_kernel(w1.bias)");
+    GemmArgs d{};
+    d.M = (int)w.NH; d.N = XIN; d.K = 64;
+    d.A = w.dxh; d.sam = 64; d.sak = 1;
+    d.B = P + P_W1_W; d.sbk = XIN; d.sbn = 1;
+    d.C = w.dxin_h; d.scm = XIN; d.scn = 1;
+    const int rc = launch_gemm<EPI_NONE>(d, 1, s);
+    if (rc < 0) return rc;
+  }
+  NRM_TRY(launch_small_linear_grads(in, w, G, s));
+  NRM_TRY(launch_table_grads(w, G, s));
+  return NRM_OK;
+}
+
+}  // namespace nrm
+
+using namespace nrm;
+
+extern "C" int nrm_version(void) { return 100; }
+extern "C" const char* nrm_last_error(void) { return g_err; }
+extern "C" int nrm_layout_entries(void) { return kLayoutEntries; }
+extern "C" const char* nrm_layout_name(int i) { return (i >= 0 && i < kLayoutEntries) ? kLayout[i].name : nullptr; }
+extern "C" long long nrm_layout_offset(int i) { return (i >= 0 && i < kLayoutEntries) ? kLayout[i].offset : -1; }
+extern "C" long long nrm_layout_numel(int i) { return (i >= 0 && i < kLayoutEntries) ? kLayout[i].numel : -1; }
+extern "C" long long nrm_layout_fixed_floats(void) { return P_DELTA; }
+
+extern "C" size_t nrm_workspace_bytes(int B, int H, int C, int mode) {
+  if (B <= 0 || H <= 0 || C <= 0) return 0;
+  Workspace w;
+  return carve_workspace(w, nullptr, B, H, C, mode);
+}
+
+extern "C" int nrm_forward_encoder(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
+                                   long long xg_bs, int B, int H, int C, const float* params, int mode, int precision,
+                                   double* bn_sums, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape("nrm_forward_encoder", B, H, C));
+  if (!x_history || !x_target || !x_global || !params) { set_error("nrm_forward_encoder: null pointer"); return NRM_EINVAL; }
+  if (xt_bs < (long long)C * TC || xg_bs < (long long)C * GC) { set_error("nrm_forward_encoder: batch stride smaller than one impression"); return NRM_EINVAL; }
+  Workspace w;
+  NRM_TRY(get_workspace("nrm_forward_encoder", w, workspace, workspace_bytes, B, H, C, mode));
+  cudaStream_t s = (cudaStream_t)stream;
+  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
+  NRM_TRY(encoder_forward(in, params, w, mode, precision, s));
+  if (mode & NRM_MODE_BN_BATCH_STATS) {
+    NRM_TRY(launch_bn_partial_sums(w, s));
+    if (bn_sums != nullptr && bn_sums != w.bn_sums)
+      NRM_CUDA(cudaMemcpyAsync(bn_sums, w.bn_sums, sizeof(double) * 2 * E, cudaMemcpyDeviceToDevice, s));
+  }
+  return NRM_OK;
+}
+
+extern "C" int nrm_forward_head(int B, int H, int C, const float* params, float* bn_running_mean, float* bn_running_var,
+                                  long long* bn_num_batches_tracked, int mode, const double* bn_sums,
+                                  long long bn_global_rows, float* logits, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  const int training = mode & NRM_MODE_BN_BATCH_STATS;
+  NRM_TRY(check_shape("nrm_forward_head", B, H, C));
+  if (!params || !bn_running_mean || !bn_running_var || !logits) { set_error("nrm_forward_head: null pointer"); return NRM_EINVAL; }
+  if (training && !bn_num_batches_tracked) { set_error("nrm_forward_head: null num_batches_tracked"); return NRM_EINVAL; }
+  Workspace w;
+  NRM_TRY(get_workspace("nrm_forward_head", w, workspace, workspace_bytes, B, H, C, mode));
+  const double* sums = bn_sums ? bn_sums : w.bn_sums;
+  const long long rows = bn_global_rows > 0 ? bn_global_rows : w.R;
+  return launch_head_forward(params, w, bn_running_mean, bn_running_var, bn_num_batches_tracked, training, sums, rows,
+                             logits, (cudaStream_t)stream);
+}
+
+extern "C" int nrm_forward(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
+                           long long xg_bs, int B, int H, int C, const float* params, float* bn_running_mean,
+                           float* bn_running_var, long long* bn_num_batches_tracked, int mode, int precision,
+                           float* logits, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(nrm_forward_encoder(x_history, x_target, xt_bs, x_global, xg_bs, B, H, C, params, mode, precision, nullptr,
+                              workspace, workspace_bytes, stream));
+  return nrm_forward_head(B, H, C, params, bn_running_mean, bn_running_var, bn_num_batches_tracked, mode, nullptr, 0,
+                            logits, workspace, workspace_bytes, stream);
+}
+
+extern "C" int nrm_backward_head(int B, int H, int C, const float* params, const float* dlogits, float* grads,
+                                   double* bn_bwd_sums, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape("nrm_backward_head", B, H, C));
+  if (!params || !dlogits || !grads) { set_error("nrm_backward_head: null pointer"); return NRM_EINVAL; }
+  Workspace w;
+  NRM_TRY(get_workspace("nrm_backward_head", w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
+  cudaStream_t s = (cudaStream_t)stream;
+  NRM_TRY(launch_head_backward(params, w, dlogits, grads, s));
+  if (bn_bwd_sums != nullptr && bn_bwd_sums != w.bn_bwd_sums)
+    NRM_CUDA(cudaMemcpyAsync(bn_bwd_sums, w.bn_bwd_sums, sizeof(double) * 2 * E, cudaMemcpyDeviceToDevice, s));
+  return NRM_OK;
+}
+
+extern "C" int nrm_backward_encoder(const double* x_history, const double* x_target, long long xt_bs,
+                                    const double* x_global, long long xg_bs, int B, int H, int C, const float* params,
+                                    int mode, int precision, const double* bn_bwd_sums, long long bn_global_rows,
+                                    float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  const int training = mode & NRM_MODE_BN_BATCH_STATS;
+  NRM_TRY(check_shape("nrm_backward_encoder", B, H, C));
+  if (!x_history || !x_target || !x_global || !params || !grads) { set_error("nrm_backward_encoder: null pointer"); return NRM_EINVAL; }
+  Workspace w;
+  NRM_TRY(get_workspace("nrm_backward_encoder", w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
+  cudaStream_t s = (cudaStream_t)stream;
+  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
+  const double* sums = bn_bwd_sums ? bn_bwd_sums : w.bn_bwd_sums;
+  const long long rows = bn_global_rows > 0 ? bn_global_rows : w.R;
+  NRM_TRY(launch_bn_backward_combine(params, w, training, sums, rows, s));
+  return encoder_backward(in, params, w, precision, grads, s);
+}
+
+extern "C" int nrm_backward(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
+                            long long xg_bs, int B, int H, int C, const float* params, int mode, int precision,
+                            const float* dlogits, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(nrm_backward_head(B, H, C, params, dlogits, grads, nullptr, workspace, workspace_bytes, stream));
+  return nrm_backward_encoder(x_history, x_target, xt_bs, x_global, xg_bs, B, H, C, params, mode, precision, nullptr, 0,
+                              grads, workspace, workspace_bytes, stream);
+}

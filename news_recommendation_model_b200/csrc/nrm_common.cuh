@@ -1,0 +1,176 @@
+// Shared definitions for libnrm_b200: flat parameter layout, workspace carving, small
+// device helpers.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+
+#include "../../include/nrm_b200.h"
+
+namespace nrm {
+
+// ----------------------------------------------------------------------------
+// problem constants (configs/model_config.py of the reference)
+// ----------------------------------------------------------------------------
+constexpr int D = 64;            // label-feature width == PCA width
+constexpr int HC = 80;           // doubles per history row
+constexpr int TC = 78;           // doubles per target row
+constexpr int GC = 3;            // doubles per x_global row
+constexpr int XIN = 66;          // w1 input width (56 feat + 8 time + read_time + scroll)
+constexpr int E = 264;           // e_concat width  [eu_H 128 | eu_L 8 | ec 128]
+constexpr int HID = 66;          // hidden width of the three head MLPs
+constexpr int NCAT = 3000, NTYPE = 16, NYEAR = 100, NMONTH = 13, NDAY = 32, NHOUR = 24;
+constexpr int NKEY32 = NCAT;                                   // keys of the 32-wide table
+constexpr int K8_TYPE = 0, K8_YEAR = 16, K8_MONTH = 116, K8_DAY = 129, K8_HOUR = 161;
+constexpr int NKEY8 = 185;                                     // keys of the 8-wide tables
+constexpr float BN_EPS = 1e-5f;
+constexpr float BN_MOMENTUM = 0.1f;
+
+// e_concat column offsets
+constexpr int E_LAB = 0, E_TI = 64, E_INST = 128, E_XT = 136, E_PCAT = 200;
+
+// ----------------------------------------------------------------------------
+// flat parameter layout (floats).  Order == reference state_dict order, delta last.
+// Every entry starts on a 4-float (16 B) boundary; padding floats are kept at zero.
+// ----------------------------------------------------------------------------
+constexpr long long al4(long long x) { return (x + 3) & ~3LL; }
+constexpr long long P_CAT = 0;
+constexpr long long P_SENT_W = al4(P_CAT + NCAT * 32);
+constexpr long long P_SENT_B = al4(P_SENT_W + 16 * 3);
+constexpr long long P_TYPE = al4(P_SENT_B + 16);
+constexpr long long P_W1_W = al4(P_TYPE + NTYPE * 8);
+constexpr long long P_W1_B = al4(P_W1_W + 64 * XIN);
+constexpr long long P_YEAR = al4(P_W1_B + 64);
+constexpr long long P_MONTH = al4(P_YEAR + NYEAR * 8);
+constexpr long long P_DAY = al4(P_MONTH + NMONTH * 8);
+constexpr long long P_HOUR = al4(P_DAY + NDAY * 8);
+constexpr long long P_LA_FC1_W = al4(P_HOUR + NHOUR * 8);
+constexpr long long P_LA_FC1_B = al4(P_LA_FC1_W + 64 * 256);
+constexpr long long P_LA_FC2_W = al4(P_LA_FC1_B + 64);
+constexpr long long P_LA_FC2_B = al4(P_LA_FC2_W + 64);
+constexpr long long P_TI_FC1_W = al4(P_LA_FC2_B + 1);
+constexpr long long P_TI_FC1_B = al4(P_TI_FC1_W + 64 * 256);
+constexpr long long P_TI_FC2_W = al4(P_TI_FC1_B + 64);
+constexpr long long P_TI_FC2_B = al4(P_TI_FC2_W + 64);
+constexpr long long P_INST_W = al4(P_TI_FC2_B + 1);
+constexpr long long P_INST_B = al4(P_INST_W + 8 * 3);
+constexpr long long P_BN_W = al4(P_INST_B + 8);
+constexpr long long P_BN_B = al4(P_BN_W + E);
+constexpr long long P_GATE_FC1_W = al4(P_BN_B + E);
+constexpr long long P_GATE_FC1_B = al4(P_GATE_FC1_W + HID * E);
+constexpr long long P_GATE_FC2_W = al4(P_GATE_FC1_B + HID);
+constexpr long long P_GATE_FC2_B = al4(P_GATE_FC2_W + E * HID);
+constexpr long long P_MLP_FC1_W = al4(P_GATE_FC2_B + E);
+constexpr long long P_MLP_FC1_B = al4(P_MLP_FC1_W + HID * E);
+constexpr long long P_MLP_FC2_W = al4(P_MLP_FC1_B + HID);
+constexpr long long P_MLP_FC2_B = al4(P_MLP_FC2_W + E * HID);
+constexpr long long P_OUT_FC1_W = al4(P_MLP_FC2_B + E);
+constexpr long long P_OUT_FC1_B = al4(P_OUT_FC1_W + HID * E);
+constexpr long long P_OUT_FC2_W = al4(P_OUT_FC1_B + HID);
+constexpr long long P_OUT_FC2_B = al4(P_OUT_FC2_W + HID);
+constexpr long long P_DELTA = al4(P_OUT_FC2_B + 1);      // == nrm_layout_fixed_floats()
+
+// offsets of the four per-branch attention tensors relative to the branch base
+struct AttOffsets { long long fc1_w, fc1_b, fc2_w, fc2_b; };
+constexpr AttOffsets ATT_LABEL = {P_LA_FC1_W, P_LA_FC1_B, P_LA_FC2_W, P_LA_FC2_B};
+constexpr AttOffsets ATT_TI = {P_TI_FC1_W, P_TI_FC1_B, P_TI_FC2_W, P_TI_FC2_B};
+
+// ----------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define NRM_CUDA(call)                                              \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) return ::nrm::cuda_fail(e__, #call);    \
+  } while (0)
+#define NRM_LAUNCH_CHECK(name)                                      \
+  do {                                                              \
+    cudaError_t e__ = cudaGetLastError();                           \
+    if (e__ != cudaSuccess) return ::nrm::cuda_fail(e__, name);     \
+  } while (0)
+#define NRM_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != NRM_OK) return rc__; \
+  } while (0)
+
+int sm_count();
+
+// ----------------------------------------------------------------------------
+// workspace
+// ----------------------------------------------------------------------------
+constexpr int SORT_CHUNK = 2048;       // entries per counting-sort CTA
+constexpr int SEG_GROUP = 128;         // sorted entries per level-1 segment group
+constexpr int ATT_BWD_CTAS_MAX = 148;  // persistent grid of the attention backward
+constexpr int ATT_PARTIAL = 2 * D * D + 64 + 4;   // dA | dWd | dw2 | db2 (+pad) floats per CTA
+constexpr int STAT_BLOCKS = 64;        // row chunks of the column-statistics kernels
+constexpr int WGRAD_SPLITS = 16;       // split-K factor of the weight-gradient GEMMs
+
+struct Workspace {
+  // sizes
+  int B, H, C;
+  long long NH, R, N;                  // history rows, candidate rows, NH + R
+  // forward (always)
+  float* xin_h;        // [NH,66]   embedded history rows (w1 input)
+  float* xh;           // [NH,64]   w1 output
+  float* e;            // [R,264]   e_concat
+  float* mean;         // [264]
+  float* rstd;         // [264]
+  double* bn_sums;     // [2,264]   column sum / sum of squares of e
+  double* stat_part;   // [STAT_BLOCKS,2,264]
+  float* z;            // [R,264]   BN output
+  float* a1; float* u1;   // [R,66]
+  float* gate;         // [R,264]
+  float* x;            // [R,264]   gate * e
+  float* a2; float* u2;   // [R,66]
+  float* y;            // [R,264]
+  float* a3; float* u3;   // [R,66]
+  // backward (training only)
+  float* da3; float* da2; float* da1;   // [R,66]
+  float* dy;           // [R,264]
+  float* dgate;        // [R,264]
+  float* de;           // [R,264]   dL/de (direct path, then + BN path)
+  float* dz;           // [R,264]
+  double* bn_bwd_sums; // [2,264]
+  float* gt;           // [2][R,64]  per-candidate sums of dhid (label, text/img)
+  float* dxh;          // [NH,64]
+  float* dxt;          // [R,64]
+  float* dxin_h;       // [NH,66]
+  float* att_part;     // [2][ATT_BWD_CTAS_MAX][ATT_PARTIAL]
+  float* splitk;       // [WGRAD_SPLITS][max wgrad size] split-K partial sums
+  float* small_part;   // partial sums of the small reductions
+  // sorted-segment machinery for the embedding-table gradients
+  int* keys32;  int* keys8;            // [6N], [5N]
+  int* perm32;  int* perm8;            // sorted entry -> entry id
+  int* chunk_hist32; int* chunk_hist8; // [chunks][keys]
+  int* seg32; int* seg8;               // per key: start[keys+1] | group_start[keys+1]
+  int* gkey32; int* gkey8;             // group -> key
+  float* gpart32; float* gpart8;       // [groups][W]
+  size_t bytes;
+};
+
+// Carves `base` (may be null to only measure).  Returns total bytes.
+size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode);
+
+// ----------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// returns gelu(x), writes d gelu / dx
+__device__ __forceinline__ float gelu_both(float x, float& grad) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  grad = cdf + x * pdf;
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float g; (void)gelu_both(x, g); return g;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+}  // namespace nrm

@@ -1,0 +1,31 @@
+// Internal launcher interface between the translation units of libnrm_b200.
+#pragma once
+#include "nrm_common.cuh"
+
+namespace nrm {
+
+struct BatchPtrs {
+  const double* xh;               // [B,H,80]
+  const double* xt; long long xt_bs;   // [B,C,78], batch stride in doubles
+  const double* xg; long long xg_bs;   // [B,C,3]
+};
+
+// nrm_embed.cu
+int launch_embed_rows(const BatchPtrs& in, const float* P, Workspace& w, bool with_keys, cudaStream_t s);
+int launch_table_grads(Workspace& w, float* grads, cudaStream_t s);
+int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, cudaStream_t s);
+
+// nrm_attention.cu  (branch 0 = label attention on w1-projected features, 1 = text/img PCA)
+int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
+int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
+int launch_attention_finish(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s);
+
+// nrm_head.cu
+int launch_bn_partial_sums(Workspace& w, cudaStream_t s);                 // -> w.bn_sums
+int launch_head_forward(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt,
+                        int training, const double* bn_sums, long long global_rows, float* logits, cudaStream_t s);
+int launch_head_backward(const float* P, Workspace& w, const float* dlogits, float* grads, cudaStream_t s);  // -> w.bn_bwd_sums
+int launch_bn_backward_combine(const float* P, Workspace& w, int training, const double* bn_bwd_sums,
+                               long long global_rows, cudaStream_t s);  // w.de += BN path
+
+}  // namespace nrm

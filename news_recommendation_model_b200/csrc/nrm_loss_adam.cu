@@ -1,0 +1,233 @@
+// UserModel.loss (models/user_model.py:37-43) forward + backward, and the fused Adam step
+// (torch.optim.Adam with coupled weight decay, train.py:48,74).
+#include "nrm_kernels.cuh"
+
+namespace nrm {
+
+constexpr int LOSS_BLOCKS = 64;
+
+struct LossScratch {
+  float* dlog;      // [B*C]  d loss / d logits for grad_loss == 1
+  float* drow;      // [B]    d loss / d delta[user_id[b]] contribution of impression b
+  double* lpart;    // [LOSS_BLOCKS][2]
+};
+static size_t carve_loss(LossScratch& ls, void* base, int B, int C) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
+  ls.dlog = (float*)take(sizeof(float) * (size_t)B * C);
+  ls.drow = (float*)take(sizeof(float) * (size_t)B);
+  ls.lpart = (double*)take(sizeof(double) * LOSS_BLOCKS * 2);
+  return off;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One softmax + BCE term of one impression, handled by one warp.
+// Returns this lane's share of sum_c bce(c); adds coef * dlogit to dl[c]; returns row sum of
+// dlogit through *rowsum (all lanes).
+__device__ __forceinline__ float bce_softmax_term(const float* __restrict__ out, const double* __restrict__ label, int C,
+                                                  float shift, float invN, float coef, float* __restrict__ dl,
+                                                  bool accumulate, float* rowsum) {
+  const int lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, out[c] + shift);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += expf(out[c] + shift - mx);
+  sum = warp_sum(sum);
+  float loss = 0.f, dot = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float p = expf(out[c] + shift - mx) / sum;
+    const float y = (float)label[c];
+    loss -= y * fmaxf(logf(p), -100.f) + (1.f - y) * fmaxf(logf(1.f - p), -100.f);
+    const float dp = (p - y) / fmaxf((1.f - p) * p, 1e-12f) * invN;
+    dot = fmaf(dp, p, dot);
+  }
+  dot = warp_sum(dot);
+  float rs = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float p = expf(out[c] + shift - mx) / sum;
+    const float y = (float)label[c];
+    const float dp = (p - y) / fmaxf((1.f - p) * p, 1e-12f) * invN;
+    const float d = coef * p * (dp - dot);
+    dl[c] = accumulate ? dl[c] + d : d;
+    rs += d;
+  }
+  *rowsum = warp_sum(rs);
+  return loss;
+}
+
+__global__ void __launch_bounds__(256)
+loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ delta, const long long* __restrict__ uid,
+                    const double* __restrict__ label, int B, int C, float alpha, float* __restrict__ dlog,
+                    float* __restrict__ drow, double* __restrict__ lpart) {
+  __shared__ double red[8][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float invN = 1.0f / ((float)B * (float)C);
+  double l1 = 0.0, l2 = 0.0;
+  for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
+    const float* o = logits + (long long)b * C;
+    const double* y = label + (long long)b * C;
+    float* dl = dlog + (long long)b * C;
+    const float sh = delta[uid[b]];
+    float rs1, rs2;
+    const float a = bce_softmax_term(o, y, C, 0.f, invN, 1.f - alpha, dl, false, &rs1);
+    __syncwarp();
+    const float c = bce_softmax_term(o, y, C, sh, invN, alpha, dl, true, &rs2);
+    l1 += (double)warp_sum(a);
+    l2 += (double)warp_sum(c);
+    if (lane == 0) drow[b] = rs2;
+  }
+  if (lane == 0) { red[warp][0] = l1; red[warp][1] = l2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < 8; ++i) { s1 += red[i][0]; s2 += red[i][1]; }
+    lpart[blockIdx.x * 2 + 0] = s1; lpart[blockIdx.x * 2 + 1] = s2;
+  }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ lpart, int nblocks, int B, int C, float alpha,
+                                     float* __restrict__ loss) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < nblocks; ++i) { s1 += lpart[i * 2]; s2 += lpart[i * 2 + 1]; }
+  const double n = (double)B * (double)C;
+  const float a = (float)(s1 / n), c = (float)(s2 / n);
+  *loss = (1.f - alpha) * a + alpha * c;
+}
+
+__global__ void __launch_bounds__(256)
+loss_scale_kernel(const float* __restrict__ dlog, const float* __restrict__ grad_loss, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = dlog[i] * __ldg(grad_loss);
+}
+
+// ddelta[user] = grad_loss * sum of drow over the impressions of that user, in batch order.
+// The first occurrence of every user id owns the sum (no atomics, deterministic).
+__global__ void __launch_bounds__(256)
+delta_grad_kernel(const long long* __restrict__ uid, const float* __restrict__ drow, int B,
+                  const float* __restrict__ grad_loss, float* __restrict__ ddelta, long long delta_numel) {
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= B) return;
+  const long long id = uid[b];
+  if (id < 0 || id >= delta_numel) return;
+  for (int j = 0; j < b; ++j) if (uid[j] == id) return;
+  float acc = drow[b];
+  for (int j = b + 1; j < B; ++j) if (uid[j] == id) acc += drow[j];
+  ddelta[id] = acc * __ldg(grad_loss);
+}
+
+// ---------------------------------------------------------------------------------
+// Adam
+// ---------------------------------------------------------------------------------
+struct AdamArgs { float step_size, bc2_sqrt, beta1, beta2, eps, wd, grad_scale; };
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a) {
+  g = fmaf(a.wd, p, g * a.grad_scale);                     // grad.add(param, alpha=wd)
+  m = m + (g - m) * (1.f - a.beta1);                       // exp_avg.lerp_(grad, 1-beta1)
+  v = fmaf((1.f - a.beta2) * g, g, v * a.beta2);           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  p = p - a.step_size * (m / denom);                       // param.addcdiv_(m, denom, value=-step_size)
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, AdamArgs a) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, a); adam_one(pp.y, gg.y, mm.y, vv.y, a);
+    adam_one(pp.z, gg.z, mm.z, vv.z, a); adam_one(pp.w, gg.w, mm.w, vv.w, a);
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride)
+    adam_one(p[i], g[i], m[i], v[i], a);
+}
+
+__global__ void __launch_bounds__(256)
+adam_scalar_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                   long long n, AdamArgs a) {
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) adam_one(p[i], g[i], m[i], v[i], a);
+}
+
+}  // namespace nrm
+
+using namespace nrm;
+
+extern "C" size_t nrm_loss_scratch_bytes(int B, int C) {
+  LossScratch ls;
+  return carve_loss(ls, nullptr, B > 0 ? B : 1, C > 0 ? C : 1);
+}
+
+extern "C" int nrm_loss_forward(const float* logits, const float* delta, const long long* user_id, const double* label,
+                                int B, int C, float alpha, float* loss, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!logits || !delta || !user_id || !label || !loss || !scratch || B <= 0 || C <= 0) {
+    set_error("nrm_loss_forward: bad argument"); return NRM_EINVAL;
+  }
+  LossScratch ls;
+  if (carve_loss(ls, scratch, B, C) > scratch_bytes) { set_error("nrm_loss_forward: scratch too small"); return NRM_EWORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = min(LOSS_BLOCKS, (B + 7) / 8);
+  loss_forward_kernel<<<blocks, 256, 0, s>>>(logits, delta, user_id, label, B, C, alpha, ls.dlog, ls.drow, ls.lpart);
+  NRM_LAUNCH_CHECK("loss_forward_kernel");
+  loss_finalize_kernel<<<1, 32, 0, s>>>(ls.lpart, blocks, B, C, alpha, loss);
+  NRM_LAUNCH_CHECK("loss_finalize_kernel");
+  return NRM_OK;
+}
+
+extern "C" int nrm_loss_backward(const long long* user_id, int B, int C, const float* grad_loss, float* dlogits,
+                                 float* ddelta, long long delta_numel, const void* scratch, size_t scratch_bytes, void* stream) {
+  if (!user_id || !grad_loss || !dlogits || !scratch || B <= 0 || C <= 0) {
+    set_error("nrm_loss_backward: bad argument"); return NRM_EINVAL;
+  }
+  LossScratch ls;
+  if (carve_loss(ls, const_cast<void*>(scratch), B, C) > scratch_bytes) { set_error("nrm_loss_backward: scratch too small"); return NRM_EWORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = (long long)B * C;
+  loss_scale_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(ls.dlog, grad_loss, n, dlogits);
+  NRM_LAUNCH_CHECK("loss_scale_kernel");
+  if (ddelta != nullptr && delta_numel > 0) {
+    NRM_CUDA(cudaMemsetAsync(ddelta, 0, sizeof(float) * (size_t)delta_numel, s));
+    delta_grad_kernel<<<(B + 255) / 256, 256, 0, s>>>(user_id, ls.drow, B, grad_loss, ddelta, delta_numel);
+    NRM_LAUNCH_CHECK("delta_grad_kernel");
+  }
+  return NRM_OK;
+}
+
+extern "C" int nrm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,
+                             void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || step < 1) { set_error("nrm_adam_step: bad argument"); return NRM_EINVAL; }
+  if (n == 0) return NRM_OK;
+  AdamArgs a;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  a.step_size = (float)((double)lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool aligned = (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0;
+  const long long work = aligned ? (n + 3) / 4 : n;
+  long long blocks = (work + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (aligned) adam_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, a);
+  else adam_scalar_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, a);
+  NRM_LAUNCH_CHECK("adam_kernel");
+  return NRM_OK;
+}

@@ -1,0 +1,119 @@
+"""CPU-side checks of the drop-in boundary: module surface, state_dict contract, seeded
+initialisation, C-ABI exports.  No kernel is launched here."""
+import ctypes
+import os
+import pickle
+import re
+import sys
+
+import pytest
+import torch
+
+import news_recommendation_model_b200 as nrm
+from news_recommendation_model_b200 import _lib, engine
+from fixtures import load_weights
+from oracle import reference_port as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+
+
+def test_state_dict_contract():
+    m = nrm.UserModel(7)
+    sd = m.state_dict()
+    assert list(sd.keys()) == ['delta'] + [k for k, _ in O.STATE_KEYS]
+    for k, shape in O.STATE_KEYS:
+        assert tuple(sd[k].shape) == shape, k
+    assert sd['delta'].shape == (8,)
+    assert [k for k, _ in m.named_parameters()][0] == 'delta'            # train.py:96 pops it by name
+    res = m.load_state_dict(load_weights('train'), strict=False)         # test.py:160
+    assert res.missing_keys == ['delta'] and res.unexpected_keys == []
+    assert int(m.bn.num_batches_tracked) == 3000
+    assert m.bn.num_features == 264 and m.instant_interest_model.output_dim == 8
+    assert m.invariant_interest_model.embed_setting == [32, 16, 8, 8]
+
+
+def test_model_survives_pickle_and_deepcopy():
+    import copy
+    m = nrm.UserModel(3)
+    m2 = pickle.loads(pickle.dumps(m))                                   # test.py:177 ships models to a child process
+    m3 = copy.deepcopy(m)
+    for a, b, c in zip(m.parameters(), m2.parameters(), m3.parameters()):
+        assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_cpu_forward_fails_loudly():
+    from news_recommendation_model_b200.synthetic import make_batch
+    b = make_batch(2, 3, 2)
+    m = nrm.UserModel(5)
+    with pytest.raises(nrm.NrmError, match='CUDA'):
+        m(b.x_history, b.x_target, b.x_global)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not mounted on this host')
+def test_seeded_init_matches_reference():
+    """train.py:42-46: torch.manual_seed(seed); UserModel(max_user_id) -- same constructors in the
+    same order must leave the same initial weights."""
+    import subprocess
+    code = ("import sys, torch; sys.path.insert(0, %r); sys.dont_write_bytecode = True\n"
+            "from models.user_model import UserModel\n"
+            "torch.manual_seed(1234); m = UserModel(11)\n"
+            "torch.save(m.state_dict(), sys.argv[1])\n") % REF
+    path = '/tmp/_nrm_ref_init.pth'
+    subprocess.run([sys.executable, '-c', code, path], check=True, cwd='/tmp')
+    ref = torch.load(path)
+    torch.manual_seed(1234)
+    ours = nrm.UserModel(11).state_dict()
+    assert list(ref.keys()) == list(ours.keys())
+    for k in ref:
+        assert torch.equal(ref[k], ours[k]), k
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not mounted on this host')
+def test_shipped_checkpoints_load_unchanged():
+    for name in ('train', 'validation'):
+        sd = torch.load(f'{REF}/ckpt/ckpt_ebnerd_large_{name}_final.pth', map_location='cpu')
+        m = nrm.UserModel()
+        res = m.load_state_dict(sd, strict=False)
+        assert res.missing_keys == ['delta'] and res.unexpected_keys == []
+        gold = load_weights(name)
+        for k, v in m.state_dict().items():
+            if k != 'delta':
+                assert torch.equal(v, gold[k]), k
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'nrm_b200.h')).read()
+    declared = set(re.findall(r'\b(nrm_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().nrm_version() >= 100
+
+
+def test_flat_layout_matches_reference_keys():
+    entries, fixed = engine.layout()
+    names = [n for n, _, _ in entries]
+    assert names == list(O.TRAINABLE_KEYS) + ['delta']
+    shapes = dict(O.STATE_KEYS)
+    end = 0
+    for name, off, numel in entries[:-1]:
+        n = 1
+        for d in shapes[name]:
+            n *= d
+        assert numel == n and off % 4 == 0 and off >= end, name
+        end = off + numel
+    assert entries[-1][1] == fixed and fixed % 4 == 0 and fixed >= end
+    lib = _lib.load()
+    assert lib.nrm_workspace_bytes(0, 1, 1, 0) == 0
+    small, big = lib.nrm_workspace_bytes(4, 5, 3, 0), lib.nrm_workspace_bytes(4, 5, 3, 3)
+    assert 0 < small < big
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    lib = _lib.load()
+    rc = lib.nrm_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None)
+    assert rc == -1 and b'nrm_adam_step' in lib.nrm_last_error()
+    rc = lib.nrm_forward(None, None, 0, None, 0, 0, 1, 1, None, None, None, None, 0, 0, None, None, 0, None)
+    assert rc == -1
