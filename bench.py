@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: training-step throughput of the EB-NeRD recommender hot path.
+
+  python bench.py --gpus 1 --steps K --warmup W            (our CUDA path)
+  python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, oracle port)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (data parallel)
+
+One "step" = train.py:69-75 on one batch of synthetic EB-NeRD-shaped impressions:
+forward -> loss -> backward -> Adam -> zero_grad.  Workload = BASELINE.json configs[1]
+(B=1024 impressions per GPU, history 50, 1 positive + 4 negatives, fp32), weights from the
+shipped train checkpoint.  Prints ONE JSON line (see DESIGN.md section 6 for every field).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+D = 64
+N_POOL = 6            # distinct batches rotated through: 6 x 36 MB of inputs > the 126 MB L2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='impressions per GPU per step')
+    ap.add_argument('--history', type=int, default=50)
+    ap.add_argument('--candidates', type=int, default=5)
+    ap.add_argument('--user-num', type=int, default=1000)
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--sync-bn', action='store_true', help='all-reduce BatchNorm statistics across ranks')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-steps', type=int, default=8)
+    return ap.parse_args()
+
+
+def load_weights():
+    from fixtures import load_weights as lw
+    return lw('train')
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p['hbm_gbs']), tensor=float(p.get('bf16_tflops_sustained', p['bf16_tflops'])), source='measured')
+    return dict(hbm=6650.0, tensor=1400.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the oracle port of the reference's CPU path (oracle/reference_port.py)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_rate(args, steps, warmup):
+    from oracle import reference_port as O
+    from news_recommendation_model_b200.synthetic import make_batch
+    torch.set_num_threads(os.cpu_count())
+    p = O.load_params(load_weights(), user_num=args.user_num)
+    leaves = [p[k].requires_grad_(True) for k in O.TRAINABLE_KEYS + ('delta',)]
+    opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-5)
+    batches = [make_batch(args.batch, args.history, args.candidates, seed=100 + i, user_num=args.user_num) for i in range(2)]
+    times = []
+    for i in range(warmup + steps):
+        b = batches[i % len(batches)]
+        t0 = time.perf_counter()
+        out = O.user_model_forward(p, b.x_history, b.x_target, b.x_global, training=True)
+        loss = O.user_model_loss(p['delta'], b.user_id, out, b.label)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    return args.batch * steps / total, total / steps * 1e3, os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    rate, ms, cores = cpu_reference_rate(args, steps, warmup)
+    line = {
+        'impl': 'reference', 'metric': 'train_impressions_per_sec', 'value': rate, 'unit': 'impressions/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, 1),
+        'cpu_baseline': {'value': rate, 'unit': 'impressions/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{steps} full train steps (B={args.batch}) of oracle/reference_port.py on the host CPU, '
+                                   f'{warmup} warm-up'},
+        'e2e': {'value': rate, 'unit': 'impressions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {'workload': f'train step (fwd+loss+bwd+Adam), B={args.batch}/GPU, H={args.history}, C={args.candidates} '
+                        f'(1 pos + {args.candidates - 1} neg), user_num={args.user_num}, ckpt_ebnerd_large_train_final weights',
+            'global_batch': args.batch * world, 'history': args.history, 'candidates': args.candidates,
+            'parallelism': f'dp{world}', 'precision': args.precision, 'sync_bn': bool(args.sync_bn),
+            'l2_policy': f'{N_POOL} distinct input batches rotated (~{N_POOL * 36} MB of inputs > 126 MB L2)'}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import news_recommendation_model_b200 as nrm
+    from news_recommendation_model_b200 import _lib
+    from news_recommendation_model_b200.dp import DataParallel
+    from news_recommendation_model_b200.synthetic import make_batch
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    model = nrm.UserModel(args.user_num)
+    model.load_state_dict(load_weights(), strict=False)
+    model.to(dev).train()
+    model.set_precision(args.precision)
+    if world > 1:
+        DataParallel(model, sync_bn=args.sync_bn)
+    opt = nrm.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+
+    B, H, C = args.batch, args.history, args.candidates
+    host = [make_batch(B, H, C, seed=1234 + 97 * rank + i, user_num=args.user_num).pin() for i in range(N_POOL)]
+    pool = [b.to(dev) for b in host]
+    torch.cuda.synchronize()
+
+    def step(b):
+        out = model(b.x_history, b.x_target, b.x_global)
+        loss = model.loss(b.user_id, out, b.label)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    K, W = args.steps, max(3, args.warmup)
+    for i in range(W):
+        step(pool[i % N_POOL])
+    # ---- device-resident timed region
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = lib.nrm_launch_count()
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(K):
+            step(pool[i % N_POOL])
+        e1.record()
+        barrier()
+    launches = (lib.nrm_launch_count() - launches0) // K
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    value = world * B * K / (ms_total / 1e3)
+
+    # ---- end to end: pinned host batches, H2D inside the timed region, loss read back every step
+    def e2e_step(hb):
+        xh = hb.x_history.to(dev, non_blocking=True); xt = hb.x_target.to(dev, non_blocking=True)
+        xg = hb.x_global.to(dev, non_blocking=True); lab = hb.label.to(dev, non_blocking=True)
+        uid = hb.user_id.to(dev, non_blocking=True)
+        out = model(xh, xt, xg)
+        loss = model.loss(uid, out, lab)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return loss.item()
+    for i in range(2):
+        e2e_step(host[i % N_POOL])
+    barrier()
+    e0.record()
+    for i in range(K):
+        e2e_step(host[i % N_POOL])
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * K / (e2e_ms / 1e3)
+    h2d = host[0].input_bytes()
+
+    # ---- per-kernel timing pass (CUDA events on the launch stream inside the library)
+    lib.nrm_timing_enable(1)
+    kt_steps = min(K, 8)
+    for i in range(kt_steps):
+        step(pool[i % N_POOL])
+    torch.cuda.synchronize()
+    import ctypes
+    cbuf = ctypes.create_string_buffer(8192)
+    _lib.check(lib.nrm_timing_report(cbuf, 8192), 'nrm_timing_report')
+    lib.nrm_timing_enable(0)
+    kern = {}
+    for ln in cbuf.value.decode().strip().splitlines():
+        name, cnt, tot = ln.split()
+        kern[name] = {'launch_groups': int(cnt), 'ms_per_step': float(tot) / kt_steps}
+    pk = peaks()
+    top = max(kern, key=lambda k: kern[k]['ms_per_step']) if kern else None
+    roofline = None
+    if top is not None:
+        pairs = B * C * H
+        gemms = {'attention_backward_label': 3, 'attention_backward_textimg': 2,
+                 'attention_forward_label': 1, 'attention_forward_textimg': 1}.get(top)
+        dur = kern[top]['ms_per_step'] / 1e3
+        if gemms is not None:
+            flops = gemms * 2.0 * pairs * D * D
+            ach = flops / dur / 1e12
+            roofline = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
+                        'frac': ach / pk['tensor'], 'traffic': None, 'peak_source': pk['source'] + ' bf16 sustained',
+                        'algorithmic_flops_per_launch': flops, 'launch_ms': dur * 1e3,
+                        'note': 'fp32 FFMA path: the pair GEMMs run on CUDA cores' if args.precision == 'fp32' else 'tcgen05 tiles'}
+        else:
+            nbytes = 8.0 * (80 * H + 81 * C) * B
+            ach = nbytes / dur / 1e9
+            roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
+                        'frac': ach / pk['hbm'], 'traffic': None, 'peak_source': pk['source'],
+                        'algorithmic_bytes_per_launch': nbytes, 'launch_ms': dur * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, ms, cores = cpu_reference_rate(args, args.cpu_steps, 2)
+        cpu = {'value': rate, 'unit': 'impressions/s', 'cores': cores, 'kind': 'port', 'ms_per_step': ms,
+               'sample': f'{args.cpu_steps} full train steps (B={B}) of oracle/reference_port.py, 2 warm-up'}
+    line = {
+        'metric': 'train_impressions_per_sec', 'value': value, 'unit': 'impressions/s', 'n_gpus': world, 'steps': K,
+        'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32' if args.precision == 'fp32' else 'bf16', 'data': 'synthetic', 'config': workload_config(args, world),
+        'clocks': clk.summary(),
+        'e2e': {'value': e2e_value, 'unit': 'impressions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                'ms_per_step': e2e_ms / K},
+        'gpu_launches': int(launches) * K, 'gpu_launches_per_step': int(launches),
+        'roofline': roofline, 'kernels_ms_per_step': {k: round(v['ms_per_step'], 4) for k, v in kern.items()},
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py --impl ours needs a CUDA device (there is no CPU fallback)')
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

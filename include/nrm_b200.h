@@ -64,6 +64,15 @@ extern "C" {
 int         nrm_version(void);
 const char* nrm_last_error(void);
 
+/* ---- instrumentation (bench.py) --------------------------------------------------- */
+/* Kernels launched by this library in this process so far. */
+unsigned long long nrm_launch_count(void);
+/* While enabled, the major kernel groups are bracketed with CUDA events on their launch
+ * stream; nrm_timing_report writes one "name count total_ms" line per group into buf
+ * (synchronising on the recorded events) and returns 0.  Enabling resets the counters. */
+void        nrm_timing_enable(int on);
+int         nrm_timing_report(char* buf, size_t buf_bytes);
+
 /* ---- flat parameter layout (reference state_dict order) ---- */
 int         nrm_layout_entries(void);                 /* trainable tensors incl. delta     */
 const char* nrm_layout_name(int i);                   /* reference state_dict key          */

@@ -23,6 +23,9 @@ vp, ll, i32, f32, sz = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
     'nrm_version': (i32, []),
     'nrm_last_error': (C.c_char_p, []),
+    'nrm_launch_count': (C.c_ulonglong, []),
+    'nrm_timing_enable': (None, [i32]),
+    'nrm_timing_report': (i32, [C.c_char_p, sz]),
     'nrm_layout_entries': (i32, []),
     'nrm_layout_name': (C.c_char_p, [i32]),
     'nrm_layout_offset': (ll, [i32]),

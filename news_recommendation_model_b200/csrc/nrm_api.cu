@@ -32,6 +32,34 @@ int sm_count() {
   return n;
 }
 
+// ---- launch counter and optional per-kernel event timing ------------------------------
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+
+constexpr int kTimerSlots = 24, kTimerRing = 256;
+struct TimerSlot { const char* name; cudaEvent_t beg[kTimerRing], end[kTimerRing]; int used; bool made; };
+static TimerSlot g_timers[kTimerSlots];
+static int g_ntimers = 0;
+static bool g_timing = false;
+
+KernelTimer::KernelTimer(const char* name, cudaStream_t stream) : slot_(-1), stream_(stream) {
+  if (!g_timing) return;
+  int s = -1;
+  for (int i = 0; i < g_ntimers; ++i) if (strcmp(g_timers[i].name, name) == 0) { s = i; break; }
+  if (s < 0) { if (g_ntimers == kTimerSlots) return; s = g_ntimers++; g_timers[s].name = name; g_timers[s].used = 0; g_timers[s].made = false; }
+  TimerSlot& t = g_timers[s];
+  if (!t.made) { for (int i = 0; i < kTimerRing; ++i) { cudaEventCreate(&t.beg[i]); cudaEventCreate(&t.end[i]); } t.made = true; }
+  if (t.used >= kTimerRing) return;
+  slot_ = s;
+  cudaEventRecord(t.beg[t.used], stream_);
+}
+KernelTimer::~KernelTimer() {
+  if (slot_ < 0) return;
+  TimerSlot& t = g_timers[slot_];
+  cudaEventRecord(t.end[t.used], stream_);
+  t.used++;
+}
+
 struct LayoutEntry { const char* name; long long offset; long long numel; };
 #define II "invariant_interest_model."
 static const LayoutEntry kLayout[] = {
@@ -142,7 +170,8 @@ static int get_workspace(const char* fn, Workspace& w, void* ws, size_t ws_bytes
 }
 
 static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, int mode, int precision, cudaStream_t s) {
-  NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s));
+  { KernelTimer t("embed_rows", s);
+    NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
   // xh = w1(xin_h)   (user_invariant_interest_model.py:78)
   GemmArgs g{};
   g.M = (int)w.NH; g.N = 64; g.K = XIN;
@@ -150,20 +179,24 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   g.B = P + P_W1_W; g.sbk = 1; g.sbn = XIN;
   g.C = w.xh; g.scm = 64; g.scn = 1;
   g.bias = P + P_W1_B;
-  const int rc = launch_gemm<EPI_BIAS>(g, 1, s);
-  if (rc < 0) return rc;
-  NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s));
-  NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s));
+  {
+    KernelTimer t("w1_gemm", s);
+    const int rc = launch_gemm<EPI_BIAS>(g, 1, s);
+    if (rc < 0) return rc;
+  }
+  { KernelTimer t("attention_forward_label", s); NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s)); }
+  { KernelTimer t("attention_forward_textimg", s); NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s)); }
   return NRM_OK;
 }
 
 static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, int precision, float* G, cudaStream_t s) {
-  NRM_TRY(launch_attention_backward(in, P, w, 0, precision, s));
-  NRM_TRY(launch_attention_finish(P, w, 0, G, s));
-  NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s));
-  NRM_TRY(launch_attention_finish(P, w, 1, G, s));
+  { KernelTimer t("attention_backward_label", s); NRM_TRY(launch_attention_backward(in, P, w, 0, precision, s)); }
+  { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 0, G, s)); }
+  { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
+  { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 1, G, s)); }
   // w1: dW = dxh^T xin_h, db = colsum(dxh), dxin_h = dxh W1
   {
+    KernelTimer t("w1_backward", s);
     GemmArgs g{};
     g.M = 64; g.N = XIN; g.K = (int)w.NH;
     g.A = w.dxh; g.sam = 1; g.sak = 64;
@@ -188,8 +221,8 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
     const int rc = launch_gemm<EPI_NONE>(d, 1, s);
     if (rc < 0) return rc;
   }
-  NRM_TRY(launch_small_linear_grads(in, w, G, s));
-  NRM_TRY(launch_table_grads(w, G, s));
+  { KernelTimer t("small_linear_grads", s); NRM_TRY(launch_small_linear_grads(in, w, G, s)); }
+  { KernelTimer t("table_grads", s); NRM_TRY(launch_table_grads(w, G, s)); }
   return NRM_OK;
 }
 
@@ -198,6 +231,31 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
 using namespace nrm;
 
 extern "C" int nrm_version(void) { return 100; }
+extern "C" unsigned long long nrm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+extern "C" void nrm_timing_enable(int on) {
+  g_timing = on != 0;
+  for (int i = 0; i < g_ntimers; ++i) g_timers[i].used = 0;
+}
+// Writes "name count total_ms\n" lines for every timed kernel group; synchronises the events.
+extern "C" int nrm_timing_report(char* buf, size_t buf_bytes) {
+  if (!buf || buf_bytes == 0) { set_error("nrm_timing_report: bad buffer"); return NRM_EINVAL; }
+  size_t off = 0;
+  buf[0] = 0;
+  for (int i = 0; i < g_ntimers; ++i) {
+    TimerSlot& t = g_timers[i];
+    double total = 0.0;
+    for (int k = 0; k < t.used; ++k) {
+      float ms = 0.f;
+      NRM_CUDA(cudaEventSynchronize(t.end[k]));
+      NRM_CUDA(cudaEventElapsedTime(&ms, t.beg[k], t.end[k]));
+      total += ms;
+    }
+    const int n = snprintf(buf + off, buf_bytes - off, "%s %d %.6f\n", t.name, t.used, total);
+    if (n < 0 || (size_t)n >= buf_bytes - off) break;
+    off += (size_t)n;
+  }
+  return NRM_OK;
+}
 extern "C" const char* nrm_last_error(void) { return g_err; }
 extern "C" int nrm_layout_entries(void) { return kLayoutEntries; }
 extern "C" const char* nrm_layout_name(int i) { return (i >= 0 && i < kLayoutEntries) ? kLayout[i].name : nullptr; }
@@ -223,6 +281,7 @@ extern "C" int nrm_forward_encoder(const double* x_history, const double* x_targ
   const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
   NRM_TRY(encoder_forward(in, params, w, mode, precision, s));
   if (mode & NRM_MODE_BN_BATCH_STATS) {
+    KernelTimer t("bn_statistics", s);
     NRM_TRY(launch_bn_partial_sums(w, s));
     if (bn_sums != nullptr && bn_sums != w.bn_sums)
       NRM_CUDA(cudaMemcpyAsync(bn_sums, w.bn_sums, sizeof(double) * 2 * E, cudaMemcpyDeviceToDevice, s));
@@ -242,6 +301,7 @@ extern "C" int nrm_forward_head(int B, int H, int C, const float* params, float*
   NRM_TRY(get_workspace("nrm_forward_head", w, workspace, workspace_bytes, B, H, C, mode));
   const double* sums = bn_sums ? bn_sums : w.bn_sums;
   const long long rows = bn_global_rows > 0 ? bn_global_rows : w.R;
+  KernelTimer t("head_forward", (cudaStream_t)stream);
   return launch_head_forward(params, w, bn_running_mean, bn_running_var, bn_num_batches_tracked, training, sums, rows,
                              logits, (cudaStream_t)stream);
 }
@@ -263,7 +323,7 @@ extern "C" int nrm_backward_head(int B, int H, int C, const float* params, const
   Workspace w;
   NRM_TRY(get_workspace("nrm_backward_head", w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
   cudaStream_t s = (cudaStream_t)stream;
-  NRM_TRY(launch_head_backward(params, w, dlogits, grads, s));
+  { KernelTimer t("head_backward", s); NRM_TRY(launch_head_backward(params, w, dlogits, grads, s)); }
   if (bn_bwd_sums != nullptr && bn_bwd_sums != w.bn_bwd_sums)
     NRM_CUDA(cudaMemcpyAsync(bn_bwd_sums, w.bn_bwd_sums, sizeof(double) * 2 * E, cudaMemcpyDeviceToDevice, s));
   return NRM_OK;

@@ -88,6 +88,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 #define NRM_LAUNCH_CHECK(name)                                      \
   do {                                                              \
+    ::nrm::count_launch();                                          \
     cudaError_t e__ = cudaGetLastError();                           \
     if (e__ != cudaSuccess) return ::nrm::cuda_fail(e__, name);     \
   } while (0)
@@ -98,6 +99,15 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int sm_count();
+void count_launch();
+
+// Optional per-kernel device timing (nrm_timing_enable): brackets the launches issued
+// during its lifetime with CUDA events on `stream`.  A no-op unless enabled.
+struct KernelTimer {
+  KernelTimer(const char* name, cudaStream_t stream);
+  ~KernelTimer();
+  int slot_; cudaStream_t stream_;
+};
 
 // ----------------------------------------------------------------------------
 // workspace

@@ -226,6 +226,7 @@ extern "C" int nrm_adam_step(float* param, const float* grad, float* exp_avg, fl
   long long blocks = (work + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  KernelTimer t("adam", s);
   if (aligned) adam_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, a);
   else adam_scalar_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, a);
   NRM_LAUNCH_CHECK("adam_kernel");

@@ -1,0 +1,104 @@
+"""Data-parallel training glue: one process per GPU, impressions sharded by rank.
+
+The reference is single-process; north_star asks for data-parallel
+training with the gradient all-reduce bucketed behind backward.  The flat gradient buffer
+makes that two NCCL calls: the head bucket ([bn .. out_mlp] + delta, contiguous at the end
+of the layout) is reduced while the encoder backward still runs, the encoder bucket right
+after it.  With `sync_bn=True` the BatchNorm batch statistics (2x264 doubles forward, 2x264
+backward) are all-reduced too, which makes N ranks x B impressions bit-for-bit the same
+model as one process on the N*B batch; the default keeps per-replica statistics (standard
+DDP behaviour, no collective in the forward).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous [begin, end) slice of `total` impressions owned by `rank` (sizes differ by <= 1)."""
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class GradientBuckets:
+    """Average the flat gradient buffer across ranks in two buckets."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self._avg = dist.get_backend(group) == 'nccl'
+        self.handles = []
+
+    def _reduce(self, t: torch.Tensor):
+        if self._avg:
+            self.handles.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:                                   # gloo (CPU tests): SUM then scale
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world)
+
+    def reduce(self, flat_grad: torch.Tensor, begin: int, end: int):
+        if end > begin:
+            self._reduce(flat_grad[begin:end])
+
+    def wait(self):
+        for h in self.handles:
+            h.wait()
+        self.handles = []
+
+
+class DataParallel:
+    """Attach to a UserModel: `DataParallel(model)`; afterwards model.forward / backward
+    run the collectives described in the module docstring."""
+
+    def __init__(self, model, group=None, sync_bn: bool = False, broadcast: bool = True):
+        if not dist.is_initialized():
+            raise RuntimeError('torch.distributed is not initialised')
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.sync_bn = sync_bn
+        self.buckets = GradientBuckets(group)
+        self.comm_stream: Optional[torch.cuda.Stream] = None
+        self._head_begin = None
+        model._dp = self
+        if broadcast:
+            flat = model.flat_parameters()
+            dist.broadcast(flat.buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            for b in (model.bn.running_mean, model.bn.running_var, model.bn.num_batches_tracked):
+                dist.broadcast(b, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+
+    # ---- BatchNorm statistics -----------------------------------------------------------
+    def all_reduce_stats(self, sums: torch.Tensor, local_rows: int) -> int:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        return local_rows * self.world       # equal shards (bench / tests); ragged shards all-reduce the count too
+
+    # ---- gradient buckets ---------------------------------------------------------------
+    def _split(self, flat):
+        if self._head_begin is None:
+            self._head_begin = next(off for name, off, _, _ in flat.slots if name == 'bn.weight')
+        return self._head_begin
+
+    def _on_comm_stream(self, fn):
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(cur)          # the gradients just written are visible
+        with torch.cuda.stream(self.comm_stream):
+            fn()
+
+    def reduce_head_bucket(self, g: torch.Tensor, flat):
+        hb = self._split(flat)
+        self._on_comm_stream(lambda: self.buckets.reduce(g, hb, g.numel()))
+
+    def reduce_encoder_bucket(self, g: torch.Tensor, flat):
+        hb = self._split(flat)
+        self._on_comm_stream(lambda: self.buckets.reduce(g, 0, hb))
+
+    def wait(self):
+        self.buckets.wait()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
