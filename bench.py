@@ -235,23 +235,31 @@ def run_ours(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * K / (ms_total / 1e3)
 
-    # ---- end to end: pinned host batches, H2D inside the timed region, loss read back every step
-    def e2e_step(hb):
-        xh = hb.x_history.to(dev, non_blocking=True); xt = hb.x_target.to(dev, non_blocking=True)
-        xg = hb.x_global.to(dev, non_blocking=True); lab = hb.label.to(dev, non_blocking=True)
-        uid = hb.user_id.to(dev, non_blocking=True)
-        out = model(xh, xt, xg)
-        loss = model.loss(uid, out, lab)
-        loss.backward()
-        opt.step()
-        opt.zero_grad()
-        return loss.item()
-    for i in range(2):
-        e2e_step(host[i % N_POOL])
+    # ---- end to end: pinned host batches -> H2D on a copy stream (prefetching the next batch while
+    # the current step runs, as a data loader would) -> step -> loss read back every step.
+    copy_stream = torch.cuda.Stream(dev)
+
+    def prefetch(hb):
+        with torch.cuda.stream(copy_stream):
+            db = hb.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return db, ev
+
+    def e2e_loop(n):
+        cur = prefetch(host[0])
+        last = 0.0
+        for i in range(n):
+            nxt = prefetch(host[(i + 1) % N_POOL]) if i + 1 < n else None
+            db, ev = cur
+            torch.cuda.current_stream().wait_event(ev)
+            last = step(db).item()            # D2H of the loss: the host sees every step's result
+            cur = nxt
+        return last
+    e2e_loop(2)
     barrier()
     e0.record()
-    for i in range(K):
-        e2e_step(host[i % N_POOL])
+    e2e_loop(K)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))

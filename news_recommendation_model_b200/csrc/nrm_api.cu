@@ -136,20 +136,23 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
     w.de = (float*)take(f * R * E);
     w.dz = (float*)take(f * R * E);
     w.bn_bwd_sums = (double*)take(sizeof(double) * 2 * E);
-    w.gt = (float*)take(f * 2 * R * 64);
     w.dxh = (float*)take(f * NH * 64);
     w.dxt = (float*)take(f * R * 64);
     w.dxin_h = (float*)take(f * NH * XIN);
     w.att_part = (float*)take(f * 2 * ATT_BWD_CTAS_MAX * ATT_PARTIAL);
-    w.splitk = (float*)take(f * 32 * (size_t)(HID * E));      // >= WGRAD_SPLITS x largest weight, >= 32 x 64x64
-    w.small_part = (float*)take(f * 128 * E);
+    {
+      const size_t head = (size_t)(P_DELTA - P_GATE_FC1_W) * (WGRAD_SPLITS + 1);
+      const size_t w1 = (size_t)(64 * XIN + 64) * (W1_SPLITS + 1);
+      w.splitk = (float*)take(f * (head > w1 ? head : w1));   // split partials of the head / w1 weight gradients
+    }
+    w.small_part = (float*)take(f * 1024 * 96);
     const size_t n32 = N * 6, n8 = N * 5;
     const size_t c32 = (n32 + SORT_CHUNK - 1) / SORT_CHUNK, c8 = (n8 + SORT_CHUNK - 1) / SORT_CHUNK;
     const size_t g32 = n32 / SEG_GROUP + NKEY32 + 1, g8 = n8 / SEG_GROUP + NKEY8 + 1;
     w.keys32 = (int*)take(sizeof(int) * n32); w.keys8 = (int*)take(sizeof(int) * n8);
     w.perm32 = (int*)take(sizeof(int) * n32); w.perm8 = (int*)take(sizeof(int) * n8);
     w.chunk_hist32 = (int*)take(sizeof(int) * c32 * NKEY32); w.chunk_hist8 = (int*)take(sizeof(int) * c8 * NKEY8);
-    w.seg32 = (int*)take(sizeof(int) * 2 * (NKEY32 + 1)); w.seg8 = (int*)take(sizeof(int) * 2 * (NKEY8 + 1));
+    w.seg32 = (int*)take(sizeof(int) * 3 * (NKEY32 + 1)); w.seg8 = (int*)take(sizeof(int) * 3 * (NKEY8 + 1));   // starts | group starts | totals
     w.gkey32 = (int*)take(sizeof(int) * g32); w.gkey8 = (int*)take(sizeof(int) * g8);
     w.gpart32 = (float*)take(f * g32 * 32); w.gpart8 = (float*)take(f * g8 * 8);
   }
@@ -194,25 +197,22 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
   { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 0, G, s)); }
   { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
   { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 1, G, s)); }
-  // w1: dW = dxh^T xin_h, db = colsum(dxh), dxin_h = dxh W1
+  // w1: dW = dxh^T xin_h and db = colsum(dxh) (virtual ones column) by one split GEMM; dxin_h = dxh W1
   {
     KernelTimer t("w1_backward", s);
+    constexpr int LEN = 64 * XIN + 64;      // w1.weight and w1.bias are adjacent in the flat layout
+    static_assert(P_W1_B == P_W1_W + 64 * XIN, "w1.weight / w1.bias must be contiguous");
     GemmArgs g{};
     g.M = 64; g.N = XIN; g.K = (int)w.NH;
     g.A = w.dxh; g.sam = 1; g.sak = 64;
     g.B = w.xin_h; g.sbk = XIN; g.sbn = 1;
     g.C = w.splitk; g.scm = XIN; g.scn = 1;
-    g.split_stride = 64 * XIN;
-    const int nsplit = launch_gemm<EPI_NONE>(g, 32, s);
+    g.ones_col = 1; g.Cb = w.splitk + 64 * XIN;
+    g.split_stride = LEN;
+    const int nsplit = launch_gemm<EPI_NONE>(g, W1_SPLITS, s);
     if (nsplit < 0) return nsplit;
-    reduce_splits_kernel<<<(64 * XIN + 255) / 256, 256, 0, s>>>(w.splitk, nsplit, 64 * XIN, G + P_W1_W, 64 * XIN);
+    reduce_splits_kernel<<<(LEN + 255) / 256, 256, 0, s>>>(w.splitk, nsplit, LEN, G + P_W1_W, LEN);
     NRM_LAUNCH_CHECK("reduce_splits_kernel(w1)");
-    const int rp = (int)((w.NH + STAT_BLOCKS - 1) / STAT_BLOCKS);
-    const int nch = (int)((w.NH + rp - 1) / rp);
-    colsum_partial_kernel<<<dim3(1, nch), 64, 0, s>>>(w.dxh, 64, w.NH, 64, rp, w.small_part);
-    NRM_LAUNCH_CHECK("colsum_partial_kernel(dxh)");
-    reduce_splits_kernel<<<1, 256, 0, s>>>(w.small_part, nch, 64, G + P_W1_B, 64);
-    NRM_LAUNCH_CHECK("reduce_splits_kernel(w1.bias)");
     GemmArgs d{};
     d.M = (int)w.NH; d.N = XIN; d.K = 64;
     d.A = w.dxh; d.sam = 64; d.sak = 1;

@@ -42,7 +42,7 @@ struct AttSmemBwd {
   float Wc[64 * 64];         // [j][k]
   float dhid[HT * 64];       // [row][j]
   float dhidT[64 * TS];      // [j][row]
-  float dA[64 * 64], dWd[64 * 64];   // per-CTA accumulators [j][k]
+  float dA[64 * 64], dWd[64 * 64], dBm[64 * 64];   // per-CTA accumulators [j][k]
   float t[CCH * 64], tp[CCH * 64], dP[CCH * 64], ds[CCH * HT], s[CCH * HT];
   float Gt[64];
   float gpart[16 * 64];      // per row-group partial sums of dhid columns; reused for the final dw2/db2 reduce
@@ -204,16 +204,15 @@ attention_forward_kernel(const double* __restrict__ xh, const float* __restrict_
 // backward: persistent grid (<= 148 CTAs), 256 threads, ~203 KB shared.
 // Recomputes the hidden tile, then per candidate:
 //   dhid = ds w2 gelu'(hid);  Gt = sum_h dhid;  S = dhid^T h;
-//   dA += S; dWd += S diag(t); dt = Gt Bm + sum_j S.Wd;  dh += dhid W_c   (dt, dh: label only)
-// Per-CTA partial sums of dA, dWd, dfc2 go to part[]; Gt goes to gt[R,64] (dBm, db1 are
-// formed from it by a split GEMM afterwards).
+//   dA += S; dWd += S diag(t); dBm += Gt t^T; db1 += Gt;
+//   dt = Gt Bm + sum_j S.Wd;  dh += dhid W_c   (dt, dh: label only)
+// Per-CTA partial sums of dA, dWd, dBm, db1, dfc2 go to part[blockIdx.x].
 // ---------------------------------------------------------------------------------
 template <int BRANCH>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_backward_kernel(const double* __restrict__ xh, const float* __restrict__ xhp, int B, int H, int C,
                           const float* __restrict__ P, const float* __restrict__ e, const float* __restrict__ de,
-                          float* __restrict__ gt, float* __restrict__ dxh, float* __restrict__ dxt,
-                          float* __restrict__ part) {
+                          float* __restrict__ dxh, float* __restrict__ dxt, float* __restrict__ part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttSmemBwd& sm = *reinterpret_cast<AttSmemBwd*>(smem_raw);
   constexpr AttOffsets off = BRANCH == 0 ? ATT_LABEL : ATT_TI;
@@ -222,9 +221,10 @@ attention_backward_kernel(const double* __restrict__ xh, const float* __restrict
   constexpr bool INPUT_GRADS = (BRANCH == 0);
   const int tid = threadIdx.x, tr = tid >> 4, tc = tid & 15;
   load_att_weights(P, off, sm.Wd, sm.A, sm.Bm, sm.b1, sm.w2);
-  for (int i = tid; i < 64 * 64; i += ATT_THREADS) { sm.dA[i] = 0.f; sm.dWd[i] = 0.f; }
+  for (int i = tid; i < 64 * 64; i += ATT_THREADS) { sm.dA[i] = 0.f; sm.dWd[i] = 0.f; sm.dBm[i] = 0.f; }
   const float b2 = __ldg(P + off.fc2_b);
   float dw2_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float db1_acc[4] = {0.f, 0.f, 0.f, 0.f};      // only the tc == 0 lane of each row group keeps these
   float db2_acc = 0.f;
 
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {
@@ -301,13 +301,31 @@ attention_backward_kernel(const double* __restrict__ xh, const float* __restrict
             }
           }
           __syncthreads();                                   // (c) dhid, dhidT, gpart visible
-          if (tid < 64) {
+          if (INPUT_GRADS && tid < 64) {
             float g = 0.f;
 #pragma unroll
             for (int q = 0; q < 16; ++q) g += sm.gpart[q * 64 + tid];
             sm.Gt[tid] = g;
-            float* dst = gt + rc * 64 + tid;
-            if (r0 == 0) *dst = g; else *dst += g;
+          }
+          {
+            // Gt[j] = sum_h dhid[h][j] for this thread's four j (= 4tr..4tr+3)
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float4 v = *reinterpret_cast<const float4*>(sm.gpart + q * 64 + 4 * tr);
+              g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+            }
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+            const float4 tq0 = *reinterpret_cast<const float4*>(sm.t + cl * 64 + 4 * tc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4* pb = reinterpret_cast<float4*>(sm.dBm + (4 * tr + j) * 64 + 4 * tc);
+              float4 vb = *pb;
+              vb.x = fmaf(gv[j], tq0.x, vb.x); vb.y = fmaf(gv[j], tq0.y, vb.y);
+              vb.z = fmaf(gv[j], tq0.z, vb.z); vb.w = fmaf(gv[j], tq0.w, vb.w);
+              *pb = vb;
+              if (tc == 0) db1_acc[j] += gv[j];
+            }
           }
           {
             // S[jj][kk] = sum_row dhid[row][4tr+jj] * h[row][4tc+kk]   (here tr indexes j, tc indexes k)
@@ -402,7 +420,13 @@ attention_backward_kernel(const double* __restrict__ xh, const float* __restrict
   // ---- per-CTA partial sums -> part[blockIdx.x]
   __syncthreads();
   float* out = part + (long long)blockIdx.x * ATT_PARTIAL;
-  for (int i = tid; i < 64 * 64; i += ATT_THREADS) { out[i] = sm.dA[i]; out[64 * 64 + i] = sm.dWd[i]; }
+  for (int i = tid; i < 64 * 64; i += ATT_THREADS) {
+    out[i] = sm.dA[i]; out[64 * 64 + i] = sm.dWd[i]; out[2 * 64 * 64 + i] = sm.dBm[i];
+  }
+  if (tc == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[3 * 64 * 64 + 64 + 4 * tr + j] = db1_acc[j];
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) sm.gpart[tr * 64 + 4 * tc + j] = dw2_acc[j];
   sm.dtpart[tid] = db2_acc;
@@ -411,27 +435,26 @@ attention_backward_kernel(const double* __restrict__ xh, const float* __restrict
     float g = 0.f;
 #pragma unroll
     for (int q = 0; q < 16; ++q) g += sm.gpart[q * 64 + tid];
-    out[2 * 64 * 64 + tid] = g;
+    out[3 * 64 * 64 + tid] = g;
   }
   if (tid == 0) {
     float d = 0.f;
     for (int q = 0; q < ATT_THREADS; q += 16) d += sm.dtpart[q];   // only tc == 0 lanes accumulated
-    out[2 * 64 * 64 + 64] = d;
+    out[3 * 64 * 64 + 128] = d;
   }
 }
 
-// fc1.weight grad [64,256] = [dA | dBm | dBm - dA | dWd]; fc1.bias = colsum(gt); fc2 from the partials.
+// Sum the per-CTA partials in fixed order and scatter them into the flat gradient:
+// fc1.weight grad [64,256] = [dA | dBm | dBm - dA | dWd]; fc1.bias = db1; fc2.weight = dw2; fc2.bias = db2.
 __global__ void __launch_bounds__(256)
-attention_compose_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ dBm_splits, int nsplits,
-                         const float* __restrict__ gsum_part, int ngsum, AttOffsets off, float* __restrict__ grads) {
+attention_compose_kernel(const float* __restrict__ part, int nparts, AttOffsets off, float* __restrict__ grads) {
   const int i = blockIdx.x * 256 + threadIdx.x;      // j*64 + k
   if (i < 64 * 64) {
     float dA = 0.f, dWd = 0.f, dBm = 0.f;
     for (int p = 0; p < nparts; ++p) {
-      dA += part[(long long)p * ATT_PARTIAL + i];
-      dWd += part[(long long)p * ATT_PARTIAL + 64 * 64 + i];
+      const float* q = part + (long long)p * ATT_PARTIAL + i;
+      dA += q[0]; dWd += q[64 * 64]; dBm += q[2 * 64 * 64];
     }
-    for (int z = 0; z < nsplits; ++z) dBm += dBm_splits[(long long)z * 64 * 64 + i];
     const int j = i >> 6, k = i & 63;
     float* row = grads + off.fc1_w + j * 256;
     row[k] = dA; row[64 + k] = dBm; row[128 + k] = dBm - dA; row[192 + k] = dWd;
@@ -439,13 +462,15 @@ attention_compose_kernel(const float* __restrict__ part, int nparts, const float
   if (blockIdx.x == 0 && threadIdx.x < 64) {
     const int j = threadIdx.x;
     float w = 0.f, b1 = 0.f;
-    for (int p = 0; p < nparts; ++p) w += part[(long long)p * ATT_PARTIAL + 2 * 64 * 64 + j];
-    for (int p = 0; p < ngsum; ++p) b1 += gsum_part[(long long)p * 64 + j];
+    for (int p = 0; p < nparts; ++p) {
+      w += part[(long long)p * ATT_PARTIAL + 3 * 64 * 64 + j];
+      b1 += part[(long long)p * ATT_PARTIAL + 3 * 64 * 64 + 64 + j];
+    }
     grads[off.fc2_w + j] = w;
     grads[off.fc1_b + j] = b1;
     if (j == 0) {
       float d = 0.f;
-      for (int p = 0; p < nparts; ++p) d += part[(long long)p * ATT_PARTIAL + 2 * 64 * 64 + 64];
+      for (int p = 0; p < nparts; ++p) d += part[(long long)p * ATT_PARTIAL + 3 * 64 * 64 + 128];
       grads[off.fc2_b] = d;
     }
   }
@@ -475,13 +500,12 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
   const size_t smem = sizeof(AttSmemBwd);
   const int grid = att_bwd_grid(w.B);
   float* part = w.att_part + (long long)branch * ATT_BWD_CTAS_MAX * ATT_PARTIAL;
-  float* gt = w.gt + (long long)branch * w.R * 64;
   if (branch == 0) {
     NRM_CUDA(cudaFuncSetAttribute(attention_backward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_backward_kernel<0><<<grid, ATT_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, P, w.e, w.de, gt, w.dxh, w.dxt, part);
+    attention_backward_kernel<0><<<grid, ATT_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, P, w.e, w.de, w.dxh, w.dxt, part);
   } else {
     NRM_CUDA(cudaFuncSetAttribute(attention_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_backward_kernel<1><<<grid, ATT_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, P, w.e, w.de, gt, w.dxh, w.dxt, part);
+    attention_backward_kernel<1><<<grid, ATT_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, P, w.e, w.de, w.dxh, w.dxt, part);
   }
   NRM_LAUNCH_CHECK("attention_backward_kernel");
   return NRM_OK;
@@ -489,35 +513,8 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
 
 int launch_attention_finish(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s) {
   (void)P;
-  const float* gt = w.gt + (long long)branch * w.R * 64;
-  const int toff = branch == 0 ? E_XT : E_PCAT;
-  // dBm[j][k] = sum_r gt[r][j] * t[r][k], split over rows
-  GemmArgs g{};
-  g.M = 64; g.N = 64; g.K = (int)w.R;
-  g.A = gt; g.sam = 1; g.sak = 64;
-  g.B = w.e + toff; g.sbk = E; g.sbn = 1;
-  g.C = w.splitk; g.scm = 64; g.scn = 1;
-  g.split_stride = 64 * 64;
-  int want = (int)min((long long)32, (w.R + 127) / 128);
-  GemmArgs gg = g; gg.split_stride = 64 * 64;
-  int nsplits;
-  {
-    if (want <= 1) { want = 1; }
-    gg.k_chunk = (gg.K + want - 1) / want;
-    gg.k_chunk = (gg.k_chunk + 15) / 16 * 16;
-    nsplits = (gg.K + gg.k_chunk - 1) / gg.k_chunk;
-    dim3 grid(1, 1, nsplits);
-    gemm_kernel<64, 64, 4, 4, EPI_NONE><<<grid, 256, 0, s>>>(gg);
-    NRM_LAUNCH_CHECK("gemm_kernel(dBm)");
-  }
-  // db1 = column sums of gt
-  const int rows_per_chunk = (int)((w.R + STAT_BLOCKS - 1) / STAT_BLOCKS);
-  const int nchunks = (int)((w.R + rows_per_chunk - 1) / rows_per_chunk);
-  colsum_partial_kernel<<<dim3(1, nchunks), 64, 0, s>>>(gt, 64, w.R, 64, rows_per_chunk, w.small_part);
-  NRM_LAUNCH_CHECK("colsum_partial_kernel(gt)");
   const float* part = w.att_part + (long long)branch * ATT_BWD_CTAS_MAX * ATT_PARTIAL;
-  attention_compose_kernel<<<16, 256, 0, s>>>(part, att_bwd_grid(w.B), w.splitk, nsplits, w.small_part, nchunks,
-                                             branch == 0 ? ATT_LABEL : ATT_TI, grads);
+  attention_compose_kernel<<<16, 256, 0, s>>>(part, att_bwd_grid(w.B), branch == 0 ? ATT_LABEL : ATT_TI, grads);
   NRM_LAUNCH_CHECK("attention_compose_kernel");
   return NRM_OK;
 }

@@ -115,9 +115,10 @@ struct KernelTimer {
 constexpr int SORT_CHUNK = 2048;       // entries per counting-sort CTA
 constexpr int SEG_GROUP = 128;         // sorted entries per level-1 segment group
 constexpr int ATT_BWD_CTAS_MAX = 148;  // persistent grid of the attention backward
-constexpr int ATT_PARTIAL = 2 * D * D + 64 + 4;   // dA | dWd | dw2 | db2 (+pad) floats per CTA
+constexpr int ATT_PARTIAL = 3 * D * D + 64 + 64 + 4;   // dA | dWd | dBm | dw2 | db1 | db2 (+pad) floats per CTA
 constexpr int STAT_BLOCKS = 64;        // row chunks of the column-statistics kernels
-constexpr int WGRAD_SPLITS = 16;       // split-K factor of the weight-gradient GEMMs
+constexpr int WGRAD_SPLITS = 32;       // split-K factor of the head weight-gradient GEMMs
+constexpr int W1_SPLITS = 256;         // split-K factor of the w1 weight gradient (K = B*H rows)
 
 struct Workspace {
   // sizes
@@ -145,7 +146,6 @@ struct Workspace {
   float* de;           // [R,264]   dL/de (direct path, then + BN path)
   float* dz;           // [R,264]
   double* bn_bwd_sums; // [2,264]
-  float* gt;           // [2][R,64]  per-candidate sums of dhid (label, text/img)
   float* dxh;          // [NH,64]
   float* dxt;          // [R,64]
   float* dxin_h;       // [NH,66]

@@ -105,13 +105,14 @@ embed_rows_kernel(const double* __restrict__ xh, const double* __restrict__ xt, 
 }
 
 // ---------------------------------------------------------------------------------
-// Deterministic counting sort of table ids (keys < nkeys <= 3000), three kernels:
+// Deterministic counting sort of table ids (keys < nkeys <= 3000):
 //   sort_hist:    per 2048-entry chunk, histogram of keys           -> chunk_hist[chunk][key]
-//   sort_scan:    per key, exclusive scan over chunks (in place), then exclusive scan over
-//                 keys of the totals -> seg[0..nkeys] (segment starts), and the same for the
-//                 number of SEG_GROUP-sized groups -> seg[nkeys+1 .. 2nkeys+1], group -> key
+//   sort_colscan: per key (a warp each), exclusive scan over chunks (in place) + key totals
+//   sort_keyscan: exclusive scan over keys of the totals -> seg[0..nkeys] (segment starts),
+//                 the same for the number of SEG_GROUP-sized groups -> seg[nkeys+1 .. 2nkeys+1],
+//                 and the group -> key map
 //   sort_scatter: stable rank of each entry inside its chunk + the two offsets -> perm
-// Integer atomics are used only for counts (order independent).
+// (four kernels.)  Integer atomics are used only for counts (order independent).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 sort_hist_kernel(const int* __restrict__ keys, long long n, int nkeys, int* __restrict__ chunk_hist) {
@@ -126,10 +127,31 @@ sort_hist_kernel(const int* __restrict__ keys, long long n, int nkeys, int* __re
   for (int i = threadIdx.x; i < nkeys; i += blockDim.x) out[i] = hist[i];
 }
 
+// Per key (one warp each): exclusive scan of the chunk histograms over chunks, in place, and
+// the key's total count.
+__global__ void __launch_bounds__(256)
+sort_colscan_kernel(int* __restrict__ chunk_hist, int nchunks, int nkeys, int* __restrict__ totals) {
+  const int key = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (key >= nkeys) return;
+  int carry = 0;
+  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+    const int c = c0 + lane;
+    int* p = chunk_hist + (long long)c * nkeys + key;
+    const int own = (c < nchunks) ? *p : 0;
+    int v = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (c < nchunks) *p = carry + v - own;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+  if (lane == 0) totals[key] = carry;
+}
+
+// One CTA: exclusive scan over keys of the totals -> segment starts, and of the number of
+// SEG_GROUP-sized groups -> group starts; also the group -> key map.
 __global__ void __launch_bounds__(1024)
-sort_scan_kernel(int* __restrict__ chunk_hist, int nchunks, int nkeys, int* __restrict__ seg,
-                 int* __restrict__ group_key) {
-  // one CTA of 1024 threads; keys are processed in blocks of 1024 with a running carry
+sort_keyscan_kernel(const int* __restrict__ totals, int nkeys, int* __restrict__ seg, int* __restrict__ group_key) {
   __shared__ int warp_off[2][32];
   __shared__ int block_tot[2];
   __shared__ int carry[2];
@@ -140,13 +162,7 @@ sort_scan_kernel(int* __restrict__ chunk_hist, int nchunks, int nkeys, int* __re
   __syncthreads();
   for (int k0 = 0; k0 < nkeys; k0 += 1024) {
     const int key = k0 + threadIdx.x;
-    int total = 0;
-    if (key < nkeys) {
-      for (int c = 0; c < nchunks; ++c) {          // exclusive scan over chunks, in place
-        int* p = chunk_hist + (long long)c * nkeys + key;
-        const int v = *p; *p = total; total += v;
-      }
-    }
+    const int total = key < nkeys ? totals[key] : 0;
     const int vals[2] = {total, (total + SEG_GROUP - 1) / SEG_GROUP};
     int excl[2];
 #pragma unroll
@@ -373,8 +389,11 @@ static int sort_stream(const int* keys, long long n, int nkeys, int* chunk_hist,
   const int nchunks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
   sort_hist_kernel<<<nchunks, 1024, nkeys * sizeof(int), s>>>(keys, n, nkeys, chunk_hist);
   NRM_LAUNCH_CHECK("sort_hist_kernel");
-  sort_scan_kernel<<<1, 1024, 0, s>>>(chunk_hist, nchunks, nkeys, seg, gkey);
-  NRM_LAUNCH_CHECK("sort_scan_kernel");
+  int* totals = seg + 2 * (nkeys + 1);
+  sort_colscan_kernel<<<(nkeys + 7) / 8, 256, 0, s>>>(chunk_hist, nchunks, nkeys, totals);
+  NRM_LAUNCH_CHECK("sort_colscan_kernel");
+  sort_keyscan_kernel<<<1, 1024, 0, s>>>(totals, nkeys, seg, gkey);
+  NRM_LAUNCH_CHECK("sort_keyscan_kernel");
   sort_scatter_kernel<<<nchunks, 32, nkeys * sizeof(int), s>>>(keys, n, nkeys, chunk_hist, seg, perm);
   NRM_LAUNCH_CHECK("sort_scatter_kernel");
   return NRM_OK;
@@ -397,7 +416,7 @@ int launch_table_grads(Workspace& w, float* grads, cudaStream_t s) {
 }
 
 int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, cudaStream_t s) {
-  const int nparts = 128;
+  const int nparts = 1024;
   const int rows_per_cta = (int)((w.N + nparts - 1) / nparts);
   small_linear_grad_kernel<<<nparts, 256, 0, s>>>(in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.C, w.NH, w.N, w.xin_h, w.e,
                                                   w.dxin_h, w.dxt, w.de, rows_per_cta, w.small_part);

@@ -5,9 +5,17 @@
 //
 // All three operands are addressed through (row, col) strides so that the forward
 // (x W^T), data-gradient (dy W) and weight-gradient (dy^T x, split over rows) products of
-// the head MLPs, of w1 and of the attention fc1 blocks share one kernel.  gridDim.z > 1
-// splits K; split z writes its partial to C + z*split_stride (summed later in fixed order
-// by reduce_splits_kernel, so results are run-to-run deterministic without atomics).
+// the head MLPs, of w1 and of the attention blocks share one kernel.
+//
+// Every reduction here is short per CTA (K <= 264 for the layer products, a <= 256-row
+// slice for the split weight gradients), so a CTA stages its whole operand slabs in shared
+// memory 128 k-steps at a time: all global loads of a slab are in flight together and the
+// FFMA loop runs uninterrupted; 2-4 CTAs per SM overlap each other's load phases.
+//
+// gridDim.z > 1 splits K; split z writes its partial to C + z*split_stride (summed later in
+// fixed order by reduce_splits_kernel: run-to-run deterministic, no atomics).
+// ones_row / ones_col append a virtual all-ones row to A (m == M) or column to B (n == N):
+// the extra output row/column is the bias gradient and goes to Cb[n] / Cb[m].
 #pragma once
 #include "nrm_common.cuh"
 
@@ -31,23 +39,32 @@ struct GemmArgs {
   const float* bias;         // [N]
   const float* aux1; const float* aux2; long long saux;   // aux(m,n) = aux[m*saux + n]
   int k_chunk;               // K range per split (== K when gridDim.z == 1)
-  long long split_stride;    // floats between split partials
+  long long split_stride;    // floats between split partials (applies to C and Cb)
+  int ones_row, ones_col;    // virtual ones row of A / ones column of B (bias gradients)
+  float* Cb;                 // destination of the virtual row / column
 };
 
-template <int BM, int BN, int TM, int TN, int EPI>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+constexpr int GEMM_BK = 128;
+
+template <int BM, int BN>
+constexpr size_t gemm_smem_bytes() { return sizeof(float) * GEMM_BK * ((BM + 4) + (BN + 4)); }
+
+template <int BM, int BN, int EPI>
+__global__ void __launch_bounds__((BM / 4) * (BN / 4))
 gemm_kernel(const GemmArgs g) {
-  constexpr int BK = 16;
+  constexpr int TM = 4, TN = 4;
   constexpr int NT = (BM / TM) * (BN / TN);
-  static_assert(TM == 4 && TN == 4, "micro-tile is 4x4 (float4 shared loads)");
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+  constexpr int LDA = BM + 4, LDB = BN + 4;
+  extern __shared__ __align__(16) float gemm_smem[];
+  float* As = gemm_smem;                 // [GEMM_BK][LDA]
+  float* Bs = gemm_smem + GEMM_BK * LDA; // [GEMM_BK][LDB]
 
   const int tid = threadIdx.x;
   const int tn = tid % (BN / TN), tm = tid / (BN / TN);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * g.k_chunk;
   const int kend = min(g.K, kbeg + g.k_chunk);
+  const int Mx = g.M + g.ones_row, Nx = g.N + g.ones_col;
   const bool a_kfast = (g.sak == 1);     // which index varies fastest across threads on load
   const bool b_nfast = (g.sbn == 1);
 
@@ -57,24 +74,32 @@ gemm_kernel(const GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
-    for (int i = tid; i < BM * BK; i += NT) {
+  for (int k0 = kbeg; k0 < kend; k0 += GEMM_BK) {
+    const int kc = min(GEMM_BK, kend - k0);
+    if (k0 != kbeg) __syncthreads();
+    for (int i = tid; i < BM * kc; i += NT) {
       int m, k;
-      if (a_kfast) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
-      const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < g.M && gk < kend) ? __ldg(g.A + gm * g.sam + gk * g.sak) : 0.f;
+      if (a_kfast) { k = i % kc; m = i / kc; } else { m = i % BM; k = i / BM; }
+      const int gm = m0 + m;
+      float v = 0.f;
+      if (gm < g.M) v = __ldg(g.A + gm * g.sam + (k0 + k) * g.sak);
+      else if (gm < Mx) v = 1.f;
+      As[k * LDA + m] = v;
     }
-    for (int i = tid; i < BN * BK; i += NT) {
+    for (int i = tid; i < BN * kc; i += NT) {
       int n, k;
-      if (b_nfast) { n = i % BN; k = i / BN; } else { k = i % BK; n = i / BK; }
-      const int gn = n0 + n, gk = k0 + k;
-      Bs[k][n] = (gn < g.N && gk < kend) ? __ldg(g.B + gk * g.sbk + gn * g.sbn) : 0.f;
+      if (b_nfast) { n = i % BN; k = i / BN; } else { k = i % kc; n = i / kc; }
+      const int gn = n0 + n;
+      float v = 0.f;
+      if (gn < g.N) v = __ldg(g.B + (k0 + k) * g.sbk + gn * g.sbn);
+      else if (gn < Nx) v = 1.f;
+      Bs[k * LDB + n] = v;
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][tm * TM]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tn * TN]);
+#pragma unroll 8
+    for (int kk = 0; kk < kc; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(As + kk * LDA + tm * TM);
+      const float4 b = *reinterpret_cast<const float4*>(Bs + kk * LDB + tn * TN);
       const float av[4] = {a.x, a.y, a.z, a.w};
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -82,20 +107,25 @@ gemm_kernel(const GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    __syncthreads();
   }
 
-  float* C = g.C + (long long)blockIdx.z * g.split_stride;
+  const long long zoff = (long long)blockIdx.z * g.split_stride;
+  float* C = g.C + zoff;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + tm * TM + i;
-    if (m >= g.M) continue;
+    if (m >= Mx) continue;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tn * TN + j;
-      if (n >= g.N) continue;
-      const long long ci = m * g.scm + n * g.scn;
+      if (n >= Nx) continue;
       float v = acc[i][j];
+      if (m >= g.M || n >= g.N) {          // bias-gradient row / column (EPI_NONE only)
+        if (m >= g.M && n >= g.N) continue;
+        g.Cb[zoff + (m >= g.M ? n : m)] = v;
+        continue;
+      }
+      const long long ci = m * g.scm + n * g.scn;
       if (EPI == EPI_NONE) {
         C[ci] = v;
       } else if (EPI == EPI_BIAS) {
@@ -122,32 +152,42 @@ gemm_kernel(const GemmArgs g) {
 __global__ void reduce_splits_kernel(const float* __restrict__ src, int nsplit, long long stride,
                                      float* __restrict__ dst, long long count);
 
-// Column sums of src[M,N] (row stride ld) split over STAT-style row chunks:
-// part[blockIdx.y][n] = sum over this chunk's rows; follow with reduce_splits_kernel.
-__global__ void colsum_partial_kernel(const float* __restrict__ src, long long ld, long long M, int N,
-                                      int rows_per_chunk, float* __restrict__ part);
+template <int BM, int BN, int EPI>
+int launch_gemm_tile(const GemmArgs& g, int splits, cudaStream_t s) {
+  constexpr size_t smem = gemm_smem_bytes<BM, BN>();
+  static bool configured = false;
+  if (!configured) {
+    NRM_CUDA(cudaFuncSetAttribute(gemm_kernel<BM, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int Mx = g.M + g.ones_row, Nx = g.N + g.ones_col;
+  dim3 grid((Nx + BN - 1) / BN, (Mx + BM - 1) / BM, splits);
+  gemm_kernel<BM, BN, EPI><<<grid, (BM / 4) * (BN / 4), smem, s>>>(g);
+  NRM_LAUNCH_CHECK("gemm_kernel");
+  return NRM_OK;
+}
 
+// Returns the number of K splits actually written (>= 1) or a negative error code.
 template <int EPI>
 int launch_gemm(GemmArgs g, int splits, cudaStream_t s) {
-  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return NRM_OK;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 1;
   if (splits <= 1) {
     splits = 1; g.k_chunk = g.K; g.split_stride = 0;
   } else {
     g.k_chunk = (g.K + splits - 1) / splits;
-    g.k_chunk = (g.k_chunk + 15) / 16 * 16;
+    g.k_chunk = (g.k_chunk + 7) / 8 * 8;
     splits = (g.K + g.k_chunk - 1) / g.k_chunk;
   }
-  // 64x64 tiles when N is a multiple of 64 or large; a 64x72 tile covers the 66-wide
-  // hidden layers of the head MLPs in one column tile.
-  if (g.N > 64 && g.N <= 72) {
-    dim3 grid(1, (g.M + 63) / 64, splits);
-    gemm_kernel<64, 72, 4, 4, EPI><<<grid, 288, 0, s>>>(g);
-  } else {
-    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, splits);
-    gemm_kernel<64, 64, 4, 4, EPI><<<grid, 256, 0, s>>>(g);
-  }
-  NRM_LAUNCH_CHECK("gemm_kernel");
-  return splits;   // > 0: number of partials actually written
+  const int Nx = g.N + g.ones_col, Mx = g.M + g.ones_row;
+  // column tile: 72 covers the 66(+1)-wide hidden layers in one tile and 264(+1) in four;
+  // row tile: 32 when that is what it takes to fill the machine
+  const bool wide72 = (Nx > 64 && Nx <= 72) || (Nx > 128 && (Nx + 71) / 72 < (Nx + 63) / 64);
+  const long long ctas64 = (long long)((Mx + 63) / 64) * ((Nx + (wide72 ? 71 : 63)) / (wide72 ? 72 : 64)) * splits;
+  const bool small_rows = ctas64 < 2LL * sm_count();
+  int rc;
+  if (wide72) rc = small_rows ? launch_gemm_tile<32, 72, EPI>(g, splits, s) : launch_gemm_tile<64, 72, EPI>(g, splits, s);
+  else rc = small_rows ? launch_gemm_tile<32, 64, EPI>(g, splits, s) : launch_gemm_tile<64, 64, EPI>(g, splits, s);
+  return rc < 0 ? rc : splits;
 }
 
 }  // namespace nrm

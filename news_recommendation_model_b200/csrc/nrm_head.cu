@@ -16,15 +16,23 @@ __global__ void reduce_splits_kernel(const float* __restrict__ src, int nsplit, 
   dst[i] = acc;
 }
 
-__global__ void colsum_partial_kernel(const float* __restrict__ src, long long ld, long long M, int N,
-                                      int rows_per_chunk, float* __restrict__ part) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
-  const long long r1 = min(M, r0 + rows_per_chunk);
+// Sum the split partials of the head weight/bias gradients (region [P_GATE_FC1_W, P_DELTA) of
+// the flat layout, mirrored in every partial) into the flat gradient.  Alignment padding
+// between entries is never written by the GEMMs, so it is skipped here (stays zero).
+__global__ void __launch_bounds__(256)
+reduce_head_splits_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ grads) {
+  constexpr long long BEG = P_GATE_FC1_W, LEN = P_DELTA - P_GATE_FC1_W;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= LEN) return;
+  const long long o = BEG + i;
+  // entries with a padded tail: 66-wide biases / out_mlp.fc2.weight (2 pad floats) and the scalar bias (3)
+  const bool pad = (o >= P_GATE_FC1_B + HID && o < P_GATE_FC2_W) || (o >= P_MLP_FC1_B + HID && o < P_MLP_FC2_W) ||
+                   (o >= P_OUT_FC1_B + HID && o < P_OUT_FC2_W) || (o >= P_OUT_FC2_W + HID && o < P_OUT_FC2_B) ||
+                   (o >= P_OUT_FC2_B + 1);
+  if (pad) return;
   float acc = 0.f;
-  for (long long r = r0; r < r1; ++r) acc += src[r * ld + n];
-  part[(long long)blockIdx.y * N + n] = acc;
+  for (int z = 0; z < nsplit; ++z) acc += part[z * LEN + i];
+  grads[o] = acc;
 }
 
 // ---------------------------------------------------------------------------------
@@ -206,65 +214,63 @@ int launch_head_forward(const float* P, Workspace& w, float* run_mean, float* ru
   return NRM_OK;
 }
 
-// dW (layout of the nn.Linear weight, [out,in]) = dY^T X, summed over rows with a split GEMM,
-// and db = column sums of dY.  X: [R,in], dY: [R,out].
-static int weight_grad(const float* dY, int out, const float* X, int in, long long R, float* dW, float* db,
+// dW (layout of the nn.Linear weight, [out,in]) = dY^T X and db = colsum(dY), summed over rows by
+// a split GEMM whose partials mirror the flat layout of the head region (one reduce at the end).
+// X: [R,in], dY: [R,out].  Returns the number of splits (same for every head layer) or < 0.
+static int weight_grad(const float* dY, int out, const float* X, int in, long long R, long long w_off, long long b_off,
                        Workspace& w, cudaStream_t s) {
+  constexpr long long BEG = P_GATE_FC1_W, LEN = P_DELTA - P_GATE_FC1_W;
   GemmArgs g{};
   g.K = (int)R;
-  if (out == HID || out == 1) {        // dW[o][i]: put the narrow dimension on N
+  if (out == HID || out == 1) {        // dW[o][i]: put the narrow dimension on N; bias = virtual ones row of A
     g.M = in; g.N = out;
     g.A = X; g.sam = 1; g.sak = in;
     g.B = dY; g.sbk = out; g.sbn = 1;
     g.scm = 1; g.scn = in;
-  } else {
+    g.ones_row = 1;
+  } else {                             // bias = virtual ones column of B
     g.M = out; g.N = in;
     g.A = dY; g.sam = 1; g.sak = out;
     g.B = X; g.sbk = in; g.sbn = 1;
     g.scm = in; g.scn = 1;
+    g.ones_col = 1;
   }
-  g.C = w.splitk;
-  g.split_stride = (long long)out * in;
-  const int nsplit = launch_gemm<EPI_NONE>(g, WGRAD_SPLITS, s);
-  if (nsplit < 0) return nsplit;
-  const long long cnt = (long long)out * in;
-  reduce_splits_kernel<<<(int)((cnt + 255) / 256), 256, 0, s>>>(w.splitk, nsplit, cnt, dW, cnt);
-  NRM_LAUNCH_CHECK("reduce_splits_kernel");
-  if (db != nullptr) {
-    const int rp = stat_rows(R), nch = stat_chunks(R);
-    colsum_partial_kernel<<<dim3((out + 63) / 64, nch), 64, 0, s>>>(dY, out, R, out, rp, w.small_part);
-    NRM_LAUNCH_CHECK("colsum_partial_kernel");
-    reduce_splits_kernel<<<(out + 255) / 256, 256, 0, s>>>(w.small_part, nch, out, db, out);
-    NRM_LAUNCH_CHECK("reduce_splits_kernel");
-  }
-  return NRM_OK;
+  g.C = w.splitk + (w_off - BEG);
+  g.Cb = w.splitk + (b_off - BEG);
+  g.split_stride = LEN;
+  return launch_gemm<EPI_NONE>(g, WGRAD_SPLITS, s);
 }
 
 int launch_head_backward(const float* P, Workspace& w, const float* dlogits, float* G, cudaStream_t s) {
   const long long R = w.R;
   int rc;
   // out_mlp.fc2: r = u3 . O2 + f2
-  NRM_TRY(weight_grad(dlogits, 1, w.u3, HID, R, G + P_OUT_FC2_W, G + P_OUT_FC2_B, w, s));
+  int nsplit = weight_grad(dlogits, 1, w.u3, HID, R, P_OUT_FC2_W, P_OUT_FC2_B, w, s); if (nsplit < 0) return nsplit;
   out_fc2_backward_kernel<<<(int)((R * HID + 255) / 256), 256, 0, s>>>(dlogits, P + P_OUT_FC2_W, w.a3, R * HID, w.da3);
   NRM_LAUNCH_CHECK("out_fc2_backward_kernel");
   // out_mlp.fc1
-  NRM_TRY(weight_grad(w.da3, HID, w.y, E, R, G + P_OUT_FC1_W, G + P_OUT_FC1_B, w, s));
+  rc = weight_grad(w.da3, HID, w.y, E, R, P_OUT_FC1_W, P_OUT_FC1_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
   rc = launch_gemm<EPI_NONE>(linear_bwd_data(w.da3, HID, P + P_OUT_FC1_W, w.dy, nullptr, E, R), 1, s); if (rc < 0) return rc;
   // mlp.fc2
-  NRM_TRY(weight_grad(w.dy, E, w.u2, HID, R, G + P_MLP_FC2_W, G + P_MLP_FC2_B, w, s));
+  rc = weight_grad(w.dy, E, w.u2, HID, R, P_MLP_FC2_W, P_MLP_FC2_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
   { GemmArgs g = linear_bwd_data(w.dy, E, P + P_MLP_FC2_W, w.da2, nullptr, HID, R); g.aux1 = w.a2; g.saux = HID;
     rc = launch_gemm<EPI_MUL_GELUGRAD>(g, 1, s); if (rc < 0) return rc; }
   // mlp.fc1 ; dx -> dgate = dx * e, de = dx * gate
-  NRM_TRY(weight_grad(w.da2, HID, w.x, E, R, G + P_MLP_FC1_W, G + P_MLP_FC1_B, w, s));
+  rc = weight_grad(w.da2, HID, w.x, E, R, P_MLP_FC1_W, P_MLP_FC1_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
   { GemmArgs g = linear_bwd_data(w.da2, HID, P + P_MLP_FC1_W, w.dgate, w.de, E, R); g.aux1 = w.e; g.aux2 = w.gate; g.saux = E;
     rc = launch_gemm<EPI_DX2>(g, 1, s); if (rc < 0) return rc; }
   // gate.fc2
-  NRM_TRY(weight_grad(w.dgate, E, w.u1, HID, R, G + P_GATE_FC2_W, G + P_GATE_FC2_B, w, s));
+  rc = weight_grad(w.dgate, E, w.u1, HID, R, P_GATE_FC2_W, P_GATE_FC2_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
   { GemmArgs g = linear_bwd_data(w.dgate, E, P + P_GATE_FC2_W, w.da1, nullptr, HID, R); g.aux1 = w.a1; g.saux = HID;
     rc = launch_gemm<EPI_MUL_GELUGRAD>(g, 1, s); if (rc < 0) return rc; }
   // gate.fc1 ; dz
-  NRM_TRY(weight_grad(w.da1, HID, w.z, E, R, G + P_GATE_FC1_W, G + P_GATE_FC1_B, w, s));
+  rc = weight_grad(w.da1, HID, w.z, E, R, P_GATE_FC1_W, P_GATE_FC1_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
   rc = launch_gemm<EPI_NONE>(linear_bwd_data(w.da1, HID, P + P_GATE_FC1_W, w.dz, nullptr, E, R), 1, s); if (rc < 0) return rc;
+  {
+    constexpr long long LEN = P_DELTA - P_GATE_FC1_W;
+    reduce_head_splits_kernel<<<(int)((LEN + 255) / 256), 256, 0, s>>>(w.splitk, nsplit, G);
+    NRM_LAUNCH_CHECK("reduce_head_splits_kernel");
+  }
   // BatchNorm: column sums of dz and dz*xhat (this rank's rows)
   const int rp = stat_rows(R), nch = stat_chunks(R);
   bn_bwd_partial_kernel<<<nch, E, 0, s>>>(w.dz, w.e, w.mean, w.rstd, R, rp, w.stat_part);

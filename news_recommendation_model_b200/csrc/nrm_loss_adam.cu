@@ -113,18 +113,27 @@ loss_scale_kernel(const float* __restrict__ dlog, const float* __restrict__ grad
 }
 
 // ddelta[user] = grad_loss * sum of drow over the impressions of that user, in batch order.
-// The first occurrence of every user id owns the sum (no atomics, deterministic).
+// One warp per impression: it owns the sum iff no earlier impression has the same user id
+// (no atomics, deterministic).
 __global__ void __launch_bounds__(256)
 delta_grad_kernel(const long long* __restrict__ uid, const float* __restrict__ drow, int B,
                   const float* __restrict__ grad_loss, float* __restrict__ ddelta, long long delta_numel) {
-  const int b = blockIdx.x * 256 + threadIdx.x;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const long long id = uid[b];
   if (id < 0 || id >= delta_numel) return;
-  for (int j = 0; j < b; ++j) if (uid[j] == id) return;
-  float acc = drow[b];
-  for (int j = b + 1; j < B; ++j) if (uid[j] == id) acc += drow[j];
-  ddelta[id] = acc * __ldg(grad_loss);
+  bool dup = false;
+  for (int j0 = 0; j0 < b && !dup; j0 += 32) {
+    const int j = j0 + lane;
+    dup = __any_sync(0xffffffffu, j < b && uid[j] == id);
+  }
+  if (dup) return;
+  float acc = 0.f;                                   // lane-strided partial sums, combined in lane order
+  for (int j = b + lane; j < B; j += 32) if (uid[j] == id) acc += drow[j];
+  float tot = 0.f;
+  for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, acc, l);
+  if (lane == 0) ddelta[id] = tot * __ldg(grad_loss);
 }
 
 // ---------------------------------------------------------------------------------
@@ -203,7 +212,7 @@ extern "C" int nrm_loss_backward(const long long* user_id, int B, int C, const f
   NRM_LAUNCH_CHECK("loss_scale_kernel");
   if (ddelta != nullptr && delta_numel > 0) {
     NRM_CUDA(cudaMemsetAsync(ddelta, 0, sizeof(float) * (size_t)delta_numel, s));
-    delta_grad_kernel<<<(B + 255) / 256, 256, 0, s>>>(user_id, ls.drow, B, grad_loss, ddelta, delta_numel);
+    delta_grad_kernel<<<(B + 7) / 8, 256, 0, s>>>(user_id, ls.drow, B, grad_loss, ddelta, delta_numel);
     NRM_LAUNCH_CHECK("delta_grad_kernel");
   }
   return NRM_OK;
