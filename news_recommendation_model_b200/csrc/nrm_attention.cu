@@ -448,19 +448,28 @@ attention_backward_kernel(const double* __restrict__ xh, const float* __restrict
 // fc1.weight grad [64,256] = [dA | dBm | dBm - dA | dWd]; fc1.bias = db1; fc2.weight = dw2; fc2.bias = db2.
 __global__ void __launch_bounds__(256)
 attention_compose_kernel(const float* __restrict__ part, int nparts, AttOffsets off, float* __restrict__ grads) {
-  const int i = blockIdx.x * 256 + threadIdx.x;      // j*64 + k
-  if (i < 64 * 64) {
-    float dA = 0.f, dWd = 0.f, dBm = 0.f;
-    for (int p = 0; p < nparts; ++p) {
-      const float* q = part + (long long)p * ATT_PARTIAL + i;
-      dA += q[0]; dWd += q[64 * 64]; dBm += q[2 * 64 * 64];
-    }
+  // block = 64 consecutive (j,k) entries x 4 interleaved groups of partials, combined in group order
+  __shared__ float red[4][3][64];
+  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + lane;              // j*64 + k, grid = 64 blocks
+  float dA = 0.f, dWd = 0.f, dBm = 0.f;
+#pragma unroll 4
+  for (int p = grp; p < nparts; p += 4) {
+    const float* q = part + (long long)p * ATT_PARTIAL + i;
+    dA += q[0]; dWd += q[64 * 64]; dBm += q[2 * 64 * 64];
+  }
+  red[grp][0][lane] = dA; red[grp][1][lane] = dWd; red[grp][2][lane] = dBm;
+  __syncthreads();
+  if (grp == 0) {
+    dA = ((red[0][0][lane] + red[1][0][lane]) + red[2][0][lane]) + red[3][0][lane];
+    dWd = ((red[0][1][lane] + red[1][1][lane]) + red[2][1][lane]) + red[3][1][lane];
+    dBm = ((red[0][2][lane] + red[1][2][lane]) + red[2][2][lane]) + red[3][2][lane];
     const int j = i >> 6, k = i & 63;
     float* row = grads + off.fc1_w + j * 256;
     row[k] = dA; row[64 + k] = dBm; row[128 + k] = dBm - dA; row[192 + k] = dWd;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 64) {
-    const int j = threadIdx.x;
+  if (blockIdx.x == 0 && grp == 1) {
+    const int j = lane;
     float w = 0.f, b1 = 0.f;
     for (int p = 0; p < nparts; ++p) {
       w += part[(long long)p * ATT_PARTIAL + 3 * 64 * 64 + j];
@@ -514,7 +523,7 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
 int launch_attention_finish(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s) {
   (void)P;
   const float* part = w.att_part + (long long)branch * ATT_BWD_CTAS_MAX * ATT_PARTIAL;
-  attention_compose_kernel<<<16, 256, 0, s>>>(part, att_bwd_grid(w.B), branch == 0 ? ATT_LABEL : ATT_TI, grads);
+  attention_compose_kernel<<<64, 256, 0, s>>>(part, att_bwd_grid(w.B), branch == 0 ? ATT_LABEL : ATT_TI, grads);
   NRM_LAUNCH_CHECK("attention_compose_kernel");
   return NRM_OK;
 }

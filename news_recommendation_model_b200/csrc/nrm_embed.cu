@@ -358,12 +358,21 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
   }
 }
 
-// Scatter the reduced [96] vector into the flat gradient entries.
-__global__ void small_linear_grad_finish_kernel(const float* __restrict__ part, int nparts, float* __restrict__ grads) {
-  const int k = threadIdx.x;
-  if (k >= 96) return;
+// Reduce the per-CTA partials (8 interleaved groups, combined in group order) and scatter the
+// [96] vector into the flat gradient entries.
+__global__ void __launch_bounds__(768)
+small_linear_grad_finish_kernel(const float* __restrict__ part, int nparts, float* __restrict__ grads) {
+  __shared__ float red[8][96];
+  const int k = threadIdx.x % 96, grp = threadIdx.x / 96;
   float acc = 0.f;
-  for (int p = 0; p < nparts; ++p) acc += part[(long long)p * 96 + k];
+#pragma unroll 4
+  for (int p = grp; p < nparts; p += 8) acc += part[(long long)p * 96 + k];
+  red[grp][k] = acc;
+  __syncthreads();
+  if (grp != 0) return;
+  acc = red[0][k];
+#pragma unroll
+  for (int q = 1; q < 8; ++q) acc += red[q][k];
   if (k < 64) {
     const int o = k >> 2, i = k & 3;
     if (i < 3) grads[P_SENT_W + o * 3 + i] = acc; else grads[P_SENT_B + o] = acc;
@@ -421,7 +430,7 @@ int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, c
   small_linear_grad_kernel<<<nparts, 256, 0, s>>>(in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.C, w.NH, w.N, w.xin_h, w.e,
                                                   w.dxin_h, w.dxt, w.de, rows_per_cta, w.small_part);
   NRM_LAUNCH_CHECK("small_linear_grad_kernel");
-  small_linear_grad_finish_kernel<<<1, 96, 0, s>>>(w.small_part, nparts, grads);
+  small_linear_grad_finish_kernel<<<1, 768, 0, s>>>(w.small_part, nparts, grads);
   NRM_LAUNCH_CHECK("small_linear_grad_finish_kernel");
   return NRM_OK;
 }

@@ -46,6 +46,12 @@ struct GemmArgs {
 
 constexpr int GEMM_BK = 128;
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 template <int BM, int BN>
 constexpr size_t gemm_smem_bytes() { return sizeof(float) * GEMM_BK * ((BM + 4) + (BN + 4)); }
 
@@ -77,24 +83,28 @@ gemm_kernel(const GemmArgs g) {
   for (int k0 = kbeg; k0 < kend; k0 += GEMM_BK) {
     const int kc = min(GEMM_BK, kend - k0);
     if (k0 != kbeg) __syncthreads();
-    for (int i = tid; i < BM * kc; i += NT) {
+    // Stage the slabs with 4-byte cp.async: every copy of the slab is in flight at once and
+    // lands directly in its transposed (k-major) slot; one wait for the whole slab.
+    // Index split uses compile-time divisors only (GEMM_BK, BM, BN); k >= kc lanes are skipped.
+    for (int i = tid; i < BM * GEMM_BK; i += NT) {
       int m, k;
-      if (a_kfast) { k = i % kc; m = i / kc; } else { m = i % BM; k = i / BM; }
+      if (a_kfast) { k = i % GEMM_BK; m = i / GEMM_BK; } else { m = i % BM; k = i / BM; }
+      if (k >= kc) continue;
       const int gm = m0 + m;
-      float v = 0.f;
-      if (gm < g.M) v = __ldg(g.A + gm * g.sam + (k0 + k) * g.sak);
-      else if (gm < Mx) v = 1.f;
-      As[k * LDA + m] = v;
+      float* dst = As + k * LDA + m;
+      if (gm < g.M) cp_async4(dst, g.A + gm * g.sam + (k0 + k) * g.sak);
+      else *dst = (gm < Mx) ? 1.f : 0.f;
     }
-    for (int i = tid; i < BN * kc; i += NT) {
+    for (int i = tid; i < BN * GEMM_BK; i += NT) {
       int n, k;
-      if (b_nfast) { n = i % BN; k = i / BN; } else { k = i % kc; n = i / kc; }
+      if (b_nfast) { n = i % BN; k = i / BN; } else { k = i % GEMM_BK; n = i / GEMM_BK; }
+      if (k >= kc) continue;
       const int gn = n0 + n;
-      float v = 0.f;
-      if (gn < g.N) v = __ldg(g.B + (k0 + k) * g.sbk + gn * g.sbn);
-      else if (gn < Nx) v = 1.f;
-      Bs[k * LDB + n] = v;
+      float* dst = Bs + k * LDB + n;
+      if (gn < g.N) cp_async4(dst, g.B + (k0 + k) * g.sbk + gn * g.sbn);
+      else *dst = (gn < Nx) ? 1.f : 0.f;
     }
+    cp_async_wait_all();
     __syncthreads();
 #pragma unroll 8
     for (int kk = 0; kk < kc; ++kk) {
