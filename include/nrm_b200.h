@@ -72,6 +72,12 @@ unsigned long long nrm_launch_count(void);
  * (synchronising on the recorded events) and returns 0.  Enabling resets the counters. */
 void        nrm_timing_enable(int on);
 int         nrm_timing_report(char* buf, size_t buf_bytes);
+/* Self test of the tcgen05 building blocks used by the bf16 path: out[q] (q = 0,1; [64,64]
+ * fp32) = bf16(a_q) * bf16(b_q)^T with fp32 accumulation, a_q / b_q [64,64] fp32 row-major.
+ * Exercises descriptor encoding, TMEM allocation, the half-lane accumulator pairing,
+ * mbarrier completion and tcgen05.ld. */
+int         nrm_debug_umma_selftest(const float* a0, const float* a1, const float* b0, const float* b1,
+                                    float* out, void* stream);
 
 /* ---- flat parameter layout (reference state_dict order) ---- */
 int         nrm_layout_entries(void);                 /* trainable tensors incl. delta     */

@@ -129,6 +129,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   w.a2 = (float*)take(f * R * HID); w.u2 = (float*)take(f * R * HID);
   w.y = (float*)take(f * R * E);
   w.a3 = (float*)take(f * R * HID); w.u3 = (float*)take(f * R * HID);
+  w.att_derived = (float*)take(f * 2 * 12420);
   if (training) {
     w.da3 = (float*)take(f * R * HID); w.da2 = (float*)take(f * R * HID); w.da1 = (float*)take(f * R * HID);
     w.dy = (float*)take(f * R * E);
@@ -187,6 +188,7 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
     const int rc = launch_gemm<EPI_BIAS>(g, 1, s);
     if (rc < 0) return rc;
   }
+  if (precision == NRM_PRECISION_BF16) NRM_TRY(launch_attention_prep(P, w, s));
   { KernelTimer t("attention_forward_label", s); NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s)); }
   { KernelTimer t("attention_forward_textimg", s); NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s)); }
   return NRM_OK;

@@ -139,6 +139,7 @@ struct Workspace {
   float* a2; float* u2;   // [R,66]
   float* y;            // [R,264]
   float* a3; float* u3;   // [R,66]
+  float* att_derived;  // [2][12420] derived attention weights (bf16 tensor-core path)
   // backward (training only)
   float* da3; float* da2; float* da1;   // [R,66]
   float* dy;           // [R,264]

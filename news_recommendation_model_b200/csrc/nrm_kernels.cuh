@@ -20,6 +20,10 @@ int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, 
 int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
 int launch_attention_finish(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s);
 
+// nrm_attention_tc.cu  (precision = bf16: tcgen05 tensor-core tiles)
+int launch_attention_prep(const float* P, Workspace& w, cudaStream_t s);          // derived weights -> w.att_derived
+int launch_attention_forward_tc(const BatchPtrs& in, Workspace& w, int branch, cudaStream_t s);
+
 // nrm_head.cu
 int launch_bn_partial_sums(Workspace& w, cudaStream_t s);                 // -> w.bn_sums
 int launch_head_forward(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt,
