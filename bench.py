@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
     ap.add_argument('--sync-bn', action='store_true', help='all-reduce BatchNorm statistics across ranks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='FusedTrainStep issues the C-ABI calls eagerly instead of replaying a CUDA graph')
     ap.add_argument('--cpu-steps', type=int, default=8)
     return ap.parse_args()
 
@@ -191,20 +192,9 @@ def run_ours(args):
     model.set_precision(args.precision)
     if world > 1:
         DataParallel(model, sync_bn=args.sync_bn)
-    opt = nrm.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
 
     B, H, C = args.batch, args.history, args.candidates
     host = [make_batch(B, H, C, seed=1234 + 97 * rank + i, user_num=args.user_num).pin() for i in range(N_POOL)]
-    pool = [b.to(dev) for b in host]
-    torch.cuda.synchronize()
-
-    def step(b):
-        out = model(b.x_history, b.x_target, b.x_global)
-        loss = model.loss(b.user_id, out, b.label)
-        loss.backward()
-        opt.step()
-        opt.zero_grad()
-        return loss
 
     def barrier():
         if world > 1:
@@ -219,44 +209,40 @@ def run_ours(args):
         return ms
 
     K, W = args.steps, max(3, args.warmup)
-    for i in range(W):
-        step(pool[i % N_POOL])
-    # ---- device-resident timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- A. the pipelined public API (news_recommendation_model_b200.FusedTrainStep): the five
+    #         C-ABI calls of train.py:69-75 per step, CUDA-graph replayed, N_POOL input slots.
+    tr = nrm.FusedTrainStep(model, B, H, C, lr=1e-3, weight_decay=1e-5, nslots=N_POOL, use_graph=not args.no_graph)
+    slots = [tr.load(hb) for hb in host]          # all slots resident in HBM
+    torch.cuda.synchronize()
+    for i in range(W):
+        tr.run(slots[i % N_POOL])
     barrier()
-    launches0 = lib.nrm_launch_count()
     with ClockSampler(local) as clk:
         e0.record()
         for i in range(K):
-            step(pool[i % N_POOL])
+            tr.run(slots[i % N_POOL])
         e1.record()
         barrier()
-    launches = (lib.nrm_launch_count() - launches0) // K
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * K / (ms_total / 1e3)
 
-    # ---- end to end: pinned host batches -> H2D on a copy stream (prefetching the next batch while
-    # the current step runs, as a data loader would) -> step -> loss read back every step.
-    copy_stream = torch.cuda.Stream(dev)
-
-    def prefetch(hb):
-        with torch.cuda.stream(copy_stream):
-            db = hb.to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return db, ev
-
+    # ---- B. end to end through the same API: every step copies its batch from pinned host memory
+    #         into a device slot (copy stream, one batch ahead) and the host reads every step's loss.
     def e2e_loop(n):
-        cur = prefetch(host[0])
-        last = 0.0
+        nxt = tr.load(host[0])
+        prev, last = None, 0.0
         for i in range(n):
-            nxt = prefetch(host[(i + 1) % N_POOL]) if i + 1 < n else None
-            db, ev = cur
-            torch.cuda.current_stream().wait_event(ev)
-            last = step(db).item()            # D2H of the loss: the host sees every step's result
             cur = nxt
-        return last
-    e2e_loop(2)
+            if i + 1 < n:
+                nxt = tr.load(host[(i + 1) % N_POOL])
+            h = tr.run(cur)
+            if prev is not None:
+                last = prev.item()                # D2H result of the previous step (never stalls the GPU)
+            prev = h
+        return prev.item()
+    e2e_loop(3)
     barrier()
     e0.record()
     e2e_loop(K)
@@ -265,6 +251,28 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * B * K / (e2e_ms / 1e3)
     h2d = host[0].input_bytes()
+
+    # ---- C. the drop-in nn.Module path driven exactly like train.py (autograd + FusedAdam), device-resident
+    opt = nrm.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    pool = [b.to(dev) for b in host]
+
+    def step(b):
+        out = model(b.x_history, b.x_target, b.x_global)
+        loss = model.loss(b.user_id, out, b.label)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return loss
+    for i in range(W):
+        step(pool[i % N_POOL])
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(pool[i % N_POOL])
+    e1.record()
+    barrier()
+    mod_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = tr.launches_per_step                  # kernels of ours per step (counted while the step was recorded)
 
     # ---- per-kernel timing pass (CUDA events on the launch stream inside the library)
     lib.nrm_timing_enable(1)
@@ -320,6 +328,9 @@ def run_ours(args):
         'e2e': {'value': e2e_value, 'unit': 'impressions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': e2e_ms / K},
         'gpu_launches': int(launches) * K, 'gpu_launches_per_step': int(launches),
+        'module_path': {'value': world * B * K / (mod_ms / 1e3), 'unit': 'impressions/s', 'ms_per_step': mod_ms / K,
+                        'note': 'drop-in nn.Module path driven like train.py:69-75 (autograd + FusedAdam), device-resident'},
+        'api': 'FusedTrainStep (CUDA-graph replay of the 5 C-ABI calls)' if not args.no_graph else 'FusedTrainStep (eager C-ABI calls)',
         'roofline': roofline, 'kernels_ms_per_step': {k: round(v['ms_per_step'], 4) for k, v in kern.items()},
         'cpu_baseline': cpu,
     }

@@ -162,6 +162,13 @@ int nrm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float lr, float beta1, float beta2, float eps, float weight_decay,
                   long long step, float grad_scale, void* stream);
 
+/* Same update with the hyper-parameters and the step counter on the device, so that a whole
+ * training step can be captured in a CUDA graph and replayed: adam_state points to
+ * { int64 step; float lr, beta1, beta2, eps, weight_decay, grad_scale, step_size, bc2_sqrt; }
+ * (40 bytes).  Each call increments `step` and derives the bias corrections on the device. */
+int nrm_adam_step_device(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                         void* adam_state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

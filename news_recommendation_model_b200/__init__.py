@@ -3,7 +3,8 @@
 from .models import (MLP, PointwiseAttention, PointwiseAttentionExpanded, UserInstantInterestModel,
                      UserInvariantInterestModel, UserModel)
 from .optim import FusedAdam
+from .trainer import FusedTrainStep
 from ._lib import NrmError, build
 
 __all__ = ['MLP', 'PointwiseAttention', 'PointwiseAttentionExpanded', 'UserInstantInterestModel',
-           'UserInvariantInterestModel', 'UserModel', 'FusedAdam', 'NrmError', 'build']
+           'UserInvariantInterestModel', 'UserModel', 'FusedAdam', 'FusedTrainStep', 'NrmError', 'build']

@@ -43,6 +43,7 @@ SIGNATURES = {
     'nrm_loss_forward': (i32, [vp, vp, vp, vp, i32, i32, f32, vp, vp, sz, vp]),
     'nrm_loss_backward': (i32, [vp, i32, i32, vp, vp, vp, ll, vp, sz, vp]),
     'nrm_adam_step': (i32, [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, ll, f32, vp]),
+    'nrm_adam_step_device': (i32, [vp, vp, vp, vp, ll, vp, vp]),
 }
 
 

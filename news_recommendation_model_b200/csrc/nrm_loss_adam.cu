@@ -174,9 +174,67 @@ adam_scalar_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) adam_one(p[i], g[i], m[i], v[i], a);
 }
 
+// ---- graph-capturable variant: hyper-parameters and the step counter live on the device ----
+struct AdamDeviceState {          // mirrored by FusedTrainStep (python): 1 x int64 + 8 x float32
+  long long step;
+  float lr, beta1, beta2, eps, wd, grad_scale;
+  float step_size, bc2_sqrt;      // derived by adam_prepare_kernel every step
+};
+static_assert(sizeof(AdamDeviceState) == 40, "AdamDeviceState layout is part of the C ABI");
+
+__global__ void adam_prepare_kernel(AdamDeviceState* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long t = ++st->step;
+  const double bc1 = 1.0 - pow((double)st->beta1, (double)t);
+  const double bc2 = 1.0 - pow((double)st->beta2, (double)t);
+  st->step_size = (float)((double)st->lr / bc1);
+  st->bc2_sqrt = (float)sqrt(bc2);
+}
+
+__global__ void __launch_bounds__(256)
+adam_device_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                   long long n, const AdamDeviceState* __restrict__ st) {
+  AdamArgs a;
+  a.step_size = st->step_size; a.bc2_sqrt = st->bc2_sqrt; a.beta1 = st->beta1; a.beta2 = st->beta2;
+  a.eps = st->eps; a.wd = st->wd; a.grad_scale = st->grad_scale;
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, a); adam_one(pp.y, gg.y, mm.y, vv.y, a);
+    adam_one(pp.z, gg.z, mm.z, vv.z, a); adam_one(pp.w, gg.w, mm.w, vv.w, a);
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride)
+    adam_one(p[i], g[i], m[i], v[i], a);
+}
+
 }  // namespace nrm
 
 using namespace nrm;
+
+extern "C" int nrm_adam_step_device(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                    void* adam_state, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !adam_state || n < 0) { set_error("nrm_adam_step_device: bad argument"); return NRM_EINVAL; }
+  if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) {
+    set_error("nrm_adam_step_device: buffers must be 16-byte aligned"); return NRM_EINVAL;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  AdamDeviceState* st = (AdamDeviceState*)adam_state;
+  adam_prepare_kernel<<<1, 32, 0, s>>>(st);
+  NRM_LAUNCH_CHECK("adam_prepare_kernel");
+  if (n == 0) return NRM_OK;
+  long long blocks = ((n + 3) / 4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  KernelTimer t("adam", s);
+  adam_device_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, st);
+  NRM_LAUNCH_CHECK("adam_device_kernel");
+  return NRM_OK;
+}
 
 extern "C" size_t nrm_loss_scratch_bytes(int B, int C) {
   LossScratch ls;

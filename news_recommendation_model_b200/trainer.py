@@ -1,0 +1,190 @@
+"""Pipelined training step: the train.py:66-75 loop body as one replayable unit.
+
+`train.py` runs, per batch: H2D of the float64 features, `model(...)`, `model.loss(...)`,
+`loss.backward()`, `optimizer.step()`, `optimizer.zero_grad()`, then reads `loss.item()`.
+Driven from Python that is ~60 kernel launches through autograd plus a device sync per
+step.  `FusedTrainStep` keeps the same arithmetic (the same C-ABI calls in the same order on
+the same flat buffers) but
+
+  * stages the batch into one of two static device slots on a copy stream, so the H2D of
+    batch i+1 overlaps the compute of batch i;
+  * captures the five calls (forward, loss, loss backward, backward, Adam) of each slot in a
+    CUDA graph and replays it with a single launch;
+  * returns the loss through a pinned host ring, read one step late, so the host never
+    stalls the pipeline.
+
+Under data parallelism the graph is split around the gradient all-reduce.
+"""
+from __future__ import annotations
+
+import ctypes
+import struct
+from typing import List, Optional
+
+import torch
+
+from . import _lib, engine
+from .config import HIST_COLS, TGT_COLS, GLOBAL_COLS
+
+_p = engine._ptr
+
+
+class _Slot:
+    def __init__(self, B, H, C, dev):
+        self.xh = torch.empty(B, H, HIST_COLS, dtype=torch.float64, device=dev)
+        self.xt = torch.empty(B, C, TGT_COLS, dtype=torch.float64, device=dev)
+        self.xg = torch.empty(B, C, GLOBAL_COLS, dtype=torch.float64, device=dev)
+        self.label = torch.empty(B, C, dtype=torch.float64, device=dev)
+        self.uid = torch.empty(B, dtype=torch.int64, device=dev)
+        self.ready = torch.cuda.Event()        # H2D of this slot finished
+        self.consumed = torch.cuda.Event()     # compute that read this slot finished
+        self.graph_fb: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_adam: Optional[torch.cuda.CUDAGraph] = None
+        self.used = False
+
+
+class LossHandle:
+    """Result of one step; `.item()` waits for that step only."""
+
+    def __init__(self, host_slot: torch.Tensor, event: torch.cuda.Event):
+        self._host, self._event = host_slot, event
+
+    def item(self) -> float:
+        self._event.synchronize()
+        return float(self._host.item())
+
+
+class FusedTrainStep:
+    def __init__(self, model, B: int, H: int, C: int, *, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5,
+                 alpha=0.95, use_graph=True, ring=8, nslots=2):
+        self.model, self.B, self.H, self.C, self.alpha = model, B, H, C, float(alpha)
+        self.flat = model.flat_parameters()
+        dev = self.flat.device
+        self.dev, self.lib = dev, _lib.load()
+        self.dp = model._dp
+        world = self.dp.world if self.dp is not None else 1
+        self.precision = model._precision_code()
+        self.mode = engine.MODE_BN_BATCH_STATS | engine.MODE_KEEP_FOR_BWD
+        n = self.flat.total
+        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        # AdamDeviceState: int64 step | lr, beta1, beta2, eps, wd, grad_scale, step_size, bc2_sqrt
+        raw = struct.pack('<q8f', 0, lr, betas[0], betas[1], eps, weight_decay, 1.0, 0.0, 0.0)
+        self.adam_state = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        ws_bytes = int(self.lib.nrm_workspace_bytes(B, H, C, self.mode))
+        self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ls_bytes = int(self.lib.nrm_loss_scratch_bytes(B, C))
+        self.loss_scratch = torch.empty(ls_bytes, dtype=torch.uint8, device=dev)
+        self.logits = torch.empty(B, C, dtype=torch.float32, device=dev)
+        self.dlogits = torch.empty(B, C, dtype=torch.float32, device=dev)
+        self.one = torch.ones((), dtype=torch.float32, device=dev)
+        self.loss_dev = torch.zeros(ring, dtype=torch.float32, device=dev)
+        self.loss_host = torch.zeros(ring, dtype=torch.float32).pin_memory()
+        self.ring, self.count = ring, 0
+        self.slots: List[_Slot] = [_Slot(B, H, C, dev) for _ in range(nslots)]
+        self.loaded = 0
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.use_graph = use_graph
+        self.world = world
+        self._warmup()
+
+    def _warmup(self):
+        """Run every kernel of the step once on scratch state (zero inputs, cloned BatchNorm buffers
+        and optimizer state) so that module loading and function attributes are settled before
+        the first graph capture.  Leaves the model, the gradients and Adam untouched."""
+        lib, m, f, s = self.lib, self.model, self.flat, self.slots[0]
+        for t in (s.xh, s.xt, s.xg, s.label, s.uid):
+            t.zero_()
+        saved = (m.bn.running_mean.clone(), m.bn.running_var.clone(), m.bn.num_batches_tracked.clone())
+        scratch_loss = self.loss_dev.new_zeros(())
+        n0 = lib.nrm_launch_count()
+        self._forward_backward(s, scratch_loss)
+        self.launches_per_step = int(lib.nrm_launch_count() - n0) + 2      # + Adam prepare / update
+        with torch.no_grad():
+            m.bn.running_mean.copy_(saved[0]); m.bn.running_var.copy_(saved[1]); m.bn.num_batches_tracked.copy_(saved[2])
+        self.grads.zero_()
+        st = self.adam_state.clone()
+        tiny = [torch.zeros(4, dtype=torch.float32, device=self.dev) for _ in range(4)]
+        _lib.check(lib.nrm_adam_step_device(_p(tiny[0]), _p(tiny[1]), _p(tiny[2]), _p(tiny[3]), 4, _p(st),
+                                            engine._stream(self.dev)), 'nrm_adam_step_device')
+        torch.cuda.synchronize(self.dev)
+
+    # ---- the five C-ABI calls of one step (train.py:69-75) --------------------------------
+    def _forward_backward(self, s: _Slot, loss_out: torch.Tensor):
+        lib, m, f = self.lib, self.model, self.flat
+        st = engine._stream(self.dev)
+        B, H, C = self.B, self.H, self.C
+        if self.dp is not None and self.dp.sync_bn:
+            raise _lib.NrmError('FusedTrainStep: sync_bn needs the two-phase calls; use model.forward/backward')
+        _lib.check(lib.nrm_forward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf),
+                                   _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked), self.mode,
+                                   self.precision, _p(self.logits), _p(self.ws), self.ws.numel(), st), 'nrm_forward')
+        delta = f.buf[f.fixed:f.fixed + f.delta_numel]
+        _lib.check(lib.nrm_loss_forward(_p(self.logits), _p(delta), _p(s.uid), _p(s.label), B, C, self.alpha, _p(loss_out),
+                                        _p(self.loss_scratch), self.loss_scratch.numel(), st), 'nrm_loss_forward')
+        ddelta = self.grads[f.fixed:f.fixed + f.delta_numel]
+        _lib.check(lib.nrm_loss_backward(_p(s.uid), B, C, _p(self.one), _p(self.dlogits), _p(ddelta), f.delta_numel,
+                                         _p(self.loss_scratch), self.loss_scratch.numel(), st), 'nrm_loss_backward')
+        _lib.check(lib.nrm_backward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
+                                    self.precision, _p(self.dlogits), _p(self.grads), _p(self.ws), self.ws.numel(), st),
+                   'nrm_backward')
+
+    def _adam(self):
+        _lib.check(self.lib.nrm_adam_step_device(_p(self.flat.buf), _p(self.grads), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                                 self.flat.total, _p(self.adam_state), engine._stream(self.dev)),
+                   'nrm_adam_step_device')
+
+    # ---- pipeline -------------------------------------------------------------------------
+    def load(self, batch) -> _Slot:
+        """Enqueue the H2D copy of a (pinned) host batch into the next slot (round robin)."""
+        s = self.slots[self.loaded % len(self.slots)]
+        self.loaded += 1
+        with torch.cuda.stream(self.copy_stream):
+            if s.used:
+                self.copy_stream.wait_event(s.consumed)      # do not overwrite a slot still being read
+            s.xh.copy_(batch.x_history, non_blocking=True)
+            s.xt.copy_(batch.x_target, non_blocking=True)
+            s.xg.copy_(batch.x_global, non_blocking=True)
+            s.label.copy_(batch.label, non_blocking=True)
+            s.uid.copy_(batch.user_id, non_blocking=True)
+            s.ready.record(self.copy_stream)
+        return s
+
+    def run(self, s: _Slot) -> LossHandle:
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(s.ready)
+        k = self.count % self.ring
+        loss_out = self.loss_dev[k:k + 1]
+        if self.use_graph:
+            if s.graph_fb is None:
+                # eager warm-up pass is NOT wanted (it would be an extra optimizer step): capture directly
+                s.graph_fb = torch.cuda.CUDAGraph()
+                s.loss_slot = self.loss_dev.new_zeros(())
+                with torch.cuda.graph(s.graph_fb):
+                    self._forward_backward(s, s.loss_slot)
+                s.graph_adam = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(s.graph_adam):
+                    self._adam()
+            s.graph_fb.replay()
+            if self.dp is not None:
+                self.dp.buckets.reduce(self.grads, 0, self.grads.numel())
+                self.dp.buckets.wait()
+            s.graph_adam.replay()
+            loss_out = s.loss_slot.view(1)
+        else:
+            self._forward_backward(s, loss_out)
+            if self.dp is not None:
+                self.dp.buckets.reduce(self.grads, 0, self.grads.numel())
+                self.dp.buckets.wait()
+            self._adam()
+        s.consumed.record(cur)
+        s.used = True
+        self.loss_host[k:k + 1].copy_(loss_out, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.count += 1
+        return LossHandle(self.loss_host[k], ev)
+
+    def step(self, batch) -> LossHandle:
+        return self.run(self.load(batch))

@@ -186,3 +186,31 @@ def test_full_size_properties_config2():
             continue
         scale = float(g_s[k].abs().max())
         assert float((g_b[k] - g_s[k]).abs().max()) <= 2e-4 * scale + 1e-7, k
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_fused_train_step_equals_module_path(use_graph):
+    """FusedTrainStep (pipelined C-ABI calls, optionally CUDA-graph replayed) must leave exactly the
+    weights that the train.py-style loop (autograd + FusedAdam) leaves."""
+    B, H, C, U = 32, 50, 5, 30
+    batches = [make_batch(B, H, C, seed=300 + i, user_num=U) for i in range(4)]
+    w = load_weights('train')
+    ma, _ = P.build_models(w, U)
+    mb, _ = P.build_models(w, U)
+    ma.train(); mb.train()
+    opt = nrm.FusedAdam(ma.parameters(), lr=1e-3, weight_decay=1e-5)
+    losses_a = []
+    for b in batches:
+        d = b.to('cuda')
+        out = ma(d.x_history, d.x_target, d.x_global)
+        loss = ma.loss(d.user_id, out, d.label)
+        loss.backward(); opt.step(); opt.zero_grad()
+        losses_a.append(loss.item())
+    tr = nrm.FusedTrainStep(mb, B, H, C, lr=1e-3, weight_decay=1e-5, use_graph=use_graph)
+    losses_b = [tr.step(b.pin()).item() for b in batches]
+    torch.cuda.synchronize()
+    assert np.allclose(losses_a, losses_b, rtol=0, atol=1e-6), (losses_a, losses_b)
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert torch.equal(pa, pb), k
+    for k in ('running_mean', 'running_var', 'num_batches_tracked'):
+        assert torch.equal(getattr(ma.bn, k), getattr(mb.bn, k)), k
