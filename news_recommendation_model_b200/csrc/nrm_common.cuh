@@ -169,14 +169,36 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode);
 // ----------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------
+// Exact-erf GELU (nn.GELU() default of the reference, attention_model.py:21) and its derivative.
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated with Abramowitz-Stegun 7.1.26:
+//   erfc(z) = (a1 t + ... + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z = |x| / sqrt 2,   |error| <= 1.5e-7,
+// i.e. one MUFU.RCP + one MUFU.EX2 + 8 FMA-pipe operations instead of erff's ~35 instructions.
+// Measured against float64 over [-12, 12] (tests/test_host_surface.py restates it in numpy):
+// max |gelu error| 4.2e-7, max |gelu' error| 3.2e-7 -- below torch's own fp32 GELU error (1.2e-6).
+// exp(-z^2) = exp(-x^2 / 2) is also sqrt(2 pi) times the normal pdf, so the derivative is free.
+__device__ __forceinline__ float gelu_tail(float x, float& ex) {   // returns 0.5 * erfc(|x| / sqrt 2); ex = exp(-x^2 / 2)
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  ex = __expf(-z * z);
+  return 0.5f * poly * ex;
+}
 __device__ __forceinline__ float gelu_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float ex;
+  const float half = gelu_tail(x, ex);
+  return x * (x >= 0.f ? 1.0f - half : half);
 }
 // returns gelu(x), writes d gelu / dx
 __device__ __forceinline__ float gelu_both(float x, float& grad) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  grad = cdf + x * pdf;
+  float ex;
+  const float half = gelu_tail(x, ex);
+  const float cdf = x >= 0.f ? 1.0f - half : half;
+  grad = fmaf(x * 0.39894228040143267794f, ex, cdf);
   return x * cdf;
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
