@@ -41,7 +41,7 @@ def parse():
     ap.add_argument('--history', type=int, default=50)
     ap.add_argument('--candidates', type=int, default=5)
     ap.add_argument('--user-num', type=int, default=1000)
-    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16', 'bf16x3'])
     ap.add_argument('--sync-bn', action='store_true', help='all-reduce BatchNorm statistics across ranks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='FusedTrainStep issues the C-ABI calls eagerly instead of replaying a CUDA graph')

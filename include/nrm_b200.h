@@ -33,8 +33,14 @@
  *   - parameters live in ONE flat float32 buffer whose layout is given by the
  *     nrm_layout_* functions (state_dict order of the reference, 16-byte aligned
  *     entries, `delta` last); gradients use the same layout;
- *   - `precision`: 0 = fp32 (FFMA everywhere), 1 = bf16 tensor-core tiles with fp32
- *     accumulation for the pairwise attention GEMMs (everything else stays fp32).
+ *   - `precision` selects how the pairwise attention products (forward and backward) are
+ *     evaluated; everything else is fp32 in every mode:
+ *       0 = fp32    FFMA on the CUDA cores (bit-for-bit fp32 products);
+ *       1 = bf16    tcgen05 tensor-core tiles, operands rounded to bf16, fp32 accumulation;
+ *       2 = bf16x3  tcgen05 tiles with every operand split in hi + lo bf16 parts and three
+ *                   products per tile (a_hi b_hi + a_hi b_lo + a_lo b_hi), fp32 accumulation:
+ *                   relative operand error 2^-16 (torch's float32 matmul precision "high");
+ *                   meets the fp32 parity tolerances of tests/parity.py.
  */
 #ifndef NRM_B200_H
 #define NRM_B200_H
@@ -54,6 +60,7 @@ extern "C" {
 
 #define NRM_PRECISION_FP32 0
 #define NRM_PRECISION_BF16 1
+#define NRM_PRECISION_BF16X3 2
 
 /* `mode` bit flags of the forward/backward entry points */
 #define NRM_MODE_BN_BATCH_STATS 1   /* module.training: BatchNorm uses (and records) batch statistics */
@@ -72,12 +79,14 @@ unsigned long long nrm_launch_count(void);
  * (synchronising on the recorded events) and returns 0.  Enabling resets the counters. */
 void        nrm_timing_enable(int on);
 int         nrm_timing_report(char* buf, size_t buf_bytes);
-/* Self test of the tcgen05 building blocks used by the bf16 path: out[q] (q = 0,1; [64,64]
- * fp32) = bf16(a_q) * bf16(b_q)^T with fp32 accumulation, a_q / b_q [64,64] fp32 row-major.
- * Exercises descriptor encoding, TMEM allocation, the half-lane accumulator pairing,
- * mbarrier completion and tcgen05.ld. */
+/* Self test of the tcgen05 building blocks used by the tensor-core paths: out[q] (q = 0,1;
+ * [64,64] fp32) from a_q / b_q [64,64] fp32 row-major with fp32 accumulation.
+ * mode 0: a_q b_q^T (both operands K-major); 1: a_q^T b_q (both read MN-major);
+ * 2: a_q b_q (A K-major, B MN-major).  split 1: operands rounded to bf16; 3: hi/lo split.
+ * Exercises descriptor encoding for both majors, TMEM allocation, the half-lane accumulator
+ * pairing, mbarrier completion and tcgen05.ld. */
 int         nrm_debug_umma_selftest(const float* a0, const float* a1, const float* b0, const float* b1,
-                                    float* out, void* stream);
+                                    float* out, int mode, int split, void* stream);
 
 /* ---- flat parameter layout (reference state_dict order) ---- */
 int         nrm_layout_entries(void);                 /* trainable tensors incl. delta     */

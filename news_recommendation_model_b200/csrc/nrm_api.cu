@@ -140,7 +140,13 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
     w.dxh = (float*)take(f * NH * 64);
     w.dxt = (float*)take(f * R * 64);
     w.dxin_h = (float*)take(f * NH * XIN);
-    w.att_part = (float*)take(f * 2 * ATT_BWD_CTAS_MAX * ATT_PARTIAL);
+    {
+      const size_t ffma = (size_t)ATT_BWD_CTAS_MAX * ATT_PARTIAL, tc = (size_t)ATT_TC_PARTS_MAX * ATT_TC_PARTIAL;
+      w.att_part = (float*)take(f * 2 * (ffma > tc ? ffma : tc));
+    }
+    w.dtp = (float*)take(f * 2 * R * 64);
+    w.att_dA = (float*)take(f * 2 * 4096);
+    w.tp_part = (float*)take(f * ((R + 63) / 64) * (4096 + 64));
     {
       const size_t head = (size_t)(P_DELTA - P_GATE_FC1_W) * (WGRAD_SPLITS + 1);
       const size_t w1 = (size_t)(64 * XIN + 64) * (W1_SPLITS + 1);
@@ -188,7 +194,7 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
     const int rc = launch_gemm<EPI_BIAS>(g, 1, s);
     if (rc < 0) return rc;
   }
-  if (precision == NRM_PRECISION_BF16) NRM_TRY(launch_attention_prep(P, w, s));
+  if (precision != NRM_PRECISION_FP32) NRM_TRY(launch_attention_prep(P, w, s));
   { KernelTimer t("attention_forward_label", s); NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s)); }
   { KernelTimer t("attention_forward_textimg", s); NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s)); }
   return NRM_OK;
@@ -196,9 +202,9 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
 
 static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, int precision, float* G, cudaStream_t s) {
   { KernelTimer t("attention_backward_label", s); NRM_TRY(launch_attention_backward(in, P, w, 0, precision, s)); }
-  { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 0, G, s)); }
+  { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 0, precision, G, s)); }
   { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
-  { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 1, G, s)); }
+  { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 1, precision, G, s)); }
   // w1: dW = dxh^T xin_h and db = colsum(dxh) (virtual ones column) by one split GEMM; dxin_h = dxh W1
   {
     KernelTimer t("w1_backward", s);

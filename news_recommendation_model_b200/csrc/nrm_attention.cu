@@ -491,7 +491,7 @@ attention_compose_kernel(const float* __restrict__ part, int nparts, AttOffsets 
 static int att_bwd_grid(int B) { return min(B, min(sm_count(), ATT_BWD_CTAS_MAX)); }
 
 int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s) {
-  if (precision == NRM_PRECISION_BF16) return launch_attention_forward_tc(in, w, branch, s);
+  if (precision == NRM_PRECISION_BF16 || precision == NRM_PRECISION_BF16X3) return launch_attention_forward_tc(in, w, branch, precision, s);
   if (precision != NRM_PRECISION_FP32) { set_error("attention: precision %d not built", precision); return NRM_EUNSUPPORTED; }
   const size_t smem = sizeof(AttSmemFwd);
   if (branch == 0) {
@@ -506,8 +506,8 @@ int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, 
 }
 
 int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s) {
-  // the backward recomputes the hidden tile in fp32 for both precisions (tensor-core backward: DESIGN.md section 7)
-  if (precision != NRM_PRECISION_FP32 && precision != NRM_PRECISION_BF16) { set_error("attention: precision %d not built", precision); return NRM_EUNSUPPORTED; }
+  if (precision == NRM_PRECISION_BF16 || precision == NRM_PRECISION_BF16X3) return launch_attention_backward_tc(in, P, w, branch, precision, s);
+  if (precision != NRM_PRECISION_FP32) { set_error("attention: precision %d not built", precision); return NRM_EUNSUPPORTED; }
   const size_t smem = sizeof(AttSmemBwd);
   const int grid = att_bwd_grid(w.B);
   float* part = w.att_part + (long long)branch * ATT_BWD_CTAS_MAX * ATT_PARTIAL;
@@ -522,8 +522,8 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
   return NRM_OK;
 }
 
-int launch_attention_finish(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s) {
-  (void)P;
+int launch_attention_finish(const float* P, Workspace& w, int branch, int precision, float* grads, cudaStream_t s) {
+  if (precision != NRM_PRECISION_FP32) return launch_attention_finish_tc(P, w, branch, grads, s);
   const float* part = w.att_part + (long long)branch * ATT_BWD_CTAS_MAX * ATT_PARTIAL;
   attention_compose_kernel<<<64, 256, 0, s>>>(part, att_bwd_grid(w.B), branch == 0 ? ATT_LABEL : ATT_TI, grads);
   NRM_LAUNCH_CHECK("attention_compose_kernel");

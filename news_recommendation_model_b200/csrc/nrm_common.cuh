@@ -116,6 +116,8 @@ constexpr int SORT_CHUNK = 2048;       // entries per counting-sort CTA
 constexpr int SEG_GROUP = 128;         // sorted entries per level-1 segment group
 constexpr int ATT_BWD_CTAS_MAX = 148;  // persistent grid of the attention backward
 constexpr int ATT_PARTIAL = 3 * D * D + 64 + 64 + 4;   // dA | dWd | dBm | dw2 | db1 | db2 (+pad) floats per CTA
+constexpr int ATT_TC_PARTS_MAX = 512; // CTAs of the tensor-core attention backward (2 per SM)
+constexpr int ATT_TC_PARTIAL = 4 * 4096 + 68;   // dA^T[2] | dWd^T[2] | dw2 | db2 floats per CTA
 constexpr int STAT_BLOCKS = 64;        // row chunks of the column-statistics kernels
 constexpr int WGRAD_SPLITS = 32;       // split-K factor of the head weight-gradient GEMMs
 constexpr int W1_SPLITS = 256;         // split-K factor of the w1 weight gradient (K = B*H rows)
@@ -150,7 +152,10 @@ struct Workspace {
   float* dxh;          // [NH,64]
   float* dxt;          // [R,64]
   float* dxin_h;       // [NH,66]
-  float* att_part;     // [2][ATT_BWD_CTAS_MAX][ATT_PARTIAL]
+  float* att_part;     // [2][max(ATT_BWD_CTAS_MAX*ATT_PARTIAL, ATT_TC_PARTS_MAX*ATT_TC_PARTIAL)]
+  float* dtp;          // [2][R,64]  dL/dtp per candidate row (tensor-core backward)
+  float* att_dA;       // [2][64,64] summed dA per branch
+  float* tp_part;      // [ceil(R/64)][4096+64] partial dBm | db1
   float* splitk;       // [WGRAD_SPLITS][max wgrad size] split-K partial sums
   float* small_part;   // partial sums of the small reductions
   // sorted-segment machinery for the embedding-table gradients

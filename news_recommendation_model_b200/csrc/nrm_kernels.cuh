@@ -18,11 +18,13 @@ int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, c
 // nrm_attention.cu  (branch 0 = label attention on w1-projected features, 1 = text/img PCA)
 int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
 int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
-int launch_attention_finish(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s);
+int launch_attention_finish(const float* P, Workspace& w, int branch, int precision, float* grads, cudaStream_t s);
 
-// nrm_attention_tc.cu  (precision = bf16: tcgen05 tensor-core tiles)
+// nrm_attention_tc.cu  (precision = bf16 / bf16x3: tcgen05 tensor-core tiles)
 int launch_attention_prep(const float* P, Workspace& w, cudaStream_t s);          // derived weights -> w.att_derived
-int launch_attention_forward_tc(const BatchPtrs& in, Workspace& w, int branch, cudaStream_t s);
+int launch_attention_forward_tc(const BatchPtrs& in, Workspace& w, int branch, int precision, cudaStream_t s);
+int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
+int launch_attention_finish_tc(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s);
 
 // nrm_head.cu
 int launch_bn_partial_sums(Workspace& w, cudaStream_t s);                 // -> w.bn_sums

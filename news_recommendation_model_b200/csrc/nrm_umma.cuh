@@ -30,10 +30,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 
 // ---- instruction descriptor: kind::f16, bf16 x bf16 -> fp32, both operands K-major -------------
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// a_mn / b_mn: the operand is read MN-major (bit 15 / 16), i.e. the tile in shared memory holds the
+// TRANSPOSE of what a K-major descriptor would describe.  The canonical un-swizzled MN-major layout
+//   byte offset of element (mn, k) = (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2
+// is the K-major layout above with the roles of the two indices exchanged, so ONE tile written as
+// K-major X[r][c] (SBO_k between 8-row groups, LBO_k between 8-column blocks) doubles as the
+// MN-major operand X^T with SBO = LBO_k and LBO = SBO_k -- no transposed copy is ever built.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
   return (1u << 4)                     // D format  : f32
          | (1u << 7)                   // A format  : bf16
          | (1u << 10)                  // B format  : bf16
+         | ((a_mn ? 1u : 0u) << 15)    // A major   : 0 = K, 1 = MN
+         | ((b_mn ? 1u : 0u) << 16)    // B major   : 0 = K, 1 = MN
          | ((uint32_t)(N >> 3) << 17)  // N / 8
          | ((uint32_t)(M >> 4) << 24); // M / 16
 }
@@ -103,6 +111,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 / 1 consecutive fp32 columns of this thread's lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  return __uint_as_float(r);
+}
+
 // ---- operand tile helpers ------------------------------------------------------------------
 // 8 fp32 -> 8 bf16 (round to nearest even) packed in one 16-byte store at `dst`.
 __device__ __forceinline__ void store_bf16x8(void* dst, const float* v) {
@@ -112,6 +152,29 @@ __device__ __forceinline__ void store_bf16x8(void* dst, const float* v) {
   u.x = *reinterpret_cast<const uint32_t*>(&p0); u.y = *reinterpret_cast<const uint32_t*>(&p1);
   u.z = *reinterpret_cast<const uint32_t*>(&p2); u.w = *reinterpret_cast<const uint32_t*>(&p3);
   *reinterpret_cast<uint4*>(dst) = u;
+}
+
+// hi / lo split of 8 fp32 values: hi = bf16(v), lo = bf16(v - hi).  a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi keeps
+// ~16 mantissa bits per operand (relative error <= 2^-16), which is what torch calls float32 matmul precision
+// "high" (3 x bf16); the products are accumulated in fp32 by the tensor core.
+__device__ __forceinline__ void store_bf16x8_split(void* dst_hi, void* dst_lo, const float* v) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  *reinterpret_cast<uint4*>(dst_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(dst_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// NP = 1: one bf16 tile; NP = 2: hi tile followed by lo tile `part_bytes` later.
+template <int NP>
+__device__ __forceinline__ void store_operand8(unsigned char* tile, uint32_t off, uint32_t part_bytes, const float* v) {
+  if (NP == 1) store_bf16x8(tile + off, v);
+  else store_bf16x8_split(tile + off, tile + part_bytes + off, v);
 }
 
 // Canonical K-major tile of 64 rows x 64 k (bf16): 8 KB, SBO = 128, LBO = 1024.
@@ -129,6 +192,27 @@ __device__ __forceinline__ void mma_tile64(uint32_t tmem_d, uint32_t a_smem, uin
     mma_bf16(tmem_d, da, db, idesc, (accumulate || ks > 0) ? 1u : 0u);
   }
 }
+
+// Generic product over a K range of KSTEPS * 16, operands given as (base address, LBO, SBO, bytes per K=16 step,
+// bytes between the hi and lo parts).  SPLIT = 1: A_hi B_hi.  SPLIT = 3: A_hi B_hi + A_hi B_lo + A_lo B_hi.
+struct Operand { uint32_t addr, lbo, sbo, kstep, part; };
+template <int SPLIT, int KSTEPS>
+__device__ __forceinline__ void mma_product(uint32_t tmem_d, const Operand a, const Operand b, uint32_t idesc, bool accumulate) {
+  constexpr int NT = SPLIT == 3 ? 3 : 1;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const uint32_t ao = (t == 2) ? a.part : 0u, bo = (t == 1) ? b.part : 0u;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const uint64_t da = make_desc(a.addr + ao + ks * a.kstep, a.lbo, a.sbo);
+      const uint64_t db = make_desc(b.addr + bo + ks * b.kstep, b.lbo, b.sbo);
+      mma_bf16(tmem_d, da, db, idesc, (accumulate || t > 0 || ks > 0) ? 1u : 0u);
+    }
+  }
+}
+// 64 x 64 bf16 tile written K-major (tile64_offset): as a K-major operand, and as the MN-major operand of its transpose
+__device__ __forceinline__ Operand op_tile64_k(uint32_t addr) { return Operand{addr, TILE64_LBO, TILE64_SBO, 2 * TILE64_LBO, TILE64_BYTES}; }
+__device__ __forceinline__ Operand op_tile64_mn(uint32_t addr) { return Operand{addr, TILE64_SBO, TILE64_LBO, 2 * TILE64_SBO, TILE64_BYTES}; }
 
 }  // namespace umma
 }  // namespace nrm

@@ -21,7 +21,7 @@ from .config import E_DIM, HIST_COLS, TGT_COLS, GLOBAL_COLS
 MODE_EVAL = 0
 MODE_BN_BATCH_STATS = 1
 MODE_KEEP_FOR_BWD = 2
-PRECISION = {'fp32': 0, 'bf16': 1}
+PRECISION = {'fp32': 0, 'bf16': 1, 'bf16x3': 2}
 
 _LAYOUT: Optional[Tuple[List[Tuple[str, int, int]], int]] = None
 

@@ -52,7 +52,7 @@ class UserModel(nn.Module):
         return engine.PRECISION[self.precision]
 
     def set_precision(self, precision: str):
-        """'fp32' (default, FFMA) or 'bf16' (tensor-core tiles, fp32 accumulation)."""
+        """'fp32' (default, FFMA), 'bf16x3' (tcgen05 tiles, hi/lo split operands, fp32-grade) or 'bf16' (tcgen05 tiles)."""
         if precision not in engine.PRECISION:
             raise ValueError(f'precision must be one of {sorted(engine.PRECISION)}')
         self.precision = precision
