@@ -88,6 +88,15 @@ int         nrm_timing_report(char* buf, size_t buf_bytes);
 int         nrm_debug_umma_selftest(const float* a0, const float* a1, const float* b0, const float* b1,
                                     float* out, int mode, int split, void* stream);
 
+/* Cycle counts of back-to-back tcgen05 products (tools/mma_microbench.py): out[0] = issue cycles, out[1] = cycles
+ * until the mbarrier completes.  variant 0: M64 N64 K-major; 1: M64 N64 MN-major; 2: M128 N64; 3: M64 N8;
+ * 4: tcgen05.ld only.  `reps` products of `nk` K=16 steps each. */
+int         nrm_debug_mma_microbench(long long* out, int variant, int reps, int nk, void* stream);
+
+/* Phase cycle counters of the tensor-core attention forward (only in a -DNRM_TC_PROFILE build; otherwise returns
+ * NRM_EUNSUPPORTED): 16 host int64 = clock64 cycles accumulated by CTA 0 per phase since the last call. */
+int         nrm_debug_tcprof(long long* host_out16);
+
 /* ---- flat parameter layout (reference state_dict order) ---- */
 int         nrm_layout_entries(void);                 /* trainable tensors incl. delta     */
 const char* nrm_layout_name(int i);                   /* reference state_dict key          */

@@ -130,6 +130,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   w.y = (float*)take(f * R * E);
   w.a3 = (float*)take(f * R * HID); w.u3 = (float*)take(f * R * HID);
   w.att_derived = (float*)take(f * 2 * 12420);
+  w.tp = (float*)take(f * 2 * R * 64);
   if (training) {
     w.da3 = (float*)take(f * R * HID); w.da2 = (float*)take(f * R * HID); w.da1 = (float*)take(f * R * HID);
     w.dy = (float*)take(f * R * E);
@@ -146,7 +147,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
     }
     w.dtp = (float*)take(f * 2 * R * 64);
     w.att_dA = (float*)take(f * 2 * 4096);
-    w.tp_part = (float*)take(f * ((R + 63) / 64) * (4096 + 64));
+    w.tp_part = (float*)take(f * ((R + 31) / 32) * (4096 + 64));
     {
       const size_t head = (size_t)(P_DELTA - P_GATE_FC1_W) * (WGRAD_SPLITS + 1);
       const size_t w1 = (size_t)(64 * XIN + 64) * (W1_SPLITS + 1);

@@ -36,15 +36,32 @@
 // product is issued as A_hi B_hi + A_hi B_lo + A_lo B_hi ("bf16x3", relative operand error 2^-16; this is
 // torch's float32 matmul precision "high").  Accumulation is fp32 in both.
 #include "nrm_kernels.cuh"
+#include <cstddef>
+
 #include "nrm_umma.cuh"
 
 namespace nrm {
 
+// Optional phase timing (make EXTRA=-DNRM_TC_PROFILE): CTA 0 / thread 0 accumulates clock64 deltas per phase of the
+// forward kernel into g_tcprof; nrm_debug_tcprof() returns and clears them.  Compiled out by default.
+#ifdef NRM_TC_PROFILE
+__device__ long long g_tcprof[16];
+#define TCPROF_DECL long long tcp_t = clock64();
+#define TCPROF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n__ = clock64(); g_tcprof[i] += n__ - tcp_t; tcp_t = n__; } } while (0)
+#else
+#define TCPROF_DECL
+#define TCPROF(i) do { } while (0)
+#endif
+
 constexpr int TC_THREADS = 128;
 constexpr int TC_MAXC = 8;           // candidates per chunk (N of the ds / pooling products)
 
-// derived weights per branch in the workspace (att_prep_kernel): Wd | A | BmT | b1 | w2 | b2
-constexpr int DER_WD = 0, DER_A = 4096, DER_BMT = 8192, DER_B1 = 12288, DER_W2 = 12352, DER_B2 = 12416, DER_SIZE = 12420;
+// derived weights per branch in the workspace (att_prep_kernel): Wd | A | w2 | b2.
+// Wd and A = Wa - Wc are stored in operand-build order [k/8][(k/4)%2][j][k%4]: the thread that builds the 8 k-values
+// (j, k/8) of a W_c tile reads two 16-byte vectors per matrix and consecutive lanes (j) read consecutive vectors,
+// from global memory when a CTA stages the blocks and from shared memory (conflict-free) for every item after that.
+constexpr int DER_WD = 0, DER_A = 4096, DER_W2 = 8192, DER_B2 = 8256, DER_SIZE = 12420;
+__host__ __device__ constexpr int wda_index(int j, int k) { return (((k >> 3) * 2 + ((k >> 2) & 1)) * 64 + j) * 4 + (k & 3); }
 
 __global__ void __launch_bounds__(256)
 att_prep_kernel(const float* __restrict__ P, float* __restrict__ der) {
@@ -53,61 +70,120 @@ att_prep_kernel(const float* __restrict__ P, float* __restrict__ der) {
   const float* W = P + off.fc1_w;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < 4096; i += gridDim.x * 256) {
     const int j = i >> 6, k = i & 63;
-    const float wa = W[j * 256 + k], wb = W[j * 256 + 64 + k], wc = W[j * 256 + 128 + k], wd = W[j * 256 + 192 + k];
-    const int blk = (k >> 3) * 512 + j * 8 + (k & 7);      // [k/8][j][k%8]: coalesced for lane = j readers
-    d[DER_WD + blk] = wd;
-    d[DER_A + blk] = wa - wc;
-    d[DER_BMT + k * 64 + j] = wb + wc;
+    const float wa = W[j * 256 + k], wc = W[j * 256 + 128 + k], wd = W[j * 256 + 192 + k];
+    d[DER_WD + wda_index(j, k)] = wd;
+    d[DER_A + wda_index(j, k)] = wa - wc;
   }
   if (blockIdx.x == 0 && threadIdx.x < 64) {
-    d[DER_B1 + threadIdx.x] = P[off.fc1_b + threadIdx.x];
     d[DER_W2 + threadIdx.x] = P[off.fc2_w + threadIdx.x];
     if (threadIdx.x == 0) d[DER_B2] = P[off.fc2_b];
+  }
+}
+
+// tp[branch][r][j] = b1[j] + sum_k (Wb + Wc)[j][k] t[r][k] for every candidate row r (t = the candidate's label
+// features / PCA vector inside e_concat).  32 rows per CTA, blockIdx.y = branch.
+__global__ void __launch_bounds__(256)
+candidate_tp_kernel(const float* __restrict__ P, const float* __restrict__ e, long long R, float* __restrict__ tp_all) {
+  __shared__ float st[32][65];          // t rows
+  __shared__ float sBT[64][65];         // Bm^T: [k][j]
+  const AttOffsets off = blockIdx.y == 0 ? ATT_LABEL : ATT_TI;
+  const int toff = blockIdx.y == 0 ? E_XT : E_PCAT;
+  const float* W = P + off.fc1_w;
+  float* tp = tp_all + (long long)blockIdx.y * R * 64;
+  const int tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int nr = (int)min(32LL, R - r0);
+  for (int i = tid; i < 32 * 64; i += 256) {
+    const int r = i >> 6, k = i & 63;
+    st[r][k] = r < nr ? __ldg(e + (r0 + r) * E + toff + k) : 0.f;
+  }
+  for (int i = tid; i < 64 * 64; i += 256) {
+    const int j = i >> 6, k = i & 63;
+    sBT[k][j] = __ldg(W + j * 256 + 64 + k) + __ldg(W + j * 256 + 128 + k);
+  }
+  __syncthreads();
+  const int r = tid >> 3, jq = tid & 7;          // thread owns j = jq + 8 i
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __ldg(P + off.fc1_b + jq + 8 * i);
+#pragma unroll 4
+  for (int k = 0; k < 64; ++k) {
+    const float tv = st[r][k];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(sBT[k][jq + 8 * i], tv, v[i]);
+  }
+  if (r < nr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tp[(r0 + r) * 64 + jq + 8 * i] = v[i];
   }
 }
 
 // ---- small operand tiles -------------------------------------------------------------------------
 // [8 rows][64 k] K-major: byte offset of (r, 8*kb) = kb*128 + r*16   (LBO = 128, one 8-row group)
 constexpr uint32_t T8_LBO = 128, T8_SBO = 128, T8_BYTES = 1024;
-__device__ __forceinline__ umma::Operand op_tile8_k(uint32_t addr) { return umma::Operand{addr, T8_LBO, T8_SBO, 2 * T8_LBO, T8_BYTES}; }
+__device__ __forceinline__ umma::Operand op_tile8_k(uint32_t addr) { return umma::make_operand(addr, T8_LBO, T8_SBO, 2 * T8_LBO, T8_BYTES); }
 
 template <int NP> struct TileBytes { static constexpr uint32_t T64 = NP * umma::TILE64_BYTES, T8 = NP * T8_BYTES; };
 
-// history rows [r0, r0+64) of impression b -> canonical K-major tile(s); rows >= H are zero
+// history rows [r0, r0+64) of impression b -> canonical K-major tile(s); rows >= H are zero.
+// All global loads of the tile are issued before the first conversion (one memory round trip per tile).
 template <int BRANCH, int NP>
 __device__ __forceinline__ void stage_history(const double* __restrict__ xh, const float* __restrict__ xhp,
                                               long long b, int H, int r0, unsigned char* tile) {
-  for (int it = threadIdx.x; it < 64 * 8; it += TC_THREADS) {
-    const int row = it & 63, kb = it >> 6;
-    float v[8];
-    if (r0 + row < H) {
-      if (BRANCH == 0) {
+  constexpr int ITERS = 64 * 8 / TC_THREADS;
+  if (BRANCH == 0) {
+    float4 raw[ITERS][2];
+#pragma unroll
+    for (int u = 0; u < ITERS; ++u) {
+      const int it = threadIdx.x + u * TC_THREADS, row = it & 63, kb = it >> 6;
+      raw[u][0] = raw[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + row < H) {
         const float4* src = reinterpret_cast<const float4*>(xhp + (b * H + r0 + row) * 64 + kb * 8);
-        const float4 a = __ldg(src), c = __ldg(src + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-      } else {
+        raw[u][0] = __ldg(src); raw[u][1] = __ldg(src + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ITERS; ++u) {
+      const int it = threadIdx.x + u * TC_THREADS, row = it & 63, kb = it >> 6;
+      const float v[8] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w, raw[u][1].x, raw[u][1].y, raw[u][1].z, raw[u][1].w};
+      umma::store_operand8<NP>(tile, umma::tile64_offset(row, kb), umma::TILE64_BYTES, v);
+    }
+  } else {
+    double2 raw[ITERS][4];
+#pragma unroll
+    for (int u = 0; u < ITERS; ++u) {
+      const int it = threadIdx.x + u * TC_THREADS, row = it & 63, kb = it >> 6;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) raw[u][i] = make_double2(0.0, 0.0);
+      if (r0 + row < H) {
         const double2* src = reinterpret_cast<const double2*>(xh + (b * H + r0 + row) * HC + 4 + kb * 8);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const double2 d = __ldg(src + i); v[2 * i] = (float)d.x; v[2 * i + 1] = (float)d.y; }
+        for (int i = 0; i < 4; ++i) raw[u][i] = __ldg(src + i);
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
     }
-    umma::store_operand8<NP>(tile, umma::tile64_offset(row, kb), umma::TILE64_BYTES, v);
+#pragma unroll
+    for (int u = 0; u < ITERS; ++u) {
+      const int it = threadIdx.x + u * TC_THREADS, row = it & 63, kb = it >> 6;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = (float)raw[u][i].x; v[2 * i + 1] = (float)raw[u][i].y; }
+      umma::store_operand8<NP>(tile, umma::tile64_offset(row, kb), umma::TILE64_BYTES, v);
+    }
   }
 }
 
-// W_c[j][k] = Wd[j][k] * t[k] + A[j][k] -> K-major tile(s) (rows = j).  Wd / A come from the derived-weight
-// buffer in [k/8][j][8] order (32 KB per branch, L1-resident, coalesced for lane = j); t is the candidate vector.
+// W_c[j][k] = Wd[j][k] * t[k] + A[j][k] -> K-major tile(s) (rows = j).  wda = Wd | A in shared memory (operand-build
+// order, see wda_index); t = the candidate vector in shared memory.
 template <int NP>
-__device__ __forceinline__ void build_Wc(const float* __restrict__ der, const float* __restrict__ t, unsigned char* tile) {
+__device__ __forceinline__ void build_Wc(const float* wda, const float* t, unsigned char* tile) {
+#pragma unroll 2
   for (int it = threadIdx.x; it < 64 * 8; it += TC_THREADS) {
     const int j = it & 63, kb = it >> 6;
-    const float4* wd = reinterpret_cast<const float4*>(der + DER_WD + kb * 512 + j * 8);
-    const float4* wa = reinterpret_cast<const float4*>(der + DER_A + kb * 512 + j * 8);
-    const float4 d0 = __ldg(wd), d1 = __ldg(wd + 1), a0 = __ldg(wa), a1 = __ldg(wa + 1);
-    const float4 t0 = __ldg(reinterpret_cast<const float4*>(t + kb * 8)), t1 = __ldg(reinterpret_cast<const float4*>(t + kb * 8 + 4));
+    const float4 d0 = *reinterpret_cast<const float4*>(wda + DER_WD + ((kb * 2 + 0) * 64 + j) * 4);
+    const float4 d1 = *reinterpret_cast<const float4*>(wda + DER_WD + ((kb * 2 + 1) * 64 + j) * 4);
+    const float4 a0 = *reinterpret_cast<const float4*>(wda + DER_A + ((kb * 2 + 0) * 64 + j) * 4);
+    const float4 a1 = *reinterpret_cast<const float4*>(wda + DER_A + ((kb * 2 + 1) * 64 + j) * 4);
+    const float4 t0 = *reinterpret_cast<const float4*>(t + kb * 8), t1 = *reinterpret_cast<const float4*>(t + kb * 8 + 4);
     float v[8];
     v[0] = fmaf(d0.x, t0.x, a0.x); v[1] = fmaf(d0.y, t0.y, a0.y); v[2] = fmaf(d0.z, t0.z, a0.z); v[3] = fmaf(d0.w, t0.w, a0.w);
     v[4] = fmaf(d1.x, t1.x, a1.x); v[5] = fmaf(d1.y, t1.y, a1.y); v[6] = fmaf(d1.z, t1.z, a1.z); v[7] = fmaf(d1.w, t1.w, a1.w);
@@ -115,22 +191,28 @@ __device__ __forceinline__ void build_Wc(const float* __restrict__ der, const fl
   }
 }
 
-// tp[q][j] = b1[j] + sum_k Bm[j][k] t_q[k] for the (up to) two items of a pair; thread = (q, j)
-__device__ __forceinline__ void compute_tp(const float* __restrict__ der, const float* __restrict__ t0,
-                                           const float* __restrict__ t1, int nimp, float* tp) {
-  const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
-  if (q >= nimp) return;
-  const float* t = q == 0 ? t0 : t1;
-  float v = __ldg(der + DER_B1 + j);
-#pragma unroll 8
-  for (int k4 = 0; k4 < 16; ++k4) {
-    const float4 tv = __ldg(reinterpret_cast<const float4*>(t) + k4);
-    v = fmaf(__ldg(der + DER_BMT + (4 * k4 + 0) * 64 + j), tv.x, v);
-    v = fmaf(__ldg(der + DER_BMT + (4 * k4 + 1) * 64 + j), tv.y, v);
-    v = fmaf(__ldg(der + DER_BMT + (4 * k4 + 2) * 64 + j), tv.z, v);
-    v = fmaf(__ldg(der + DER_BMT + (4 * k4 + 3) * 64 + j), tv.w, v);
+// Candidate vector t and tp = Bm t + b1 of the two items of a pair: thread (q = tid / 64, i = tid % 64) moves t_q[i] and
+// tp_q[i].  Loaded one pair ahead into registers, parked in shared memory as tt[q][0:64] = t, tt[q][64:128] = tp.
+struct PairVec { float t, tp; };
+__device__ __forceinline__ PairVec load_pair_vec(const float* __restrict__ e, const float* __restrict__ tp, long long b0, int C,
+                                                 int c, int toff, int nimp) {
+  const int q = threadIdx.x >> 6, i = threadIdx.x & 63;
+  PairVec v{0.f, 0.f};
+  if (q < nimp) {
+    const long long rc = (b0 + q) * C + c;
+    v.t = __ldg(e + rc * E + toff + i);
+    v.tp = __ldg(tp + rc * 64 + i);
   }
-  tp[q * 64 + j] = v;
+  return v;
+}
+__device__ __forceinline__ void park_pair_vec(float* tt, const PairVec v) {
+  const int q = threadIdx.x >> 6, i = threadIdx.x & 63;
+  tt[q * 128 + i] = v.t;
+  tt[q * 128 + 64 + i] = v.tp;
+}
+__device__ __forceinline__ void stage_weights(const float* __restrict__ der, float* wda) {
+  for (int i = threadIdx.x; i < 8192 / 4; i += TC_THREADS)
+    reinterpret_cast<float4*>(wda)[i] = __ldg(reinterpret_cast<const float4*>(der) + i);
 }
 
 __device__ __forceinline__ void st_bf16(unsigned char* p, float v) {
@@ -144,6 +226,20 @@ __device__ __forceinline__ void store_operand1(unsigned char* tile, uint32_t off
   if (NP == 2) *reinterpret_cast<__nv_bfloat16*>(tile + part_bytes + off) = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// Work units = (impression pair, candidate), dealt to the CTAs as contiguous, equally long ranges so that the
+// last wave is as full as the first; `whole_pairs` keeps a pair's candidates together (needed when its outputs
+// are accumulated over candidates or history tiles inside one CTA).
+__device__ __forceinline__ void unit_range(int npairs, int C, bool whole_pairs, int& u0, int& u1) {
+  if (whole_pairs) {
+    u0 = (int)((long long)npairs * blockIdx.x / gridDim.x) * C;
+    u1 = (int)((long long)npairs * (blockIdx.x + 1) / gridDim.x) * C;
+  } else {
+    const long long U = (long long)npairs * C;
+    u0 = (int)(U * blockIdx.x / gridDim.x);
+    u1 = (int)(U * (blockIdx.x + 1) / gridDim.x);
+  }
+}
+
 // =====================================================================================================
 // forward
 // =====================================================================================================
@@ -152,7 +248,8 @@ struct TcSmemFwd {
   __align__(128) unsigned char opA[2][TileBytes<NP>::T64];   // history tiles, one per impression of the pair
   __align__(128) unsigned char opB[2][TileBytes<NP>::T64];   // W_c of the two items of a candidate pair
   __align__(128) unsigned char opS[2][TileBytes<NP>::T8];    // scores [c][h] per impression (B operand of the pooling product)
-  float tp[2 * 64];
+  __align__(16) float wda[8192];                             // Wd | A, operand-build order
+  __align__(16) float tt[2][2 * 128];                        // [buffer][item q][t 64 | tp 64]
   float w2[64];
   uint64_t mbar;
   uint32_t tmem_base;
@@ -162,9 +259,9 @@ struct TcSmemFwd {
 constexpr uint32_t FWD_TMEM_COLS = 128, FWD_COL_HID = 0, FWD_COL_POOL = 64;
 
 template <int BRANCH, int SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, SPLIT == 3 ? 3 : 4)
+__global__ void __launch_bounds__(TC_THREADS, SPLIT == 3 ? 2 : 3)
 attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restrict__ xhp, int B, int H, int C,
-                            const float* __restrict__ der_all, float* __restrict__ e) {
+                            const float* __restrict__ der_all, const float* __restrict__ tp_all, float* __restrict__ e) {
   constexpr int NP = SPLIT == 3 ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmemFwd<NP>& sm = *reinterpret_cast<TcSmemFwd<NP>*>(smem_raw);
@@ -175,7 +272,9 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* der = der_all + (long long)BRANCH * DER_SIZE;
 
+  const float* tpg = tp_all + (long long)BRANCH * B * C * 64;
   if (tid < 64) sm.w2[tid] = __ldg(der + DER_W2 + tid);
+  stage_weights(der, sm.wda);
   const float b2 = __ldg(der + DER_B2);
   if (warp == 0) umma::tmem_alloc(&sm.tmem_base, FWD_TMEM_COLS);
   if (tid == 0) umma::mbar_init(&sm.mbar, 1);
@@ -190,35 +289,49 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
   const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
 
   const int npairs_b = (B + 1) / 2;
-  for (int pb = blockIdx.x; pb < npairs_b; pb += gridDim.x) {
+  int u0, u1;
+  TCPROF_DECL
+  unit_range(npairs_b, C, H > 64, u0, u1);            // pooled sums over history tiles stay inside one CTA
+  for (int u = u0; u < u1;) {
+    const int pb = u / C, ca = u - pb * C, cend = min(C, ca + (u1 - u));   // candidates [ca, cend) of pair pb
+    u += cend - ca;
     const long long b0 = 2LL * pb;
     const int nimp = (b0 + 1 < B) ? 2 : 1;
     for (int r0 = 0; r0 < H; r0 += 64) {
-      for (int c0 = 0; c0 < C; c0 += TC_MAXC) {
-        const int nc = min(TC_MAXC, C - c0);
-        if (c0 == 0) {
+      for (int c0 = ca; c0 < cend; c0 += TC_MAXC) {
+        const int nc = min(TC_MAXC, cend - c0);
+        if (c0 == ca) {
           __syncthreads();                              // previous tile's products have completed (waited below)
+          TCPROF(0);
           for (int imp = 0; imp < nimp; ++imp) stage_history<BRANCH, NP>(xh, xhp, b0 + imp, H, r0, sm.opA[imp]);
+          TCPROF(1);
         }
+        park_pair_vec(sm.tt[0], load_pair_vec(e, tpg, b0, C, c0, TOFF, nimp));
+        __syncthreads();
+        TCPROF(2);
         for (int c = 0; c < nc; ++c) {
-          const float* t0 = e + ((b0 * C + c0 + c) * E) + TOFF;
-          const float* t1 = e + (((b0 + 1) * C + c0 + c) * E) + TOFF;
-          compute_tp(der, t0, t1, nimp, sm.tp);
-          build_Wc<NP>(der, t0, sm.opB[0]);
-          if (nimp == 2) build_Wc<NP>(der, t1, sm.opB[1]);
+          const float* tt = sm.tt[c & 1];
+          PairVec nxt{0.f, 0.f};
+          if (c + 1 < nc) nxt = load_pair_vec(e, tpg, b0, C, c0 + c + 1, TOFF, nimp);     // one pair ahead
+          build_Wc<NP>(sm.wda, tt, sm.opB[0]);
+          if (nimp == 2) build_Wc<NP>(sm.wda, tt + 128, sm.opB[1]);
+          TCPROF(3);
           umma::fence_async_smem();
           umma::fence_before_sync();
           __syncthreads();
-          if (tid == 0) {
+          TCPROF(4);
+          if (warp == 0 && umma::elect_one()) {
             umma::fence_after_sync();
             for (int q = 0; q < nimp; ++q)
               umma::mma_product<SPLIT, 4>(tmem + FWD_COL_HID + ((uint32_t)(16 * q) << 16), umma::op_tile64_k(umma::smem_u32(sm.opA[q])),
                                           umma::op_tile64_k(umma::smem_u32(sm.opB[q])), IDESC_HID, false);
             umma::mma_commit(&sm.mbar);
           }
+          TCPROF(5);
           umma::mbar_wait(&sm.mbar, phase);
           phase ^= 1;
           umma::fence_after_sync();
+          TCPROF(6);
           {
             float acc = 0.f;
 #pragma unroll
@@ -226,7 +339,7 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
               float v[32];
               umma::tmem_ld32(my_tmem + FWD_COL_HID + cb * 32, v);       // all lanes take part (.sync.aligned)
               if (half < nimp) {
-                const float* tp = sm.tp + half * 64 + cb * 32;
+                const float* tp = tt + half * 128 + 64 + cb * 32;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc = fmaf(gelu_f(v[j] + tp[j]), sm.w2[cb * 32 + j], acc);
               }
@@ -235,12 +348,15 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
             if (half < nimp)
               store_operand1<NP>(sm.opS[half], (uint32_t)(row >> 3) * T8_LBO + (uint32_t)c * 16 + (uint32_t)(row & 7) * 2, T8_BYTES, acc + b2);
           }
+          TCPROF(7);
+          if (c + 1 < nc) park_pair_vec(sm.tt[(c + 1) & 1], nxt);
           umma::fence_async_smem();
           umma::fence_before_sync();
           __syncthreads();                                    // TMEM hid, opB and tp free for the next pair; opS visible
         }
+        TCPROF(8);
         // pooled^T[k][c] = sum_h H[h][k] s[c][h]  for both impressions (columns c >= nc are never read)
-        if (tid == 0) {
+        if (warp == 0 && umma::elect_one()) {
           umma::fence_after_sync();
           for (int q = 0; q < nimp; ++q)
             umma::mma_product<SPLIT, 4>(tmem + FWD_COL_POOL + ((uint32_t)(16 * q) << 16), umma::op_tile64_mn(umma::smem_u32(sm.opA[q])),
@@ -261,6 +377,7 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
           }
         }
         umma::fence_before_sync();
+        TCPROF(9);
       }
     }
   }
@@ -271,15 +388,18 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
 // =====================================================================================================
 // backward
 // =====================================================================================================
-template <int NP>
+// NBD = 2: separate W_c and dhid tiles (label branch: dH = dhid W_c needs both at once);
+// NBD = 1: dhid overwrites W_c once hid has been read (text/img branch: no input gradients)
+template <int NP, int NBD>
 struct TcSmemBwd {
   __align__(128) unsigned char opA[2][TileBytes<NP>::T64];   // history tiles [h][k]
-  __align__(128) unsigned char opBD[2][2][TileBytes<NP>::T64];   // [0][q]: W_c [j][k] of item q;  [1][q]: dhid [h][j] of item q
+  __align__(128) unsigned char opBD[NBD][2][TileBytes<NP>::T64];   // [0][q]: W_c [j][k] of item q;  [NBD-1][q]: dhid [h][j] of item q
   __align__(128) unsigned char opP[2][TileBytes<NP>::T8];    // dP [c][k] per impression (B operand of the ds product)
   __align__(128) unsigned char ones[T8_BYTES];               // [8][64] ones (B operand of the Gt product)
   float ds[2][TC_MAXC][64];                                  // [impression][candidate][history row]
-  float sc[2][TC_MAXC][64];                                  // attention scores, same indexing (label branch)
-  float tp[2 * 64];
+  float sc[NBD == 2 ? 2 * TC_MAXC * 64 : 64];                // attention scores, same indexing (label branch only)
+  __align__(16) float wda[8192];                             // Wd | A, operand-build order
+  __align__(16) float tt[2][2 * 128];                        // [buffer][item q][t 64 | tp 64]
   float w2[64];
   uint64_t mbar;
   uint32_t tmem_base;
@@ -287,19 +407,20 @@ struct TcSmemBwd {
 
 // TMEM columns: [0,64) hid, then Gt in [0,8);  [64,128) ds in [64,72), then S^T;  [128,192) dH;  [192,256) dA^T
 constexpr uint32_t BWD_TMEM_COLS = 256, BWD_COL_HID = 0, BWD_COL_S = 64, BWD_COL_DH = 128, BWD_COL_DA = 192;
-// per-CTA partial sums (floats): dA^T [2 halves][64 k][64 j] | dWd^T [2][64][64] | dw2 [64] | db2 [1] (+3 pad)
-constexpr int TCP_DA = 0, TCP_DWD = 2 * 4096, TCP_DW2 = 4 * 4096, TCP_DB2 = 4 * 4096 + 64, TC_PARTIAL = ATT_TC_PARTIAL;
+// per-CTA partial sums (floats): dA^T [64 k][64 j] | dWd^T [64][64] | dw2 [64] | db2 [1] (+3 pad)
+constexpr int TCP_DA = 0, TCP_DWD = 4096, TCP_DW2 = 2 * 4096, TCP_DB2 = 2 * 4096 + 64, TC_PARTIAL = ATT_TC_PARTIAL;
 
 template <int BRANCH, int SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restrict__ xhp, int B, int H, int C,
-                             const float* __restrict__ der_all, const float* __restrict__ P, const float* __restrict__ e,
-                             const float* __restrict__ de, float* __restrict__ dxh, float* __restrict__ dxt,
+                             const float* __restrict__ der_all, const float* __restrict__ tp_all, const float* __restrict__ P,
+                             const float* __restrict__ e, const float* __restrict__ de, float* __restrict__ dxh, float* __restrict__ dxt,
                              float* __restrict__ dtp, float* __restrict__ part) {
   constexpr int NP = SPLIT == 3 ? 2 : 1;
   constexpr bool INPUT_GRADS = (BRANCH == 0);
+  constexpr int NBD = INPUT_GRADS ? 2 : 1, DH = NBD - 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  TcSmemBwd<NP>& sm = *reinterpret_cast<TcSmemBwd<NP>*>(smem_raw);
+  TcSmemBwd<NP, NBD>& sm = *reinterpret_cast<TcSmemBwd<NP, NBD>*>(smem_raw);
   constexpr AttOffsets off = BRANCH == 0 ? ATT_LABEL : ATT_TI;
   constexpr int TOFF = BRANCH == 0 ? E_XT : E_PCAT;
   constexpr int POFF = BRANCH == 0 ? E_LAB : E_TI;
@@ -312,7 +433,9 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   const float* der = der_all + (long long)BRANCH * DER_SIZE;
   const float* Wd_rm = P + off.fc1_w + 192;            // Wd[j][k] = fc1.weight[j][192 + k]
 
+  const float* tpg = tp_all + (long long)BRANCH * B * C * 64;
   if (tid < 64) sm.w2[tid] = __ldg(der + DER_W2 + tid);
+  stage_weights(der, sm.wda);
   for (int i = tid; i < (int)T8_BYTES / 2; i += TC_THREADS) reinterpret_cast<__nv_bfloat16*>(sm.ones)[i] = __float2bfloat16_rn(1.0f);
   const float b2 = __ldg(der + DER_B2);
   if (warp == 0) umma::tmem_alloc(&sm.tmem_base, BWD_TMEM_COLS);
@@ -337,7 +460,17 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   bool da_started[2] = {false, false};
 
   const int npairs_b = (B + 1) / 2;
-  for (int pb = blockIdx.x; pb < npairs_b; pb += gridDim.x) {
+  int u0, u1;
+  // A pair's candidates may be split between two CTAs unless its outputs are accumulated in global memory over
+  // history tiles or candidate chunks.  With the label branch a split pair has exactly two contributors to dxh
+  // (ranges are at least C units long), each adding its finished partial sum once to a zeroed destination:
+  // 0 + a + b == 0 + b + a bit for bit, so the result does not depend on which CTA gets there first.
+  unit_range(npairs_b, C, H > 64 || (INPUT_GRADS && C > TC_MAXC), u0, u1);
+  for (int u = u0; u < u1;) {
+    const int pb = u / C, ca = u - pb * C, cend = min(C, ca + (u1 - u));   // candidates [ca, cend) of pair pb
+    u += cend - ca;
+    const bool split_pair = (ca > 0 || cend < C);
+    const bool single_chunk = (cend - ca <= TC_MAXC);
     const long long b0 = 2LL * pb;
     const int nimp = (b0 + 1 < B) ? 2 : 1;
     const long long bmine = b0 + half;                 // this thread's impression (valid when half < nimp)
@@ -345,8 +478,8 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
       __syncthreads();                                 // every product of the previous tile has completed
       for (int imp = 0; imp < nimp; ++imp) stage_history<BRANCH, NP>(xh, xhp, b0 + imp, H, r0, sm.opA[imp]);
       bool dh_started = false;
-      for (int c0 = 0; c0 < C; c0 += TC_MAXC) {
-        const int nc = min(TC_MAXC, C - c0);
+      for (int c0 = ca; c0 < cend; c0 += TC_MAXC) {
+        const int nc = min(TC_MAXC, cend - c0);
         // ---- ds[c][h] = sum_k dP_c[k] H[h][k] for the chunk's candidates of both impressions
         for (int i = tid; i < nimp * TC_MAXC * 8; i += TC_THREADS) {
           const int imp = i / (TC_MAXC * 8), c = (i / 8) % TC_MAXC, kb = i & 7;
@@ -364,7 +497,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         umma::fence_async_smem();
         umma::fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && umma::elect_one()) {
           umma::fence_after_sync();
           for (int q = 0; q < nimp; ++q)
             umma::mma_product<SPLIT, 4>(tmem + BWD_COL_S + half_off[q], umma::op_tile64_k(umma::smem_u32(sm.opA[q])),
@@ -384,18 +517,19 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         }
         umma::fence_before_sync();
 
+        park_pair_vec(sm.tt[0], load_pair_vec(e, tpg, b0, C, c0, TOFF, nimp));
+        __syncthreads();
         for (int c = 0; c < nc; ++c) {
-          const long long rc0 = b0 * C + c0 + c, rc1 = (b0 + 1) * C + c0 + c;
           const long long rcm = bmine * C + c0 + c;
-          const float* t0 = e + rc0 * E + TOFF;
-          const float* t1 = e + rc1 * E + TOFF;
-          compute_tp(der, t0, t1, nimp, sm.tp);
-          build_Wc<NP>(der, t0, sm.opBD[0][0]);
-          if (nimp == 2) build_Wc<NP>(der, t1, sm.opBD[0][1]);
+          const float* tt = sm.tt[c & 1];
+          PairVec nxt{0.f, 0.f};
+          if (c + 1 < nc) nxt = load_pair_vec(e, tpg, b0, C, c0 + c + 1, TOFF, nimp);     // one pair ahead
+          build_Wc<NP>(sm.wda, tt, sm.opBD[0][0]);
+          if (nimp == 2) build_Wc<NP>(sm.wda, tt + 128, sm.opBD[0][1]);
           umma::fence_async_smem();
           umma::fence_before_sync();
           __syncthreads();                               // (1) operands visible; previous S^T / Gt reads done
-          if (tid == 0) {
+          if (warp == 0 && umma::elect_one()) {
             umma::fence_after_sync();
             for (int q = 0; q < nimp; ++q)
               umma::mma_product<SPLIT, 4>(tmem + BWD_COL_HID + half_off[q], umma::op_tile64_k(umma::smem_u32(sm.opA[q])),
@@ -415,7 +549,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
               float v[32];
               umma::tmem_ld32(my_tmem + BWD_COL_HID + cb * 32, v);
               if (act) {
-                const float* tp = sm.tp + half * 64 + cb * 32;
+                const float* tp = tt + half * 128 + 64 + cb * 32;
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                   float dh[8];
@@ -429,24 +563,25 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
                     dw2_acc[cb * 32 + j] = fmaf(dsr, g, dw2_acc[cb * 32 + j]);
                     dh[jj] = dsr * w * gp;
                   }
-                  umma::store_operand8<NP>(sm.opBD[1][half], umma::tile64_offset(row, cb * 4 + j8), umma::TILE64_BYTES, dh);
+                  umma::store_operand8<NP>(sm.opBD[DH][half], umma::tile64_offset(row, cb * 4 + j8), umma::TILE64_BYTES, dh);
                 }
               }
             }
             if (act) {
               db2_acc += dsr;
-              if (INPUT_GRADS) sm.sc[half][c][row] = sacc + b2;
+              if (INPUT_GRADS) sm.sc[(half * TC_MAXC + c) * 64 + row] = sacc + b2;
             }
           }
+          if (c + 1 < nc) park_pair_vec(sm.tt[(c + 1) & 1], nxt);
           umma::fence_async_smem();
           umma::fence_before_sync();
           __syncthreads();                               // (2) dhid tiles visible; hid columns free
-          if (tid == 0) {
+          if (warp == 0 && umma::elect_one()) {
             umma::fence_after_sync();
             for (int q = 0; q < nimp; ++q) {
               const umma::Operand h_mn = umma::op_tile64_mn(umma::smem_u32(sm.opA[q]));
-              const umma::Operand d_mn = umma::op_tile64_mn(umma::smem_u32(sm.opBD[1][q]));
-              const umma::Operand d_k = umma::op_tile64_k(umma::smem_u32(sm.opBD[1][q]));
+              const umma::Operand d_mn = umma::op_tile64_mn(umma::smem_u32(sm.opBD[DH][q]));
+              const umma::Operand d_k = umma::op_tile64_k(umma::smem_u32(sm.opBD[DH][q]));
               const umma::Operand w_mn = umma::op_tile64_mn(umma::smem_u32(sm.opBD[0][q]));
               umma::mma_product<SPLIT, 4>(tmem + BWD_COL_S + half_off[q], h_mn, d_mn, IDESC_ST, false);
               umma::mma_product<SPLIT, 4>(tmem + BWD_COL_DA + half_off[q], h_mn, d_mn, IDESC_ST, da_started[q]);
@@ -458,9 +593,8 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
                 for (int t = 0; t < NP; ++t)
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks)
-                    umma::mma_bf16(tmem + BWD_COL_HID + half_off[q],
-                                   umma::make_desc(d_mn.addr + t * d_mn.part + ks * d_mn.kstep, d_mn.lbo, d_mn.sbo),
-                                   umma::make_desc(one.addr + ks * one.kstep, one.lbo, one.sbo), IDESC_GT, (t > 0 || ks > 0) ? 1u : 0u);
+                    umma::mma_bf16(tmem + BWD_COL_HID + half_off[q], d_mn.desc + (uint64_t)(t * d_mn.part16 + ks * d_mn.kstep16),
+                                   one.desc + (uint64_t)(ks * one.kstep16), IDESC_GT, (t > 0 || ks > 0) ? 1u : 0u);
               }
             }
             umma::mma_commit(&sm.mbar);
@@ -473,7 +607,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           // ---- epilogue 2: thread = (impression half, feature k = row) for S^T, (half, j = row) for Gt
           {
             const bool act = half < nimp;
-            const float tk = act ? __ldg(e + rcm * E + TOFF + row) : 0.f;
+            const float tk = act ? tt[half * 128 + row] : 0.f;
             float dt = 0.f;
 #pragma unroll
             for (int cb = 0; cb < 2; ++cb) {
@@ -501,15 +635,15 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           umma::fence_before_sync();
         }
         __syncthreads();                                 // ds / opP of this chunk consumed before the next chunk rewrites them
-        if (INPUT_GRADS) {
-          // pooling path of this chunk: dxh[row][k] (+)= sum_c s_c[row] dP_c[k]; kept in global (each thread owns its row)
-          // so that candidate chunks compose; the W_c path is added from tensor memory at the end of the tile
+        if (INPUT_GRADS && !single_chunk) {
+          // several candidate chunks (whole pair in this CTA): the pooling path dxh[row][k] (+)= sum_c s_c[row] dP_c[k]
+          // of each chunk is accumulated in global memory (each thread owns its row)
           if (half < nimp && r0 + row < H) {
             float* dst = dxh + (bmine * H + r0 + row) * 64;
             for (int k4 = 0; k4 < 16; ++k4) {
-              float4 acc = (c0 == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(dst + 4 * k4);
+              float4 acc = (c0 == ca) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(dst + 4 * k4);
               for (int c = 0; c < nc; ++c) {
-                const float s = sm.sc[half][c][row];
+                const float s = sm.sc[(half * TC_MAXC + c) * 64 + row];
                 const float4 dp = __ldg(reinterpret_cast<const float4*>(de + (bmine * C + c0 + c) * E + POFF) + k4);
                 acc.x = fmaf(s, dp.x, acc.x); acc.y = fmaf(s, dp.y, acc.y); acc.z = fmaf(s, dp.z, acc.z); acc.w = fmaf(s, dp.w, acc.w);
               }
@@ -519,18 +653,33 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         }
       }
       if (INPUT_GRADS) {
-        // dH of this tile (all candidates) from TMEM + the pooling-path partial already in global
+        // dH of this tile (W_c path, all candidates of the range) from tensor memory + the pooling path
+        const int ncs = cend - ca;                       // candidates of the single chunk
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           float v[32];
           umma::tmem_ld32(my_tmem + BWD_COL_DH + cb * 32, v);
           if (half < nimp && r0 + row < H) {
-            float4* dst = reinterpret_cast<float4*>(dxh + (bmine * H + r0 + row) * 64 + cb * 32);
+            float* dstf = dxh + (bmine * H + r0 + row) * 64 + cb * 32;
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4) {
-              float4 a = dst[k4];
-              a.x += v[4 * k4]; a.y += v[4 * k4 + 1]; a.z += v[4 * k4 + 2]; a.w += v[4 * k4 + 3];
-              dst[k4] = a;
+              float4 a = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+              if (single_chunk) {
+                for (int c = 0; c < ncs; ++c) {
+                  const float s = sm.sc[(half * TC_MAXC + c) * 64 + row];
+                  const float4 dp = __ldg(reinterpret_cast<const float4*>(de + (bmine * C + ca + c) * E + POFF + cb * 32) + k4);
+                  a.x = fmaf(s, dp.x, a.x); a.y = fmaf(s, dp.y, a.y); a.z = fmaf(s, dp.z, a.z); a.w = fmaf(s, dp.w, a.w);
+                }
+              } else {
+                const float4 g = *reinterpret_cast<float4*>(dstf + 4 * k4);
+                a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+              }
+              if (split_pair) {
+                atomicAdd(dstf + 4 * k4 + 0, a.x); atomicAdd(dstf + 4 * k4 + 1, a.y);
+                atomicAdd(dstf + 4 * k4 + 2, a.z); atomicAdd(dstf + 4 * k4 + 3, a.w);
+              } else {
+                *reinterpret_cast<float4*>(dstf + 4 * k4) = a;
+              }
             }
           }
         }
@@ -543,17 +692,29 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   __syncthreads();
   float* out = part + (long long)blockIdx.x * TC_PARTIAL;
   {
-    // dA^T from TMEM: thread (half, k) -> out[TCP_DA + half*4096 + k*64 + j]
+    // dA^T from TMEM and dWd^T from registers: thread (half, k); the two halves (lanes l and l ^ 16) are summed
+    // in the warp and the lower half writes out[TCP_DA / TCP_DWD + k*64 + j]
 #pragma unroll
     for (int cb = 0; cb < 2; ++cb) {
       float v[32];
       umma::tmem_ld32(my_tmem + BWD_COL_DA + cb * 32, v);
-      float4* dst = reinterpret_cast<float4*>(out + TCP_DA + half * 4096 + row * 64 + cb * 32);
-      float4* dst2 = reinterpret_cast<float4*>(out + TCP_DWD + half * 4096 + row * 64 + cb * 32);
 #pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        dst[k4] = da_started[half] ? make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        dst2[k4] = make_float4(dwd_acc[cb * 32 + 4 * k4], dwd_acc[cb * 32 + 4 * k4 + 1], dwd_acc[cb * 32 + 4 * k4 + 2], dwd_acc[cb * 32 + 4 * k4 + 3]);
+      for (int j = 0; j < 32; ++j) {
+        float a = da_started[half] ? v[j] : 0.f;
+        a += __shfl_xor_sync(0xffffffffu, a, 16);
+        v[j] = a;
+        float d = dwd_acc[cb * 32 + j];
+        d += __shfl_xor_sync(0xffffffffu, d, 16);
+        dwd_acc[cb * 32 + j] = d;
+      }
+      if (half == 0) {
+        float4* dst = reinterpret_cast<float4*>(out + TCP_DA + row * 64 + cb * 32);
+        float4* dst2 = reinterpret_cast<float4*>(out + TCP_DWD + row * 64 + cb * 32);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          dst[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+          dst2[k4] = make_float4(dwd_acc[cb * 32 + 4 * k4], dwd_acc[cb * 32 + 4 * k4 + 1], dwd_acc[cb * 32 + 4 * k4 + 2], dwd_acc[cb * 32 + 4 * k4 + 3]);
+        }
       }
     }
   }
@@ -561,10 +722,13 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   __syncthreads();
   {
     // dw2[j] = sum over the 128 threads of dw2_acc[j]: transpose through shared memory (operand buffers are free now)
-    float* red = reinterpret_cast<float*>(sm.opBD);          // [128][65] floats = 33 KB <= sizeof(opBD)
-    static_assert(sizeof(sm.opBD) >= 128 * 65 * sizeof(float) || NP == 1, "reduce scratch");
-    float* red2 = reinterpret_cast<float*>(sm.opA);          // db2 partials
-    if (NP == 2) {
+    float* red = reinterpret_cast<float*>(sm.opA);           // opA and opBD are contiguous
+    constexpr bool ONE_PASS = sizeof(sm.opA) + sizeof(sm.opBD) >= 128 * 65 * sizeof(float);
+    static_assert(sizeof(sm.opA) + sizeof(sm.opBD) >= 64 * 65 * sizeof(float), "reduce scratch");
+    using SmemT = TcSmemBwd<NP, NBD>;
+    static_assert(offsetof(SmemT, opBD) == sizeof(sm.opA), "opA / opBD must be contiguous");
+    float* red2 = &sm.ds[0][0][0];                           // db2 partials (128 floats)
+    if (ONE_PASS) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) red[tid * 65 + j] = dw2_acc[j];
       red2[tid] = db2_acc;
@@ -575,7 +739,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         out[TCP_DW2 + tid] = s;
       }
     } else {
-      // NP == 1: opBD is 32 KB = 128 x 64 floats exactly; use an unpadded layout in two passes of 64 threads
+      // small operand buffers: two passes of 64 threads over a [64][65] scratch (opA + opBD are contiguous)
       for (int pass = 0; pass < 2; ++pass) {
         __syncthreads();
         if ((tid >> 6) == pass) {
@@ -607,30 +771,34 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 __global__ void __launch_bounds__(256)
 attention_tc_compose_kernel(const float* __restrict__ part, int nparts, AttOffsets off, float* __restrict__ grads,
                             float* __restrict__ dA_out) {
-  __shared__ float red[4][2][64];
-  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  const int i = blockIdx.x * 64 + lane;              // k*64 + j, grid = 64 blocks
+  // block = 32 consecutive (k,j) entries x 8 interleaved groups of partials, combined in group order; grid = 128
+  __shared__ float red[8][2][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;              // k*64 + j
   float dA = 0.f, dWd = 0.f;
-  for (int p = grp; p < nparts; p += 4) {
+#pragma unroll 4
+  for (int p = grp; p < nparts; p += 8) {
     const float* q = part + (long long)p * TC_PARTIAL;
-    dA += q[TCP_DA + i] + q[TCP_DA + 4096 + i];
-    dWd += q[TCP_DWD + i] + q[TCP_DWD + 4096 + i];
+    dA += q[TCP_DA + i];
+    dWd += q[TCP_DWD + i];
   }
   red[grp][0][lane] = dA; red[grp][1][lane] = dWd;
   __syncthreads();
   if (grp == 0) {
-    dA = ((red[0][0][lane] + red[1][0][lane]) + red[2][0][lane]) + red[3][0][lane];
-    dWd = ((red[0][1][lane] + red[1][1][lane]) + red[2][1][lane]) + red[3][1][lane];
+    dA = red[0][0][lane]; dWd = red[0][1][lane];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) { dA += red[g][0][lane]; dWd += red[g][1][lane]; }
     const int k = i >> 6, j = i & 63;
     float* rowp = grads + off.fc1_w + j * 256;
     rowp[k] = dA; rowp[192 + k] = dWd;
     dA_out[j * 64 + k] = dA;
   }
-  if (blockIdx.x == 0 && grp == 1) {
+  if (blockIdx.x == 0 && grp >= 1 && grp <= 2) {
+    const int j = (grp - 1) * 32 + lane;
     float w = 0.f;
-    for (int p = 0; p < nparts; ++p) w += part[(long long)p * TC_PARTIAL + TCP_DW2 + lane];
-    grads[off.fc2_w + lane] = w;
-    if (lane == 0) {
+    for (int p = 0; p < nparts; ++p) w += part[(long long)p * TC_PARTIAL + TCP_DW2 + j];
+    grads[off.fc2_w + j] = w;
+    if (j == 0) {
       float d = 0.f;
       for (int p = 0; p < nparts; ++p) d += part[(long long)p * TC_PARTIAL + TCP_DB2];
       grads[off.fc2_b] = d;
@@ -639,29 +807,31 @@ attention_tc_compose_kernel(const float* __restrict__ part, int nparts, AttOffse
 }
 
 // The tp = Bm t + b1 path, over the R candidate rows: dBm[j][k] = sum_r dtp[r][j] t[r][k], db1[j] = sum_r dtp[r][j],
-// and (label branch) dxt[r][k] += sum_j dtp[r][j] Bm[j][k].  Row chunks per CTA -> partials, summed by the finish kernel.
-constexpr int TPG_ROWS = 64;
+// and (label branch) dxt[r][k] += sum_j dtp[r][j] Bm[j][k].  32 rows per CTA -> partials, summed by the finish kernel.
+constexpr int TPG_ROWS = 32, TPG_PART = 4096 + 64;
 __global__ void __launch_bounds__(256)
 attention_tp_grad_kernel(const float* __restrict__ dtp, const float* __restrict__ e, int toff, long long R,
-                         const float* __restrict__ der, int input_grads, float* __restrict__ dxt, float* __restrict__ part) {
-  __shared__ float sd[TPG_ROWS][64];    // dtp rows
+                         const float* __restrict__ W /* fc1.weight [64,256] */, int input_grads,
+                         float* __restrict__ dxt, float* __restrict__ part) {
+  __shared__ float sd[TPG_ROWS][65];    // dtp rows
   __shared__ float st[TPG_ROWS][64];    // t rows
+  __shared__ float sB[64][65];          // Bm[j][k] = Wb + Wc
   const int tid = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * TPG_ROWS;
   const int nr = (int)min((long long)TPG_ROWS, R - r0);
-  for (int i = tid; i < TPG_ROWS * 16; i += 256) {
-    const int r = i >> 4, k4 = i & 15;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (r < nr) {
-      a = __ldg(reinterpret_cast<const float4*>(dtp + (r0 + r) * 64) + k4);
-      b = __ldg(reinterpret_cast<const float4*>(e + (r0 + r) * E + toff) + k4);
-    }
-    *reinterpret_cast<float4*>(&sd[r][4 * k4]) = a;
-    *reinterpret_cast<float4*>(&st[r][4 * k4]) = b;
+  for (int i = tid; i < TPG_ROWS * 64; i += 256) {
+    const int r = i >> 6, k = i & 63;
+    sd[r][k] = r < nr ? __ldg(dtp + (r0 + r) * 64 + k) : 0.f;
+    st[r][k] = r < nr ? __ldg(e + (r0 + r) * E + toff + k) : 0.f;
   }
+  if (input_grads)
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int j = i >> 6, k = i & 63;
+      sB[j][k] = __ldg(W + j * 256 + 64 + k) + __ldg(W + j * 256 + 128 + k);
+    }
   __syncthreads();
-  // dBm partial: thread (tj, tk) owns a 4 x 4 block of [j][k]
   {
+    // dBm partial: thread (tj, tk) owns a 4 x 4 block of [j][k]
     const int tj = tid >> 4, tk = tid & 15;
     float acc[4][4];
 #pragma unroll
@@ -669,10 +839,11 @@ attention_tp_grad_kernel(const float* __restrict__ dtp, const float* __restrict_
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     float b1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int r = 0; r < TPG_ROWS; ++r) {
-      const float4 dj = *reinterpret_cast<const float4*>(&sd[r][4 * tj]);
+      const float dv[4] = {sd[r][4 * tj], sd[r][4 * tj + 1], sd[r][4 * tj + 2], sd[r][4 * tj + 3]};
       const float4 tk4 = *reinterpret_cast<const float4*>(&st[r][4 * tk]);
-      const float dv[4] = {dj.x, dj.y, dj.z, dj.w}, tv[4] = {tk4.x, tk4.y, tk4.z, tk4.w};
+      const float tv[4] = {tk4.x, tk4.y, tk4.z, tk4.w};
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         b1[a] += dv[a];
@@ -680,7 +851,7 @@ attention_tp_grad_kernel(const float* __restrict__ dtp, const float* __restrict_
         for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], tv[b], acc[a][b]);
       }
     }
-    float* out = part + (long long)blockIdx.x * (4096 + 64);
+    float* out = part + (long long)blockIdx.x * TPG_PART;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       *reinterpret_cast<float4*>(out + (4 * tj + a) * 64 + 4 * tk) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
@@ -688,25 +859,36 @@ attention_tp_grad_kernel(const float* __restrict__ dtp, const float* __restrict_
     }
   }
   if (input_grads) {
-    // dxt[r][k] += sum_j dtp[r][j] BmT[j... ] : BmT is stored [k][j] -> Bm[j][k] = BmT[k*64 + j]
-    for (int i = tid; i < nr * 64; i += 256) {
-      const int r = i >> 6, k = i & 63;
-      float v = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < 64; ++j) v = fmaf(sd[r][j], __ldg(der + DER_BMT + k * 64 + j), v);
-      dxt[(r0 + r) * 64 + k] += v;
+    // dxt[r][k] += sum_j dtp[r][j] Bm[j][k]; thread (r, kq) owns k = kq + 8 i
+    const int r = tid >> 3, kq = tid & 7;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int j = 0; j < 64; ++j) {
+      const float d = sd[r][j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(d, sB[j][kq + 8 * i], v[i]);
+    }
+    if (r < nr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dxt[(r0 + r) * 64 + kq + 8 * i] += v[i];
     }
   }
 }
 
-// fc1.weight grad blocks [:, 64:128] = dBm and [:, 128:192] = dBm - dA; fc1.bias = db1
+// fc1.weight grad blocks [:, 64:128] = dBm and [:, 128:192] = dBm - dA; fc1.bias = db1.
+// block = 64 consecutive entries x 4 interleaved groups of partials, combined in group order
 __global__ void __launch_bounds__(256)
 attention_tp_finish_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ dA, AttOffsets off,
                            float* __restrict__ grads) {
-  const int i = blockIdx.x * 256 + threadIdx.x;      // 0 .. 4096+64
-  if (i >= 4096 + 64) return;
+  __shared__ float red[4][64];
+  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + lane;              // 0 .. 4096+64, grid = 65 blocks
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(long long)p * (4096 + 64) + i];
+  for (int p = grp; p < nparts; p += 4) s += part[(long long)p * TPG_PART + i];
+  red[grp][lane] = s;
+  __syncthreads();
+  if (grp != 0) return;
+  s = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
   if (i < 4096) {
     const int j = i >> 6, k = i & 63;
     grads[off.fc1_w + j * 256 + 64 + k] = s;
@@ -753,7 +935,7 @@ umma_selftest_kernel(const float* __restrict__ a0, const float* __restrict__ a1,
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {
+  if (warp == 0 && umma::elect_one()) {
     for (int q = 0; q < 2; ++q) {
       const uint32_t d = tmem + ((uint32_t)(16 * q) << 16);
       const uint32_t aa = umma::smem_u32(opA[q]), bb = umma::smem_u32(opB[q]);
@@ -784,18 +966,28 @@ umma_selftest_kernel(const float* __restrict__ a0, const float* __restrict__ a1,
 int launch_attention_prep(const float* P, Workspace& w, cudaStream_t s) {
   att_prep_kernel<<<dim3(4, 2), 256, 0, s>>>(P, w.att_derived);
   NRM_LAUNCH_CHECK("att_prep_kernel");
+  candidate_tp_kernel<<<dim3((unsigned)((w.R + 31) / 32), 2), 256, 0, s>>>(P, w.e, w.R, w.tp);
+  NRM_LAUNCH_CHECK("candidate_tp_kernel");
   return NRM_OK;
+}
+
+// Shared memory is requested with some padding so that exactly `per_sm` CTAs fit: tensor memory serves at most
+// 512 columns per SM, and what the CTAs leave of the 228 KB stays L1, which has to hold the 48 KB of derived
+// weights every operand build reads.
+static size_t padded_smem(size_t need, int per_sm) {
+  const size_t floor_bytes = (227 * 1024) / (per_sm + 1) + 1024;     // one more CTA must not fit
+  return need > floor_bytes ? need : floor_bytes;
 }
 
 template <int BRANCH, int SPLIT>
 static int launch_fwd(const BatchPtrs& in, Workspace& w, cudaStream_t s) {
   constexpr int NP = SPLIT == 3 ? 2 : 1;
-  // pad the request so that no more CTAs become resident than tensor memory can serve (512 columns / 128)
-  const size_t smem = sizeof(TcSmemFwd<NP>) < 57 * 1024 ? 57 * 1024 : sizeof(TcSmemFwd<NP>);
-  const int per_sm = SPLIT == 3 ? 3 : 4;
+  const int per_sm = SPLIT == 3 ? 2 : 3;
+  const size_t smem = padded_smem(sizeof(TcSmemFwd<NP>), per_sm);
+  if (smem > 227 * 1024) { set_error("attention forward: shared memory"); return NRM_EUNSUPPORTED; }
   const int grid = min((w.B + 1) / 2, per_sm * sm_count());
   NRM_CUDA(cudaFuncSetAttribute(attention_forward_tc_kernel<BRANCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_forward_tc_kernel<BRANCH, SPLIT><<<grid, TC_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, w.att_derived, w.e);
+  attention_forward_tc_kernel<BRANCH, SPLIT><<<grid, TC_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, w.att_derived, w.tp, w.e);
   NRM_LAUNCH_CHECK("attention_forward_tc_kernel");
   return NRM_OK;
 }
@@ -805,18 +997,22 @@ int launch_attention_forward_tc(const BatchPtrs& in, Workspace& w, int branch, i
   return branch == 0 ? launch_fwd<0, 3>(in, w, s) : launch_fwd<1, 3>(in, w, s);
 }
 
-static int att_tc_bwd_grid(int B) { return min((B + 1) / 2, min(2 * sm_count(), ATT_TC_PARTS_MAX)); }
+static int ctas_per_sm(size_t smem, int cap) { return (int)max((size_t)1, min((size_t)cap, (size_t)(227 * 1024) / (smem + 1024))); }
+static int att_tc_bwd_grid(int B, int per_sm) { return min((B + 1) / 2, min(per_sm * sm_count(), ATT_TC_PARTS_MAX)); }
 
 template <int BRANCH, int SPLIT>
 static int launch_bwd(const BatchPtrs& in, const float* P, Workspace& w, cudaStream_t s) {
   constexpr int NP = SPLIT == 3 ? 2 : 1;
-  // two CTAs per SM at most (2 x 256 tensor-memory columns): pad small requests accordingly
-  const size_t smem = sizeof(TcSmemBwd<NP>) < 80 * 1024 ? 80 * 1024 : sizeof(TcSmemBwd<NP>);
-  const int grid = att_tc_bwd_grid(w.B);
+  constexpr int NBD = BRANCH == 0 ? 2 : 1;
+  const size_t smem = padded_smem(sizeof(TcSmemBwd<NP, NBD>), 2);    // at most two CTAs per SM (2 x 256 tensor-memory columns)
+  if (smem > 227 * 1024) { set_error("attention backward: shared memory"); return NRM_EUNSUPPORTED; }
+  const int grid = att_tc_bwd_grid(w.B, ctas_per_sm(smem, 2));
+  w.att_tc_parts[BRANCH] = grid;
+  if (BRANCH == 0) NRM_CUDA(cudaMemsetAsync(w.dxh, 0, sizeof(float) * (size_t)w.NH * 64, s));   // split pairs add into it
   float* part = w.att_part + (long long)BRANCH * ATT_TC_PARTS_MAX * TC_PARTIAL;
   float* dtp = w.dtp + (long long)BRANCH * w.R * 64;
   NRM_CUDA(cudaFuncSetAttribute(attention_backward_tc_kernel<BRANCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_backward_tc_kernel<BRANCH, SPLIT><<<grid, TC_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, w.att_derived, P, w.e, w.de,
+  attention_backward_tc_kernel<BRANCH, SPLIT><<<grid, TC_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, w.att_derived, w.tp, P, w.e, w.de,
                                                                             w.dxh, w.dxt, dtp, part);
   NRM_LAUNCH_CHECK("attention_backward_tc_kernel");
   return NRM_OK;
@@ -828,19 +1024,17 @@ int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace&
 }
 
 int launch_attention_finish_tc(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s) {
-  (void)P;
   const AttOffsets off = branch == 0 ? ATT_LABEL : ATT_TI;
   const float* part = w.att_part + (long long)branch * ATT_TC_PARTS_MAX * TC_PARTIAL;
   float* dA = w.att_dA + branch * 4096;
-  attention_tc_compose_kernel<<<64, 256, 0, s>>>(part, att_tc_bwd_grid(w.B), off, grads, dA);
+  attention_tc_compose_kernel<<<128, 256, 0, s>>>(part, w.att_tc_parts[branch], off, grads, dA);
   NRM_LAUNCH_CHECK("attention_tc_compose_kernel");
   const int nparts = (int)((w.R + TPG_ROWS - 1) / TPG_ROWS);
-  float* tpart = w.tp_part;
+  float* tpart = w.tp_part;   // [nparts][TPG_PART]
   const float* dtp = w.dtp + (long long)branch * w.R * 64;
-  attention_tp_grad_kernel<<<nparts, 256, 0, s>>>(dtp, w.e, branch == 0 ? E_XT : E_PCAT, w.R, w.att_derived + (long long)branch * DER_SIZE,
-                                                  branch == 0 ? 1 : 0, w.dxt, tpart);
+  attention_tp_grad_kernel<<<nparts, 256, 0, s>>>(dtp, w.e, branch == 0 ? E_XT : E_PCAT, w.R, P + off.fc1_w, branch == 0 ? 1 : 0, w.dxt, tpart);
   NRM_LAUNCH_CHECK("attention_tp_grad_kernel");
-  attention_tp_finish_kernel<<<(4096 + 64 + 255) / 256, 256, 0, s>>>(tpart, nparts, dA, off, grads);
+  attention_tp_finish_kernel<<<TPG_PART / 64, 256, 0, s>>>(tpart, nparts, dA, off, grads);
   NRM_LAUNCH_CHECK("attention_tp_finish_kernel");
   return NRM_OK;
 }
@@ -867,4 +1061,99 @@ extern "C" int nrm_debug_umma_selftest(const float* a0, const float* a1, const f
   }
   NRM_LAUNCH_CHECK("umma_selftest_kernel");
   return NRM_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Micro-benchmark of the tensor-core building blocks (tools/mma_microbench.py): cycles (clock64 on the issuing
+// thread, from first issue to mbarrier completion) for `reps` back-to-back products of `nk` K=16 steps each.
+//   variant 0: M=64  N=64  K-major x K-major      1: M=64 N=64 MN x MN      2: M=128 N=64 K x K
+//   variant 3: M=64  N=8   K x K                  4: only tcgen05.ld 32x32b.x32 x reps (all four warps)
+// ---------------------------------------------------------------------------------
+namespace nrm {
+__global__ void __launch_bounds__(TC_THREADS)
+mma_microbench_kernel(long long* __restrict__ out, int variant, int reps, int nk) {
+  extern __shared__ __align__(128) unsigned char mb_raw[];
+  unsigned char* opA = mb_raw;                       // 128 x 64 bf16 = 16 KB
+  unsigned char* opB = mb_raw + 16384;               // 64 x 64 bf16 = 8 KB
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 8192) / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(mb_raw)[i] = 0x3c003c00u;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+  if (tid == 0) umma::mbar_init(&mbar, 1);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (variant < 4) {
+    if (warp == 0 && umma::elect_one()) {
+      const uint32_t aa = umma::smem_u32(opA), bb = umma::smem_u32(opB);
+      const uint64_t a_k = umma::make_desc(aa, 1024, 128), b_k = umma::make_desc(bb, 1024, 128);
+      const uint64_t a_mn = umma::make_desc(aa, 128, 1024), b_mn = umma::make_desc(bb, 128, 1024);
+      const uint64_t a_128 = umma::make_desc(aa, 2048, 128), b_8 = umma::make_desc(bb, 128, 128);
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        if (variant == 0) {
+#pragma unroll 4
+          for (int ks = 0; ks < nk; ++ks) umma::mma_bf16(tmem, a_k + (uint64_t)((ks & 3) * 128), b_k + (uint64_t)((ks & 3) * 128), umma::make_idesc_bf16(64, 64), ks > 0);
+        } else if (variant == 1) {
+#pragma unroll 4
+          for (int ks = 0; ks < nk; ++ks) umma::mma_bf16(tmem, a_mn + (uint64_t)((ks & 3) * 16), b_mn + (uint64_t)((ks & 3) * 16), umma::make_idesc_bf16(64, 64, true, true), ks > 0);
+        } else if (variant == 2) {
+#pragma unroll 4
+          for (int ks = 0; ks < nk; ++ks) umma::mma_bf16(tmem, a_128 + (uint64_t)((ks & 3) * 256), b_k + (uint64_t)((ks & 3) * 128), umma::make_idesc_bf16(128, 64), ks > 0);
+        } else {
+#pragma unroll 4
+          for (int ks = 0; ks < nk; ++ks) umma::mma_bf16(tmem, a_k + (uint64_t)((ks & 3) * 128), b_8 + (uint64_t)((ks & 3) * 16), umma::make_idesc_bf16(64, 8), ks > 0);
+        }
+      }
+      t1 = clock64();
+      umma::mma_commit(&mbar);
+      umma::mbar_wait(&mbar, 0);
+      t2 = clock64();
+      out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    umma::mbar_wait(&mbar, 0);
+  } else {
+    umma::fence_after_sync();
+    float acc = 0.f;
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      float v[32];
+      umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (r & 1) * 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc += v[j];
+    }
+    t1 = clock64();
+    if (tid == 0) { out[0] = t1 - t0; out[1] = t1 - t0; }
+    if (acc == 123.456f) out[2] = 1;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
+}  // namespace nrm
+
+extern "C" int nrm_debug_mma_microbench(long long* out, int variant, int reps, int nk, void* stream) {
+  if (!out || variant < 0 || variant > 4 || reps < 1 || nk < 1) { set_error("nrm_debug_mma_microbench: bad argument"); return NRM_EINVAL; }
+  const size_t smem = 16384 + 8192;
+  mma_microbench_kernel<<<1, TC_THREADS, smem, (cudaStream_t)stream>>>(out, variant, reps, nk);
+  NRM_LAUNCH_CHECK("mma_microbench_kernel");
+  return NRM_OK;
+}
+
+extern "C" int nrm_debug_tcprof(long long* host_out16) {
+#ifdef NRM_TC_PROFILE
+  long long zero[16] = {0};
+  NRM_CUDA(cudaDeviceSynchronize());
+  NRM_CUDA(cudaMemcpyFromSymbol(host_out16, nrm::g_tcprof, sizeof(zero)));
+  NRM_CUDA(cudaMemcpyToSymbol(nrm::g_tcprof, zero, sizeof(zero)));
+  return NRM_OK;
+#else
+  (void)host_out16;
+  set_error("nrm_debug_tcprof: library built without -DNRM_TC_PROFILE");
+  return NRM_EUNSUPPORTED;
+#endif
 }

@@ -117,7 +117,7 @@ constexpr int SEG_GROUP = 128;         // sorted entries per level-1 segment gro
 constexpr int ATT_BWD_CTAS_MAX = 148;  // persistent grid of the attention backward
 constexpr int ATT_PARTIAL = 3 * D * D + 64 + 64 + 4;   // dA | dWd | dBm | dw2 | db1 | db2 (+pad) floats per CTA
 constexpr int ATT_TC_PARTS_MAX = 512; // CTAs of the tensor-core attention backward (2 per SM)
-constexpr int ATT_TC_PARTIAL = 4 * 4096 + 68;   // dA^T[2] | dWd^T[2] | dw2 | db2 floats per CTA
+constexpr int ATT_TC_PARTIAL = 2 * 4096 + 68;   // dA^T | dWd^T | dw2 | db2 floats per CTA
 constexpr int STAT_BLOCKS = 64;        // row chunks of the column-statistics kernels
 constexpr int WGRAD_SPLITS = 32;       // split-K factor of the head weight-gradient GEMMs
 constexpr int W1_SPLITS = 256;         // split-K factor of the w1 weight gradient (K = B*H rows)
@@ -141,7 +141,8 @@ struct Workspace {
   float* a2; float* u2;   // [R,66]
   float* y;            // [R,264]
   float* a3; float* u3;   // [R,66]
-  float* att_derived;  // [2][12420] derived attention weights (bf16 tensor-core path)
+  float* att_derived;  // [2][12420] derived attention weights (tensor-core paths)
+  float* tp;           // [2][R,64]  tp = (Wb + Wc) t + b1 per candidate row and branch (tensor-core paths)
   // backward (training only)
   float* da3; float* da2; float* da1;   // [R,66]
   float* dy;           // [R,264]
@@ -155,7 +156,8 @@ struct Workspace {
   float* att_part;     // [2][max(ATT_BWD_CTAS_MAX*ATT_PARTIAL, ATT_TC_PARTS_MAX*ATT_TC_PARTIAL)]
   float* dtp;          // [2][R,64]  dL/dtp per candidate row (tensor-core backward)
   float* att_dA;       // [2][64,64] summed dA per branch
-  float* tp_part;      // [ceil(R/64)][4096+64] partial dBm | db1
+  float* tp_part;      // [ceil(R/32)][4096+64] partial dBm | db1
+  int att_tc_parts[2]; // CTAs (= partials) of the last tensor-core attention backward per branch (host side)
   float* splitk;       // [WGRAD_SPLITS][max wgrad size] split-K partial sums
   float* small_part;   // partial sums of the small reductions
   // sorted-segment machinery for the embedding-table gradients

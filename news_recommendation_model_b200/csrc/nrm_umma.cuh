@@ -193,26 +193,42 @@ __device__ __forceinline__ void mma_tile64(uint32_t tmem_d, uint32_t a_smem, uin
   }
 }
 
-// Generic product over a K range of KSTEPS * 16, operands given as (base address, LBO, SBO, bytes per K=16 step,
-// bytes between the hi and lo parts).  SPLIT = 1: A_hi B_hi.  SPLIT = 3: A_hi B_hi + A_hi B_lo + A_lo B_hi.
-struct Operand { uint32_t addr, lbo, sbo, kstep, part; };
+// One elected lane of a converged warp (elect.sync): MMAs are issued inside `if (warp == w) { if (elect_one()) ... }`
+// so that the tcgen05 instructions sit in warp-uniform control flow -- under a per-thread condition such as
+// `threadIdx.x == 0` the compiler wraps every MMA in a lane-election loop (~120 cycles of issue per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// Generic product over a K range of KSTEPS * 16.  An operand = descriptor of its first K step plus the (>> 4)
+// distances between K = 16 steps and between its hi and lo parts: every further descriptor is one 64-bit add.
+// SPLIT = 1: A_hi B_hi.  SPLIT = 3: A_hi B_hi + A_hi B_lo + A_lo B_hi.
+struct Operand { uint64_t desc; uint32_t kstep16, part16; };
+__device__ __forceinline__ Operand make_operand(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t kstep, uint32_t part) {
+  return Operand{make_desc(addr, lbo, sbo), kstep >> 4, part >> 4};
+}
 template <int SPLIT, int KSTEPS>
 __device__ __forceinline__ void mma_product(uint32_t tmem_d, const Operand a, const Operand b, uint32_t idesc, bool accumulate) {
   constexpr int NT = SPLIT == 3 ? 3 : 1;
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
-    const uint32_t ao = (t == 2) ? a.part : 0u, bo = (t == 1) ? b.part : 0u;
+    const uint32_t ao = (t == 2) ? a.part16 : 0u, bo = (t == 1) ? b.part16 : 0u;
 #pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-      const uint64_t da = make_desc(a.addr + ao + ks * a.kstep, a.lbo, a.sbo);
-      const uint64_t db = make_desc(b.addr + bo + ks * b.kstep, b.lbo, b.sbo);
-      mma_bf16(tmem_d, da, db, idesc, (accumulate || t > 0 || ks > 0) ? 1u : 0u);
-    }
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      mma_bf16(tmem_d, a.desc + (uint64_t)(ao + ks * a.kstep16), b.desc + (uint64_t)(bo + ks * b.kstep16), idesc,
+               (accumulate || t > 0 || ks > 0) ? 1u : 0u);
   }
 }
 // 64 x 64 bf16 tile written K-major (tile64_offset): as a K-major operand, and as the MN-major operand of its transpose
-__device__ __forceinline__ Operand op_tile64_k(uint32_t addr) { return Operand{addr, TILE64_LBO, TILE64_SBO, 2 * TILE64_LBO, TILE64_BYTES}; }
-__device__ __forceinline__ Operand op_tile64_mn(uint32_t addr) { return Operand{addr, TILE64_SBO, TILE64_LBO, 2 * TILE64_SBO, TILE64_BYTES}; }
+__device__ __forceinline__ Operand op_tile64_k(uint32_t addr) { return make_operand(addr, TILE64_LBO, TILE64_SBO, 2 * TILE64_LBO, TILE64_BYTES); }
+__device__ __forceinline__ Operand op_tile64_mn(uint32_t addr) { return make_operand(addr, TILE64_SBO, TILE64_LBO, 2 * TILE64_SBO, TILE64_BYTES); }
 
 }  // namespace umma
 }  // namespace nrm
