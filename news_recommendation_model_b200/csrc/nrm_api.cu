@@ -129,6 +129,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   w.a2 = (float*)take(f * R * HID); w.u2 = (float*)take(f * R * HID);
   w.y = (float*)take(f * R * E);
   w.a3 = (float*)take(f * R * HID); w.u3 = (float*)take(f * R * HID);
+  w.head_wt = (float*)take(f * 5 * HID * E);
   w.att_derived = (float*)take(f * 2 * 12420);
   w.tp = (float*)take(f * 2 * R * 64);
   if (training) {
@@ -138,6 +139,9 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
     w.de = (float*)take(f * R * E);
     w.dz = (float*)take(f * R * E);
     w.bn_bwd_sums = (double*)take(sizeof(double) * 2 * E);
+    w.head_part_f = (float*)take(f * ((R + 31) / 32) * 68);
+    w.head_part_bn = (double*)take(sizeof(double) * ((R + 31) / 32) * 2 * E);
+    w.head_part_w = (float*)take(f * 5 * HEAD_WG_CHUNKS_MAX * (HID * E + E));
     w.dxh = (float*)take(f * NH * 64);
     w.dxt = (float*)take(f * R * 64);
     w.dxin_h = (float*)take(f * NH * XIN);
@@ -311,7 +315,8 @@ extern "C" int nrm_forward_head(int B, int H, int C, const float* params, float*
   const double* sums = bn_sums ? bn_sums : w.bn_sums;
   const long long rows = bn_global_rows > 0 ? bn_global_rows : w.R;
   KernelTimer t("head_forward", (cudaStream_t)stream);
-  return launch_head_forward(params, w, bn_running_mean, bn_running_var, bn_num_batches_tracked, training, sums, rows,
+  return launch_head_forward(params, w, bn_running_mean, bn_running_var, bn_num_batches_tracked, training,
+                             (mode & NRM_MODE_KEEP_FOR_BWD) != 0, sums, rows,
                              logits, (cudaStream_t)stream);
 }
 

@@ -118,6 +118,7 @@ constexpr int ATT_BWD_CTAS_MAX = 148;  // persistent grid of the attention backw
 constexpr int ATT_PARTIAL = 3 * D * D + 64 + 64 + 4;   // dA | dWd | dBm | dw2 | db1 | db2 (+pad) floats per CTA
 constexpr int ATT_TC_PARTS_MAX = 512; // CTAs of the tensor-core attention backward (2 per SM)
 constexpr int ATT_TC_PARTIAL = 2 * 4096 + 68;   // dA^T | dWd^T | dw2 | db2 floats per CTA
+constexpr int HEAD_WG_CHUNKS_MAX = 64; // row chunks of the head weight-gradient kernel
 constexpr int STAT_BLOCKS = 64;        // row chunks of the column-statistics kernels
 constexpr int WGRAD_SPLITS = 32;       // split-K factor of the head weight-gradient GEMMs
 constexpr int W1_SPLITS = 256;         // split-K factor of the w1 weight gradient (K = B*H rows)
@@ -141,6 +142,10 @@ struct Workspace {
   float* a2; float* u2;   // [R,66]
   float* y;            // [R,264]
   float* a3; float* u3;   // [R,66]
+  float* head_wt;      // [5][66*264] transposed head matrices (forward)
+  float* head_part_f;  // [tiles][68]   out_mlp.fc2 partial gradients per row tile
+  double* head_part_bn;// [tiles][2,264] BatchNorm backward partial sums per row tile
+  float* head_part_w;  // [5][chunks][66*264+264] weight-gradient partials
   float* att_derived;  // [2][12420] derived attention weights (tensor-core paths)
   float* tp;           // [2][R,64]  tp = (Wb + Wc) t + b1 per candidate row and branch (tensor-core paths)
   // backward (training only)

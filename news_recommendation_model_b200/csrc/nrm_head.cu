@@ -194,24 +194,11 @@ static GemmArgs linear_bwd_data(const float* dY, int N, const float* W, float* d
   return g;
 }
 
-int launch_head_forward(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt, int training,
+int launch_head_forward(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt, int training, int keep,
                         const double* bn_sums, long long global_rows, float* logits, cudaStream_t s) {
-  const long long R = w.R, total = R * E;
   bn_finalize_kernel<<<1, E, 0, s>>>(bn_sums, global_rows, training, run_mean, run_var, nbt, w.mean, w.rstd);
   NRM_LAUNCH_CHECK("bn_finalize_kernel");
-  bn_apply_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(w.e, w.mean, w.rstd, P + P_BN_W, P + P_BN_B, total, w.z);
-  NRM_LAUNCH_CHECK("bn_apply_kernel");
-  int rc;
-  // gate = fc2(gelu(fc1(z)));  x = gate * e
-  rc = launch_gemm<EPI_BIAS_GELU2>(linear_fwd(w.z, E, P + P_GATE_FC1_W, P + P_GATE_FC1_B, w.a1, w.u1, HID, R), 1, s); if (rc < 0) return rc;
-  { GemmArgs g = linear_fwd(w.u1, HID, P + P_GATE_FC2_W, P + P_GATE_FC2_B, w.gate, w.x, E, R); g.aux1 = w.e; g.saux = E;
-    rc = launch_gemm<EPI_BIAS_MUL2>(g, 1, s); if (rc < 0) return rc; }
-  rc = launch_gemm<EPI_BIAS_GELU2>(linear_fwd(w.x, E, P + P_MLP_FC1_W, P + P_MLP_FC1_B, w.a2, w.u2, HID, R), 1, s); if (rc < 0) return rc;
-  rc = launch_gemm<EPI_BIAS>(linear_fwd(w.u2, HID, P + P_MLP_FC2_W, P + P_MLP_FC2_B, w.y, nullptr, E, R), 1, s); if (rc < 0) return rc;
-  rc = launch_gemm<EPI_BIAS_GELU2>(linear_fwd(w.y, E, P + P_OUT_FC1_W, P + P_OUT_FC1_B, w.a3, w.u3, HID, R), 1, s); if (rc < 0) return rc;
-  rowdot_kernel<<<(int)((R + 7) / 8), 256, 0, s>>>(w.u3, P + P_OUT_FC2_W, P + P_OUT_FC2_B, R, logits);
-  NRM_LAUNCH_CHECK("rowdot_kernel");
-  return NRM_OK;
+  return launch_head_forward_fused(P, w, keep, logits, s);
 }
 
 // dW (layout of the nn.Linear weight, [out,in]) = dY^T X and db = colsum(dY), summed over rows by
@@ -242,44 +229,7 @@ static int weight_grad(const float* dY, int out, const float* X, int in, long lo
 }
 
 int launch_head_backward(const float* P, Workspace& w, const float* dlogits, float* G, cudaStream_t s) {
-  const long long R = w.R;
-  int rc;
-  // out_mlp.fc2: r = u3 . O2 + f2
-  int nsplit = weight_grad(dlogits, 1, w.u3, HID, R, P_OUT_FC2_W, P_OUT_FC2_B, w, s); if (nsplit < 0) return nsplit;
-  out_fc2_backward_kernel<<<(int)((R * HID + 255) / 256), 256, 0, s>>>(dlogits, P + P_OUT_FC2_W, w.a3, R * HID, w.da3);
-  NRM_LAUNCH_CHECK("out_fc2_backward_kernel");
-  // out_mlp.fc1
-  rc = weight_grad(w.da3, HID, w.y, E, R, P_OUT_FC1_W, P_OUT_FC1_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
-  rc = launch_gemm<EPI_NONE>(linear_bwd_data(w.da3, HID, P + P_OUT_FC1_W, w.dy, nullptr, E, R), 1, s); if (rc < 0) return rc;
-  // mlp.fc2
-  rc = weight_grad(w.dy, E, w.u2, HID, R, P_MLP_FC2_W, P_MLP_FC2_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
-  { GemmArgs g = linear_bwd_data(w.dy, E, P + P_MLP_FC2_W, w.da2, nullptr, HID, R); g.aux1 = w.a2; g.saux = HID;
-    rc = launch_gemm<EPI_MUL_GELUGRAD>(g, 1, s); if (rc < 0) return rc; }
-  // mlp.fc1 ; dx -> dgate = dx * e, de = dx * gate
-  rc = weight_grad(w.da2, HID, w.x, E, R, P_MLP_FC1_W, P_MLP_FC1_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
-  { GemmArgs g = linear_bwd_data(w.da2, HID, P + P_MLP_FC1_W, w.dgate, w.de, E, R); g.aux1 = w.e; g.aux2 = w.gate; g.saux = E;
-    rc = launch_gemm<EPI_DX2>(g, 1, s); if (rc < 0) return rc; }
-  // gate.fc2
-  rc = weight_grad(w.dgate, E, w.u1, HID, R, P_GATE_FC2_W, P_GATE_FC2_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
-  { GemmArgs g = linear_bwd_data(w.dgate, E, P + P_GATE_FC2_W, w.da1, nullptr, HID, R); g.aux1 = w.a1; g.saux = HID;
-    rc = launch_gemm<EPI_MUL_GELUGRAD>(g, 1, s); if (rc < 0) return rc; }
-  // gate.fc1 ; dz
-  rc = weight_grad(w.da1, HID, w.z, E, R, P_GATE_FC1_W, P_GATE_FC1_B, w, s); if (rc != nsplit) return rc < 0 ? rc : NRM_EINVAL;
-  rc = launch_gemm<EPI_NONE>(linear_bwd_data(w.da1, HID, P + P_GATE_FC1_W, w.dz, nullptr, E, R), 1, s); if (rc < 0) return rc;
-  {
-    constexpr long long LEN = P_DELTA - P_GATE_FC1_W;
-    reduce_head_splits_kernel<<<(int)((LEN + 255) / 256), 256, 0, s>>>(w.splitk, nsplit, G);
-    NRM_LAUNCH_CHECK("reduce_head_splits_kernel");
-  }
-  // BatchNorm: column sums of dz and dz*xhat (this rank's rows)
-  const int rp = stat_rows(R), nch = stat_chunks(R);
-  bn_bwd_partial_kernel<<<nch, E, 0, s>>>(w.dz, w.e, w.mean, w.rstd, R, rp, w.stat_part);
-  NRM_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_partial_reduce_kernel<<<1, E, 0, s>>>(w.stat_part, nch, w.bn_bwd_sums);
-  NRM_LAUNCH_CHECK("bn_partial_reduce_kernel");
-  bn_param_grad_kernel<<<1, E, 0, s>>>(w.bn_bwd_sums, G);
-  NRM_LAUNCH_CHECK("bn_param_grad_kernel");
-  return NRM_OK;
+  return launch_head_backward_fused(P, w, dlogits, G, s);
 }
 
 int launch_bn_backward_combine(const float* P, Workspace& w, int training, const double* bn_bwd_sums,

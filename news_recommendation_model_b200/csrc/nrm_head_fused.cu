@@ -1,0 +1,549 @@
+// Scoring head of UserModel (models/user_model.py:31-35), fused:
+//     z = BatchNorm(e);  gate = fc2(gelu(fc1(z)));  x = gate * e;  y = fc2(gelu(fc1(x)));  r = fc2(gelu(fc1(y)))
+// Forward: ONE kernel takes a tile of candidate rows through all six layers with the activations in shared
+// memory (the five 264 <-> 66 matrices stream through L2, 350 KB per tile); only what the backward needs
+// (a1, gate, a2, y, a3) goes back to global memory.
+// Backward: kernel A walks the same tile backwards through the data-gradient chain (it reads the nn.Linear
+// weights in their natural [out][in] layout: every contraction here has the output index contiguous), writes the
+// per-layer gradients of the pre-activations and per-tile partial sums for BatchNorm and out_mlp.fc2; kernel B
+// forms the five weight gradients dW = P^T Q over row chunks with one accumulator column per thread; a last
+// kernel adds the chunk partials in fixed order (deterministic, no atomics).
+#include "nrm_kernels.cuh"
+
+namespace nrm {
+
+constexpr int HT_ROWS = 32;        // candidate rows per tile
+constexpr int HT_RPT = 8;          // rows per thread (4 row groups)
+constexpr int HT_THREADS = 288;    // 4 x 66 = 264 working threads, 9 warps
+constexpr int LDW = 268;           // row stride of the 264-wide shared buffers (16-byte aligned rows)
+constexpr int LDN = 68;            // row stride of the 66-wide shared buffers
+
+constexpr int WCHUNK = 64 * HID;   // floats per staged weight chunk: 64 contraction rows x 66 or 16 x 264
+struct HeadSmem {
+  __align__(16) float w0[HT_ROWS * LDW];
+  __align__(16) float w1[HT_ROWS * LDW];   // forward: the e tile; backward: cross row-group reduction scratch [4][2][264]
+  __align__(16) float nb[HT_ROWS * LDN];
+  __align__(16) float wbuf[2][WCHUNK];   // double-buffered weight chunks (cp.async)
+};
+
+// Transposed copies of the five matrices for the forward pass: wt = [G1^T | G2^T | M1^T | M2^T | O1^T], each stored
+// [contraction index][output index] (output contiguous), same element count as the original.
+constexpr int WT_G1 = 0, WT_G2 = HID * E, WT_M1 = 2 * HID * E, WT_M2 = 3 * HID * E, WT_O1 = 4 * HID * E, WT_TOTAL = 5 * HID * E;
+
+__global__ void __launch_bounds__(256)
+head_transpose_kernel(const float* __restrict__ P, float* __restrict__ wt) {
+  const int m = blockIdx.y;                                  // matrix
+  const long long src_off[5] = {P_GATE_FC1_W, P_GATE_FC2_W, P_MLP_FC1_W, P_MLP_FC2_W, P_OUT_FC1_W};
+  const int rows = (m == 1 || m == 3) ? E : HID;             // source is [rows][cols] = [out][in]
+  const int cols = (m == 1 || m == 3) ? HID : E;
+  const float* src = P + src_off[m];
+  float* dst = wt + (long long)m * HID * E;                  // [cols][rows]
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < rows * cols; i += gridDim.x * 256) {
+    const int c = i / rows, r = i - c * rows;                // consecutive threads write consecutive dst elements
+    dst[i] = __ldg(src + r * cols + c);
+  }
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// acc[i][q] += sum_k in[(rg*8+i)][k] * W[k][n + 66 q]   (W = [K][66 NQ] in global memory, output index contiguous).
+// The weight rows stream through shared memory in chunks of KC contraction rows (16.9 KB), double-buffered with
+// cp.async so that the next chunk lands while the current one is multiplied.  Called by EVERY thread of the CTA
+// (it synchronises); threads with work == false only help with the copies.
+template <int K, int NQ, int LDI>
+__device__ __forceinline__ void head_layer(const float* in, const float* __restrict__ W, float (*wbuf)[WCHUNK], bool work, int rg, int n,
+                                           float acc[HT_RPT][NQ]) {
+  constexpr int NOUT = HID * NQ;
+  constexpr int KC = WCHUNK / NOUT;                      // 64 (NQ = 1) or 16 (NQ = 4)
+  constexpr int NCH = (K + KC - 1) / KC;
+  const float* inr = in + rg * HT_RPT * LDI;
+  auto prefetch = [&](int c) {
+    const int rows = (K - c * KC) < KC ? (K - c * KC) : KC;
+    const float* src = W + (long long)c * KC * NOUT;
+    float* dst = wbuf[c & 1];
+    for (int i = threadIdx.x; i < rows * NOUT / 4; i += HT_THREADS) cp_async16(dst + 4 * i, src + 4 * i);
+    cp_async_commit();
+  };
+  prefetch(0);
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    if (c + 1 < NCH) { prefetch(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();                                     // chunk c visible to every thread
+    if (work) {
+      const float* wb = wbuf[c & 1];
+      const int kc = (K - c * KC) < KC ? (K - c * KC) : KC;
+      const int kc4 = kc & ~3;
+      const float* inc = inr + c * KC;
+#pragma unroll 4
+      for (int k0 = 0; k0 < kc4; k0 += 4) {
+        float w[4][NQ];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) w[kk][q] = wb[(k0 + kk) * NOUT + n + HID * q];
+#pragma unroll
+        for (int i = 0; i < HT_RPT; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(inc + i * LDI + k0);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            acc[i][q] = fmaf(a.x, w[0][q], acc[i][q]);
+            acc[i][q] = fmaf(a.y, w[1][q], acc[i][q]);
+            acc[i][q] = fmaf(a.z, w[2][q], acc[i][q]);
+            acc[i][q] = fmaf(a.w, w[3][q], acc[i][q]);
+          }
+        }
+      }
+      for (int k = kc4; k < kc; ++k) {
+        float w[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) w[q] = wb[k * NOUT + n + HID * q];
+#pragma unroll
+        for (int i = 0; i < HT_RPT; ++i) {
+          const float a = inc[i * LDI + k];
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) acc[i][q] = fmaf(a, w[q], acc[i][q]);
+        }
+      }
+    }
+    __syncthreads();                                     // chunk buffer (c & 1) free for chunk c + 2
+  }
+}
+
+template <int NQ>
+__device__ __forceinline__ void zero_acc(float acc[HT_RPT][NQ]) {
+#pragma unroll
+  for (int i = 0; i < HT_RPT; ++i)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[i][q] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HT_THREADS, 2)
+head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ P, const float* __restrict__ wt, long long R, int keep,
+                    float* __restrict__ a1g, float* __restrict__ gateg, float* __restrict__ a2g, float* __restrict__ yg,
+                    float* __restrict__ a3g, float* __restrict__ logits) {
+  extern __shared__ __align__(16) unsigned char hs_raw[];
+  HeadSmem& sm = *reinterpret_cast<HeadSmem*>(hs_raw);
+  const int tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * HT_ROWS;
+  const int nr = (int)min((long long)HT_ROWS, R - r0);
+  // e tile -> w1 (kept for the gating product), z = BatchNorm(e) -> w0
+  for (int i = tid; i < HT_ROWS * (E / 4); i += HT_THREADS) {
+    const int r = i / (E / 4), c4 = i - r * (E / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), z = v;
+    if (r < nr) {
+      v = __ldg(reinterpret_cast<const float4*>(e + (r0 + r) * E) + c4);
+      const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(P + P_BN_W) + c4), be = __ldg(reinterpret_cast<const float4*>(P + P_BN_B) + c4);
+      z.x = (v.x - mu.x) * rs.x * ga.x + be.x; z.y = (v.y - mu.y) * rs.y * ga.y + be.y;
+      z.z = (v.z - mu.z) * rs.z * ga.z + be.z; z.w = (v.w - mu.w) * rs.w * ga.w + be.w;
+    }
+    *reinterpret_cast<float4*>(sm.w1 + r * LDW + 4 * c4) = v;
+    *reinterpret_cast<float4*>(sm.w0 + r * LDW + 4 * c4) = z;
+  }
+  __syncthreads();
+  const bool work = tid < 4 * HID;
+  const int rg = work ? tid / HID : 0, n = work ? tid % HID : 0;
+  const int rb = rg * HT_RPT;
+
+  // narrow layer: out[r][n] = acc + bias[n]; keep -> global [R][66]; nb = gelu(out)
+  auto narrow_out = [&](float acc[HT_RPT][1], const float* bias, float* glob) {
+    const float b = __ldg(bias + n);
+#pragma unroll
+    for (int i = 0; i < HT_RPT; ++i) {
+      const float v = acc[i][0] + b;
+      if (keep && rb + i < nr) glob[(r0 + rb + i) * HID + n] = v;
+      sm.nb[(rb + i) * LDN + n] = gelu_f(v);
+    }
+  };
+
+  {  // gate.fc1
+    float acc[HT_RPT][1]; zero_acc<1>(acc);
+    head_layer<E, 1, LDW>(sm.w0, wt + WT_G1, sm.wbuf, work, rg, n, acc);
+    if (work) narrow_out(acc, P + P_GATE_FC1_B, a1g);
+  }
+  __syncthreads();
+  {  // gate.fc2; x = gate * e -> w0
+    float acc[HT_RPT][4]; zero_acc<4>(acc);
+    head_layer<HID, 4, LDN>(sm.nb, wt + WT_G2, sm.wbuf, work, rg, n, acc);
+    if (work) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = n + HID * q;
+        const float b = __ldg(P + P_GATE_FC2_B + k);
+#pragma unroll
+        for (int i = 0; i < HT_RPT; ++i) {
+          const float g = acc[i][q] + b;
+          if (keep && rb + i < nr) gateg[(r0 + rb + i) * E + k] = g;
+          sm.w0[(rb + i) * LDW + k] = g * sm.w1[(rb + i) * LDW + k];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {  // mlp.fc1
+    float acc[HT_RPT][1]; zero_acc<1>(acc);
+    head_layer<E, 1, LDW>(sm.w0, wt + WT_M1, sm.wbuf, work, rg, n, acc);
+    if (work) narrow_out(acc, P + P_MLP_FC1_B, a2g);
+  }
+  __syncthreads();
+  {  // mlp.fc2 -> y -> w0
+    float acc[HT_RPT][4]; zero_acc<4>(acc);
+    head_layer<HID, 4, LDN>(sm.nb, wt + WT_M2, sm.wbuf, work, rg, n, acc);
+    if (work) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = n + HID * q;
+        const float b = __ldg(P + P_MLP_FC2_B + k);
+#pragma unroll
+        for (int i = 0; i < HT_RPT; ++i) {
+          const float v = acc[i][q] + b;
+          if (keep && rb + i < nr) yg[(r0 + rb + i) * E + k] = v;
+          sm.w0[(rb + i) * LDW + k] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {  // out_mlp.fc1
+    float acc[HT_RPT][1]; zero_acc<1>(acc);
+    head_layer<E, 1, LDW>(sm.w0, wt + WT_O1, sm.wbuf, work, rg, n, acc);
+    if (work) narrow_out(acc, P + P_OUT_FC1_B, a3g);
+  }
+  __syncthreads();
+  // out_mlp.fc2: one warp per row
+  for (int r = tid >> 5; r < nr; r += HT_THREADS / 32) {
+    const int lane = tid & 31;
+    float acc = 0.f;
+    for (int c = lane; c < HID; c += 32) acc = fmaf(sm.nb[r * LDN + c], __ldg(P + P_OUT_FC2_W + c), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) logits[r0 + r] = acc + __ldg(P + P_OUT_FC2_B);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// backward A: data-gradient chain per row tile.
+// tile partial (floats): dO2[66] | do2 | pad -> 68 ; then doubles: bn sums [2][264]
+// ---------------------------------------------------------------------------------
+constexpr int HB_F = 68;
+
+__global__ void __launch_bounds__(HT_THREADS, 2)
+head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ P, long long R, const float* __restrict__ dr,
+                     const float* __restrict__ a1g, const float* __restrict__ gateg, const float* __restrict__ a2g,
+                     const float* __restrict__ a3g,
+                     float* __restrict__ da3g, float* __restrict__ dyg, float* __restrict__ da2g, float* __restrict__ dgateg,
+                     float* __restrict__ da1g, float* __restrict__ dzg, float* __restrict__ deg,
+                     float* __restrict__ part_f, double* __restrict__ part_bn) {
+  extern __shared__ __align__(16) unsigned char hs_raw[];
+  HeadSmem& sm = *reinterpret_cast<HeadSmem*>(hs_raw);
+  const int tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * HT_ROWS;
+  const int nr = (int)min((long long)HT_ROWS, R - r0);
+  const bool work = tid < 4 * HID;
+  const int rg = work ? tid / HID : 0, n = work ? tid % HID : 0;
+  const int rb = rg * HT_RPT;
+  float* red = sm.w1;
+
+  // da3 = dr * O2 * gelu'(a3) -> nb; dO2 / do2 partial sums
+  if (work) {
+    const float o2 = __ldg(P + P_OUT_FC2_W + n);
+    float dw = 0.f, db = 0.f;
+#pragma unroll
+    for (int i = 0; i < HT_RPT; ++i) {
+      float d = 0.f;
+      if (rb + i < nr) {
+        const float drr = __ldg(dr + r0 + rb + i);
+        float gp;
+        const float g = gelu_both(__ldg(a3g + (r0 + rb + i) * HID + n), gp);
+        d = drr * o2 * gp;
+        dw = fmaf(drr, g, dw);
+        db += drr;
+        da3g[(r0 + rb + i) * HID + n] = d;
+      }
+      sm.nb[(rb + i) * LDN + n] = d;
+    }
+    red[rg * 2 * E + n] = dw;
+    if (n == 0) red[rg * 2 * E + E] = db;
+  }
+  __syncthreads();
+  if (tid < HID) part_f[(long long)blockIdx.x * HB_F + tid] = ((red[tid] + red[2 * E + tid]) + red[4 * E + tid]) + red[6 * E + tid];
+  if (tid == HID) part_f[(long long)blockIdx.x * HB_F + HID] = ((red[E] + red[2 * E + E]) + red[4 * E + E]) + red[6 * E + E];
+
+  {  // dy = da3 O1 -> w0
+    float acc[HT_RPT][4]; zero_acc<4>(acc);
+    head_layer<HID, 4, LDN>(sm.nb, P + P_OUT_FC1_W, sm.wbuf, work, rg, n, acc);
+    if (work) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < HT_RPT; ++i) {
+          const int k = n + HID * q;
+          if (rb + i < nr) dyg[(r0 + rb + i) * E + k] = acc[i][q];
+          sm.w0[(rb + i) * LDW + k] = acc[i][q];
+        }
+    }
+  }
+  __syncthreads();
+  {  // da2 = (dy M2) * gelu'(a2) -> nb
+    float acc[HT_RPT][1]; zero_acc<1>(acc);
+    head_layer<E, 1, LDW>(sm.w0, P + P_MLP_FC2_W, sm.wbuf, work, rg, n, acc);
+    if (work) {
+#pragma unroll
+      for (int i = 0; i < HT_RPT; ++i) {
+        float d = 0.f;
+        if (rb + i < nr) {
+          d = acc[i][0] * gelu_grad_f(__ldg(a2g + (r0 + rb + i) * HID + n));
+          da2g[(r0 + rb + i) * HID + n] = d;
+        }
+        sm.nb[(rb + i) * LDN + n] = d;
+      }
+    }
+  }
+  __syncthreads();
+  {  // dx = da2 M1;  dgate = dx * e -> w0;  de (direct path) = dx * gate
+    float acc[HT_RPT][4]; zero_acc<4>(acc);
+    head_layer<HID, 4, LDN>(sm.nb, P + P_MLP_FC1_W, sm.wbuf, work, rg, n, acc);
+    if (work) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < HT_RPT; ++i) {
+          const int k = n + HID * q;
+          float dg = 0.f;
+          if (rb + i < nr) {
+            const long long gi = (r0 + rb + i) * E + k;
+            dg = acc[i][q] * __ldg(e + gi);
+            dgateg[gi] = dg;
+            deg[gi] = acc[i][q] * __ldg(gateg + gi);
+          }
+          sm.w0[(rb + i) * LDW + k] = dg;
+        }
+    }
+  }
+  __syncthreads();
+  {  // da1 = (dgate G2) * gelu'(a1) -> nb
+    float acc[HT_RPT][1]; zero_acc<1>(acc);
+    head_layer<E, 1, LDW>(sm.w0, P + P_GATE_FC2_W, sm.wbuf, work, rg, n, acc);
+    if (work) {
+#pragma unroll
+      for (int i = 0; i < HT_RPT; ++i) {
+        float d = 0.f;
+        if (rb + i < nr) {
+          d = acc[i][0] * gelu_grad_f(__ldg(a1g + (r0 + rb + i) * HID + n));
+          da1g[(r0 + rb + i) * HID + n] = d;
+        }
+        sm.nb[(rb + i) * LDN + n] = d;
+      }
+    }
+  }
+  __syncthreads();
+  {  // dz = da1 G1; BatchNorm partial sums of dz and dz * xhat over this tile's rows
+    float acc[HT_RPT][4]; zero_acc<4>(acc);
+    head_layer<HID, 4, LDN>(sm.nb, P + P_GATE_FC1_W, sm.wbuf, work, rg, n, acc);
+    if (work) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = n + HID * q;
+        const float mu = __ldg(mean + k), rs = __ldg(rstd + k);
+        float s = 0.f, sx = 0.f;
+#pragma unroll
+        for (int i = 0; i < HT_RPT; ++i) {
+          if (rb + i < nr) {
+            const long long gi = (r0 + rb + i) * E + k;
+            const float d = acc[i][q];
+            dzg[gi] = d;
+            s += d;
+            sx = fmaf(d, (__ldg(e + gi) - mu) * rs, sx);
+          }
+        }
+        red[rg * 2 * E + k] = s;
+        red[rg * 2 * E + E + k] = sx;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * E; i += HT_THREADS)
+    part_bn[(long long)blockIdx.x * 2 * E + i] = ((double)red[i] + (double)red[2 * E + i]) + ((double)red[4 * E + i] + (double)red[6 * E + i]);
+}
+
+// ---------------------------------------------------------------------------------
+// backward B: weight gradients.  blockIdx.y = layer, blockIdx.x = row chunk.
+//   dW[nn][kk] = sum_r Pm[r][nn] * Q[r][kk],  nn < 66 (narrow side), kk < 264 (wide side); thread kk keeps 66 sums.
+//   layer 0 out_mlp.fc1: Pm = da3,        Q = y          bias = colsum(Pm)        weight is [66][264]
+//   layer 1 mlp.fc2    : Pm = gelu(a2),   Q = dy         bias = colsum(Q)         weight is [264][66]
+//   layer 2 mlp.fc1    : Pm = da2,        Q = gate * e   bias = colsum(Pm)
+//   layer 3 gate.fc2   : Pm = gelu(a1),   Q = dgate      bias = colsum(Q)
+//   layer 4 gate.fc1   : Pm = da1,        Q = BN(e)      bias = colsum(Pm)
+// chunk partial (floats): [66][264] in (nn, kk) order | bias[264 (padded)]
+// ---------------------------------------------------------------------------------
+constexpr int WG_THREADS = 288, WG_TILE = 32, WG_PART = HID * E + E;
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const float* __restrict__ P, long long R, int rows_per_chunk,
+                  const float* __restrict__ a1g, const float* __restrict__ gateg, const float* __restrict__ a2g,
+                  const float* __restrict__ yg, const float* __restrict__ da3g, const float* __restrict__ dyg,
+                  const float* __restrict__ da2g, const float* __restrict__ dgateg, const float* __restrict__ da1g,
+                  float* __restrict__ part) {
+  __shared__ __align__(16) float sp[WG_TILE][LDN];
+  const int layer = blockIdx.y, tid = threadIdx.x;
+  const long long rbeg = (long long)blockIdx.x * rows_per_chunk;
+  const long long rend = min(R, rbeg + rows_per_chunk);
+  const float* Psrc = layer == 0 ? da3g : layer == 1 ? a2g : layer == 2 ? da2g : layer == 3 ? a1g : da1g;
+  const bool p_gelu = (layer == 1 || layer == 3);
+  const bool kk_ok = tid < E;
+  const int kk = kk_ok ? tid : 0;
+  float bn_mu = 0.f, bn_rs = 0.f, bn_g = 0.f, bn_b = 0.f;
+  if (layer == 4) { bn_mu = __ldg(mean + kk); bn_rs = __ldg(rstd + kk); bn_g = __ldg(P + P_BN_W + kk); bn_b = __ldg(P + P_BN_B + kk); }
+  float acc[HID];
+#pragma unroll
+  for (int i = 0; i < HID; ++i) acc[i] = 0.f;
+  float bsum = 0.f;          // wide-side bias (layers 1, 3): thread kk; narrow-side bias (layers 0, 2, 4): thread nn < 66
+  for (long long t0 = rbeg; t0 < rend; t0 += WG_TILE) {
+    const int nt = (int)min((long long)WG_TILE, rend - t0);
+    __syncthreads();
+    for (int i = tid; i < WG_TILE * HID; i += WG_THREADS) {
+      const int r = i / HID, c = i - r * HID;
+      float v = 0.f;
+      if (r < nt) { v = __ldg(Psrc + (t0 + r) * HID + c); if (p_gelu) v = gelu_f(v); }
+      sp[r][c] = v;
+    }
+    if (tid < 2 * WG_TILE) sp[tid >> 1][HID + (tid & 1)] = 0.f;
+    __syncthreads();
+    if ((layer == 0 || layer == 2 || layer == 4) && tid < HID) {
+      for (int r = 0; r < nt; ++r) bsum += sp[r][tid];
+    }
+    if (kk_ok) {
+#pragma unroll 2
+      for (int r = 0; r < nt; ++r) {
+        const long long gi = (t0 + r) * E + kk;
+        float q;
+        if (layer == 0) q = __ldg(yg + gi);
+        else if (layer == 1) q = __ldg(dyg + gi);
+        else if (layer == 2) q = __ldg(gateg + gi) * __ldg(e + gi);
+        else if (layer == 3) q = __ldg(dgateg + gi);
+        else q = (__ldg(e + gi) - bn_mu) * bn_rs * bn_g + bn_b;
+        if (layer == 1 || layer == 3) bsum += q;
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 p = *reinterpret_cast<const float4*>(&sp[r][4 * c4]);
+          acc[4 * c4] = fmaf(p.x, q, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(p.y, q, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(p.z, q, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(p.w, q, acc[4 * c4 + 3]);
+        }
+        acc[64] = fmaf(sp[r][64], q, acc[64]);
+        acc[65] = fmaf(sp[r][65], q, acc[65]);
+      }
+    }
+  }
+  float* out = part + ((long long)layer * gridDim.x + blockIdx.x) * WG_PART;
+  if (kk_ok) {
+#pragma unroll
+    for (int i = 0; i < HID; ++i) out[i * E + kk] = acc[i];
+  }
+  if (layer == 1 || layer == 3) { if (kk_ok) out[HID * E + kk] = bsum; }
+  else if (tid < HID) out[HID * E + tid] = bsum;
+}
+
+// Sum the chunk partials in chunk order and write the head gradients (transposing layers 1 and 3, whose weights
+// are [264][66]); also out_mlp.fc2 from the tile partials of kernel A and the BatchNorm sums.
+__global__ void __launch_bounds__(256)
+head_grad_finish_kernel(const float* __restrict__ part, int nchunks, const float* __restrict__ part_f, int ntiles,
+                        const double* __restrict__ part_bn, float* __restrict__ grads, double* __restrict__ bn_bwd_sums) {
+  const int layer = blockIdx.y;
+  if (layer < 5) {
+    const long long w_off[5] = {P_OUT_FC1_W, P_MLP_FC2_W, P_MLP_FC1_W, P_GATE_FC2_W, P_GATE_FC1_W};
+    const long long b_off[5] = {P_OUT_FC1_B, P_MLP_FC2_B, P_MLP_FC1_B, P_GATE_FC2_B, P_GATE_FC1_B};
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < WG_PART; i += gridDim.x * 256) {
+      const float* src = part + (long long)layer * nchunks * WG_PART + i;
+      float s = 0.f;
+      for (int c = 0; c < nchunks; ++c) s += src[(long long)c * WG_PART];
+      if (i < HID * E) {
+        const int nn = i / E, kq = i - nn * E;
+        if (layer == 1 || layer == 3) grads[w_off[layer] + (long long)kq * HID + nn] = s;
+        else grads[w_off[layer] + (long long)nn * E + kq] = s;
+      } else {
+        const int b = i - HID * E;
+        const int nb = (layer == 1 || layer == 3) ? E : HID;
+        if (b < nb) grads[b_off[layer] + b] = s;
+      }
+    }
+  } else if (layer == 5) {
+    // out_mlp.fc2 weight / bias from the tile partials
+    for (int i = blockIdx.x * 256 + threadIdx.x; i <= HID; i += gridDim.x * 256) {
+      float s = 0.f;
+      for (int t = 0; t < ntiles; ++t) s += part_f[(long long)t * HB_F + i];
+      if (i < HID) grads[P_OUT_FC2_W + i] = s; else grads[P_OUT_FC2_B] = s;
+    }
+  } else {
+    // BatchNorm: column sums of dz and dz * xhat (this rank's rows), bn.weight / bn.bias gradients
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < 2 * E; i += gridDim.x * 256) {
+      double s = 0.0;
+      for (int t = 0; t < ntiles; ++t) s += part_bn[(long long)t * 2 * E + i];
+      bn_bwd_sums[i] = s;
+      if (i < E) grads[P_BN_B + i] = (float)s; else grads[P_BN_W + (i - E)] = (float)s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------
+static inline int head_tiles(long long R) { return (int)((R + HT_ROWS - 1) / HT_ROWS); }
+int head_wgrad_chunks(long long R) {
+  // about two waves of 5-layer CTAs, at least one 32-row tile per chunk
+  int n = (2 * sm_count() + 4) / 5;
+  const int maxn = (int)((R + WG_TILE - 1) / WG_TILE);
+  if (n > maxn) n = maxn;
+  if (n > HEAD_WG_CHUNKS_MAX) n = HEAD_WG_CHUNKS_MAX;
+  return n < 1 ? 1 : n;
+}
+
+int launch_head_forward_fused(const float* P, Workspace& w, int keep, float* logits, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    NRM_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
+    NRM_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
+    configured = true;
+  }
+  head_transpose_kernel<<<dim3(8, 5), 256, 0, s>>>(P, w.head_wt);
+  NRM_LAUNCH_CHECK("head_transpose_kernel");
+  head_forward_kernel<<<head_tiles(w.R), HT_THREADS, sizeof(HeadSmem), s>>>(w.e, w.mean, w.rstd, P, w.head_wt, w.R, keep, w.a1, w.gate, w.a2,
+                                                                          w.y, w.a3, logits);
+  NRM_LAUNCH_CHECK("head_forward_kernel");
+  return NRM_OK;
+}
+
+int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogits, float* G, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    NRM_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
+    configured = true;
+  }
+  const int ntiles = head_tiles(w.R);
+  head_backward_kernel<<<ntiles, HT_THREADS, sizeof(HeadSmem), s>>>(w.e, w.mean, w.rstd, P, w.R, dlogits, w.a1, w.gate, w.a2, w.a3, w.da3, w.dy,
+                                                                  w.da2, w.dgate, w.da1, w.dz, w.de, w.head_part_f, w.head_part_bn);
+  NRM_LAUNCH_CHECK("head_backward_kernel");
+  const int nch = head_wgrad_chunks(w.R);
+  int rpc = (int)((w.R + nch - 1) / nch);
+  rpc = (rpc + WG_TILE - 1) / WG_TILE * WG_TILE;
+  const int nchunks = (int)((w.R + rpc - 1) / rpc);
+  head_wgrad_kernel<<<dim3(nchunks, 5), WG_THREADS, 0, s>>>(w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2,
+                                                            w.dgate, w.da1, w.head_part_w);
+  NRM_LAUNCH_CHECK("head_wgrad_kernel");
+  head_grad_finish_kernel<<<dim3(18, 7), 256, 0, s>>>(w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums);
+  NRM_LAUNCH_CHECK("head_grad_finish_kernel");
+  return NRM_OK;
+}
+
+}  // namespace nrm

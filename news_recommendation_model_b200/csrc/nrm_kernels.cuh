@@ -26,10 +26,14 @@ int launch_attention_forward_tc(const BatchPtrs& in, Workspace& w, int branch, i
 int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
 int launch_attention_finish_tc(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s);
 
+// nrm_head_fused.cu
+int launch_head_forward_fused(const float* P, Workspace& w, int keep, float* logits, cudaStream_t s);
+int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogits, float* grads, cudaStream_t s);   // -> w.bn_bwd_sums, w.dz, w.de
+
 // nrm_head.cu
 int launch_bn_partial_sums(Workspace& w, cudaStream_t s);                 // -> w.bn_sums
 int launch_head_forward(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt,
-                        int training, const double* bn_sums, long long global_rows, float* logits, cudaStream_t s);
+                        int training, int keep, const double* bn_sums, long long global_rows, float* logits, cudaStream_t s);
 int launch_head_backward(const float* P, Workspace& w, const float* dlogits, float* grads, cudaStream_t s);  // -> w.bn_bwd_sums
 int launch_bn_backward_combine(const float* P, Workspace& w, int training, const double* bn_bwd_sums,
                                long long global_rows, cudaStream_t s);  // w.de += BN path
