@@ -5,6 +5,7 @@ from .models import (MLP, PointwiseAttention, PointwiseAttentionExpanded, UserIn
 from .optim import FusedAdam
 from .trainer import FusedTrainStep
 from ._lib import NrmError, build
+from . import dp
 
 __all__ = ['MLP', 'PointwiseAttention', 'PointwiseAttentionExpanded', 'UserInstantInterestModel',
-           'UserInvariantInterestModel', 'UserModel', 'FusedAdam', 'FusedTrainStep', 'NrmError', 'build']
+           'UserInvariantInterestModel', 'UserModel', 'FusedAdam', 'FusedTrainStep', 'NrmError', 'build', 'dp']

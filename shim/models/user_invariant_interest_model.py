@@ -1,0 +1,2 @@
+"""Shim for the reference's `models/user_invariant_interest_model.py`: re-exports the B200 implementation."""
+from news_recommendation_model_b200.models.user_invariant_interest_model import *  # noqa: F401,F403

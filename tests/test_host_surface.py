@@ -117,3 +117,41 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -1 and b'nrm_adam_step' in lib.nrm_last_error()
     rc = lib.nrm_forward(None, None, 0, None, 0, 0, 1, 1, None, None, None, None, 0, 0, None, None, 0, None)
     assert rc == -1
+
+
+def test_gelu_approximation_restated_in_numpy():
+    """csrc/nrm_common.cuh evaluates Phi(x) with Abramowitz-Stegun 7.1.26 (float32 FMAs, approximate rcp / ex2).
+    Restated here in float32 numpy against scipy's erf in float64: the kernels' GELU and GELU' stay well
+    inside the parity tolerances (torch's own float32 GELU is accurate to ~1e-6)."""
+    import numpy as np
+    from scipy.special import erf
+    f = np.float32
+    x = np.linspace(-12, 12, 480001).astype(f)
+    z = np.abs(x) * f(0.70710678118654752440)
+    t = f(1.0) / (f(0.3275911) * z + f(1.0))
+    poly = t * f(1.061405429) + f(-1.453152027)
+    poly = t * poly + f(1.421413741)
+    poly = t * poly + f(-0.284496736)
+    poly = t * poly + f(0.254829592)
+    poly = poly * t
+    ex = np.exp(-(z * z)).astype(f)
+    half = f(0.5) * poly * ex
+    cdf = np.where(x >= 0, f(1.0) - half, half).astype(f)
+    gelu = x * cdf
+    grad = x * f(0.39894228040143267794) * ex + cdf
+    xd = x.astype(np.float64)
+    cdf_ref = 0.5 * (1.0 + erf(xd / np.sqrt(2.0)))
+    gelu_ref = xd * cdf_ref
+    grad_ref = cdf_ref + xd * np.exp(-0.5 * xd * xd) / np.sqrt(2.0 * np.pi)
+    assert np.abs(gelu - gelu_ref).max() < 1e-6
+    assert np.abs(grad - grad_ref).max() < 1e-6
+
+
+def test_models_shim_shadows_the_reference_package():
+    """shim/ first on sys.path: the reference scripts' `from models.user_model import UserModel` gets this implementation."""
+    import subprocess
+    code = ("import sys; sys.path[:0] = [%r, %r]; from models.user_model import UserModel; from models.attention_model import MLP, "
+            "PointwiseAttentionExpanded; from configs.model_config import config; import news_recommendation_model_b200 as n; "
+            "assert UserModel is n.UserModel and MLP is n.MLP and config['pca_vector'] == 64; print('ok')") % (os.path.join(ROOT, 'shim'), ROOT)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
