@@ -36,7 +36,7 @@ int sm_count() {
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 
-constexpr int kTimerSlots = 24, kTimerRing = 256;
+constexpr int kTimerSlots = 40, kTimerRing = 256;
 struct TimerSlot { const char* name; cudaEvent_t beg[kTimerRing], end[kTimerRing]; int used; bool made; };
 static TimerSlot g_timers[kTimerSlots];
 static int g_ntimers = 0;
@@ -151,7 +151,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
     }
     w.dtp = (float*)take(f * 2 * R * 64);
     w.att_dA = (float*)take(f * 2 * 4096);
-    w.tp_part = (float*)take(f * ((R + 31) / 32) * (4096 + 64));
+    w.tp_part = (float*)take(f * 2 * ((R + 31) / 32) * (4096 + 64));
     {
       const size_t head = (size_t)(P_DELTA - P_GATE_FC1_W) * (WGRAD_SPLITS + 1);
       const size_t w1 = (size_t)(64 * XIN + 64) * (W1_SPLITS + 1);
@@ -188,17 +188,7 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   { KernelTimer t("embed_rows", s);
     NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
   // xh = w1(xin_h)   (user_invariant_interest_model.py:78)
-  GemmArgs g{};
-  g.M = (int)w.NH; g.N = 64; g.K = XIN;
-  g.A = w.xin_h; g.sam = XIN; g.sak = 1;
-  g.B = P + P_W1_W; g.sbk = 1; g.sbn = XIN;
-  g.C = w.xh; g.scm = 64; g.scn = 1;
-  g.bias = P + P_W1_B;
-  {
-    KernelTimer t("w1_gemm", s);
-    const int rc = launch_gemm<EPI_BIAS>(g, 1, s);
-    if (rc < 0) return rc;
-  }
+  { KernelTimer t("w1_forward", s); NRM_TRY(launch_w1_forward(P, w, s)); }
   if (precision != NRM_PRECISION_FP32) NRM_TRY(launch_attention_prep(P, w, s));
   { KernelTimer t("attention_forward_label", s); NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s)); }
   { KernelTimer t("attention_forward_textimg", s); NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s)); }
@@ -207,35 +197,15 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
 
 static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, int precision, float* G, cudaStream_t s) {
   { KernelTimer t("attention_backward_label", s); NRM_TRY(launch_attention_backward(in, P, w, 0, precision, s)); }
-  { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 0, precision, G, s)); }
   { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
-  { KernelTimer t("attention_finish", s); NRM_TRY(launch_attention_finish(P, w, 1, precision, G, s)); }
-  // w1: dW = dxh^T xin_h and db = colsum(dxh) (virtual ones column) by one split GEMM; dxin_h = dxh W1
-  {
-    KernelTimer t("w1_backward", s);
-    constexpr int LEN = 64 * XIN + 64;      // w1.weight and w1.bias are adjacent in the flat layout
-    static_assert(P_W1_B == P_W1_W + 64 * XIN, "w1.weight / w1.bias must be contiguous");
-    GemmArgs g{};
-    g.M = 64; g.N = XIN; g.K = (int)w.NH;
-    g.A = w.dxh; g.sam = 1; g.sak = 64;
-    g.B = w.xin_h; g.sbk = XIN; g.sbn = 1;
-    g.C = w.splitk; g.scm = XIN; g.scn = 1;
-    g.ones_col = 1; g.Cb = w.splitk + 64 * XIN;
-    g.split_stride = LEN;
-    const int nsplit = launch_gemm<EPI_NONE>(g, W1_SPLITS, s);
-    if (nsplit < 0) return nsplit;
-    reduce_splits_kernel<<<(LEN + 255) / 256, 256, 0, s>>>(w.splitk, nsplit, LEN, G + P_W1_W, LEN);
-    NRM_LAUNCH_CHECK("reduce_splits_kernel(w1)");
-    GemmArgs d{};
-    d.M = (int)w.NH; d.N = XIN; d.K = 64;
-    d.A = w.dxh; d.sam = 64; d.sak = 1;
-    d.B = P + P_W1_W; d.sbk = XIN; d.sbn = 1;
-    d.C = w.dxin_h; d.scm = XIN; d.scn = 1;
-    const int rc = launch_gemm<EPI_NONE>(d, 1, s);
-    if (rc < 0) return rc;
-  }
+  { KernelTimer t("attention_finish", s);
+    NRM_TRY(launch_attention_finish(P, w, 0, precision, G, s));
+    NRM_TRY(launch_attention_finish(P, w, 1, precision, G, s)); }
+  // w1: dxin_h = dxh W1, dW1 = dxh^T xin_h, db1 = colsum(dxh)
+  { KernelTimer t("w1_backward", s); NRM_TRY(launch_w1_backward(P, w, G, s)); }
   { KernelTimer t("small_linear_grads", s); NRM_TRY(launch_small_linear_grads(in, w, G, s)); }
-  { KernelTimer t("table_grads", s); NRM_TRY(launch_table_grads(w, G, s)); }
+  NRM_TRY(launch_table_sort(w, s));
+  NRM_TRY(launch_table_grads(w, G, s));
   return NRM_OK;
 }
 

@@ -523,7 +523,7 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
 }
 
 int launch_attention_finish(const float* P, Workspace& w, int branch, int precision, float* grads, cudaStream_t s) {
-  if (precision != NRM_PRECISION_FP32) return launch_attention_finish_tc(P, w, branch, grads, s);
+  if (precision != NRM_PRECISION_FP32) return branch == 1 ? launch_attention_finish_tc(P, w, grads, s) : NRM_OK;   // one pass for both branches
   const float* part = w.att_part + (long long)branch * ATT_BWD_CTAS_MAX * ATT_PARTIAL;
   attention_compose_kernel<<<64, 256, 0, s>>>(part, att_bwd_grid(w.B), branch == 0 ? ATT_LABEL : ATT_TI, grads);
   NRM_LAUNCH_CHECK("attention_compose_kernel");

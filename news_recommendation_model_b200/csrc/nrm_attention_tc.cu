@@ -769,8 +769,13 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 //   fc1.weight grad blocks: [:, 0:64] = dA, [:, 192:256] = dWd   (the Bm-dependent blocks are completed by
 //   attention_tp_grad_kernel); fc2.weight = dw2; fc2.bias = db2.   Partials are transposed ([k][j]).
 __global__ void __launch_bounds__(256)
-attention_tc_compose_kernel(const float* __restrict__ part, int nparts, AttOffsets off, float* __restrict__ grads,
-                            float* __restrict__ dA_out) {
+attention_tc_compose_kernel(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads,
+                            float* __restrict__ dA_all) {
+  const int branch = blockIdx.y;
+  const AttOffsets off = branch == 0 ? ATT_LABEL : ATT_TI;
+  const float* part = part_all + (long long)branch * ATT_TC_PARTS_MAX * TC_PARTIAL;
+  const int nparts = branch == 0 ? nparts0 : nparts1;
+  float* dA_out = dA_all + branch * 4096;
   // block = 32 consecutive (k,j) entries x 8 interleaved groups of partials, combined in group order; grid = 128
   __shared__ float red[8][2][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -810,9 +815,14 @@ attention_tc_compose_kernel(const float* __restrict__ part, int nparts, AttOffse
 // and (label branch) dxt[r][k] += sum_j dtp[r][j] Bm[j][k].  32 rows per CTA -> partials, summed by the finish kernel.
 constexpr int TPG_ROWS = 32, TPG_PART = 4096 + 64;
 __global__ void __launch_bounds__(256)
-attention_tp_grad_kernel(const float* __restrict__ dtp, const float* __restrict__ e, int toff, long long R,
-                         const float* __restrict__ W /* fc1.weight [64,256] */, int input_grads,
-                         float* __restrict__ dxt, float* __restrict__ part) {
+attention_tp_grad_kernel(const float* __restrict__ dtp_all, const float* __restrict__ e, long long R,
+                         const float* __restrict__ P, float* __restrict__ dxt, float* __restrict__ part_all, int nparts) {
+  const int branch = blockIdx.y;
+  const float* dtp = dtp_all + (long long)branch * R * 64;
+  const int toff = branch == 0 ? E_XT : E_PCAT;
+  const float* W = P + (branch == 0 ? ATT_LABEL.fc1_w : ATT_TI.fc1_w);     // fc1.weight [64,256]
+  const int input_grads = branch == 0;
+  float* part = part_all + (long long)branch * nparts * TPG_PART;
   __shared__ float sd[TPG_ROWS][65];    // dtp rows
   __shared__ float st[TPG_ROWS][64];    // t rows
   __shared__ float sB[64][65];          // Bm[j][k] = Wb + Wc
@@ -878,8 +888,12 @@ attention_tp_grad_kernel(const float* __restrict__ dtp, const float* __restrict_
 // fc1.weight grad blocks [:, 64:128] = dBm and [:, 128:192] = dBm - dA; fc1.bias = db1.
 // block = 64 consecutive entries x 4 interleaved groups of partials, combined in group order
 __global__ void __launch_bounds__(256)
-attention_tp_finish_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ dA, AttOffsets off,
+attention_tp_finish_kernel(const float* __restrict__ part_all, int nparts, const float* __restrict__ dA_all,
                            float* __restrict__ grads) {
+  const int branch = blockIdx.y;
+  const AttOffsets off = branch == 0 ? ATT_LABEL : ATT_TI;
+  const float* part = part_all + (long long)branch * nparts * TPG_PART;
+  const float* dA = dA_all + branch * 4096;
   __shared__ float red[4][64];
   const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int i = blockIdx.x * 64 + lane;              // 0 .. 4096+64, grid = 65 blocks
@@ -1023,18 +1037,14 @@ int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace&
   return branch == 0 ? launch_bwd<0, 3>(in, P, w, s) : launch_bwd<1, 3>(in, P, w, s);
 }
 
-int launch_attention_finish_tc(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s) {
-  const AttOffsets off = branch == 0 ? ATT_LABEL : ATT_TI;
-  const float* part = w.att_part + (long long)branch * ATT_TC_PARTS_MAX * TC_PARTIAL;
-  float* dA = w.att_dA + branch * 4096;
-  attention_tc_compose_kernel<<<128, 256, 0, s>>>(part, w.att_tc_parts[branch], off, grads, dA);
+// both branches at once (after both backward kernels)
+int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaStream_t s) {
+  attention_tc_compose_kernel<<<dim3(128, 2), 256, 0, s>>>(w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA);
   NRM_LAUNCH_CHECK("attention_tc_compose_kernel");
   const int nparts = (int)((w.R + TPG_ROWS - 1) / TPG_ROWS);
-  float* tpart = w.tp_part;   // [nparts][TPG_PART]
-  const float* dtp = w.dtp + (long long)branch * w.R * 64;
-  attention_tp_grad_kernel<<<nparts, 256, 0, s>>>(dtp, w.e, branch == 0 ? E_XT : E_PCAT, w.R, P + off.fc1_w, branch == 0 ? 1 : 0, w.dxt, tpart);
+  attention_tp_grad_kernel<<<dim3(nparts, 2), 256, 0, s>>>(w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
   NRM_LAUNCH_CHECK("attention_tp_grad_kernel");
-  attention_tp_finish_kernel<<<TPG_PART / 64, 256, 0, s>>>(tpart, nparts, dA, off, grads);
+  attention_tp_finish_kernel<<<dim3(TPG_PART / 64, 2), 256, 0, s>>>(w.tp_part, nparts, w.att_dA, grads);
   NRM_LAUNCH_CHECK("attention_tp_finish_kernel");
   return NRM_OK;
 }

@@ -119,7 +119,7 @@ constexpr int ATT_PARTIAL = 3 * D * D + 64 + 64 + 4;   // dA | dWd | dBm | dw2 |
 constexpr int ATT_TC_PARTS_MAX = 512; // CTAs of the tensor-core attention backward (2 per SM)
 constexpr int ATT_TC_PARTIAL = 2 * 4096 + 68;   // dA^T | dWd^T | dw2 | db2 floats per CTA
 constexpr int HEAD_WG_CHUNKS_MAX = 64; // row chunks of the head weight-gradient kernel
-constexpr int STAT_BLOCKS = 64;        // row chunks of the column-statistics kernels
+constexpr int STAT_BLOCKS = 256;       // row chunks of the column-statistics kernels
 constexpr int WGRAD_SPLITS = 32;       // split-K factor of the head weight-gradient GEMMs
 constexpr int W1_SPLITS = 256;         // split-K factor of the w1 weight gradient (K = B*H rows)
 

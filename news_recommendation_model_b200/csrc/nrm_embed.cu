@@ -105,58 +105,75 @@ embed_rows_kernel(const double* __restrict__ xh, const double* __restrict__ xt, 
 }
 
 // ---------------------------------------------------------------------------------
-// Deterministic counting sort of table ids (keys < nkeys <= 3000):
-//   sort_hist:    per 2048-entry chunk, histogram of keys           -> chunk_hist[chunk][key]
+// Deterministic counting sort of table ids.  Both streams are sorted by the same launches:
+//   stream 0: keys32 (6 per row: category + 5 sub-categories, keys < 3000)
+//   stream 1: keys8  (5 per row: type / year / month / day / hour, keys < 185)
+//   sort_hist:    per 2048-entry chunk, histogram of keys                    -> chunk_hist[chunk][key]
 //   sort_colscan: per key (a warp each), exclusive scan over chunks (in place) + key totals
-//   sort_keyscan: exclusive scan over keys of the totals -> seg[0..nkeys] (segment starts),
-//                 the same for the number of SEG_GROUP-sized groups -> seg[nkeys+1 .. 2nkeys+1],
-//                 and the group -> key map
+//   sort_keyscan: per stream (a CTA each), exclusive scan over keys of the totals -> seg[0..nkeys] (segment
+//                 starts), the same for the number of SEG_GROUP-sized groups, and the group -> key map
 //   sort_scatter: stable rank of each entry inside its chunk + the two offsets -> perm
-// (four kernels.)  Integer atomics are used only for counts (order independent).
+// Integer atomics are used only for counts (order independent).
 // ---------------------------------------------------------------------------------
+struct SortStream {
+  const int* keys; long long n; int nkeys; int nchunks;
+  int* chunk_hist; int* seg; int* gkey; int* perm;
+};
+struct SortPair { SortStream s[2]; };
+
 __global__ void __launch_bounds__(1024)
-sort_hist_kernel(const int* __restrict__ keys, long long n, int nkeys, int* __restrict__ chunk_hist) {
+sort_hist_kernel(const SortPair sp) {
   extern __shared__ int hist[];
-  for (int i = threadIdx.x; i < nkeys; i += blockDim.x) hist[i] = 0;
+  const int st = blockIdx.x < sp.s[0].nchunks ? 0 : 1;
+  const SortStream& S = sp.s[st];
+  const int chunk = blockIdx.x - (st ? sp.s[0].nchunks : 0);
+  for (int i = threadIdx.x; i < S.nkeys; i += blockDim.x) hist[i] = 0;
   __syncthreads();
-  const long long base = (long long)blockIdx.x * SORT_CHUNK;
+  const long long base = (long long)chunk * SORT_CHUNK;
   for (int i = threadIdx.x; i < SORT_CHUNK; i += blockDim.x)
-    if (base + i < n) atomicAdd(&hist[keys[base + i]], 1);
+    if (base + i < S.n) atomicAdd(&hist[S.keys[base + i]], 1);
   __syncthreads();
-  int* out = chunk_hist + (long long)blockIdx.x * nkeys;
-  for (int i = threadIdx.x; i < nkeys; i += blockDim.x) out[i] = hist[i];
+  int* out = S.chunk_hist + (long long)chunk * S.nkeys;
+  for (int i = threadIdx.x; i < S.nkeys; i += blockDim.x) out[i] = hist[i];
 }
 
-// Per key (one warp each): exclusive scan of the chunk histograms over chunks, in place, and
-// the key's total count.
+// Per key (one warp each): exclusive scan of the chunk histograms over chunks, in place, and the key's total.
 __global__ void __launch_bounds__(256)
-sort_colscan_kernel(int* __restrict__ chunk_hist, int nchunks, int nkeys, int* __restrict__ totals) {
-  const int key = blockIdx.x * 8 + (threadIdx.x >> 5);
+sort_colscan_kernel(const SortPair sp) {
+  int key = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int st = key < sp.s[0].nkeys ? 0 : 1;
+  const SortStream& S = sp.s[st];
+  if (st) key -= sp.s[0].nkeys;
   const int lane = threadIdx.x & 31;
-  if (key >= nkeys) return;
+  if (key >= S.nkeys) return;
+  int* totals = S.seg + 2 * (S.nkeys + 1);
   int carry = 0;
-  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+  for (int c0 = 0; c0 < S.nchunks; c0 += 32) {
     const int c = c0 + lane;
-    int* p = chunk_hist + (long long)c * nkeys + key;
-    const int own = (c < nchunks) ? *p : 0;
+    int* p = S.chunk_hist + (long long)c * S.nkeys + key;
+    const int own = (c < S.nchunks) ? *p : 0;
     int v = own;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
-    if (c < nchunks) *p = carry + v - own;
+    if (c < S.nchunks) *p = carry + v - own;
     carry += __shfl_sync(0xffffffffu, v, 31);
   }
   if (lane == 0) totals[key] = carry;
 }
 
-// One CTA: exclusive scan over keys of the totals -> segment starts, and of the number of
+// One CTA per stream: exclusive scan over keys of the totals -> segment starts, and of the number of
 // SEG_GROUP-sized groups -> group starts; also the group -> key map.
 __global__ void __launch_bounds__(1024)
-sort_keyscan_kernel(const int* __restrict__ totals, int nkeys, int* __restrict__ seg, int* __restrict__ group_key) {
+sort_keyscan_kernel(const SortPair sp) {
   __shared__ int warp_off[2][32];
   __shared__ int block_tot[2];
   __shared__ int carry[2];
-  int* seg_start = seg;
-  int* grp_start = seg + nkeys + 1;
+  const SortStream& S = sp.s[blockIdx.x];
+  const int nkeys = S.nkeys;
+  const int* totals = S.seg + 2 * (nkeys + 1);
+  int* seg_start = S.seg;
+  int* grp_start = S.seg + nkeys + 1;
+  int* group_key = S.gkey;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
   __syncthreads();
@@ -200,29 +217,37 @@ sort_keyscan_kernel(const int* __restrict__ totals, int nkeys, int* __restrict__
   if (threadIdx.x == 0) { seg_start[nkeys] = carry[0]; grp_start[nkeys] = carry[1]; }
 }
 
-// One warp per chunk walks its entries in order, 32 at a time: entries with equal keys
-// inside a round are ranked with match_any, earlier rounds through a shared counter.
-__global__ void __launch_bounds__(32)
-sort_scatter_kernel(const int* __restrict__ keys, long long n, int nkeys, const int* __restrict__ chunk_hist,
-                    const int* __restrict__ seg, int* __restrict__ perm) {
-  extern __shared__ int cnt[];
+// One CTA (4 warps) per chunk.  All warps first stage the chunk's keys and the per-key base position
+// (segment start + offset of this chunk inside the segment) in shared memory; then warp 0 walks the entries in
+// order, 32 at a time: entries with equal keys inside a round are ranked with match_any, earlier rounds through
+// the shared counter.  The walk touches shared memory and registers only.
+__global__ void __launch_bounds__(128)
+sort_scatter_kernel(const SortPair sp) {
+  extern __shared__ int ssm[];                      // keys[SORT_CHUNK] | pos[nkeys]
+  const int st = blockIdx.x < sp.s[0].nchunks ? 0 : 1;
+  const SortStream& S = sp.s[st];
+  const int chunk = blockIdx.x - (st ? sp.s[0].nchunks : 0);
+  int* skeys = ssm;
+  int* pos = ssm + SORT_CHUNK;
+  const long long base = (long long)chunk * SORT_CHUNK;
+  const int total = (int)min((long long)SORT_CHUNK, S.n - base);
+  const int* cb = S.chunk_hist + (long long)chunk * S.nkeys;      // exclusive per-chunk offsets
+  for (int i = threadIdx.x; i < total; i += 128) skeys[i] = S.keys[base + i];
+  for (int i = threadIdx.x; i < S.nkeys; i += 128) pos[i] = S.seg[i] + cb[i];
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
-  for (int i = lane; i < nkeys; i += 32) cnt[i] = 0;
-  __syncwarp();
-  const long long base = (long long)blockIdx.x * SORT_CHUNK;
-  const int total = (int)min((long long)SORT_CHUNK, n - base);
-  const int* cb = chunk_hist + (long long)blockIdx.x * nkeys;    // exclusive per-chunk offsets
   for (int r0 = 0; r0 < total; r0 += 32) {
     const int i = r0 + lane;
     const bool valid = i < total;
-    const int key = valid ? keys[base + i] : (nkeys + lane);     // distinct dummy keys never match
+    const int key = valid ? skeys[i] : (S.nkeys + lane);           // distinct dummy keys never match
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     const int leader = __ffs(peers) - 1;
     const int rank = __popc(peers & ((1u << lane) - 1u));
     int before = 0;
-    if (valid && lane == leader) { before = cnt[key]; cnt[key] = before + __popc(peers); }
+    if (valid && lane == leader) { before = pos[key]; pos[key] = before + __popc(peers); }
     before = __shfl_sync(0xffffffffu, before, leader);
-    if (valid) perm[seg[key] + cb[key] + before + rank] = (int)(base + i);
+    if (valid) S.perm[before + rank] = (int)(base + i);
     __syncwarp();
   }
 }
@@ -245,36 +270,57 @@ __device__ __forceinline__ float seg_load(int entry, const float* __restrict__ d
   return (W == 32 && slot != 0) ? v / 5.0f : v;     // d mean(sub)/d sub_i = 1/5
 }
 
+// The group's entry ids are fetched with one coalesced load per 32 entries and handed around with shuffles, so the
+// row loads of a group are independent of each other (8 in flight per lane) instead of chained behind perm[i].
 template <int W>
-__global__ void __launch_bounds__(256)
-table_grad_l1_kernel(const int* __restrict__ perm, const int* __restrict__ seg, const int* __restrict__ group_key,
-                     int nkeys, const float* __restrict__ dxin_h, const float* __restrict__ dxt, long long NH,
-                     float* __restrict__ gpart) {
-  const int* seg_start = seg;
-  const int* grp_start = seg + nkeys + 1;
-  const int ngroups = grp_start[nkeys];
-  const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (g >= ngroups) return;
+__device__ __forceinline__ void table_grad_l1(const SortStream& S, int g, const float* __restrict__ dxin_h,
+                                              const float* __restrict__ dxt, long long NH, float* __restrict__ gpart) {
+  const int* seg_start = S.seg;
+  const int* grp_start = S.seg + S.nkeys + 1;
   const int lane = threadIdx.x & 31;
-  const int key = group_key[g];
+  const int key = S.gkey[g];
   const int beg = seg_start[key] + (g - grp_start[key]) * SEG_GROUP;
   const int end = min(beg + SEG_GROUP, seg_start[key + 1]);
+  const int n = end - beg;
+  int ids[SEG_GROUP / 32];
+#pragma unroll
+  for (int q = 0; q < SEG_GROUP / 32; ++q) ids[q] = (q * 32 + lane < n) ? S.perm[beg + q * 32 + lane] : 0;
   if (W == 32) {
     float acc = 0.f;
-    int i = beg;
-    for (; i + 4 <= end; i += 4) {
-      const int e0 = perm[i], e1 = perm[i + 1], e2 = perm[i + 2], e3 = perm[i + 3];
-      const float v0 = seg_load<32>(e0, dxin_h, dxt, NH, lane), v1 = seg_load<32>(e1, dxin_h, dxt, NH, lane);
-      const float v2 = seg_load<32>(e2, dxin_h, dxt, NH, lane), v3 = seg_load<32>(e3, dxin_h, dxt, NH, lane);
-      acc += v0; acc += v1; acc += v2; acc += v3;
+#pragma unroll
+    for (int q = 0; q < SEG_GROUP / 32; ++q) {
+      const int m = min(32, n - q * 32);
+      if (m <= 0) break;
+      int i = 0;
+      for (; i + 8 <= m; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = seg_load<32>(__shfl_sync(0xffffffffu, ids[q], i + u), dxin_h, dxt, NH, lane);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+      for (; i < m; ++i) acc += seg_load<32>(__shfl_sync(0xffffffffu, ids[q], i), dxin_h, dxt, NH, lane);
     }
-    for (; i < end; ++i) acc += seg_load<32>(perm[i], dxin_h, dxt, NH, lane);
     gpart[(long long)g * 32 + lane] = acc;
   } else {
+    // four entries per step (8 lanes each); the four interleaved partial sums are combined in a fixed order
     const int sub = lane >> 3, col = lane & 7;
     float acc = 0.f;
-    for (int i = beg + sub; i < end; i += 4) acc += seg_load<8>(perm[i], dxin_h, dxt, NH, col);
-    // combine the four interleaved partial sums in a fixed order
+#pragma unroll
+    for (int q = 0; q < SEG_GROUP / 32; ++q) {
+      const int m = min(32, n - q * 32);
+      if (m <= 0) break;
+      for (int i = 0; i < m; i += 8) {
+        float v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = i + 4 * u + sub;
+          const int id = __shfl_sync(0xffffffffu, ids[q], j & 31);
+          v[u] = (j < m) ? seg_load<8>(id, dxin_h, dxt, NH, col) : 0.f;
+        }
+        acc += v[0]; acc += v[1];
+      }
+    }
     const float a1 = __shfl_down_sync(0xffffffffu, acc, 8);
     const float a2 = __shfl_down_sync(0xffffffffu, acc, 16);
     const float a3 = __shfl_down_sync(0xffffffffu, acc, 24);
@@ -282,37 +328,70 @@ table_grad_l1_kernel(const int* __restrict__ perm, const int* __restrict__ seg, 
   }
 }
 
-// out_row(key) points into the flat gradient buffer.
-template <int W>
+// groups of stream 0 first (grid sized from upper bounds; surplus warps exit)
 __global__ void __launch_bounds__(256)
-table_grad_l2_kernel(const int* __restrict__ seg, int nkeys, const float* __restrict__ gpart, float* __restrict__ grads) {
-  const int* grp_start = seg + nkeys + 1;
-  constexpr int KPW = 32 / W;                      // keys per warp
-  const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const int key = warp * KPW + lane / W;
-  const int col = lane % W;
-  if (key >= nkeys) return;
-  const int g0 = grp_start[key], g1 = grp_start[key + 1];
-  float acc = 0.f;
-  int g = g0;
-  for (; g + 4 <= g1; g += 4) {
-    const float v0 = gpart[(long long)g * W + col], v1 = gpart[(long long)(g + 1) * W + col];
-    const float v2 = gpart[(long long)(g + 2) * W + col], v3 = gpart[(long long)(g + 3) * W + col];
-    acc += v0; acc += v1; acc += v2; acc += v3;
-  }
-  for (; g < g1; ++g) acc += gpart[(long long)g * W + col];
-  float* dst;
-  if (W == 32) {
-    dst = grads + P_CAT + (long long)key * 32;
+table_grad_l1_kernel(const SortPair sp, int warps0, const float* __restrict__ dxin_h, const float* __restrict__ dxt,
+                     long long NH, float* __restrict__ gpart32, float* __restrict__ gpart8) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w < warps0) {
+    const SortStream& S = sp.s[0];
+    if (w < S.seg[2 * S.nkeys + 1]) table_grad_l1<32>(S, w, dxin_h, dxt, NH, gpart32);
   } else {
+    const SortStream& S = sp.s[1];
+    const int g = w - warps0;
+    if (g < S.seg[2 * S.nkeys + 1]) table_grad_l1<8>(S, g, dxin_h, dxt, NH, gpart8);
+  }
+}
+
+// Level 2.  32-wide table: one CTA (4 warps) per key -- the padding id 0 of the sub-category slots collects ~40 % of
+// all entries (>1000 groups), so its groups are split in four contiguous ranges, each summed by one warp with 8
+// independent loads in flight, and the four partial sums are combined in warp order.  8-wide tables: one warp per
+// 4 keys (at most ~150 groups each).
+__global__ void __launch_bounds__(128)
+table_grad_l2_kernel(const SortPair sp, const float* __restrict__ gpart32, const float* __restrict__ gpart8,
+                     float* __restrict__ grads) {
+  __shared__ float red[4][32];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x < NKEY32) {
+    const int key = blockIdx.x;
+    const int* grp_start = sp.s[0].seg + NKEY32 + 1;
+    const int g0 = grp_start[key], g1 = grp_start[key + 1];
+    const int per = (g1 - g0 + 3) / 4;
+    const int a = g0 + wid * per, b = min(g1, a + per);
+    float acc = 0.f;
+    int g = a;
+    for (; g + 8 <= b; g += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = gpart32[(long long)(g + u) * 32 + lane];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; g < b; ++g) acc += gpart32[(long long)g * 32 + lane];
+    red[wid][lane] = acc;
+    __syncthreads();
+    if (wid == 0) grads[P_CAT + (long long)key * 32 + lane] = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
+  } else {
+    const int key = ((blockIdx.x - NKEY32) * 4 + wid) * 4 + (lane >> 3), col = lane & 7;
+    if (key >= NKEY8) return;
+    const int* grp_start = sp.s[1].seg + NKEY8 + 1;
+    const int g0 = grp_start[key], g1 = grp_start[key + 1];
+    float acc = 0.f;
+    int g = g0;
+    for (; g + 4 <= g1; g += 4) {
+      const float v0 = gpart8[(long long)g * 8 + col], v1 = gpart8[(long long)(g + 1) * 8 + col];
+      const float v2 = gpart8[(long long)(g + 2) * 8 + col], v3 = gpart8[(long long)(g + 3) * 8 + col];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; g < g1; ++g) acc += gpart8[(long long)g * 8 + col];
+    float* dst;
     if (key < K8_YEAR) dst = grads + P_TYPE + (long long)(key - K8_TYPE) * 8;
     else if (key < K8_MONTH) dst = grads + P_YEAR + (long long)(key - K8_YEAR) * 8;
     else if (key < K8_DAY) dst = grads + P_MONTH + (long long)(key - K8_MONTH) * 8;
     else if (key < K8_HOUR) dst = grads + P_DAY + (long long)(key - K8_DAY) * 8;
     else dst = grads + P_HOUR + (long long)(key - K8_HOUR) * 8;
+    dst[col] = acc;
   }
-  dst[col] = acc;
 }
 
 // ---------------------------------------------------------------------------------
@@ -332,6 +411,7 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(N, r0 + rows_per_cta);
   float acc_s = 0.f, acc_i = 0.f;
+#pragma unroll 4
   for (long long row = r0 + grp; row < r1; row += 4) {
     const bool is_hist = row < NH;
     const long long r = row - NH;
@@ -393,34 +473,44 @@ int launch_embed_rows(const BatchPtrs& in, const float* P, Workspace& w, bool wi
   return NRM_OK;
 }
 
-static int sort_stream(const int* keys, long long n, int nkeys, int* chunk_hist, int* seg, int* gkey, int* perm,
-                       cudaStream_t s) {
-  const int nchunks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
-  sort_hist_kernel<<<nchunks, 1024, nkeys * sizeof(int), s>>>(keys, n, nkeys, chunk_hist);
+static SortPair make_sort_pair(Workspace& w) {
+  SortPair sp;
+  const long long n32 = w.N * 6, n8 = w.N * 5;
+  sp.s[0] = SortStream{w.keys32, n32, NKEY32, (int)((n32 + SORT_CHUNK - 1) / SORT_CHUNK), w.chunk_hist32, w.seg32, w.gkey32, w.perm32};
+  sp.s[1] = SortStream{w.keys8, n8, NKEY8, (int)((n8 + SORT_CHUNK - 1) / SORT_CHUNK), w.chunk_hist8, w.seg8, w.gkey8, w.perm8};
+  return sp;
+}
+
+// The sort only depends on the ids decoded by embed_rows_kernel; the table gradients need it at the very end.
+int launch_table_sort(Workspace& w, cudaStream_t s) {
+  const SortPair sp = make_sort_pair(w);
+  const int nch = sp.s[0].nchunks + sp.s[1].nchunks;
+  static bool configured = false;
+  if (!configured) {
+    NRM_CUDA(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (SORT_CHUNK + NKEY32))));
+    configured = true;
+  }
+  KernelTimer t("table_sort", s);
+  sort_hist_kernel<<<nch, 1024, NKEY32 * sizeof(int), s>>>(sp);
   NRM_LAUNCH_CHECK("sort_hist_kernel");
-  int* totals = seg + 2 * (nkeys + 1);
-  sort_colscan_kernel<<<(nkeys + 7) / 8, 256, 0, s>>>(chunk_hist, nchunks, nkeys, totals);
+  sort_colscan_kernel<<<(NKEY32 + NKEY8 + 7) / 8, 256, 0, s>>>(sp);
   NRM_LAUNCH_CHECK("sort_colscan_kernel");
-  sort_keyscan_kernel<<<1, 1024, 0, s>>>(totals, nkeys, seg, gkey);
+  sort_keyscan_kernel<<<2, 1024, 0, s>>>(sp);
   NRM_LAUNCH_CHECK("sort_keyscan_kernel");
-  sort_scatter_kernel<<<nchunks, 32, nkeys * sizeof(int), s>>>(keys, n, nkeys, chunk_hist, seg, perm);
+  sort_scatter_kernel<<<nch, 128, sizeof(int) * (SORT_CHUNK + NKEY32), s>>>(sp);
   NRM_LAUNCH_CHECK("sort_scatter_kernel");
   return NRM_OK;
 }
 
 int launch_table_grads(Workspace& w, float* grads, cudaStream_t s) {
-  const long long n32 = w.N * 6, n8 = w.N * 5;
-  NRM_TRY(sort_stream(w.keys32, n32, NKEY32, w.chunk_hist32, w.seg32, w.gkey32, w.perm32, s));
-  NRM_TRY(sort_stream(w.keys8, n8, NKEY8, w.chunk_hist8, w.seg8, w.gkey8, w.perm8, s));
-  const long long g32 = n32 / SEG_GROUP + NKEY32 + 1, g8 = n8 / SEG_GROUP + NKEY8 + 1;   // upper bounds
-  table_grad_l1_kernel<32><<<(int)((g32 + 7) / 8), 256, 0, s>>>(w.perm32, w.seg32, w.gkey32, NKEY32, w.dxin_h, w.dxt, w.NH, w.gpart32);
-  NRM_LAUNCH_CHECK("table_grad_l1_kernel<32>");
-  table_grad_l1_kernel<8><<<(int)((g8 + 7) / 8), 256, 0, s>>>(w.perm8, w.seg8, w.gkey8, NKEY8, w.dxin_h, w.dxt, w.NH, w.gpart8);
-  NRM_LAUNCH_CHECK("table_grad_l1_kernel<8>");
-  table_grad_l2_kernel<32><<<(NKEY32 + 7) / 8, 256, 0, s>>>(w.seg32, NKEY32, w.gpart32, grads);
-  NRM_LAUNCH_CHECK("table_grad_l2_kernel<32>");
-  table_grad_l2_kernel<8><<<((NKEY8 + 3) / 4 + 7) / 8, 256, 0, s>>>(w.seg8, NKEY8, w.gpart8, grads);
-  NRM_LAUNCH_CHECK("table_grad_l2_kernel<8>");
+  const SortPair sp = make_sort_pair(w);
+  const long long g32 = sp.s[0].n / SEG_GROUP + NKEY32 + 1, g8 = sp.s[1].n / SEG_GROUP + NKEY8 + 1;   // upper bounds
+  { KernelTimer t("table_l1", s);
+  table_grad_l1_kernel<<<(int)((g32 + g8 + 7) / 8), 256, 0, s>>>(sp, (int)g32, w.dxin_h, w.dxt, w.NH, w.gpart32, w.gpart8);
+  NRM_LAUNCH_CHECK("table_grad_l1_kernel"); }
+  { KernelTimer t("table_l2", s);
+  table_grad_l2_kernel<<<NKEY32 + (NKEY8 + 15) / 16, 128, 0, s>>>(sp, w.gpart32, w.gpart8, grads);
+  NRM_LAUNCH_CHECK("table_grad_l2_kernel"); }
   return NRM_OK;
 }
 

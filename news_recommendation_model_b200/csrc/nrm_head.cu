@@ -45,17 +45,25 @@ bn_partial_kernel(const float* __restrict__ e, long long R, int rows_per_chunk, 
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
   const long long r1 = min(R, r0 + rows_per_chunk);
   double s = 0.0, q = 0.0;
-  for (long long r = r0; r < r1; ++r) { const double v = (double)e[r * E + n]; s += v; q += v * v; }
+#pragma unroll 8
+  for (long long r = r0; r < r1; ++r) { const double v = (double)__ldg(e + r * E + n); s += v; q += v * v; }
   part[((long long)blockIdx.x * 2 + 0) * E + n] = s;
   part[((long long)blockIdx.x * 2 + 1) * E + n] = q;
 }
 
-__global__ void __launch_bounds__(E)
+// sums[i] = sum over parts of part[p][i], i < 2*264; block = 66 entries x 4 interleaved groups of partials combined in
+// group order (8 blocks)
+__global__ void __launch_bounds__(264)
 bn_partial_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ sums) {
-  const int n = threadIdx.x;
-  double s = 0.0, q = 0.0;
-  for (int p = 0; p < nparts; ++p) { s += part[((long long)p * 2 + 0) * E + n]; q += part[((long long)p * 2 + 1) * E + n]; }
-  sums[n] = s; sums[E + n] = q;
+  __shared__ double red[4][66];
+  const int lane = threadIdx.x % 66, grp = threadIdx.x / 66;
+  const int i = blockIdx.x * 66 + lane;
+  double s = 0.0;
+#pragma unroll 4
+  for (int p = grp; p < nparts; p += 4) s += part[(long long)p * 2 * E + i];
+  red[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0) sums[i] = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
 }
 
 // training: batch mean / biased variance from (global) sums; running stats with momentum
@@ -170,7 +178,7 @@ int launch_bn_partial_sums(Workspace& w, cudaStream_t s) {
   const int rp = stat_rows(w.R), nch = stat_chunks(w.R);
   bn_partial_kernel<<<nch, E, 0, s>>>(w.e, w.R, rp, w.stat_part);
   NRM_LAUNCH_CHECK("bn_partial_kernel");
-  bn_partial_reduce_kernel<<<1, E, 0, s>>>(w.stat_part, nch, w.bn_sums);
+  bn_partial_reduce_kernel<<<2 * E / 66, 264, 0, s>>>(w.stat_part, nch, w.bn_sums);
   NRM_LAUNCH_CHECK("bn_partial_reduce_kernel");
   return NRM_OK;
 }

@@ -387,8 +387,10 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
 //   layer 4 gate.fc1   : Pm = da1,        Q = BN(e)      bias = colsum(Pm)
 // chunk partial (floats): [66][264] in (nn, kk) order | bias[264 (padded)]
 // ---------------------------------------------------------------------------------
-constexpr int WG_THREADS = 288, WG_TILE = 32, WG_PART = HID * E + E;
+constexpr int WG_THREADS = 320, WG_TILE = 32, WG_PART = HID * E + E;
+constexpr int WG_LDP = 72;          // row stride of the narrow-side tile (66 padded to 9 groups of 8)
 
+// thread (ng, kg) owns the 8 x 8 block dW[8 ng .. +8][8 kg .. +8]: per row two 16-byte reads of each operand feed 64 FMAs
 __global__ void __launch_bounds__(WG_THREADS, 1)
 head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd,
                   const float* __restrict__ P, long long R, int rows_per_chunk,
@@ -396,20 +398,24 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
                   const float* __restrict__ yg, const float* __restrict__ da3g, const float* __restrict__ dyg,
                   const float* __restrict__ da2g, const float* __restrict__ dgateg, const float* __restrict__ da1g,
                   float* __restrict__ part) {
-  __shared__ __align__(16) float sp[WG_TILE][LDN];
+  __shared__ __align__(16) float sp[WG_TILE][WG_LDP];
+  __shared__ __align__(16) float sq[WG_TILE][E];
   const int layer = blockIdx.y, tid = threadIdx.x;
   const long long rbeg = (long long)blockIdx.x * rows_per_chunk;
   const long long rend = min(R, rbeg + rows_per_chunk);
   const float* Psrc = layer == 0 ? da3g : layer == 1 ? a2g : layer == 2 ? da2g : layer == 3 ? a1g : da1g;
+  const float* Qsrc = layer == 0 ? yg : layer == 1 ? dyg : layer == 2 ? gateg : layer == 3 ? dgateg : e;
   const bool p_gelu = (layer == 1 || layer == 3);
-  const bool kk_ok = tid < E;
-  const int kk = kk_ok ? tid : 0;
-  float bn_mu = 0.f, bn_rs = 0.f, bn_g = 0.f, bn_b = 0.f;
-  if (layer == 4) { bn_mu = __ldg(mean + kk); bn_rs = __ldg(rstd + kk); bn_g = __ldg(P + P_BN_W + kk); bn_b = __ldg(P + P_BN_B + kk); }
-  float acc[HID];
+  const bool wide_bias = (layer == 1 || layer == 3);
+  const bool work = tid < 9 * 33;
+  const int ng = work ? tid / 33 : 0, kg = work ? tid % 33 : 0;
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < HID; ++i) acc[i] = 0.f;
-  float bsum = 0.f;          // wide-side bias (layers 1, 3): thread kk; narrow-side bias (layers 0, 2, 4): thread nn < 66
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = tid; i < WG_TILE * (WG_LDP - HID); i += WG_THREADS) sp[i / (WG_LDP - HID)][HID + i % (WG_LDP - HID)] = 0.f;   // pad columns
   for (long long t0 = rbeg; t0 < rend; t0 += WG_TILE) {
     const int nt = (int)min((long long)WG_TILE, rend - t0);
     __syncthreads();
@@ -419,40 +425,65 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
       if (r < nt) { v = __ldg(Psrc + (t0 + r) * HID + c); if (p_gelu) v = gelu_f(v); }
       sp[r][c] = v;
     }
-    if (tid < 2 * WG_TILE) sp[tid >> 1][HID + (tid & 1)] = 0.f;
-    __syncthreads();
-    if ((layer == 0 || layer == 2 || layer == 4) && tid < HID) {
-      for (int r = 0; r < nt; ++r) bsum += sp[r][tid];
-    }
-    if (kk_ok) {
-#pragma unroll 2
-      for (int r = 0; r < nt; ++r) {
-        const long long gi = (t0 + r) * E + kk;
-        float q;
-        if (layer == 0) q = __ldg(yg + gi);
-        else if (layer == 1) q = __ldg(dyg + gi);
-        else if (layer == 2) q = __ldg(gateg + gi) * __ldg(e + gi);
-        else if (layer == 3) q = __ldg(dgateg + gi);
-        else q = (__ldg(e + gi) - bn_mu) * bn_rs * bn_g + bn_b;
-        if (layer == 1 || layer == 3) bsum += q;
-#pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 p = *reinterpret_cast<const float4*>(&sp[r][4 * c4]);
-          acc[4 * c4] = fmaf(p.x, q, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(p.y, q, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(p.z, q, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(p.w, q, acc[4 * c4 + 3]);
+    for (int i = tid; i < WG_TILE * (E / 4); i += WG_THREADS) {
+      const int r = i / (E / 4), c4 = i - r * (E / 4);
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nt) {
+        q = __ldg(reinterpret_cast<const float4*>(Qsrc + (t0 + r) * E) + c4);
+        if (layer == 2) {
+          const float4 ev = __ldg(reinterpret_cast<const float4*>(e + (t0 + r) * E) + c4);
+          q.x *= ev.x; q.y *= ev.y; q.z *= ev.z; q.w *= ev.w;
+        } else if (layer == 4) {
+          const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(P + P_BN_W) + c4), be = __ldg(reinterpret_cast<const float4*>(P + P_BN_B) + c4);
+          q.x = (q.x - mu.x) * rs.x * ga.x + be.x; q.y = (q.y - mu.y) * rs.y * ga.y + be.y;
+          q.z = (q.z - mu.z) * rs.z * ga.z + be.z; q.w = (q.w - mu.w) * rs.w * ga.w + be.w;
         }
-        acc[64] = fmaf(sp[r][64], q, acc[64]);
-        acc[65] = fmaf(sp[r][65], q, acc[65]);
+      }
+      *reinterpret_cast<float4*>(&sq[r][4 * c4]) = q;
+    }
+    __syncthreads();
+    if (work) {
+#pragma unroll 4
+      for (int r = 0; r < WG_TILE; ++r) {
+        const float4 p0 = *reinterpret_cast<const float4*>(&sp[r][8 * ng]), p1 = *reinterpret_cast<const float4*>(&sp[r][8 * ng + 4]);
+        const float4 q0 = *reinterpret_cast<const float4*>(&sq[r][8 * kg]), q1 = *reinterpret_cast<const float4*>(&sq[r][8 * kg + 4]);
+        const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(pv[a], qv[b], acc[a][b]);
+        if (wide_bias) {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) bsum[b] += qv[b];
+        } else {
+#pragma unroll
+          for (int a = 0; a < 8; ++a) bsum[a] += pv[a];
+        }
       }
     }
   }
   float* out = part + ((long long)layer * gridDim.x + blockIdx.x) * WG_PART;
-  if (kk_ok) {
+  if (work) {
 #pragma unroll
-    for (int i = 0; i < HID; ++i) out[i * E + kk] = acc[i];
+    for (int a = 0; a < 8; ++a) {
+      const int nn = 8 * ng + a;
+      if (nn < HID) {
+        *reinterpret_cast<float4*>(out + nn * E + 8 * kg) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        *reinterpret_cast<float4*>(out + nn * E + 8 * kg + 4) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+      }
+    }
+    if (wide_bias) {
+      if (ng == 0) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) out[HID * E + 8 * kg + b] = bsum[b];
+      }
+    } else if (kg == 0) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) if (8 * ng + a < HID) out[HID * E + 8 * ng + a] = bsum[a];
+    }
   }
-  if (layer == 1 || layer == 3) { if (kk_ok) out[HID * E + kk] = bsum; }
-  else if (tid < HID) out[HID * E + tid] = bsum;
 }
 
 // Sum the chunk partials in chunk order and write the head gradients (transposing layers 1 and 3, whose weights
@@ -467,6 +498,7 @@ head_grad_finish_kernel(const float* __restrict__ part, int nchunks, const float
     for (int i = blockIdx.x * 256 + threadIdx.x; i < WG_PART; i += gridDim.x * 256) {
       const float* src = part + (long long)layer * nchunks * WG_PART + i;
       float s = 0.f;
+#pragma unroll 8
       for (int c = 0; c < nchunks; ++c) s += src[(long long)c * WG_PART];
       if (i < HID * E) {
         const int nn = i / E, kq = i - nn * E;
@@ -482,6 +514,7 @@ head_grad_finish_kernel(const float* __restrict__ part, int nchunks, const float
     // out_mlp.fc2 weight / bias from the tile partials
     for (int i = blockIdx.x * 256 + threadIdx.x; i <= HID; i += gridDim.x * 256) {
       float s = 0.f;
+#pragma unroll 8
       for (int t = 0; t < ntiles; ++t) s += part_f[(long long)t * HB_F + i];
       if (i < HID) grads[P_OUT_FC2_W + i] = s; else grads[P_OUT_FC2_B] = s;
     }
@@ -489,6 +522,7 @@ head_grad_finish_kernel(const float* __restrict__ part, int nchunks, const float
     // BatchNorm: column sums of dz and dz * xhat (this rank's rows), bn.weight / bn.bias gradients
     for (int i = blockIdx.x * 256 + threadIdx.x; i < 2 * E; i += gridDim.x * 256) {
       double s = 0.0;
+#pragma unroll 8
       for (int t = 0; t < ntiles; ++t) s += part_bn[(long long)t * 2 * E + i];
       bn_bwd_sums[i] = s;
       if (i < E) grads[P_BN_B + i] = (float)s; else grads[P_BN_W + (i - E)] = (float)s;
@@ -541,7 +575,7 @@ int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogit
   head_wgrad_kernel<<<dim3(nchunks, 5), WG_THREADS, 0, s>>>(w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2,
                                                             w.dgate, w.da1, w.head_part_w);
   NRM_LAUNCH_CHECK("head_wgrad_kernel");
-  head_grad_finish_kernel<<<dim3(18, 7), 256, 0, s>>>(w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums);
+  head_grad_finish_kernel<<<dim3(70, 7), 256, 0, s>>>(w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums);
   NRM_LAUNCH_CHECK("head_grad_finish_kernel");
   return NRM_OK;
 }

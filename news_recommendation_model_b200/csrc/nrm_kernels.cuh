@@ -12,8 +12,13 @@ struct BatchPtrs {
 
 // nrm_embed.cu
 int launch_embed_rows(const BatchPtrs& in, const float* P, Workspace& w, bool with_keys, cudaStream_t s);
-int launch_table_grads(Workspace& w, float* grads, cudaStream_t s);
+int launch_table_sort(Workspace& w, cudaStream_t s);                  // counting sort of the table ids (needs only the forward's keys)
+int launch_table_grads(Workspace& w, float* grads, cudaStream_t s);  // segmented sums -> table gradients (after launch_table_sort)
 int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, cudaStream_t s);
+
+// nrm_w1.cu
+int launch_w1_forward(const float* P, Workspace& w, cudaStream_t s);             // w.xin_h -> w.xh
+int launch_w1_backward(const float* P, Workspace& w, float* grads, cudaStream_t s);  // w.dxh -> w.dxin_h, w1 gradients
 
 // nrm_attention.cu  (branch 0 = label attention on w1-projected features, 1 = text/img PCA)
 int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
@@ -24,7 +29,7 @@ int launch_attention_finish(const float* P, Workspace& w, int branch, int precis
 int launch_attention_prep(const float* P, Workspace& w, cudaStream_t s);          // derived weights -> w.att_derived
 int launch_attention_forward_tc(const BatchPtrs& in, Workspace& w, int branch, int precision, cudaStream_t s);
 int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
-int launch_attention_finish_tc(const float* P, Workspace& w, int branch, float* grads, cudaStream_t s);
+int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaStream_t s);   // both branches
 
 // nrm_head_fused.cu
 int launch_head_forward_fused(const float* P, Workspace& w, int keep, float* logits, cudaStream_t s);
