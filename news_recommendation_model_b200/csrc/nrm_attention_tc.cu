@@ -53,7 +53,7 @@ __device__ long long g_tcprof[16];
 #define TCPROF(i) do { } while (0)
 #endif
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;       // 8 warps: warp w reads TMEM sub-partition w & 3 and accumulator columns 32 (w >> 2) .. +32
 constexpr int TC_MAXC = 8;           // candidates per chunk (N of the ds / pooling products)
 
 // derived weights per branch in the workspace (att_prep_kernel): Wd | A | w2 | b2.
@@ -122,6 +122,9 @@ candidate_tp_kernel(const float* __restrict__ P, const float* __restrict__ e, lo
 // [8 rows][64 k] K-major: byte offset of (r, 8*kb) = kb*128 + r*16   (LBO = 128, one 8-row group)
 constexpr uint32_t T8_LBO = 128, T8_SBO = 128, T8_BYTES = 1024;
 __device__ __forceinline__ umma::Operand op_tile8_k(uint32_t addr) { return umma::make_operand(addr, T8_LBO, T8_SBO, 2 * T8_LBO, T8_BYTES); }
+// [16 rows][64 k] K-major: byte offset of (r, 8*kb) = kb*256 + (r/8)*128 + (r%8)*16; hi and lo parts 2048 bytes apart
+constexpr uint32_t T16_LBO = 256;
+__device__ __forceinline__ umma::Operand op_tile16_k(uint32_t addr) { return umma::make_operand(addr, T16_LBO, 128, 2 * T16_LBO, 2 * T8_BYTES); }
 
 template <int NP> struct TileBytes { static constexpr uint32_t T64 = NP * umma::TILE64_BYTES, T8 = NP * T8_BYTES; };
 
@@ -198,7 +201,7 @@ __device__ __forceinline__ PairVec load_pair_vec(const float* __restrict__ e, co
                                                  int c, int toff, int nimp) {
   const int q = threadIdx.x >> 6, i = threadIdx.x & 63;
   PairVec v{0.f, 0.f};
-  if (q < nimp) {
+  if (q < nimp) {       // q >= 2 for threads >= 128
     const long long rc = (b0 + q) * C + c;
     v.t = __ldg(e + rc * E + toff + i);
     v.tp = __ldg(tp + rc * 64 + i);
@@ -207,6 +210,7 @@ __device__ __forceinline__ PairVec load_pair_vec(const float* __restrict__ e, co
 }
 __device__ __forceinline__ void park_pair_vec(float* tt, const PairVec v) {
   const int q = threadIdx.x >> 6, i = threadIdx.x & 63;
+  if (q >= 2) return;
   tt[q * 128 + i] = v.t;
   tt[q * 128 + 64 + i] = v.tp;
 }
@@ -247,7 +251,7 @@ template <int NP>
 struct TcSmemFwd {
   __align__(128) unsigned char opA[2][TileBytes<NP>::T64];   // history tiles, one per impression of the pair
   __align__(128) unsigned char opB[2][TileBytes<NP>::T64];   // W_c of the two items of a candidate pair
-  __align__(128) unsigned char opS[2][TileBytes<NP>::T8];    // scores [c][h] per impression (B operand of the pooling product)
+  __align__(128) unsigned char opS[2][2 * TileBytes<NP>::T8];   // partial scores [c + 8 column-half][h] per impression (B operand of the pooling product)
   __align__(16) float wda[8192];                             // Wd | A, operand-build order
   __align__(16) float tt[2][2 * 128];                        // [buffer][item q][t 64 | tp 64]
   float w2[64];
@@ -255,11 +259,11 @@ struct TcSmemFwd {
   uint32_t tmem_base;
 };
 
-// TMEM columns: [0,64) hid of the current pair, [64,72) pooled^T (N = 8)
+// TMEM columns: [0,64) hid of the current pair, [64,80) pooled^T partials (N = 16: candidate c of column half 0 | 1)
 constexpr uint32_t FWD_TMEM_COLS = 128, FWD_COL_HID = 0, FWD_COL_POOL = 64;
 
 template <int BRANCH, int SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, SPLIT == 3 ? 2 : 3)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restrict__ xhp, int B, int H, int C,
                             const float* __restrict__ der_all, const float* __restrict__ tp_all, float* __restrict__ e) {
   constexpr int NP = SPLIT == 3 ? 2 : 1;
@@ -268,7 +272,7 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
   constexpr int TOFF = BRANCH == 0 ? E_XT : E_PCAT;
   constexpr int POFF = BRANCH == 0 ? E_LAB : E_TI;
   constexpr uint32_t IDESC_HID = umma::make_idesc_bf16(64, 64);
-  constexpr uint32_t IDESC_POOL = umma::make_idesc_bf16(64, 8, true, false);
+  constexpr uint32_t IDESC_POOL = umma::make_idesc_bf16(64, 16, true, false);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* der = der_all + (long long)BRANCH * DER_SIZE;
 
@@ -284,9 +288,10 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
   const uint32_t tmem = sm.tmem_base;
   uint32_t phase = 0;
 
-  // epilogue role: sub-partition = warp, half-lanes = impression 0 / 1 of the pair
-  const int half = lane >> 4, row = warp * 16 + (lane & 15);
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  // epilogue role: sub-partition = warp & 3, column half = warp >> 2, half-lanes = impression 0 / 1 of the pair
+  const int sp = warp & 3, ch = warp >> 2;
+  const int half = lane >> 4, row = sp * 16 + (lane & 15);
+  const uint32_t my_tmem = tmem + ((uint32_t)(sp * 32) << 16);
 
   const int npairs_b = (B + 1) / 2;
   int u0, u1;
@@ -333,20 +338,18 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
           umma::fence_after_sync();
           TCPROF(6);
           {
-            float acc = 0.f;
+            // this thread's 32 of the 64 hidden units; the two column halves become two rows (c, c + 8) of the score tile,
+            // and the pooling product, being linear in the scores, adds them
+            float acc = ch == 0 ? b2 : 0.f;
+            float v[32];
+            umma::tmem_ld32(my_tmem + FWD_COL_HID + ch * 32, v);       // all lanes take part (.sync.aligned)
+            if (half < nimp) {
+              const float* tp = tt + half * 128 + 64 + ch * 32;
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-              float v[32];
-              umma::tmem_ld32(my_tmem + FWD_COL_HID + cb * 32, v);       // all lanes take part (.sync.aligned)
-              if (half < nimp) {
-                const float* tp = tt + half * 128 + 64 + cb * 32;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc = fmaf(gelu_f(v[j] + tp[j]), sm.w2[cb * 32 + j], acc);
-              }
+              for (int j = 0; j < 32; ++j) acc = fmaf(gelu_f(v[j] + tp[j]), sm.w2[ch * 32 + j], acc);
+              store_operand1<NP>(sm.opS[half], (uint32_t)(row >> 3) * T16_LBO + (uint32_t)ch * 128 + (uint32_t)c * 16 + (uint32_t)(row & 7) * 2,
+                                 2 * T8_BYTES, acc);
             }
-            // score of (impression half, candidate c, history row) -> B operand of the pooling product, [c][h] K-major
-            if (half < nimp)
-              store_operand1<NP>(sm.opS[half], (uint32_t)(row >> 3) * T8_LBO + (uint32_t)c * 16 + (uint32_t)(row & 7) * 2, T8_BYTES, acc + b2);
           }
           TCPROF(7);
           if (c + 1 < nc) park_pair_vec(sm.tt[(c + 1) & 1], nxt);
@@ -360,20 +363,20 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
           umma::fence_after_sync();
           for (int q = 0; q < nimp; ++q)
             umma::mma_product<SPLIT, 4>(tmem + FWD_COL_POOL + ((uint32_t)(16 * q) << 16), umma::op_tile64_mn(umma::smem_u32(sm.opA[q])),
-                                        op_tile8_k(umma::smem_u32(sm.opS[q])), IDESC_POOL, false);
+                                        op_tile16_k(umma::smem_u32(sm.opS[q])), IDESC_POOL, false);
           umma::mma_commit(&sm.mbar);
         }
         umma::mbar_wait(&sm.mbar, phase);
         phase ^= 1;
         umma::fence_after_sync();
-        {
-          float v[8];
-          umma::tmem_ld8(my_tmem + FWD_COL_POOL, v);
+        if (ch == 0) {
+          float v[16];
+          umma::tmem_ld16(my_tmem + FWD_COL_POOL, v);
           if (half < nimp) {
             float* dst = e + ((b0 + half) * C + c0) * E + POFF + row;     // here `row` is the feature index k
 #pragma unroll
             for (int c = 0; c < TC_MAXC; ++c)
-              if (c < nc) { if (r0 == 0) dst[(long long)c * E] = v[c]; else dst[(long long)c * E] += v[c]; }
+              if (c < nc) { const float p = v[c] + v[c + 8]; if (r0 == 0) dst[(long long)c * E] = p; else dst[(long long)c * E] += p; }
           }
         }
         umma::fence_before_sync();
@@ -397,7 +400,8 @@ struct TcSmemBwd {
   __align__(128) unsigned char opP[2][TileBytes<NP>::T8];    // dP [c][k] per impression (B operand of the ds product)
   __align__(128) unsigned char ones[T8_BYTES];               // [8][64] ones (B operand of the Gt product)
   float ds[2][TC_MAXC][64];                                  // [impression][candidate][history row]
-  float sc[NBD == 2 ? 2 * TC_MAXC * 64 : 64];                // attention scores, same indexing (label branch only)
+  float sc[NBD == 2 ? 2 * 2 * TC_MAXC * 64 : 64];            // partial attention scores [column half][impression][candidate][row] (label branch only)
+  float dtx[2 * 64];                                         // dt partial of column half 1, [impression][k]
   __align__(16) float wda[8192];                             // Wd | A, operand-build order
   __align__(16) float tt[2][2 * 128];                        // [buffer][item q][t 64 | tp 64]
   float w2[64];
@@ -411,7 +415,7 @@ constexpr uint32_t BWD_TMEM_COLS = 256, BWD_COL_HID = 0, BWD_COL_S = 64, BWD_COL
 constexpr int TCP_DA = 0, TCP_DWD = 4096, TCP_DW2 = 2 * 4096, TCP_DB2 = 2 * 4096 + 64, TC_PARTIAL = ATT_TC_PARTIAL;
 
 template <int BRANCH, int SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, BRANCH == 0 ? 1 : 2)
 attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restrict__ xhp, int B, int H, int C,
                              const float* __restrict__ der_all, const float* __restrict__ tp_all, const float* __restrict__ P,
                              const float* __restrict__ e, const float* __restrict__ de, float* __restrict__ dxh, float* __restrict__ dxt,
@@ -447,15 +451,19 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   const uint32_t tmem = sm.tmem_base;
   uint32_t phase = 0;
 
-  const int half = lane >> 4, row = warp * 16 + (lane & 15);
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  // thread = (column half ch, TMEM sub-partition sp, impression half, row): every epilogue handles the 32 accumulator
+  // columns [32 ch, 32 ch + 32) of its row
+  const int sp = warp & 3, ch = warp >> 2;
+  const int half = lane >> 4, row = sp * 16 + (lane & 15);
+  const uint32_t my_tmem = tmem + ((uint32_t)(sp * 32) << 16);
   const uint32_t half_off[2] = {0u, 16u << 16};
+  const int cb = ch;                                   // column block of this thread
 
   // persistent per-thread accumulators
-  float dw2_acc[64];       // thread (half, history row): sum over items of ds * gelu(hid[row][j])
-  float dwd_acc[64];       // thread (half, k):           sum over items of t[k] * S^T[k][j]
+  float dw2_acc[32];       // thread (ch, half, history row): sum over items of ds * gelu(hid[row][32 ch + j])
+  float dwd_acc[32];       // thread (ch, half, k):           sum over items of t[k] * S^T[k][32 ch + j]
 #pragma unroll
-  for (int j = 0; j < 64; ++j) { dw2_acc[j] = 0.f; dwd_acc[j] = 0.f; }
+  for (int j = 0; j < 32; ++j) { dw2_acc[j] = 0.f; dwd_acc[j] = 0.f; }
   float db2_acc = 0.f;
   bool da_started[2] = {false, false};
 
@@ -473,7 +481,8 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
     const bool single_chunk = (cend - ca <= TC_MAXC);
     const long long b0 = 2LL * pb;
     const int nimp = (b0 + 1 < B) ? 2 : 1;
-    const long long bmine = b0 + half;                 // this thread's impression (valid when half < nimp)
+    const bool act = half < nimp;
+    const long long bmine = b0 + half;                 // this thread's impression (valid when act)
     for (int r0 = 0; r0 < H; r0 += 64) {
       __syncthreads();                                 // every product of the previous tile has completed
       for (int imp = 0; imp < nimp; ++imp) stage_history<BRANCH, NP>(xh, xhp, b0 + imp, H, r0, sm.opA[imp]);
@@ -507,10 +516,10 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         umma::mbar_wait(&sm.mbar, phase);
         phase ^= 1;
         umma::fence_after_sync();
-        {
+        if (ch == 0) {
           float v[8];
           umma::tmem_ld8(my_tmem + BWD_COL_S, v);
-          if (half < nimp) {
+          if (act) {
 #pragma unroll
             for (int c = 0; c < TC_MAXC; ++c) sm.ds[half][c][row] = v[c];
           }
@@ -518,7 +527,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         umma::fence_before_sync();
 
         park_pair_vec(sm.tt[0], load_pair_vec(e, tpg, b0, C, c0, TOFF, nimp));
-        __syncthreads();
+        __syncthreads();                                 // ds and the first pair's vectors visible
         for (int c = 0; c < nc; ++c) {
           const long long rcm = bmine * C + c0 + c;
           const float* tt = sm.tt[c & 1];
@@ -539,37 +548,31 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           umma::mbar_wait(&sm.mbar, phase);
           phase ^= 1;
           umma::fence_after_sync();
-          // ---- epilogue 1: thread = (impression half, history row)
+          // ---- epilogue 1: thread = (column half, impression half, history row)
           {
-            const bool act = half < nimp;
             const float dsr = act ? sm.ds[half][c][row] : 0.f;
-            float sacc = 0.f;
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-              float v[32];
-              umma::tmem_ld32(my_tmem + BWD_COL_HID + cb * 32, v);
-              if (act) {
-                const float* tp = tt + half * 128 + 64 + cb * 32;
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                  float dh[8];
-#pragma unroll
-                  for (int jj = 0; jj < 8; ++jj) {
-                    const int j = j8 * 8 + jj;
-                    float gp;
-                    const float g = gelu_both(v[j] + tp[j], gp);
-                    const float w = sm.w2[cb * 32 + j];
-                    if (INPUT_GRADS) sacc = fmaf(g, w, sacc);
-                    dw2_acc[cb * 32 + j] = fmaf(dsr, g, dw2_acc[cb * 32 + j]);
-                    dh[jj] = dsr * w * gp;
-                  }
-                  umma::store_operand8<NP>(sm.opBD[DH][half], umma::tile64_offset(row, cb * 4 + j8), umma::TILE64_BYTES, dh);
-                }
-              }
-            }
+            float sacc = (ch == 0) ? b2 : 0.f;
+            float v[32];
+            umma::tmem_ld32(my_tmem + BWD_COL_HID + cb * 32, v);
             if (act) {
-              db2_acc += dsr;
-              if (INPUT_GRADS) sm.sc[(half * TC_MAXC + c) * 64 + row] = sacc + b2;
+              const float* tp = tt + half * 128 + 64 + cb * 32;
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                float dh[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const int j = j8 * 8 + jj;
+                  float gp;
+                  const float g = gelu_both(v[j] + tp[j], gp);
+                  const float w = sm.w2[cb * 32 + j];
+                  if (INPUT_GRADS) sacc = fmaf(g, w, sacc);
+                  dw2_acc[j] = fmaf(dsr, g, dw2_acc[j]);
+                  dh[jj] = dsr * w * gp;
+                }
+                umma::store_operand8<NP>(sm.opBD[DH][half], umma::tile64_offset(row, cb * 4 + j8), umma::TILE64_BYTES, dh);
+              }
+              if (ch == 0) db2_acc += dsr;
+              if (INPUT_GRADS) sm.sc[((ch * 2 + half) * TC_MAXC + c) * 64 + row] = sacc;
             }
           }
           if (c + 1 < nc) park_pair_vec(sm.tt[(c + 1) & 1], nxt);
@@ -604,31 +607,36 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           umma::mbar_wait(&sm.mbar, phase);
           phase ^= 1;
           umma::fence_after_sync();
-          // ---- epilogue 2: thread = (impression half, feature k = row) for S^T, (half, j = row) for Gt
+          // ---- epilogue 2: thread = (column half, impression half, feature k = row) for S^T, (half, j = row) for Gt
           {
-            const bool act = half < nimp;
             const float tk = act ? tt[half * 128 + row] : 0.f;
             float dt = 0.f;
+            float v[32];
+            umma::tmem_ld32(my_tmem + BWD_COL_S + cb * 32, v);
+            if (act) {
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-              float v[32];
-              umma::tmem_ld32(my_tmem + BWD_COL_S + cb * 32, v);
-              if (act) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  dwd_acc[cb * 32 + j] = fmaf(tk, v[j], dwd_acc[cb * 32 + j]);
-                  if (INPUT_GRADS) dt = fmaf(v[j], __ldg(Wd_rm + (cb * 32 + j) * 256 + row), dt);
-                }
+              for (int j = 0; j < 32; ++j) {
+                dwd_acc[j] = fmaf(tk, v[j], dwd_acc[j]);
+                if (INPUT_GRADS) dt = fmaf(v[j], __ldg(Wd_rm + (cb * 32 + j) * 256 + row), dt);
               }
             }
-            const float gt = umma::tmem_ld1(my_tmem + BWD_COL_HID);
-            if (act) {
-              float* gdst = dtp + rcm * 64 + row;
-              if (r0 == 0) *gdst = gt; else *gdst += gt;
-              if (INPUT_GRADS) {
+            if (INPUT_GRADS) {
+              // dt[k] = sum over both column halves: half 1 parks its share, half 0 adds it and writes
+              if (ch == 1 && act) sm.dtx[half * 64 + row] = dt;
+              umma::fence_before_sync();
+              __syncthreads();
+              if (ch == 0 && act) {
+                dt += sm.dtx[half * 64 + row];
                 float* dst = dxt + rcm * 64 + row;
                 if (r0 == 0) *dst = dt + __ldg(de + rcm * E + E_XT + row);   // + the direct ec path (user_model.py:31)
                 else *dst += dt;
+              }
+            }
+            if (ch == 0) {
+              const float gt = umma::tmem_ld1(my_tmem + BWD_COL_HID);
+              if (act) {
+                float* gdst = dtp + rcm * 64 + row;
+                if (r0 == 0) *gdst = gt; else *gdst += gt;
               }
             }
           }
@@ -637,49 +645,47 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         __syncthreads();                                 // ds / opP of this chunk consumed before the next chunk rewrites them
         if (INPUT_GRADS && !single_chunk) {
           // several candidate chunks (whole pair in this CTA): the pooling path dxh[row][k] (+)= sum_c s_c[row] dP_c[k]
-          // of each chunk is accumulated in global memory (each thread owns its row)
-          if (half < nimp && r0 + row < H) {
-            float* dst = dxh + (bmine * H + r0 + row) * 64;
-            for (int k4 = 0; k4 < 16; ++k4) {
+          // of each chunk is accumulated in global memory (each thread owns 32 columns of its row)
+          if (act && r0 + row < H) {
+            float* dst = dxh + (bmine * H + r0 + row) * 64 + cb * 32;
+            for (int k4 = 0; k4 < 8; ++k4) {
               float4 acc = (c0 == ca) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(dst + 4 * k4);
               for (int c = 0; c < nc; ++c) {
-                const float s = sm.sc[(half * TC_MAXC + c) * 64 + row];
-                const float4 dp = __ldg(reinterpret_cast<const float4*>(de + (bmine * C + c0 + c) * E + POFF) + k4);
+                const float s = sm.sc[((0 * 2 + half) * TC_MAXC + c) * 64 + row] + sm.sc[((1 * 2 + half) * TC_MAXC + c) * 64 + row];
+                const float4 dp = __ldg(reinterpret_cast<const float4*>(de + (bmine * C + c0 + c) * E + POFF + cb * 32) + k4);
                 acc.x = fmaf(s, dp.x, acc.x); acc.y = fmaf(s, dp.y, acc.y); acc.z = fmaf(s, dp.z, acc.z); acc.w = fmaf(s, dp.w, acc.w);
               }
               *reinterpret_cast<float4*>(dst + 4 * k4) = acc;
             }
           }
+          __syncthreads();                               // sc consumed before the next chunk's epilogues overwrite it
         }
       }
       if (INPUT_GRADS) {
         // dH of this tile (W_c path, all candidates of the range) from tensor memory + the pooling path
         const int ncs = cend - ca;                       // candidates of the single chunk
+        float v[32];
+        umma::tmem_ld32(my_tmem + BWD_COL_DH + cb * 32, v);
+        if (act && r0 + row < H) {
+          float* dstf = dxh + (bmine * H + r0 + row) * 64 + cb * 32;
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
-          float v[32];
-          umma::tmem_ld32(my_tmem + BWD_COL_DH + cb * 32, v);
-          if (half < nimp && r0 + row < H) {
-            float* dstf = dxh + (bmine * H + r0 + row) * 64 + cb * 32;
-#pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) {
-              float4 a = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-              if (single_chunk) {
-                for (int c = 0; c < ncs; ++c) {
-                  const float s = sm.sc[(half * TC_MAXC + c) * 64 + row];
-                  const float4 dp = __ldg(reinterpret_cast<const float4*>(de + (bmine * C + ca + c) * E + POFF + cb * 32) + k4);
-                  a.x = fmaf(s, dp.x, a.x); a.y = fmaf(s, dp.y, a.y); a.z = fmaf(s, dp.z, a.z); a.w = fmaf(s, dp.w, a.w);
-                }
-              } else {
-                const float4 g = *reinterpret_cast<float4*>(dstf + 4 * k4);
-                a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+          for (int k4 = 0; k4 < 8; ++k4) {
+            float4 a = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+            if (single_chunk) {
+              for (int c = 0; c < ncs; ++c) {
+                const float s = sm.sc[((0 * 2 + half) * TC_MAXC + c) * 64 + row] + sm.sc[((1 * 2 + half) * TC_MAXC + c) * 64 + row];
+                const float4 dp = __ldg(reinterpret_cast<const float4*>(de + (bmine * C + ca + c) * E + POFF + cb * 32) + k4);
+                a.x = fmaf(s, dp.x, a.x); a.y = fmaf(s, dp.y, a.y); a.z = fmaf(s, dp.z, a.z); a.w = fmaf(s, dp.w, a.w);
               }
-              if (split_pair) {
-                atomicAdd(dstf + 4 * k4 + 0, a.x); atomicAdd(dstf + 4 * k4 + 1, a.y);
-                atomicAdd(dstf + 4 * k4 + 2, a.z); atomicAdd(dstf + 4 * k4 + 3, a.w);
-              } else {
-                *reinterpret_cast<float4*>(dstf + 4 * k4) = a;
-              }
+            } else {
+              const float4 g = *reinterpret_cast<float4*>(dstf + 4 * k4);
+              a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+            }
+            if (split_pair) {
+              atomicAdd(dstf + 4 * k4 + 0, a.x); atomicAdd(dstf + 4 * k4 + 1, a.y);
+              atomicAdd(dstf + 4 * k4 + 2, a.z); atomicAdd(dstf + 4 * k4 + 3, a.w);
+            } else {
+              *reinterpret_cast<float4*>(dstf + 4 * k4) = a;
             }
           }
         }
@@ -692,67 +698,51 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   __syncthreads();
   float* out = part + (long long)blockIdx.x * TC_PARTIAL;
   {
-    // dA^T from TMEM and dWd^T from registers: thread (half, k); the two halves (lanes l and l ^ 16) are summed
-    // in the warp and the lower half writes out[TCP_DA / TCP_DWD + k*64 + j]
+    // dA^T from TMEM and dWd^T from registers: thread (ch, half, k); the two impression halves (lanes l and l ^ 16) are
+    // summed in the warp and the lower half writes out[TCP_DA / TCP_DWD + k*64 + 32 ch + j]
+    float v[32];
+    umma::tmem_ld32(my_tmem + BWD_COL_DA + cb * 32, v);
 #pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      float v[32];
-      umma::tmem_ld32(my_tmem + BWD_COL_DA + cb * 32, v);
+    for (int j = 0; j < 32; ++j) {
+      float a = da_started[half] ? v[j] : 0.f;
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      v[j] = a;
+      float d = dwd_acc[j];
+      d += __shfl_xor_sync(0xffffffffu, d, 16);
+      dwd_acc[j] = d;
+    }
+    if (half == 0) {
+      float4* dst = reinterpret_cast<float4*>(out + TCP_DA + row * 64 + cb * 32);
+      float4* dst2 = reinterpret_cast<float4*>(out + TCP_DWD + row * 64 + cb * 32);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float a = da_started[half] ? v[j] : 0.f;
-        a += __shfl_xor_sync(0xffffffffu, a, 16);
-        v[j] = a;
-        float d = dwd_acc[cb * 32 + j];
-        d += __shfl_xor_sync(0xffffffffu, d, 16);
-        dwd_acc[cb * 32 + j] = d;
-      }
-      if (half == 0) {
-        float4* dst = reinterpret_cast<float4*>(out + TCP_DA + row * 64 + cb * 32);
-        float4* dst2 = reinterpret_cast<float4*>(out + TCP_DWD + row * 64 + cb * 32);
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          dst[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-          dst2[k4] = make_float4(dwd_acc[cb * 32 + 4 * k4], dwd_acc[cb * 32 + 4 * k4 + 1], dwd_acc[cb * 32 + 4 * k4 + 2], dwd_acc[cb * 32 + 4 * k4 + 3]);
-        }
+      for (int k4 = 0; k4 < 8; ++k4) {
+        dst[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+        dst2[k4] = make_float4(dwd_acc[4 * k4], dwd_acc[4 * k4 + 1], dwd_acc[4 * k4 + 2], dwd_acc[4 * k4 + 3]);
       }
     }
   }
   umma::fence_before_sync();
   __syncthreads();
   {
-    // dw2[j] = sum over the 128 threads of dw2_acc[j]: transpose through shared memory (operand buffers are free now)
-    float* red = reinterpret_cast<float*>(sm.opA);           // opA and opBD are contiguous
-    constexpr bool ONE_PASS = sizeof(sm.opA) + sizeof(sm.opBD) >= 128 * 65 * sizeof(float);
-    static_assert(sizeof(sm.opA) + sizeof(sm.opBD) >= 64 * 65 * sizeof(float), "reduce scratch");
+    // dw2[32 ch + j] = sum over the 128 threads of column half ch: one pass per half through a [128][33] scratch
+    // (the operand buffers are free now; opA and opBD are contiguous)
+    float* red = reinterpret_cast<float*>(sm.opA);
     using SmemT = TcSmemBwd<NP, NBD>;
     static_assert(offsetof(SmemT, opBD) == sizeof(sm.opA), "opA / opBD must be contiguous");
+    static_assert(sizeof(sm.opA) + sizeof(sm.opBD) >= 128 * 33 * sizeof(float), "reduce scratch");
     float* red2 = &sm.ds[0][0][0];                           // db2 partials (128 floats)
-    if (ONE_PASS) {
-#pragma unroll
-      for (int j = 0; j < 64; ++j) red[tid * 65 + j] = dw2_acc[j];
-      red2[tid] = db2_acc;
+    for (int pass = 0; pass < 2; ++pass) {
       __syncthreads();
-      if (tid < 64) {
-        float s = 0.f;
-        for (int t = 0; t < 128; ++t) s += red[t * 65 + tid];
-        out[TCP_DW2 + tid] = s;
-      }
-    } else {
-      // small operand buffers: two passes of 64 threads over a [64][65] scratch (opA + opBD are contiguous)
-      for (int pass = 0; pass < 2; ++pass) {
-        __syncthreads();
-        if ((tid >> 6) == pass) {
+      if (ch == pass) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) red[(tid & 63) * 65 + j] = dw2_acc[j];
-        }
-        if (pass == 0) red2[tid] = db2_acc;
-        __syncthreads();
-        if (tid < 64) {
-          float s = 0.f;
-          for (int t = 0; t < 64; ++t) s += red[t * 65 + tid];
-          if (pass == 0) out[TCP_DW2 + tid] = s; else out[TCP_DW2 + tid] += s;
-        }
+        for (int j = 0; j < 32; ++j) red[(tid & 127) * 33 + j] = dw2_acc[j];
+        if (pass == 0) red2[tid & 127] = db2_acc;
+      }
+      __syncthreads();
+      if (tid < 32) {
+        float sacc = 0.f;
+        for (int t = 0; t < 128; ++t) sacc += red[t * 33 + tid];
+        out[TCP_DW2 + pass * 32 + tid] = sacc;
       }
     }
     if (tid == 0) {
@@ -961,11 +951,11 @@ umma_selftest_kernel(const float* __restrict__ a0, const float* __restrict__ a1,
   }
   umma::mbar_wait(mbar, 0);
   umma::fence_after_sync();
-  const int half = lane >> 4, row = warp * 16 + (lane & 15);
-#pragma unroll
-  for (int cb = 0; cb < 2; ++cb) {
+  // warp w reads sub-partition w & 3, column half w >> 2 (as the attention kernels do)
+  const int half = lane >> 4, row = (warp & 3) * 16 + (lane & 15), cb = warp >> 2;
+  {
     float v[32];
-    umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+    umma::tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb * 32, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) out[(half * 64 + row) * 64 + cb * 32 + j] = v[j];
   }
@@ -996,7 +986,7 @@ static size_t padded_smem(size_t need, int per_sm) {
 template <int BRANCH, int SPLIT>
 static int launch_fwd(const BatchPtrs& in, Workspace& w, cudaStream_t s) {
   constexpr int NP = SPLIT == 3 ? 2 : 1;
-  const int per_sm = SPLIT == 3 ? 2 : 3;
+  const int per_sm = 2;
   const size_t smem = padded_smem(sizeof(TcSmemFwd<NP>), per_sm);
   if (smem > 227 * 1024) { set_error("attention forward: shared memory"); return NRM_EUNSUPPORTED; }
   const int grid = min((w.B + 1) / 2, per_sm * sm_count());
@@ -1132,7 +1122,7 @@ mma_microbench_kernel(long long* __restrict__ out, int variant, int reps, int nk
     t0 = clock64();
     for (int r = 0; r < reps; ++r) {
       float v[32];
-      umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (r & 1) * 32, v);
+      umma::tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (r & 1) * 32, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc += v[j];
     }
