@@ -41,7 +41,9 @@ def parse():
     ap.add_argument('--history', type=int, default=50)
     ap.add_argument('--candidates', type=int, default=5)
     ap.add_argument('--user-num', type=int, default=1000)
-    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16', 'bf16x3'])
+    ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'bf16', 'bf16x3'],
+                    help='pair products: bf16x3 = tcgen05 with hi/lo split operands (fp32-grade, default), fp32 = FFMA, bf16 = tcgen05 bf16')
+    ap.add_argument('--no-variants', action='store_true', help='skip the short resident runs of the other two precisions')
     ap.add_argument('--sync-bn', action='store_true', help='all-reduce BatchNorm statistics across ranks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='FusedTrainStep issues the C-ABI calls eagerly instead of replaying a CUDA graph')
@@ -289,26 +291,61 @@ def run_ours(args):
         name, cnt, tot = ln.split()
         kern[name] = {'launch_groups': int(cnt), 'ms_per_step': float(tot) / kt_steps}
     pk = peaks()
-    top = max(kern, key=lambda k: kern[k]['ms_per_step']) if kern else None
+    # dominant SINGLE kernel (groups that are one launch each); algorithmic work per launch from SURVEY 8(d) / DESIGN 4
+    pairs = B * C * H
+    R = B * C
+    single = {
+        'attention_forward_label': ('tensor', 2.0 * pairs * D * D), 'attention_forward_textimg': ('tensor', 2.0 * pairs * D * D),
+        'attention_backward_label': ('tensor', 3 * 2.0 * pairs * D * D), 'attention_backward_textimg': ('tensor', 2 * 2.0 * pairs * D * D),
+        'embed_rows': ('hbm', 8.0 * (80 * H + 81 * C) * B + 4.0 * (66 * H * B + 136 * R)),
+        'w1_forward': ('hbm', 4.0 * (66 + 64) * H * B),
+    }
+    cand = {k: v for k, v in kern.items() if k in single}
+    top = max(cand, key=lambda k: cand[k]['ms_per_step']) if cand else None
     roofline = None
     if top is not None:
-        pairs = B * C * H
-        gemms = {'attention_backward_label': 3, 'attention_backward_textimg': 2,
-                 'attention_forward_label': 1, 'attention_forward_textimg': 1}.get(top)
+        bound, work = single[top]
         dur = kern[top]['ms_per_step'] / 1e3
-        if gemms is not None:
-            flops = gemms * 2.0 * pairs * D * D
-            ach = flops / dur / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.precision, {}).get(top)
+        if bound == 'tensor':
+            ach = work / dur / 1e12
             roofline = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
-                        'frac': ach / pk['tensor'], 'traffic': None, 'peak_source': pk['source'] + ' bf16 sustained',
-                        'algorithmic_flops_per_launch': flops, 'launch_ms': dur * 1e3,
-                        'note': 'fp32 FFMA path: the pair GEMMs run on CUDA cores' if args.precision == 'fp32' else 'tcgen05 tiles'}
+                        'frac': ach / pk['tensor'], 'traffic': traffic, 'peak_source': pk['source'] + ' bf16 sustained (cuBLAS)',
+                        'algorithmic_flops_per_launch': work, 'launch_ms': dur * 1e3,
+                        'note': {'fp32': 'FFMA path: the pair products run on the CUDA cores',
+                                 'bf16': 'tcgen05 tiles, bf16 operands',
+                                 'bf16x3': 'tcgen05 tiles, 3 MMAs issued per algorithmic product (hi/lo split); the kernel is bound by its '
+                                           'GELU / operand-build epilogues on the CUDA cores, see DESIGN.md section 4'}[args.precision]}
         else:
-            nbytes = 8.0 * (80 * H + 81 * C) * B
-            ach = nbytes / dur / 1e9
-            roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
-                        'frac': ach / pk['hbm'], 'traffic': None, 'peak_source': pk['source'],
-                        'algorithmic_bytes_per_launch': nbytes, 'launch_ms': dur * 1e3}
+            ach = work / dur / 1e9
+            roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
+                        'traffic': traffic, 'peak_source': pk['source'], 'algorithmic_bytes_per_launch': work, 'launch_ms': dur * 1e3}
+
+    # short resident runs of the other precisions (same step, same data), for context
+    variants = {}
+    if not args.no_variants:
+        for prec in ('fp32', 'bf16', 'bf16x3'):
+            if prec == args.precision:
+                continue
+            model.set_precision(prec)
+            trv = nrm.FusedTrainStep(model, B, H, C, lr=1e-3, weight_decay=1e-5, nslots=N_POOL, use_graph=not args.no_graph)
+            sl = [trv.load(hb) for hb in host]
+            torch.cuda.synchronize()
+            for i in range(3):
+                trv.run(sl[i % N_POOL])
+            barrier()
+            e0.record()
+            for i in range(10):
+                trv.run(sl[i % N_POOL])
+            e1.record()
+            barrier()
+            msv = max_over_ranks(e0.elapsed_time(e1))
+            variants[prec] = {'value': world * B * 10 / (msv / 1e3), 'ms_per_step': msv / 10}
+            del trv, sl
+        model.set_precision(args.precision)
 
     if rank != 0:
         if world > 1:
@@ -323,7 +360,8 @@ def run_ours(args):
     line = {
         'metric': 'train_impressions_per_sec', 'value': value, 'unit': 'impressions/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32' if args.precision == 'fp32' else 'bf16', 'data': 'synthetic', 'config': workload_config(args, world),
+        'dtype': {'fp32': 'f32', 'bf16x3': 'f32 (pair products as 3 x bf16 tcgen05 MMAs, fp32 accumulate; meets the fp32 tolerances)', 'bf16': 'bf16'}[args.precision],
+        'data': 'synthetic', 'config': workload_config(args, world),
         'clocks': clk.summary(),
         'e2e': {'value': e2e_value, 'unit': 'impressions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': e2e_ms / K},
@@ -332,7 +370,7 @@ def run_ours(args):
                         'note': 'drop-in nn.Module path driven like train.py:69-75 (autograd + FusedAdam), device-resident'},
         'api': 'FusedTrainStep (CUDA-graph replay of the 5 C-ABI calls)' if not args.no_graph else 'FusedTrainStep (eager C-ABI calls)',
         'roofline': roofline, 'kernels_ms_per_step': {k: round(v['ms_per_step'], 4) for k, v in kern.items()},
-        'cpu_baseline': cpu,
+        'cpu_baseline': cpu, 'precision_variants': variants,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

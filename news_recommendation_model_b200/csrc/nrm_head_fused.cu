@@ -12,8 +12,8 @@
 
 namespace nrm {
 
-constexpr int HT_ROWS = 32;        // candidate rows per tile
-constexpr int HT_RPT = 8;          // rows per thread (4 row groups)
+constexpr int HT_ROWS = 36;        // candidate rows per tile: 5120 rows (B=1024, C=5) -> 143 tiles, one wave of 148 SMs
+constexpr int HT_RPT = 9;          // rows per thread (4 row groups)
 constexpr int HT_THREADS = 288;    // 4 x 66 = 264 working threads, 9 warps
 constexpr int LDW = 268;           // row stride of the 264-wide shared buffers (16-byte aligned rows)
 constexpr int LDN = 68;            // row stride of the 66-wide shared buffers
@@ -126,7 +126,7 @@ __device__ __forceinline__ void zero_acc(float acc[HT_RPT][NQ]) {
 // ---------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HT_THREADS, 2)
+__global__ void __launch_bounds__(HT_THREADS, 1)
 head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ P, const float* __restrict__ wt, long long R, int keep,
                     float* __restrict__ a1g, float* __restrict__ gateg, float* __restrict__ a2g, float* __restrict__ yg,
@@ -237,7 +237,7 @@ head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean,
 // ---------------------------------------------------------------------------------
 constexpr int HB_F = 68;
 
-__global__ void __launch_bounds__(HT_THREADS, 2)
+__global__ void __launch_bounds__(HT_THREADS, 1)
 head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ P, long long R, const float* __restrict__ dr,
                      const float* __restrict__ a1g, const float* __restrict__ gateg, const float* __restrict__ a2g,
