@@ -223,7 +223,7 @@ sort_keyscan_kernel(const SortPair sp) {
 // the shared counter.  The walk touches shared memory and registers only.
 __global__ void __launch_bounds__(128)
 sort_scatter_kernel(const SortPair sp) {
-  extern __shared__ int ssm[];                      // keys[SORT_CHUNK] | pos[nkeys]
+  extern __shared__ int ssm[];                      // keys[SORT_CHUNK] | pos[nkeys] | segment starts[nkeys]
   const int st = blockIdx.x < sp.s[0].nchunks ? 0 : 1;
   const SortStream& S = sp.s[st];
   const int chunk = blockIdx.x - (st ? sp.s[0].nchunks : 0);
@@ -232,8 +232,17 @@ sort_scatter_kernel(const SortPair sp) {
   const long long base = (long long)chunk * SORT_CHUNK;
   const int total = (int)min((long long)SORT_CHUNK, S.n - base);
   const int* cb = S.chunk_hist + (long long)chunk * S.nkeys;      // exclusive per-chunk offsets
-  for (int i = threadIdx.x; i < total; i += 128) skeys[i] = S.keys[base + i];
-  for (int i = threadIdx.x; i < S.nkeys; i += 128) pos[i] = S.seg[i] + cb[i];
+  // stage keys, segment starts and this chunk's offsets with 4-byte cp.async: every request is in flight at once
+  int* segs = pos + S.nkeys;                        // scratch copy of the segment starts
+  auto cp4 = [](int* dst, const int* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+  };
+  for (int i = threadIdx.x; i < total; i += 128) cp4(skeys + i, S.keys + base + i);
+  for (int i = threadIdx.x; i < S.nkeys; i += 128) { cp4(pos + i, cb + i); cp4(segs + i, S.seg + i); }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+  for (int i = threadIdx.x; i < S.nkeys; i += 128) pos[i] += segs[i];
   __syncthreads();
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
@@ -438,21 +447,24 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
   }
 }
 
-// Reduce the per-CTA partials (8 interleaved groups, combined in group order) and scatter the
-// [96] vector into the flat gradient entries.
-__global__ void __launch_bounds__(768)
+// One block per output k (96): every thread sums a strided share of the per-CTA partials, then a fixed-shape tree in shared
+// memory (deterministic) and the scatter of the [96] vector into the flat gradient entries.
+__global__ void __launch_bounds__(256)
 small_linear_grad_finish_kernel(const float* __restrict__ part, int nparts, float* __restrict__ grads) {
-  __shared__ float red[8][96];
-  const int k = threadIdx.x % 96, grp = threadIdx.x / 96;
+  __shared__ float red[256];
+  const int k = blockIdx.x, t = threadIdx.x;
   float acc = 0.f;
 #pragma unroll 4
-  for (int p = grp; p < nparts; p += 8) acc += part[(long long)p * 96 + k];
-  red[grp][k] = acc;
+  for (int p = t; p < nparts; p += 256) acc += part[(long long)p * 96 + k];
+  red[t] = acc;
   __syncthreads();
-  if (grp != 0) return;
-  acc = red[0][k];
 #pragma unroll
-  for (int q = 1; q < 8; ++q) acc += red[q][k];
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  if (t != 0) return;
+  acc = red[0];
   if (k < 64) {
     const int o = k >> 2, i = k & 3;
     if (i < 3) grads[P_SENT_W + o * 3 + i] = acc; else grads[P_SENT_B + o] = acc;
@@ -487,7 +499,7 @@ int launch_table_sort(Workspace& w, cudaStream_t s) {
   const int nch = sp.s[0].nchunks + sp.s[1].nchunks;
   static bool configured = false;
   if (!configured) {
-    NRM_CUDA(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (SORT_CHUNK + NKEY32))));
+    NRM_CUDA(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (SORT_CHUNK + 2 * NKEY32))));
     configured = true;
   }
   KernelTimer t("table_sort", s);
@@ -497,7 +509,7 @@ int launch_table_sort(Workspace& w, cudaStream_t s) {
   NRM_LAUNCH_CHECK("sort_colscan_kernel");
   sort_keyscan_kernel<<<2, 1024, 0, s>>>(sp);
   NRM_LAUNCH_CHECK("sort_keyscan_kernel");
-  sort_scatter_kernel<<<nch, 128, sizeof(int) * (SORT_CHUNK + NKEY32), s>>>(sp);
+  sort_scatter_kernel<<<nch, 128, sizeof(int) * (SORT_CHUNK + 2 * NKEY32), s>>>(sp);
   NRM_LAUNCH_CHECK("sort_scatter_kernel");
   return NRM_OK;
 }
@@ -520,7 +532,7 @@ int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, c
   small_linear_grad_kernel<<<nparts, 256, 0, s>>>(in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.C, w.NH, w.N, w.xin_h, w.e,
                                                   w.dxin_h, w.dxt, w.de, rows_per_cta, w.small_part);
   NRM_LAUNCH_CHECK("small_linear_grad_kernel");
-  small_linear_grad_finish_kernel<<<1, 768, 0, s>>>(w.small_part, nparts, grads);
+  small_linear_grad_finish_kernel<<<96, 256, 0, s>>>(w.small_part, nparts, grads);
   NRM_LAUNCH_CHECK("small_linear_grad_finish_kernel");
   return NRM_OK;
 }

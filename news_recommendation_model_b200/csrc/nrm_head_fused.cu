@@ -136,19 +136,31 @@ head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean,
   const int tid = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * HT_ROWS;
   const int nr = (int)min((long long)HT_ROWS, R - r0);
-  // e tile -> w1 (kept for the gating product), z = BatchNorm(e) -> w0
-  for (int i = tid; i < HT_ROWS * (E / 4); i += HT_THREADS) {
-    const int r = i / (E / 4), c4 = i - r * (E / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), z = v;
-    if (r < nr) {
-      v = __ldg(reinterpret_cast<const float4*>(e + (r0 + r) * E) + c4);
-      const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
-      const float4 ga = __ldg(reinterpret_cast<const float4*>(P + P_BN_W) + c4), be = __ldg(reinterpret_cast<const float4*>(P + P_BN_B) + c4);
-      z.x = (v.x - mu.x) * rs.x * ga.x + be.x; z.y = (v.y - mu.y) * rs.y * ga.y + be.y;
-      z.z = (v.z - mu.z) * rs.z * ga.z + be.z; z.w = (v.w - mu.w) * rs.w * ga.w + be.w;
+  // e tile -> w1 (kept for the gating product), z = BatchNorm(e) -> w0.  All loads of the tile are issued first.
+  {
+    constexpr int NV = HT_ROWS * (E / 4), IT = (NV + HT_THREADS - 1) / HT_THREADS;
+    float4 ev[IT];
+#pragma unroll
+    for (int u = 0; u < IT; ++u) {
+      const int i = tid + u * HT_THREADS, r = i / (E / 4), c4 = i - r * (E / 4);
+      ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < NV && r < nr) ev[u] = __ldg(reinterpret_cast<const float4*>(e + (r0 + r) * E) + c4);
     }
-    *reinterpret_cast<float4*>(sm.w1 + r * LDW + 4 * c4) = v;
-    *reinterpret_cast<float4*>(sm.w0 + r * LDW + 4 * c4) = z;
+#pragma unroll
+    for (int u = 0; u < IT; ++u) {
+      const int i = tid + u * HT_THREADS, r = i / (E / 4), c4 = i - r * (E / 4);
+      if (i >= NV) continue;
+      const float4 v = ev[u];
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nr) {
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(P + P_BN_W) + c4), be = __ldg(reinterpret_cast<const float4*>(P + P_BN_B) + c4);
+        z.x = (v.x - mu.x) * rs.x * ga.x + be.x; z.y = (v.y - mu.y) * rs.y * ga.y + be.y;
+        z.z = (v.z - mu.z) * rs.z * ga.z + be.z; z.w = (v.w - mu.w) * rs.w * ga.w + be.w;
+      }
+      *reinterpret_cast<float4*>(sm.w1 + r * LDW + 4 * c4) = v;
+      *reinterpret_cast<float4*>(sm.w0 + r * LDW + 4 * c4) = z;
+    }
   }
   __syncthreads();
   const bool work = tid < 4 * HID;
@@ -419,28 +431,46 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
   for (long long t0 = rbeg; t0 < rend; t0 += WG_TILE) {
     const int nt = (int)min((long long)WG_TILE, rend - t0);
     __syncthreads();
-    for (int i = tid; i < WG_TILE * HID; i += WG_THREADS) {
-      const int r = i / HID, c = i - r * HID;
-      float v = 0.f;
-      if (r < nt) { v = __ldg(Psrc + (t0 + r) * HID + c); if (p_gelu) v = gelu_f(v); }
-      sp[r][c] = v;
-    }
-    for (int i = tid; i < WG_TILE * (E / 4); i += WG_THREADS) {
-      const int r = i / (E / 4), c4 = i - r * (E / 4);
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nt) {
-        q = __ldg(reinterpret_cast<const float4*>(Qsrc + (t0 + r) * E) + c4);
-        if (layer == 2) {
-          const float4 ev = __ldg(reinterpret_cast<const float4*>(e + (t0 + r) * E) + c4);
-          q.x *= ev.x; q.y *= ev.y; q.z *= ev.z; q.w *= ev.w;
-        } else if (layer == 4) {
-          const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
-          const float4 ga = __ldg(reinterpret_cast<const float4*>(P + P_BN_W) + c4), be = __ldg(reinterpret_cast<const float4*>(P + P_BN_B) + c4);
-          q.x = (q.x - mu.x) * rs.x * ga.x + be.x; q.y = (q.y - mu.y) * rs.y * ga.y + be.y;
-          q.z = (q.z - mu.z) * rs.z * ga.z + be.z; q.w = (q.w - mu.w) * rs.w * ga.w + be.w;
-        }
+    {
+      // all global loads of the two tiles first (independent requests in flight), then the transforms and stores
+      constexpr int NPV = WG_TILE * HID, ITP = (NPV + WG_THREADS - 1) / WG_THREADS;
+      constexpr int NQV = WG_TILE * (E / 4), ITQ = (NQV + WG_THREADS - 1) / WG_THREADS;
+      float pv[ITP];
+      float4 qv[ITQ], ev[ITQ];
+#pragma unroll
+      for (int u = 0; u < ITP; ++u) {
+        const int i = tid + u * WG_THREADS, r = i / HID, c = i - r * HID;
+        pv[u] = (i < NPV && r < nt) ? __ldg(Psrc + (t0 + r) * HID + c) : 0.f;
       }
-      *reinterpret_cast<float4*>(&sq[r][4 * c4]) = q;
+#pragma unroll
+      for (int u = 0; u < ITQ; ++u) {
+        const int i = tid + u * WG_THREADS, r = i / (E / 4), c4 = i - r * (E / 4);
+        const bool ok = i < NQV && r < nt;
+        qv[u] = ok ? __ldg(reinterpret_cast<const float4*>(Qsrc + (t0 + r) * E) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (layer == 2) ev[u] = ok ? __ldg(reinterpret_cast<const float4*>(e + (t0 + r) * E) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < ITP; ++u) {
+        const int i = tid + u * WG_THREADS, r = i / HID, c = i - r * HID;
+        if (i < NPV) sp[r][c] = (p_gelu && r < nt) ? gelu_f(pv[u]) : pv[u];
+      }
+#pragma unroll
+      for (int u = 0; u < ITQ; ++u) {
+        const int i = tid + u * WG_THREADS, r = i / (E / 4), c4 = i - r * (E / 4);
+        if (i >= NQV) continue;
+        float4 q = qv[u];
+        if (r < nt) {
+          if (layer == 2) {
+            q.x *= ev[u].x; q.y *= ev[u].y; q.z *= ev[u].z; q.w *= ev[u].w;
+          } else if (layer == 4) {
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(P + P_BN_W) + c4), be = __ldg(reinterpret_cast<const float4*>(P + P_BN_B) + c4);
+            q.x = (q.x - mu.x) * rs.x * ga.x + be.x; q.y = (q.y - mu.y) * rs.y * ga.y + be.y;
+            q.z = (q.z - mu.z) * rs.z * ga.z + be.z; q.w = (q.w - mu.w) * rs.w * ga.w + be.w;
+          }
+        }
+        *reinterpret_cast<float4*>(&sq[r][4 * c4]) = q;
+      }
     }
     __syncthreads();
     if (work) {

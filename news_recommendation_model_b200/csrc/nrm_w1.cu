@@ -12,12 +12,18 @@ namespace nrm {
 constexpr int W1_ROWS = 128, W1_THREADS = 256;
 constexpr int W1_PART = 64 * XIN + 64;          // dW1 [64][66] | db1 [64]
 
+// Asynchronous tile copy (cp.async, 16 bytes per request): every request of the tile is in flight at once; the caller
+// waits with copy_wait() before the __syncthreads() that publishes the tile.
 __device__ __forceinline__ void copy_tile(float* dst, const float* __restrict__ src, int nfloats) {
   // src is 16-byte aligned (tile starts are multiples of 128 rows); nfloats is a multiple of 2
   const int n4 = nfloats >> 2;
-  for (int i = threadIdx.x; i < n4; i += W1_THREADS) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+  for (int i = threadIdx.x; i < n4; i += W1_THREADS) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 4 * i);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + 4 * i) : "memory");
+  }
   for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += W1_THREADS) dst[i] = __ldg(src + i);
 }
+__device__ __forceinline__ void copy_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 struct W1SmemFwd { __align__(16) float xs[W1_ROWS * XIN]; __align__(16) float wt[XIN * 64]; };
 
@@ -34,6 +40,7 @@ w1_forward_kernel(const float* __restrict__ xin, const float* __restrict__ P, fl
     const int nr = (int)min((long long)W1_ROWS, NH - r0);
     __syncthreads();
     copy_tile(sm.xs, xin + r0 * XIN, nr * XIN);
+    copy_wait();
     __syncthreads();
     float acc[8][4];
 #pragma unroll
@@ -84,6 +91,7 @@ w1_backward_kernel(const float* __restrict__ xin, const float* __restrict__ dxh,
       for (int i = nr * 64 + tid; i < W1_ROWS * 64; i += W1_THREADS) sm.ds[i] = 0.f;
       for (int i = nr * XIN + tid; i < W1_ROWS * XIN; i += W1_THREADS) sm.xs[i] = 0.f;
     }
+    copy_wait();
     __syncthreads();
     {  // dxin tile: rows rg*8 .. +7, columns cg + 16 t
       float acc[8][5];
