@@ -19,7 +19,6 @@
 //   pooled = H^T s     k   c   h    H tile read MN-major          score tile [c][h]      (per impression, forward)
 //   ds     = H dP^T    h   c   k    H tile, K-major               dP tile [c][k]         (per impression)
 //   S^T    = H^T dhid  k   j   h    H tile read MN-major          dhid tile read MN-major
-//   dA^T  += H^T dhid  (same product again, accumulated over every item of the CTA; never read until the end)
 //   dH    += dhid W_c  h   k   j    dhid tile, K-major            W_c tile read MN-major
 //   Gt     = dhid^T 1  j   8   h    dhid tile read MN-major       constant ones tile
 //
@@ -409,7 +408,7 @@ struct TcSmemBwd {
   uint32_t tmem_base;
 };
 
-// TMEM columns: [0,64) hid, then Gt in [0,8);  [64,128) ds in [64,72), then S^T;  [128,192) dH;  [192,256) dA^T
+// TMEM columns: [0,64) hid, then Gt in [0,8);  [64,128) ds in [64,72), then S^T;  [128,192) dH;  [192,256) dA^T (text/img)
 constexpr uint32_t BWD_TMEM_COLS = 256, BWD_COL_HID = 0, BWD_COL_S = 64, BWD_COL_DH = 128, BWD_COL_DA = 192;
 // per-CTA partial sums (floats): dA^T [64 k][64 j] | dWd^T [64][64] | dw2 [64] | db2 [1] (+3 pad)
 constexpr int TCP_DA = 0, TCP_DWD = 4096, TCP_DW2 = 2 * 4096, TCP_DB2 = 2 * 4096 + 64, TC_PARTIAL = ATT_TC_PARTIAL;
@@ -423,6 +422,9 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   constexpr int NP = SPLIT == 3 ? 2 : 1;
   constexpr bool INPUT_GRADS = (BRANCH == 0);
   constexpr int NBD = INPUT_GRADS ? 2 : 1, DH = NBD - 1;
+  // dA^T = sum over items of S^T: the label kernel (one CTA per SM, registers to spare) adds the S^T it reads anyway in
+  // registers; the text/img kernel (128 registers per thread) lets the tensor core accumulate it in TMEM with a second product
+  constexpr bool DA_IN_REGS = INPUT_GRADS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmemBwd<NP, NBD>& sm = *reinterpret_cast<TcSmemBwd<NP, NBD>*>(smem_raw);
   constexpr AttOffsets off = BRANCH == 0 ? ATT_LABEL : ATT_TI;
@@ -462,13 +464,20 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   // persistent per-thread accumulators
   float dw2_acc[32];       // thread (ch, half, history row): sum over items of ds * gelu(hid[row][32 ch + j])
   float dwd_acc[32];       // thread (ch, half, k):           sum over items of t[k] * S^T[k][32 ch + j]
+  float da_acc[DA_IN_REGS ? 32 : 1];   // thread (ch, half, k): sum over items of S^T[k][32 ch + j]
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { dw2_acc[j] = 0.f; dwd_acc[j] = 0.f; }
-  float db2_acc = 0.f;
+  for (int j = 0; j < 32; ++j) { dw2_acc[j] = 0.f; dwd_acc[j] = 0.f; if (DA_IN_REGS) da_acc[j] = 0.f; }
   bool da_started[2] = {false, false};
+  float db2_acc = 0.f;
 
   const int npairs_b = (B + 1) / 2;
   int u0, u1;
+#ifdef NRM_TC_PROFILE_BWD
+  TCPROF_DECL
+#define BPROF(i) TCPROF(i)
+#else
+#define BPROF(i) do { } while (0)
+#endif
   // A pair's candidates may be split between two CTAs unless its outputs are accumulated in global memory over
   // history tiles or candidate chunks.  With the label branch a split pair has exactly two contributors to dxh
   // (ranges are at least C units long), each adding its finished partial sum once to a zeroed destination:
@@ -485,7 +494,9 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
     const long long bmine = b0 + half;                 // this thread's impression (valid when act)
     for (int r0 = 0; r0 < H; r0 += 64) {
       __syncthreads();                                 // every product of the previous tile has completed
+      BPROF(0);
       for (int imp = 0; imp < nimp; ++imp) stage_history<BRANCH, NP>(xh, xhp, b0 + imp, H, r0, sm.opA[imp]);
+      BPROF(1);
       bool dh_started = false;
       for (int c0 = ca; c0 < cend; c0 += TC_MAXC) {
         const int nc = min(TC_MAXC, cend - c0);
@@ -528,6 +539,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 
         park_pair_vec(sm.tt[0], load_pair_vec(e, tpg, b0, C, c0, TOFF, nimp));
         __syncthreads();                                 // ds and the first pair's vectors visible
+        BPROF(2);
         for (int c = 0; c < nc; ++c) {
           const long long rcm = bmine * C + c0 + c;
           const float* tt = sm.tt[c & 1];
@@ -535,6 +547,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           if (c + 1 < nc) nxt = load_pair_vec(e, tpg, b0, C, c0 + c + 1, TOFF, nimp);     // one pair ahead
           build_Wc<NP>(sm.wda, tt, sm.opBD[0][0]);
           if (nimp == 2) build_Wc<NP>(sm.wda, tt + 128, sm.opBD[0][1]);
+          BPROF(3);
           umma::fence_async_smem();
           umma::fence_before_sync();
           __syncthreads();                               // (1) operands visible; previous S^T / Gt reads done
@@ -548,6 +561,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           umma::mbar_wait(&sm.mbar, phase);
           phase ^= 1;
           umma::fence_after_sync();
+          BPROF(4);
           // ---- epilogue 1: thread = (column half, impression half, history row)
           {
             const float dsr = act ? sm.ds[half][c][row] : 0.f;
@@ -575,6 +589,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
               if (INPUT_GRADS) sm.sc[((ch * 2 + half) * TC_MAXC + c) * 64 + row] = sacc;
             }
           }
+          BPROF(5);
           if (c + 1 < nc) park_pair_vec(sm.tt[(c + 1) & 1], nxt);
           umma::fence_async_smem();
           umma::fence_before_sync();
@@ -587,7 +602,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
               const umma::Operand d_k = umma::op_tile64_k(umma::smem_u32(sm.opBD[DH][q]));
               const umma::Operand w_mn = umma::op_tile64_mn(umma::smem_u32(sm.opBD[0][q]));
               umma::mma_product<SPLIT, 4>(tmem + BWD_COL_S + half_off[q], h_mn, d_mn, IDESC_ST, false);
-              umma::mma_product<SPLIT, 4>(tmem + BWD_COL_DA + half_off[q], h_mn, d_mn, IDESC_ST, da_started[q]);
+              if (!DA_IN_REGS) umma::mma_product<SPLIT, 4>(tmem + BWD_COL_DA + half_off[q], h_mn, d_mn, IDESC_ST, da_started[q]);
               if (INPUT_GRADS) umma::mma_product<SPLIT, 4>(tmem + BWD_COL_DH + half_off[q], d_k, w_mn, IDESC_DH, dh_started);
               // Gt: ones is exact in bf16, so only the (hi, hi) and (lo, hi) terms exist
               {
@@ -602,11 +617,12 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
             }
             umma::mma_commit(&sm.mbar);
           }
-          for (int q = 0; q < nimp; ++q) da_started[q] = true;
           dh_started = true;
+          for (int q = 0; q < nimp; ++q) da_started[q] = true;
           umma::mbar_wait(&sm.mbar, phase);
           phase ^= 1;
           umma::fence_after_sync();
+          BPROF(6);
           // ---- epilogue 2: thread = (column half, impression half, feature k = row) for S^T, (half, j = row) for Gt
           {
             const float tk = act ? tt[half * 128 + row] : 0.f;
@@ -617,6 +633,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 dwd_acc[j] = fmaf(tk, v[j], dwd_acc[j]);
+                if (DA_IN_REGS) da_acc[j] += v[j];
                 if (INPUT_GRADS) dt = fmaf(v[j], __ldg(Wd_rm + (cb * 32 + j) * 256 + row), dt);
               }
             }
@@ -641,6 +658,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
             }
           }
           umma::fence_before_sync();
+          BPROF(7);
         }
         __syncthreads();                                 // ds / opP of this chunk consumed before the next chunk rewrites them
         if (INPUT_GRADS && !single_chunk) {
@@ -690,6 +708,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           }
         }
         umma::fence_before_sync();
+        BPROF(8);
       }
     }
   }
@@ -698,13 +717,13 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   __syncthreads();
   float* out = part + (long long)blockIdx.x * TC_PARTIAL;
   {
-    // dA^T from TMEM and dWd^T from registers: thread (ch, half, k); the two impression halves (lanes l and l ^ 16) are
+    // dA^T and dWd^T from registers: thread (ch, half, k); the two impression halves (lanes l and l ^ 16) are
     // summed in the warp and the lower half writes out[TCP_DA / TCP_DWD + k*64 + 32 ch + j]
     float v[32];
-    umma::tmem_ld32(my_tmem + BWD_COL_DA + cb * 32, v);
+    if (!DA_IN_REGS) umma::tmem_ld32(my_tmem + BWD_COL_DA + cb * 32, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float a = da_started[half] ? v[j] : 0.f;
+      float a = DA_IN_REGS ? da_acc[j] : (da_started[half] ? v[j] : 0.f);
       a += __shfl_xor_sync(0xffffffffu, a, 16);
       v[j] = a;
       float d = dwd_acc[j];
