@@ -5,7 +5,9 @@
  * The reference has no FFI: its hot path is Python calling torch.nn modules.  The
  * entry points below are what a binding for that path binds, one per reference call
  * site; every one takes plain device pointers and sizes, allocates nothing, never
- * synchronises, and enqueues all of its work on `stream`.
+ * synchronises, and enqueues all of its work on `stream` (a training forward also forks a
+ * library-owned side stream from `stream` for the id sort the backward needs; nrm_backward
+ * joins it back, so callers only ever see `stream` -- CUDA-graph capture included).
  *
  *   reference call (file:line)                               entry point
  *   ------------------------------------------------------   -------------------------

@@ -60,6 +60,28 @@ KernelTimer::~KernelTimer() {
   t.used++;
 }
 
+// ---- side stream for work that only depends on the inputs ---------------------------------------
+// The counting sort of the table ids needs nothing but the keys written by embed_rows_kernel, and its result is only
+// used by the very last kernels of the backward.  It is enqueued on a library-owned side stream right after the
+// embedding kernel (fork: event on the caller's stream) and joined just before the table-gradient kernels (join: event
+// on the side stream), so its four small launches run under the attention / head kernels instead of after them.
+// Fork and join are ordinary stream events, so the pattern is also valid inside a CUDA-graph capture of the caller's
+// stream.  One side stream + two events per device, created on first use and kept for the life of the process.
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; bool made; };
+static SideStream g_side[64];
+static SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& ss = g_side[dev];
+  if (!ss.made) {
+    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ss.made = true;
+  }
+  return &ss;
+}
+
 struct LayoutEntry { const char* name; long long offset; long long numel; };
 #define II "invariant_interest_model."
 static const LayoutEntry kLayout[] = {
@@ -187,6 +209,15 @@ static int get_workspace(const char* fn, Workspace& w, void* ws, size_t ws_bytes
 static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, int mode, int precision, cudaStream_t s) {
   { KernelTimer t("embed_rows", s);
     NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
+  if (mode & NRM_MODE_KEEP_FOR_BWD) {
+    // fork: sort the table ids for the backward's table gradients on the side stream (joined in encoder_backward)
+    SideStream* ss = side_stream();
+    if (ss == nullptr) { set_error("encoder_forward: cannot create the side stream"); return NRM_ECUDA; }
+    NRM_CUDA(cudaEventRecord(ss->fork, s));
+    NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    NRM_TRY(launch_table_sort(w, ss->stream));
+    NRM_CUDA(cudaEventRecord(ss->join, ss->stream));
+  }
   // xh = w1(xin_h)   (user_invariant_interest_model.py:78)
   { KernelTimer t("w1_forward", s); NRM_TRY(launch_w1_forward(P, w, s)); }
   if (precision != NRM_PRECISION_FP32) NRM_TRY(launch_attention_prep(P, w, s));
@@ -204,7 +235,12 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
   // w1: dxin_h = dxh W1, dW1 = dxh^T xin_h, db1 = colsum(dxh)
   { KernelTimer t("w1_backward", s); NRM_TRY(launch_w1_backward(P, w, G, s)); }
   { KernelTimer t("small_linear_grads", s); NRM_TRY(launch_small_linear_grads(in, w, G, s)); }
-  NRM_TRY(launch_table_sort(w, s));
+  {
+    // join: the id sort enqueued by the forward (same workspace) must have finished
+    SideStream* ss = side_stream();
+    if (ss == nullptr) { set_error("encoder_backward: cannot create the side stream"); return NRM_ECUDA; }
+    NRM_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+  }
   NRM_TRY(launch_table_grads(w, G, s));
   return NRM_OK;
 }

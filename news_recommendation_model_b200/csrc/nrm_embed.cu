@@ -502,7 +502,6 @@ int launch_table_sort(Workspace& w, cudaStream_t s) {
     NRM_CUDA(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (SORT_CHUNK + 2 * NKEY32))));
     configured = true;
   }
-  KernelTimer t("table_sort", s);
   sort_hist_kernel<<<nch, 1024, NKEY32 * sizeof(int), s>>>(sp);
   NRM_LAUNCH_CHECK("sort_hist_kernel");
   sort_colscan_kernel<<<(NKEY32 + NKEY8 + 7) / 8, 256, 0, s>>>(sp);
