@@ -5,7 +5,6 @@
 #include <cstring>
 
 #include "nrm_kernels.cuh"
-#include "nrm_gemm.cuh"
 
 namespace nrm {
 
@@ -67,7 +66,7 @@ KernelTimer::~KernelTimer() {
 // on the side stream), so its four small launches run under the attention / head kernels instead of after them.
 // Fork and join are ordinary stream events, so the pattern is also valid inside a CUDA-graph capture of the caller's
 // stream.  One side stream + two events per device, created on first use and kept for the life of the process.
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; bool made; };
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2; bool made; };
 static SideStream g_side[64];
 static SideStream* side_stream() {
   int dev = 0;
@@ -77,6 +76,8 @@ static SideStream* side_stream() {
     if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ss.made = true;
   }
   return &ss;
@@ -144,13 +145,11 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   w.rstd = (float*)take(f * E);
   w.bn_sums = (double*)take(sizeof(double) * 2 * E);
   w.stat_part = (double*)take(sizeof(double) * STAT_BLOCKS * 2 * E);
-  w.z = (float*)take(f * R * E);
-  w.a1 = (float*)take(f * R * HID); w.u1 = (float*)take(f * R * HID);
+  w.a1 = (float*)take(f * R * HID);
   w.gate = (float*)take(f * R * E);
-  w.x = (float*)take(f * R * E);
-  w.a2 = (float*)take(f * R * HID); w.u2 = (float*)take(f * R * HID);
+  w.a2 = (float*)take(f * R * HID);
   w.y = (float*)take(f * R * E);
-  w.a3 = (float*)take(f * R * HID); w.u3 = (float*)take(f * R * HID);
+  w.a3 = (float*)take(f * R * HID);
   w.head_wt = (float*)take(f * 5 * HID * E);
   w.att_derived = (float*)take(f * 2 * 12420);
   w.tp = (float*)take(f * 2 * R * 64);
@@ -174,11 +173,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
     w.dtp = (float*)take(f * 2 * R * 64);
     w.att_dA = (float*)take(f * 2 * 4096);
     w.tp_part = (float*)take(f * 2 * ((R + 31) / 32) * (4096 + 64));
-    {
-      const size_t head = (size_t)(P_DELTA - P_GATE_FC1_W) * (WGRAD_SPLITS + 1);
-      const size_t w1 = (size_t)(64 * XIN + 64) * (W1_SPLITS + 1);
-      w.splitk = (float*)take(f * (head > w1 ? head : w1));   // split partials of the head / w1 weight gradients
-    }
+    w.splitk = (float*)take(f * (size_t)(64 * XIN + 64) * W1_SPLITS);   // per-CTA partials of the w1 weight / bias gradient
     w.small_part = (float*)take(f * 1024 * 96);
     const size_t n32 = N * 6, n8 = N * 5;
     const size_t c32 = (n32 + SORT_CHUNK - 1) / SORT_CHUNK, c8 = (n8 + SORT_CHUNK - 1) / SORT_CHUNK;
@@ -227,20 +222,24 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
 }
 
 static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, int precision, float* G, cudaStream_t s) {
+  SideStream* ss = side_stream();
+  if (ss == nullptr) { set_error("encoder_backward: cannot create the side stream"); return NRM_ECUDA; }
   { KernelTimer t("attention_backward_label", s); NRM_TRY(launch_attention_backward(in, P, w, 0, precision, s)); }
+  // fork: the w1 backward only needs dxh (label attention); it runs on the side stream under the text/img attention
+  // backward and the reductions of the attention weight gradients
+  NRM_CUDA(cudaEventRecord(ss->fork2, s));
+  NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork2, 0));
+  // w1: dxin_h = dxh W1, dW1 = dxh^T xin_h, db1 = colsum(dxh)
+  { KernelTimer t("w1_backward", ss->stream); NRM_TRY(launch_w1_backward(P, w, G, ss->stream)); }
+  NRM_CUDA(cudaEventRecord(ss->join2, ss->stream));
   { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
   { KernelTimer t("attention_finish", s);
     NRM_TRY(launch_attention_finish(P, w, 0, precision, G, s));
     NRM_TRY(launch_attention_finish(P, w, 1, precision, G, s)); }
-  // w1: dxin_h = dxh W1, dW1 = dxh^T xin_h, db1 = colsum(dxh)
-  { KernelTimer t("w1_backward", s); NRM_TRY(launch_w1_backward(P, w, G, s)); }
+  NRM_CUDA(cudaStreamWaitEvent(s, ss->join2, 0));          // join: dxin_h ready
   { KernelTimer t("small_linear_grads", s); NRM_TRY(launch_small_linear_grads(in, w, G, s)); }
-  {
-    // join: the id sort enqueued by the forward (same workspace) must have finished
-    SideStream* ss = side_stream();
-    if (ss == nullptr) { set_error("encoder_backward: cannot create the side stream"); return NRM_ECUDA; }
-    NRM_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
-  }
+  // join: the id sort enqueued by the forward (same workspace) must have finished
+  NRM_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
   NRM_TRY(launch_table_grads(w, G, s));
   return NRM_OK;
 }

@@ -14,7 +14,6 @@
 // (row-major for pooling / dW products, k-major for the hidden GEMM) and reused by all C
 // candidates.  History rows past H are zero-filled, which makes them inert everywhere.
 #include "nrm_kernels.cuh"
-#include "nrm_gemm.cuh"
 
 namespace nrm {
 

@@ -777,7 +777,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 // Sum the per-CTA partials (fixed order) and write the attention-MLP gradients that do not depend on tp:
 //   fc1.weight grad blocks: [:, 0:64] = dA, [:, 192:256] = dWd   (the Bm-dependent blocks are completed by
 //   attention_tp_grad_kernel); fc2.weight = dw2; fc2.bias = db2.   Partials are transposed ([k][j]).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 attention_tc_compose_kernel(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads,
                             float* __restrict__ dA_all) {
   const int branch = blockIdx.y;
@@ -785,37 +785,45 @@ attention_tc_compose_kernel(const float* __restrict__ part_all, int nparts0, int
   const float* part = part_all + (long long)branch * ATT_TC_PARTS_MAX * TC_PARTIAL;
   const int nparts = branch == 0 ? nparts0 : nparts1;
   float* dA_out = dA_all + branch * 4096;
-  // block = 32 consecutive (k,j) entries x 8 interleaved groups of partials, combined in group order; grid = 128
-  __shared__ float red[8][2][32];
+  // block = 32 consecutive (k,j) entries x 32 interleaved groups of partials, combined in group order; grid.x = 128 (+1)
+  __shared__ float red[32][2][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + lane;              // k*64 + j
-  float dA = 0.f, dWd = 0.f;
+  if (blockIdx.x < 128) {
+    const int i = blockIdx.x * 32 + lane;              // k*64 + j
+    float dA = 0.f, dWd = 0.f;
 #pragma unroll 4
-  for (int p = grp; p < nparts; p += 8) {
-    const float* q = part + (long long)p * TC_PARTIAL;
-    dA += q[TCP_DA + i];
-    dWd += q[TCP_DWD + i];
-  }
-  red[grp][0][lane] = dA; red[grp][1][lane] = dWd;
-  __syncthreads();
-  if (grp == 0) {
-    dA = red[0][0][lane]; dWd = red[0][1][lane];
+    for (int p = grp; p < nparts; p += 32) {
+      const float* q = part + (long long)p * TC_PARTIAL;
+      dA += q[TCP_DA + i];
+      dWd += q[TCP_DWD + i];
+    }
+    red[grp][0][lane] = dA; red[grp][1][lane] = dWd;
+    __syncthreads();
+    if (grp == 0) {
+      dA = red[0][0][lane]; dWd = red[0][1][lane];
 #pragma unroll
-    for (int g = 1; g < 8; ++g) { dA += red[g][0][lane]; dWd += red[g][1][lane]; }
-    const int k = i >> 6, j = i & 63;
-    float* rowp = grads + off.fc1_w + j * 256;
-    rowp[k] = dA; rowp[192 + k] = dWd;
-    dA_out[j * 64 + k] = dA;
-  }
-  if (blockIdx.x == 0 && grp >= 1 && grp <= 2) {
-    const int j = (grp - 1) * 32 + lane;
+      for (int g = 1; g < 32; ++g) { dA += red[g][0][lane]; dWd += red[g][1][lane]; }
+      const int k = i >> 6, j = i & 63;
+      float* rowp = grads + off.fc1_w + j * 256;
+      rowp[k] = dA; rowp[192 + k] = dWd;
+      dA_out[j * 64 + k] = dA;
+    }
+  } else {
+    // fc2.weight (64 sums) and fc2.bias: 65 entries x 8 groups of partials
+    const int ent = threadIdx.x & 127, g8 = threadIdx.x >> 7;
+    float* r2 = &red[0][0][0];                         // [8][128]
     float w = 0.f;
-    for (int p = 0; p < nparts; ++p) w += part[(long long)p * TC_PARTIAL + TCP_DW2 + j];
-    grads[off.fc2_w + j] = w;
-    if (j == 0) {
-      float d = 0.f;
-      for (int p = 0; p < nparts; ++p) d += part[(long long)p * TC_PARTIAL + TCP_DB2];
-      grads[off.fc2_b] = d;
+    if (ent <= 64) {
+#pragma unroll 4
+      for (int p = g8; p < nparts; p += 8) w += part[(long long)p * TC_PARTIAL + (ent < 64 ? TCP_DW2 + ent : TCP_DB2)];
+    }
+    r2[g8 * 128 + ent] = w;
+    __syncthreads();
+    if (g8 == 0 && ent <= 64) {
+      w = r2[ent];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) w += r2[g * 128 + ent];
+      if (ent < 64) grads[off.fc2_w + ent] = w; else grads[off.fc2_b] = w;
     }
   }
 }
@@ -1048,7 +1056,7 @@ int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace&
 
 // both branches at once (after both backward kernels)
 int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaStream_t s) {
-  attention_tc_compose_kernel<<<dim3(128, 2), 256, 0, s>>>(w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA);
+  attention_tc_compose_kernel<<<dim3(129, 2), 1024, 0, s>>>(w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA);
   NRM_LAUNCH_CHECK("attention_tc_compose_kernel");
   const int nparts = (int)((w.R + TPG_ROWS - 1) / TPG_ROWS);
   attention_tp_grad_kernel<<<dim3(nparts, 2), 256, 0, s>>>(w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);

@@ -120,8 +120,7 @@ constexpr int ATT_TC_PARTS_MAX = 512; // CTAs of the tensor-core attention backw
 constexpr int ATT_TC_PARTIAL = 2 * 4096 + 68;   // dA^T | dWd^T | dw2 | db2 floats per CTA
 constexpr int HEAD_WG_CHUNKS_MAX = 64; // row chunks of the head weight-gradient kernel
 constexpr int STAT_BLOCKS = 256;       // row chunks of the column-statistics kernels
-constexpr int WGRAD_SPLITS = 32;       // split-K factor of the head weight-gradient GEMMs
-constexpr int W1_SPLITS = 256;         // split-K factor of the w1 weight gradient (K = B*H rows)
+constexpr int W1_SPLITS = 256;         // most CTAs (= partials) of the w1 backward
 
 struct Workspace {
   // sizes
@@ -135,13 +134,11 @@ struct Workspace {
   float* rstd;         // [264]
   double* bn_sums;     // [2,264]   column sum / sum of squares of e
   double* stat_part;   // [STAT_BLOCKS,2,264]
-  float* z;            // [R,264]   BN output
-  float* a1; float* u1;   // [R,66]
+  float* a1;           // [R,66]    gate.fc1 pre-activation
   float* gate;         // [R,264]
-  float* x;            // [R,264]   gate * e
-  float* a2; float* u2;   // [R,66]
+  float* a2;           // [R,66]    mlp.fc1 pre-activation
   float* y;            // [R,264]
-  float* a3; float* u3;   // [R,66]
+  float* a3;           // [R,66]    out_mlp.fc1 pre-activation
   float* head_wt;      // [5][66*264] transposed head matrices (forward)
   float* head_part_f;  // [tiles][68]   out_mlp.fc2 partial gradients per row tile
   double* head_part_bn;// [tiles][2,264] BatchNorm backward partial sums per row tile
@@ -163,7 +160,7 @@ struct Workspace {
   float* att_dA;       // [2][64,64] summed dA per branch
   float* tp_part;      // [ceil(R/32)][4096+64] partial dBm | db1
   int att_tc_parts[2]; // CTAs (= partials) of the last tensor-core attention backward per branch (host side)
-  float* splitk;       // [WGRAD_SPLITS][max wgrad size] split-K partial sums
+  float* splitk;       // [W1_SPLITS][64*66+64] per-CTA partials of the w1 gradients
   float* small_part;   // partial sums of the small reductions
   // sorted-segment machinery for the embedding-table gradients
   int* keys32;  int* keys8;            // [6N], [5N]
