@@ -301,12 +301,19 @@ __device__ __forceinline__ void table_grad_l1(const SortStream& S, int g, const 
       const int m = min(32, n - q * 32);
       if (m <= 0) break;
       int i = 0;
-      for (; i + 8 <= m; i += 8) {
-        float v[8];
+      for (; i + 16 <= m; i += 16) {
+        float v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = seg_load<32>(__shfl_sync(0xffffffffu, ids[q], i + u), dxin_h, dxt, NH, lane);
+        for (int u = 0; u < 16; ++u) v[u] = seg_load<32>(__shfl_sync(0xffffffffu, ids[q], i + u), dxin_h, dxt, NH, lane);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += v[u];
+        for (int u = 0; u < 16; ++u) acc += v[u];
+      }
+      for (; i + 4 <= m; i += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = seg_load<32>(__shfl_sync(0xffffffffu, ids[q], i + u), dxin_h, dxt, NH, lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += v[u];
       }
       for (; i < m; ++i) acc += seg_load<32>(__shfl_sync(0xffffffffu, ids[q], i), dxin_h, dxt, NH, lane);
     }
@@ -405,7 +412,10 @@ table_grad_l2_kernel(const SortPair sp, const float* __restrict__ gpart32, const
 
 // ---------------------------------------------------------------------------------
 // Sentiment Linear(3,16)+ReLU and instant Linear(3,8)+ReLU gradients.
-// Thread (o, i) of a 4-row-group x 64 layout walks its rows in order; i == 3 is the bias.
+// One LANE per row: it loads its row's 3 sentiment inputs, 16 activations and 16 upstream gradients (11 independent
+// 16/24-byte loads), and keeps all 16 x 4 products (column 3 = bias) in registers over its rows; the 32 lanes of a warp
+// are then summed with shuffles in lane order, the warps of a CTA in warp order.  Target rows add the 8 x 4 products
+// of the instant-interest layer.
 // part[blockIdx.x][0:64]  = sentiment (o*4 + i), part[..][64:96] = instant (o*4 + i)
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -413,37 +423,90 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
                          const double* __restrict__ xg, long long xg_bs, int C, long long NH, long long N,
                          const float* __restrict__ xin_h, const float* __restrict__ e,
                          const float* __restrict__ dxin_h, const float* __restrict__ dxt, const float* __restrict__ de,
-                         int rows_per_cta, float* __restrict__ part) {
-  __shared__ float red[4][96];
-  const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
-  const int o = t >> 2, i = t & 3;
-  const long long r0 = (long long)blockIdx.x * rows_per_cta;
-  const long long r1 = min(N, r0 + rows_per_cta);
-  float acc_s = 0.f, acc_i = 0.f;
-#pragma unroll 4
-  for (long long row = r0 + grp; row < r1; row += 4) {
+                         float* __restrict__ part) {
+  __shared__ float red[8][96];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float as[16][4], ai[8][4];
+#pragma unroll
+  for (int o = 0; o < 16; ++o)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) as[o][i] = 0.f;
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ai[o][i] = 0.f;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long row = (long long)blockIdx.x * 256 + threadIdx.x; row < N; row += stride) {
     const bool is_hist = row < NH;
     const long long r = row - NH;
     const double* src = is_hist ? (xh + row * HC) : (xt + (r / C) * xt_bs + (r % C) * TC);
-    const float act = is_hist ? xin_h[row * XIN + 32 + o] : e[r * E + E_XT + 32 + o];
-    const float dv = is_hist ? dxin_h[row * XIN + 32 + o] : dxt[r * D + 32 + o];
-    const float dpre = act > 0.f ? dv : 0.f;
-    const float in = (i < 3) ? (float)src[74 + i] : 1.0f;
-    acc_s = fmaf(dpre, in, acc_s);
-    if (!is_hist && o < 8) {
+    const float* actp = is_hist ? (xin_h + row * XIN + 32) : (e + r * E + E_XT + 32);
+    const float* dvp = is_hist ? (dxin_h + row * XIN + 32) : (dxt + r * D + 32);
+    const double2 s01 = __ldg(reinterpret_cast<const double2*>(src + 74));     // columns 74, 75 (16-byte aligned: rows are 640 / 624 B)
+    const double s2 = __ldg(src + 76);
+    float act[16], dv[16];
+    if (is_hist) {                                   // 66-float rows: 8-byte aligned
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(actp) + q), d = __ldg(reinterpret_cast<const float2*>(dvp) + q);
+        act[2 * q] = a.x; act[2 * q + 1] = a.y; dv[2 * q] = d.x; dv[2 * q + 1] = d.y;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(actp) + q), d = __ldg(reinterpret_cast<const float4*>(dvp) + q);
+        act[4 * q] = a.x; act[4 * q + 1] = a.y; act[4 * q + 2] = a.z; act[4 * q + 3] = a.w;
+        dv[4 * q] = d.x; dv[4 * q + 1] = d.y; dv[4 * q + 2] = d.z; dv[4 * q + 3] = d.w;
+      }
+    }
+    const float in[3] = {(float)s01.x, (float)s01.y, (float)s2};
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      const float dpre = act[o] > 0.f ? dv[o] : 0.f;
+      as[o][0] = fmaf(dpre, in[0], as[o][0]); as[o][1] = fmaf(dpre, in[1], as[o][1]);
+      as[o][2] = fmaf(dpre, in[2], as[o][2]); as[o][3] += dpre;
+    }
+    if (!is_hist) {
       const double* gsrc = xg + (r / C) * xg_bs + (r % C) * GC;
-      const float ia = e[r * E + E_INST + o];
-      const float dpi = ia > 0.f ? de[r * E + E_INST + o] : 0.f;
-      const float gi = (i < 3) ? (float)gsrc[i] : 1.0f;
-      acc_i = fmaf(dpi, gi, acc_i);
+      const float g0 = (float)__ldg(gsrc), g1 = (float)__ldg(gsrc + 1), g2 = (float)__ldg(gsrc + 2);
+      const float4 ia0 = __ldg(reinterpret_cast<const float4*>(e + r * E + E_INST)), ia1 = __ldg(reinterpret_cast<const float4*>(e + r * E + E_INST) + 1);
+      const float4 di0 = __ldg(reinterpret_cast<const float4*>(de + r * E + E_INST)), di1 = __ldg(reinterpret_cast<const float4*>(de + r * E + E_INST) + 1);
+      const float iav[8] = {ia0.x, ia0.y, ia0.z, ia0.w, ia1.x, ia1.y, ia1.z, ia1.w};
+      const float div[8] = {di0.x, di0.y, di0.z, di0.w, di1.x, di1.y, di1.z, di1.w};
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const float dpi = iav[o] > 0.f ? div[o] : 0.f;
+        ai[o][0] = fmaf(dpi, g0, ai[o][0]); ai[o][1] = fmaf(dpi, g1, ai[o][1]);
+        ai[o][2] = fmaf(dpi, g2, ai[o][2]); ai[o][3] += dpi;
+      }
     }
   }
-  red[grp][t] = acc_s;
-  if (o < 8) red[grp][64 + o * 4 + i] = acc_i;
+  // lanes -> warp (xor tree: fixed shape), warps -> CTA (warp order)
+#pragma unroll
+  for (int o = 0; o < 16; ++o)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = as[o][i];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+      if (lane == 0) red[warp][o * 4 + i] = v;
+    }
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = ai[o][i];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+      if (lane == 0) red[warp][64 + o * 4 + i] = v;
+    }
   __syncthreads();
   if (threadIdx.x < 96) {
     const int k = threadIdx.x;
-    part[(long long)blockIdx.x * 96 + k] = ((red[0][k] + red[1][k]) + red[2][k]) + red[3][k];
+    float v = red[0][k];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) v += red[q][k];
+    part[(long long)blockIdx.x * 96 + k] = v;
   }
 }
 
@@ -526,10 +589,11 @@ int launch_table_grads(Workspace& w, float* grads, cudaStream_t s) {
 }
 
 int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, cudaStream_t s) {
-  const int nparts = 1024;
-  const int rows_per_cta = (int)((w.N + nparts - 1) / nparts);
+  // one row per lane and pass: enough CTAs to cover the rows once, at most one wave of 2 CTAs per SM
+  int nparts = (int)((w.N + 255) / 256);
+  nparts = max(1, min(nparts, min(1024, 2 * sm_count())));
   small_linear_grad_kernel<<<nparts, 256, 0, s>>>(in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.C, w.NH, w.N, w.xin_h, w.e,
-                                                  w.dxin_h, w.dxt, w.de, rows_per_cta, w.small_part);
+                                                  w.dxin_h, w.dxt, w.de, w.small_part);
   NRM_LAUNCH_CHECK("small_linear_grad_kernel");
   small_linear_grad_finish_kernel<<<96, 256, 0, s>>>(w.small_part, nparts, grads);
   NRM_LAUNCH_CHECK("small_linear_grad_finish_kernel");
