@@ -129,6 +129,14 @@ template <int NP> struct TileBytes { static constexpr uint32_t T64 = NP * umma::
 
 // history rows [r0, r0+64) of impression b -> canonical K-major tile(s); rows >= H are zero.
 // All global loads of the tile are issued before the first conversion (one memory round trip per tile).
+// Work item -> (row, 8-column block): a warp covers 16 consecutive rows x 2 blocks, so its loads are 64-byte
+// segments (every fetched sector fully used) and its 16-byte tile stores fall into two 256-byte runs (2-way bank
+// conflict at worst); row-fastest would make every load touch 32 different rows.
+__device__ __forceinline__ void stage_item(int it, int& row, int& kb) {
+  const int lane = it & 31, w = it >> 5;
+  row = (w & 3) * 16 + (lane & 15);
+  kb = (w >> 2) * 2 + (lane >> 4);
+}
 template <int BRANCH, int NP>
 __device__ __forceinline__ void stage_history(const double* __restrict__ xh, const float* __restrict__ xhp,
                                               long long b, int H, int r0, unsigned char* tile) {
@@ -137,7 +145,7 @@ __device__ __forceinline__ void stage_history(const double* __restrict__ xh, con
     float4 raw[ITERS][2];
 #pragma unroll
     for (int u = 0; u < ITERS; ++u) {
-      const int it = threadIdx.x + u * TC_THREADS, row = it & 63, kb = it >> 6;
+      int row, kb; stage_item(threadIdx.x + u * TC_THREADS, row, kb);
       raw[u][0] = raw[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r0 + row < H) {
         const float4* src = reinterpret_cast<const float4*>(xhp + (b * H + r0 + row) * 64 + kb * 8);
@@ -146,7 +154,7 @@ __device__ __forceinline__ void stage_history(const double* __restrict__ xh, con
     }
 #pragma unroll
     for (int u = 0; u < ITERS; ++u) {
-      const int it = threadIdx.x + u * TC_THREADS, row = it & 63, kb = it >> 6;
+      int row, kb; stage_item(threadIdx.x + u * TC_THREADS, row, kb);
       const float v[8] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w, raw[u][1].x, raw[u][1].y, raw[u][1].z, raw[u][1].w};
       umma::store_operand8<NP>(tile, umma::tile64_offset(row, kb), umma::TILE64_BYTES, v);
     }
@@ -154,7 +162,7 @@ __device__ __forceinline__ void stage_history(const double* __restrict__ xh, con
     double2 raw[ITERS][4];
 #pragma unroll
     for (int u = 0; u < ITERS; ++u) {
-      const int it = threadIdx.x + u * TC_THREADS, row = it & 63, kb = it >> 6;
+      int row, kb; stage_item(threadIdx.x + u * TC_THREADS, row, kb);
 #pragma unroll
       for (int i = 0; i < 4; ++i) raw[u][i] = make_double2(0.0, 0.0);
       if (r0 + row < H) {
@@ -165,7 +173,7 @@ __device__ __forceinline__ void stage_history(const double* __restrict__ xh, con
     }
 #pragma unroll
     for (int u = 0; u < ITERS; ++u) {
-      const int it = threadIdx.x + u * TC_THREADS, row = it & 63, kb = it >> 6;
+      int row, kb; stage_item(threadIdx.x + u * TC_THREADS, row, kb);
       float v[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { v[2 * i] = (float)raw[u][i].x; v[2 * i + 1] = (float)raw[u][i].y; }
@@ -401,6 +409,7 @@ struct TcSmemBwd {
   float ds[2][TC_MAXC][64];                                  // [impression][candidate][history row]
   float sc[NBD == 2 ? 2 * 2 * TC_MAXC * 64 : 64];            // partial attention scores [column half][impression][candidate][row] (label branch only)
   float dtx[2 * 64];                                         // dt partial of column half 1, [impression][k]
+  __align__(16) float dpf[NBD == 2 ? 2 * TC_MAXC * 64 : 4];  // fp32 dP [impression][candidate][k] (pooling path of dH, label branch only)
   __align__(16) float wda[8192];                             // Wd | A, operand-build order
   __align__(16) float tt[2][2 * 128];                        // [buffer][item q][t 64 | tp 64]
   float w2[64];
@@ -513,6 +522,10 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
             for (int q = 0; q < 8; ++q) v[q] = 0.f;
           }
           umma::store_operand8<NP>(sm.opP[imp], (uint32_t)kb * T8_LBO + (uint32_t)c * 16, T8_BYTES, v);
+          if (INPUT_GRADS) {
+            float4* dpd = reinterpret_cast<float4*>(sm.dpf + (imp * TC_MAXC + c) * 64 + kb * 8);
+            dpd[0] = make_float4(v[0], v[1], v[2], v[3]); dpd[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
         }
         umma::fence_async_smem();
         umma::fence_before_sync();
@@ -670,7 +683,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
               float4 acc = (c0 == ca) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(dst + 4 * k4);
               for (int c = 0; c < nc; ++c) {
                 const float s = sm.sc[((0 * 2 + half) * TC_MAXC + c) * 64 + row] + sm.sc[((1 * 2 + half) * TC_MAXC + c) * 64 + row];
-                const float4 dp = __ldg(reinterpret_cast<const float4*>(de + (bmine * C + c0 + c) * E + POFF + cb * 32) + k4);
+                const float4 dp = *reinterpret_cast<const float4*>(sm.dpf + (half * TC_MAXC + c) * 64 + cb * 32 + 4 * k4);
                 acc.x = fmaf(s, dp.x, acc.x); acc.y = fmaf(s, dp.y, acc.y); acc.z = fmaf(s, dp.z, acc.z); acc.w = fmaf(s, dp.w, acc.w);
               }
               *reinterpret_cast<float4*>(dst + 4 * k4) = acc;
@@ -692,7 +705,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
             if (single_chunk) {
               for (int c = 0; c < ncs; ++c) {
                 const float s = sm.sc[((0 * 2 + half) * TC_MAXC + c) * 64 + row] + sm.sc[((1 * 2 + half) * TC_MAXC + c) * 64 + row];
-                const float4 dp = __ldg(reinterpret_cast<const float4*>(de + (bmine * C + ca + c) * E + POFF + cb * 32) + k4);
+                const float4 dp = *reinterpret_cast<const float4*>(sm.dpf + (half * TC_MAXC + c) * 64 + cb * 32 + 4 * k4);
                 a.x = fmaf(s, dp.x, a.x); a.y = fmaf(s, dp.y, a.y); a.z = fmaf(s, dp.z, a.z); a.w = fmaf(s, dp.w, a.w);
               }
             } else {
