@@ -189,6 +189,17 @@ int nrm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int nrm_adam_step_device(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                          void* adam_state, void* stream);
 
+/* ---- batched ranking metrics (tool/evaluation.py:3-5, train.py:77-80, verify.py:25-37) ----- */
+/* One result per impression b over its first n_valid[b] candidates (n_valid null = all C):
+ *   auc[b]  sklearn.metrics.roc_auc_score(label, score) (ties averaged; NaN if one class is missing),
+ *   hit[b]  argmax(score) == argmax(label)  (verify.py:32),
+ *   rr[b]   reciprocal rank of the best-ranked positive (stable descending order, test.py:124-127),
+ *   ndcg[b] nDCG@k with binary gains.   Any output pointer may be null.  scores: float32 [B, score_stride],
+ * labels: float64 [B, label_stride] (label > 0.5 = clicked).  MRR / nDCG are not in the reference (unpinned). */
+int nrm_batch_metrics(const float* scores, long long score_stride, const double* labels, long long label_stride,
+                      const int* n_valid, int B, int C, int k, float* auc, float* hit, float* rr, float* ndcg,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,7 @@ SIGNATURES = {
     'nrm_loss_backward': (i32, [vp, i32, i32, vp, vp, vp, ll, vp, sz, vp]),
     'nrm_adam_step': (i32, [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, ll, f32, vp]),
     'nrm_adam_step_device': (i32, [vp, vp, vp, vp, ll, vp, vp]),
+    'nrm_batch_metrics': (i32, [vp, ll, vp, ll, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
 }
 
 
