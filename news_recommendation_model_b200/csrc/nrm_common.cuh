@@ -194,19 +194,22 @@ __device__ __forceinline__ float gelu_tail(float x, float& ex) {   // returns 0.
   poly = fmaf(t, poly, -0.284496736f);
   poly = fmaf(t, poly, 0.254829592f);
   poly *= t;
-  ex = __expf(-z * z);
+  // exp(-x^2/2) = 2^(-w^2), w = |x| sqrt(log2(e) / 2): one multiply + ex2.approx.ftz (results below 2^-126, i.e. |x| > 13.2,
+  // flush to zero) instead of __expf's range checks
+  const float w = fabsf(x) * 0.84932180028801904272f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(w * -w));
   return 0.5f * poly * ex;
 }
 __device__ __forceinline__ float gelu_f(float x) {
   float ex;
   const float half = gelu_tail(x, ex);
-  return x * (x >= 0.f ? 1.0f - half : half);
+  return fmaf(-fabsf(x), half, fmaxf(x, 0.f));      // x >= 0: x (1 - half);  x < 0: x half
 }
 // returns gelu(x), writes d gelu / dx
 __device__ __forceinline__ float gelu_both(float x, float& grad) {
   float ex;
   const float half = gelu_tail(x, ex);
-  const float cdf = x >= 0.f ? 1.0f - half : half;
+  const float cdf = 0.5f + copysignf(0.5f - half, x);
   grad = fmaf(x * 0.39894228040143267794f, ex, cdf);
   return x * cdf;
 }

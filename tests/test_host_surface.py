@@ -134,11 +134,13 @@ def test_gelu_approximation_restated_in_numpy():
     poly = t * poly + f(-0.284496736)
     poly = t * poly + f(0.254829592)
     poly = poly * t
-    ex = np.exp(-(z * z)).astype(f)
+    w = np.abs(x) * f(0.84932180028801904272)                   # exp(-x^2/2) = 2^(-w^2): the kernels use ex2.approx
+    ex = np.exp2((w * -w).astype(f)).astype(f)
     half = f(0.5) * poly * ex
-    cdf = np.where(x >= 0, f(1.0) - half, half).astype(f)
-    gelu = x * cdf
+    gelu = (-np.abs(x)) * half + np.maximum(x, f(0))            # gelu_f
+    cdf = f(0.5) + np.copysign(f(0.5) - half, x)                # gelu_both
     grad = x * f(0.39894228040143267794) * ex + cdf
+    assert np.abs(x * cdf - gelu).max() < 1e-6
     xd = x.astype(np.float64)
     cdf_ref = 0.5 * (1.0 + erf(xd / np.sqrt(2.0)))
     gelu_ref = xd * cdf_ref
