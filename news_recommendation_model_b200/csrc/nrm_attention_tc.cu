@@ -184,8 +184,10 @@ __device__ __forceinline__ void stage_history(const double* __restrict__ xh, con
 
 // W_c[j][k] = Wd[j][k] * t[k] + A[j][k] -> K-major tile(s) (rows = j).  wda = Wd | A in shared memory (operand-build
 // order, see wda_index); t = the candidate vector in shared memory.
+// Both items of a pair in one pass: the Wd / A vectors are read once and combined with the two candidate vectors
+// (tt = [t of item 0 | tp | t of item 1 | tp], 128 floats per item).
 template <int NP>
-__device__ __forceinline__ void build_Wc(const float* wda, const float* t, unsigned char* tile) {
+__device__ __forceinline__ void build_Wc_pair(const float* wda, const float* tt, int nimp, unsigned char* tile0, unsigned char* tile1) {
 #pragma unroll 2
   for (int it = threadIdx.x; it < 64 * 8; it += TC_THREADS) {
     const int j = it & 63, kb = it >> 6;
@@ -193,11 +195,21 @@ __device__ __forceinline__ void build_Wc(const float* wda, const float* t, unsig
     const float4 d1 = *reinterpret_cast<const float4*>(wda + DER_WD + ((kb * 2 + 1) * 64 + j) * 4);
     const float4 a0 = *reinterpret_cast<const float4*>(wda + DER_A + ((kb * 2 + 0) * 64 + j) * 4);
     const float4 a1 = *reinterpret_cast<const float4*>(wda + DER_A + ((kb * 2 + 1) * 64 + j) * 4);
-    const float4 t0 = *reinterpret_cast<const float4*>(t + kb * 8), t1 = *reinterpret_cast<const float4*>(t + kb * 8 + 4);
-    float v[8];
-    v[0] = fmaf(d0.x, t0.x, a0.x); v[1] = fmaf(d0.y, t0.y, a0.y); v[2] = fmaf(d0.z, t0.z, a0.z); v[3] = fmaf(d0.w, t0.w, a0.w);
-    v[4] = fmaf(d1.x, t1.x, a1.x); v[5] = fmaf(d1.y, t1.y, a1.y); v[6] = fmaf(d1.z, t1.z, a1.z); v[7] = fmaf(d1.w, t1.w, a1.w);
-    umma::store_operand8<NP>(tile, umma::tile64_offset(j, kb), umma::TILE64_BYTES, v);
+    const uint32_t off = umma::tile64_offset(j, kb);
+    {
+      const float4 t0 = *reinterpret_cast<const float4*>(tt + kb * 8), t1 = *reinterpret_cast<const float4*>(tt + kb * 8 + 4);
+      float v[8];
+      v[0] = fmaf(d0.x, t0.x, a0.x); v[1] = fmaf(d0.y, t0.y, a0.y); v[2] = fmaf(d0.z, t0.z, a0.z); v[3] = fmaf(d0.w, t0.w, a0.w);
+      v[4] = fmaf(d1.x, t1.x, a1.x); v[5] = fmaf(d1.y, t1.y, a1.y); v[6] = fmaf(d1.z, t1.z, a1.z); v[7] = fmaf(d1.w, t1.w, a1.w);
+      umma::store_operand8<NP>(tile0, off, umma::TILE64_BYTES, v);
+    }
+    if (nimp == 2) {
+      const float4 t0 = *reinterpret_cast<const float4*>(tt + 128 + kb * 8), t1 = *reinterpret_cast<const float4*>(tt + 128 + kb * 8 + 4);
+      float v[8];
+      v[0] = fmaf(d0.x, t0.x, a0.x); v[1] = fmaf(d0.y, t0.y, a0.y); v[2] = fmaf(d0.z, t0.z, a0.z); v[3] = fmaf(d0.w, t0.w, a0.w);
+      v[4] = fmaf(d1.x, t1.x, a1.x); v[5] = fmaf(d1.y, t1.y, a1.y); v[6] = fmaf(d1.z, t1.z, a1.z); v[7] = fmaf(d1.w, t1.w, a1.w);
+      umma::store_operand8<NP>(tile1, off, umma::TILE64_BYTES, v);
+    }
   }
 }
 
@@ -325,8 +337,7 @@ attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restri
           const float* tt = sm.tt[c & 1];
           PairVec nxt{0.f, 0.f};
           if (c + 1 < nc) nxt = load_pair_vec(e, tpg, b0, C, c0 + c + 1, TOFF, nimp);     // one pair ahead
-          build_Wc<NP>(sm.wda, tt, sm.opB[0]);
-          if (nimp == 2) build_Wc<NP>(sm.wda, tt + 128, sm.opB[1]);
+          build_Wc_pair<NP>(sm.wda, tt, nimp, sm.opB[0], sm.opB[1]);
           TCPROF(3);
           umma::fence_async_smem();
           umma::fence_before_sync();
@@ -558,8 +569,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           const float* tt = sm.tt[c & 1];
           PairVec nxt{0.f, 0.f};
           if (c + 1 < nc) nxt = load_pair_vec(e, tpg, b0, C, c0 + c + 1, TOFF, nimp);     // one pair ahead
-          build_Wc<NP>(sm.wda, tt, sm.opBD[0][0]);
-          if (nimp == 2) build_Wc<NP>(sm.wda, tt + 128, sm.opBD[0][1]);
+          build_Wc_pair<NP>(sm.wda, tt, nimp, sm.opBD[0][0], sm.opBD[0][1]);
           BPROF(3);
           umma::fence_async_smem();
           umma::fence_before_sync();
