@@ -306,6 +306,7 @@ def run_ours(args):
     R = B * C
     single = {
         'attention_forward_label': ('tensor', 2.0 * pairs * D * D), 'attention_forward_textimg': ('tensor', 2.0 * pairs * D * D),
+        'attention_forward': ('tensor', 2 * 2.0 * pairs * D * D),            # both branches in one launch (tensor-core path)
         'attention_backward_label': ('tensor', 3 * 2.0 * pairs * D * D), 'attention_backward_textimg': ('tensor', 2 * 2.0 * pairs * D * D),
         'embed_rows': ('hbm', 8.0 * (80 * H + 81 * C) * B + 4.0 * (66 * H * B + 136 * R)),
         'w1_forward': ('hbm', 4.0 * (66 + 64) * H * B),

@@ -216,8 +216,15 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   // xh = w1(xin_h)   (user_invariant_interest_model.py:78)
   { KernelTimer t("w1_forward", s); NRM_TRY(launch_w1_forward(P, w, s)); }
   if (precision != NRM_PRECISION_FP32) NRM_TRY(launch_attention_prep(P, w, s));
-  { KernelTimer t("attention_forward_label", s); NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s)); }
-  { KernelTimer t("attention_forward_textimg", s); NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s)); }
+  if (precision == NRM_PRECISION_FP32) {
+    { KernelTimer t("attention_forward_label", s); NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s)); }
+    { KernelTimer t("attention_forward_textimg", s); NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s)); }
+  } else {
+    // tensor-core path: one launch covers both branches
+    KernelTimer t("attention_forward", s);
+    NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s));
+    NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s));
+  }
   return NRM_OK;
 }
 
