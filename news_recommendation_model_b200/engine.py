@@ -79,6 +79,7 @@ class FlatParams:
                 view.copy_(p.detach())
                 p.data = view
                 self.slots.append((name, off, n, p.shape))
+        self.bn_weight_off = next(off for name, off, _, _ in self.slots if name == 'bn.weight')
 
     def is_current(self, named: Dict[str, torch.nn.Parameter]) -> bool:
         base = self.buf.data_ptr()

@@ -58,9 +58,26 @@ class UserModel(nn.Module):
         self.precision = precision
         return self
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() replace the parameter storages: the flat buffer has to be rebuilt
+        rt = self.__dict__.get('_rt')
+        if rt is not None:
+            rt.flat = None
+        return super()._apply(fn, *args, **kwargs)
+
     def flat_parameters(self) -> engine.FlatParams:
-        """(Re)build the flat parameter buffer if .to()/load_state_dict moved the tensors."""
+        """(Re)build the flat parameter buffer if .to()/load_state_dict moved the tensors.  Fast path: three sentinel
+        tensors (first, middle and last entry of the layout) still point into the buffer -- the full walk over
+        named_parameters() costs more host time than the smaller kernels of a step."""
         rt = self._runtime()
+        flat = rt.flat
+        if flat is not None:
+            base = flat.buf.data_ptr()
+            first = self.invariant_interest_model.category_embedding[0].weight
+            if (self.delta.device == flat.device and first.data_ptr() == base
+                    and self.bn.weight.data_ptr() == base + 4 * flat.bn_weight_off
+                    and self.delta.data_ptr() == base + 4 * flat.fixed and self.delta.numel() == flat.delta_numel):
+                return flat
         named = dict(self.named_parameters())
         if rt.flat is None or rt.flat.device != self.delta.device or not rt.flat.is_current(named):
             if not self.delta.is_cuda:
