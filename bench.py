@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='FusedTrainStep issues the C-ABI calls eagerly instead of replaying a CUDA graph')
     ap.add_argument('--cpu-steps', type=int, default=8)
+    ap.add_argument('--no-affinity', action='store_true', help='do not bind each rank to the CPU cores local to its GPU')
     return ap.parse_args()
 
 
@@ -184,6 +185,8 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from news_recommendation_model_b200.dp import bind_to_local_cpus
+    cpus = None if args.no_affinity else bind_to_local_cpus(local)     # before any pinned buffer is allocated
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
@@ -375,7 +378,8 @@ def run_ours(args):
         'data': 'synthetic', 'config': workload_config(args, world),
         'clocks': clk.summary(),
         'e2e': {'value': e2e_value, 'unit': 'impressions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                'ms_per_step': e2e_ms / K, 'h2d_only_ms_per_step': h2d_ms},
+                'ms_per_step': e2e_ms / K, 'h2d_only_ms_per_step': h2d_ms,
+                'host_cpu_binding': (f'{len(cpus)} cores local to the GPU (NVML affinity)' if cpus else 'none')},
         'gpu_launches': int(launches) * K, 'gpu_launches_per_step': int(launches),
         'module_path': {'value': world * B * K / (mod_ms / 1e3), 'unit': 'impressions/s', 'ms_per_step': mod_ms / K,
                         'note': 'drop-in nn.Module path driven like train.py:69-75 (autograd + FusedAdam), device-resident'},

@@ -200,6 +200,27 @@ int nrm_batch_metrics(const float* scores, long long score_stride, const double*
                       const int* n_valid, int B, int C, int k, float* auc, float* hit, float* rr, float* ndcg,
                       void* stream);
 
+/* ---- scoring epilogue and submission text (test.py:58-70, test.py:118-132) ------------------ */
+/* logits: n_models stacked eval-mode outputs, model m / impression b at logits + m*model_stride + b*row_stride,
+ * C float32 each (C = the batch's candidate columns after test.py:52-56 trimmed the common pad tail).
+ * empty_num[b] (int64, device, may be null = 0) = pad candidates still at the end of row b.
+ *   scores[b][i] = mean_m softmax(logits_m[b])[i]                       (softmax over all C columns, test.py:58-63)
+ *                  then softmax over the first C - empty_num[b] entries again when empty_num[b] > 0 (test.py:65-68);
+ *                  pad entries are written as 0.
+ *   ranks[b][i]  = 1-based position of candidate i in the stable descending order of scores[b][0 : C - empty_num[b]]
+ *                  (Python sorted(..., reverse=True), test.py:124-127); -1 for pad entries.  May be null.
+ * scores: float32 [B, C], ranks: int32 [B, C]. */
+int nrm_score_epilogue(const float* logits, int n_models, long long model_stride, long long row_stride, int B, int C,
+                       const long long* empty_num, float* scores, int* ranks, void* stream);
+
+/* Text of test.py:129-130 for a whole batch: line b = "{impression_id[b]} [{ranks[b][0]},{ranks[b][1]},...]\n" over the
+ * non-pad candidates.  offsets: int64 [B + 1] (device) receives the byte offset of every line, offsets[B] = total
+ * length; out: at least `capacity` bytes (nrm_rank_strings_capacity(B, C) is always enough).  Lines that would end
+ * beyond `capacity` are not written (offsets[B] > capacity tells the caller). */
+size_t nrm_rank_strings_capacity(int B, int C);
+int nrm_rank_strings(const long long* impression_id, const int* ranks, const long long* empty_num, int B, int C,
+                     long long* offsets, char* out, long long capacity, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

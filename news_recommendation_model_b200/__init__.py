@@ -5,7 +5,7 @@ from .models import (MLP, PointwiseAttention, PointwiseAttentionExpanded, UserIn
 from .optim import FusedAdam
 from .trainer import FusedTrainStep
 from ._lib import NrmError, build
-from . import dp, metrics
+from . import dp, metrics, scoring
 
 __all__ = ['MLP', 'PointwiseAttention', 'PointwiseAttentionExpanded', 'UserInstantInterestModel',
-           'UserInvariantInterestModel', 'UserModel', 'FusedAdam', 'FusedTrainStep', 'NrmError', 'build', 'dp', 'metrics']
+           'UserInvariantInterestModel', 'UserModel', 'FusedAdam', 'FusedTrainStep', 'NrmError', 'build', 'dp', 'metrics', 'scoring']

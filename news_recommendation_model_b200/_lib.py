@@ -47,6 +47,9 @@ SIGNATURES = {
     'nrm_adam_step': (i32, [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, ll, f32, vp]),
     'nrm_adam_step_device': (i32, [vp, vp, vp, vp, ll, vp, vp]),
     'nrm_batch_metrics': (i32, [vp, ll, vp, ll, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
+    'nrm_score_epilogue': (i32, [vp, i32, ll, ll, i32, i32, vp, vp, vp, vp]),
+    'nrm_rank_strings_capacity': (sz, [i32, i32]),
+    'nrm_rank_strings': (i32, [vp, vp, vp, i32, i32, vp, vp, ll, vp]),
 }
 
 

@@ -17,6 +17,29 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_local_cpus(device_index: int):
+    """Pin this process (and the pinned host buffers it allocates afterwards: first touch) to the CPU cores NVML reports
+    as local to GPU `device_index`.  With one process per GPU every rank then stages its batches from the memory of
+    the socket its own PCIe root hangs off, instead of wherever the scheduler happened to start it.  Returns the
+    sorted core list, or None when NVML or the affinity call is not available (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:                                   # an optimisation only: never a reason to stop
+        return None
+
+
 def shard_range(total: int, rank: int, world: int):
     """Contiguous [begin, end) slice of `total` impressions owned by `rank` (sizes differ by <= 1)."""
     base, rem = divmod(total, world)

@@ -1,0 +1,151 @@
+"""Scoring epilogue and submission text on the GPU — the host side of `test.py`'s scoring loop.
+
+The reference finishes every scoring batch on the host (`test.py:58-71`): ensemble mean of the per-model softmax,
+a second softmax over the rows that still hold pad candidates, one `.cpu().numpy()` per impression, and later
+(`test.py:118-132`) `thread_num` worker processes that sort each score list in Python to build the rank string.
+Here the whole batch stays on the device until ONE copy back:
+
+    scores, ranks = nrm.scoring.ensemble_scores(model_list, x_history, x_inview, x_global, empty_num)
+    text = nrm.scoring.submission_text(impression_id, ranks, empty_num)      # bytes of predictions.txt for the batch
+
+`model_test` mirrors `test.py:model_test` (same arguments, same queue records, same id list) and
+`write_submission_file` mirrors `test.py:write_submission_file` without the worker processes."""
+from __future__ import annotations
+
+import ctypes
+import queue as _queue
+import zipfile
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def score_epilogue(logits: torch.Tensor, empty_num: Optional[torch.Tensor] = None, want_ranks: bool = True
+                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """logits: [M,B,C] (or [B,C]) eval-mode outputs of the M ensemble members on the GPU; empty_num: [B] pad candidates
+    left at the end of each row.  Returns (scores float32 [B,C], ranks int32 [B,C] or None) as `test.py:58-70` and
+    `test.py:124-127` define them; pad entries hold score 0 and rank -1."""
+    if logits.dim() == 2:
+        logits = logits.unsqueeze(0)
+    if logits.dim() != 3:
+        raise ValueError('logits must be [M, B, C] or [B, C]')
+    if not logits.is_cuda:
+        raise _lib.NrmError('score_epilogue runs on CUDA tensors only (no CPU fallback)')
+    x = logits.detach().to(torch.float32).contiguous()
+    M, B, C = x.shape
+    dev = x.device
+    en = None
+    if empty_num is not None:
+        en = empty_num.detach().to(device=dev, dtype=torch.int64).contiguous()
+        if en.shape != (B,):
+            raise ValueError('empty_num must be [B]')
+    scores = torch.empty(B, C, dtype=torch.float32, device=dev)
+    ranks = torch.empty(B, C, dtype=torch.int32, device=dev) if want_ranks else None
+    if B == 0 or C == 0:
+        return scores, ranks
+    _lib.check(_lib.load().nrm_score_epilogue(_ptr(x), M, x.stride(0), x.stride(1), B, C, _ptr(en), _ptr(scores), _ptr(ranks), _stream(dev)),
+               'nrm_score_epilogue')
+    return scores, ranks
+
+
+@torch.no_grad()
+def ensemble_scores(model_list: Sequence[torch.nn.Module], x_history, x_inview, x_global, empty_num=None, want_ranks: bool = True):
+    """`test.py:58-70` for one batch: every model's eval forward, then the fused epilogue."""
+    outs = [m(x_history, x_inview, x_global) for m in model_list]
+    return score_epilogue(torch.stack(outs, 0), empty_num, want_ranks)
+
+
+def submission_lines(impression_id: torch.Tensor, ranks: torch.Tensor, empty_num: Optional[torch.Tensor] = None
+                     ) -> Tuple[bytes, np.ndarray]:
+    """The lines `test.py:129-130` formats, for a whole batch: returns (text, offsets) where line b is
+    text[offsets[b]:offsets[b+1]] == b"{impression_id} [{r0},{r1},...]\\n"."""
+    if not ranks.is_cuda:
+        raise _lib.NrmError('submission_lines runs on CUDA tensors only (no CPU fallback)')
+    dev = ranks.device
+    rk = ranks.detach().to(torch.int32).contiguous()
+    B, C = rk.shape
+    if B == 0:
+        return b'', np.zeros(1, np.int64)
+    ids = impression_id.detach().to(device=dev, dtype=torch.int64).contiguous()
+    if ids.shape != (B,):
+        raise ValueError('impression_id must be [B]')
+    en = None
+    if empty_num is not None:
+        en = empty_num.detach().to(device=dev, dtype=torch.int64).contiguous()
+    lib = _lib.load()
+    if C == 0:
+        raise ValueError('ranks must have at least one candidate column')
+    cap = int(lib.nrm_rank_strings_capacity(B, C))
+    out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    _lib.check(lib.nrm_rank_strings(_ptr(ids), _ptr(rk), _ptr(en), B, C, _ptr(offsets), _ptr(out), cap, _stream(dev)), 'nrm_rank_strings')
+    off = offsets.cpu().numpy()
+    total = int(off[-1])
+    if total > cap:
+        raise _lib.NrmError('nrm_rank_strings: text does not fit the buffer')
+    return out[:total].cpu().numpy().tobytes(), off
+
+
+def submission_text(impression_id, ranks, empty_num=None) -> bytes:
+    return submission_lines(impression_id, ranks, empty_num)[0]
+
+
+@torch.no_grad()
+def model_test(model_list, test_data, device='cuda', prediction_queue=None, id_list=None, batch_size=1, text_sink: Optional[List[bytes]] = None):
+    """Mirror of `test.py:model_test` (`test.py:31-74`): same arguments, the same records
+    `[impression_id, user_id, scores (numpy float32, pads dropped), label_id (numpy, pads dropped)]` on `prediction_queue`
+    and the same "{impression_id}_{user_id}" strings in `id_list`, in the same order.  Per batch there is one device
+    epilogue launch and one copy back instead of one `.cpu()` per impression.  If `text_sink` is a list, the formatted
+    submission lines of every batch (`test.py:118-132`) are appended to it as bytes."""
+    loader = torch.utils.data.DataLoader(dataset=test_data, batch_size=batch_size, shuffle=False)
+    for model in model_list:
+        model.eval()
+        model.to(device)
+    if prediction_queue is None:
+        prediction_queue = _queue.Queue()
+    if id_list is None:
+        id_list = []
+    for data in loader:
+        impression_id, user_id, x_history, x_inview, x_global, _, label_id, empty_num = data
+        trim = int(torch.min(empty_num))
+        x_history = x_history.to(device)
+        x_inview = x_inview.to(device)
+        x_global = x_global.to(device)
+        if trim > 0:                                               # test.py:52-56
+            x_inview = x_inview[:, 0:-trim]
+            x_global = x_global[:, 0:-trim]
+            label_id = label_id[:, 0:-trim]
+            empty_num = empty_num - trim
+        scores, ranks = ensemble_scores(model_list, x_history, x_inview, x_global, empty_num, want_ranks=text_sink is not None)
+        if text_sink is not None:
+            text_sink.append(submission_text(impression_id, ranks, empty_num))
+        host = scores.cpu().numpy()
+        for d_i in range(host.shape[0]):
+            n = host.shape[1] - int(empty_num[d_i])
+            prediction_queue.put([impression_id[d_i], user_id[d_i], host[d_i, :n].copy(), label_id[d_i, :n].numpy()])
+            id_list.append('{}_{}'.format(int(impression_id[d_i]), int(user_id[d_i])))
+    return prediction_queue, id_list
+
+
+def write_submission_file(text_chunks: Sequence[bytes], path: str, name: str = 'predictions') -> str:
+    """`test.py:write_submission_file` (`test.py:76-116`) for text that `model_test(text_sink=...)` already formatted:
+    writes `path + "predictions.txt"` and zips it to `path + name + ".zip"`."""
+    file_path = path + 'predictions.txt'
+    zip_path = path + '{}.zip'.format(name)
+    with open(file_path, 'wb') as f:
+        for chunk in text_chunks:
+            f.write(chunk)
+    with zipfile.ZipFile(zip_path, 'w', zipfile.ZIP_DEFLATED) as z:
+        z.write(file_path, arcname=file_path.split('/')[-1])
+    return zip_path
