@@ -218,7 +218,10 @@ def run_ours(args):
 
     # ---- A. the pipelined public API (news_recommendation_model_b200.FusedTrainStep): the five
     #         C-ABI calls of train.py:69-75 per step, CUDA-graph replayed, N_POOL input slots.
-    tr = nrm.FusedTrainStep(model, B, H, C, lr=1e-3, weight_decay=1e-5, nslots=N_POOL, use_graph=not args.no_graph)
+    from news_recommendation_model_b200 import wire
+    table_host = wire.make_article_table()
+    table = table_host.to(dev)                    # 125 541 articles x 320 B = 40 MB, resident in HBM for the compact wire format
+    tr = nrm.FusedTrainStep(model, B, H, C, lr=1e-3, weight_decay=1e-5, nslots=N_POOL, use_graph=not args.no_graph, articles=table)
     slots = [tr.load(hb) for hb in host]          # all slots resident in HBM
     torch.cuda.synchronize()
     for i in range(max(W, N_POOL)):               # every slot replays its own CUDA graph: capture all of them before timing
@@ -235,7 +238,7 @@ def run_ours(args):
 
     # ---- B. end to end through the same API: every step copies its batch from pinned host memory
     #         into a device slot (copy stream, one batch ahead) and the host reads every step's loss.
-    def e2e_loop(n):
+    def e2e_loop(n, host=host):
         nxt = tr.load(host[0])
         prev, last = None, 0.0
         for i in range(n):
@@ -266,6 +269,21 @@ def run_ours(args):
         c1.record()
     torch.cuda.synchronize()
     h2d_ms = max_over_ranks(c0.elapsed_time(c1) / 10)
+
+    # ---- B2. the same loop fed in the compact wire format (wire.py, the additional entry point of SURVEY section 8f N3):
+    #          ids into the resident article table instead of packed float64 rows; the step starts with the expansion kernel
+    host_c = [wire.make_compact_batch(table_host, B, H, C, seed=4321 + 97 * rank + i, user_num=args.user_num).pin() for i in range(N_POOL)]
+    e2e_loop(max(3, N_POOL), host_c)              # re-captures every slot's graph with the expansion in front
+    barrier()
+    e0.record()
+    e2e_loop(K, host_c)
+    e1.record()
+    barrier()
+    e2ec_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2ec = {'value': world * B * K / (e2ec_ms / 1e3), 'unit': 'impressions/s', 'h2d_bytes_per_step': host_c[0].input_bytes(),
+            'd2h_bytes_per_step': 4, 'ms_per_step': e2ec_ms / K,
+            'note': 'same FusedTrainStep fed wire.CompactBatch (article ids + click features, article table resident in HBM); '
+                    'NOT the reference wire format - e2e above is'}
 
     # ---- C. the drop-in nn.Module path driven exactly like train.py (autograd + FusedAdam), device-resident
     opt = nrm.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
@@ -380,6 +398,7 @@ def run_ours(args):
         'e2e': {'value': e2e_value, 'unit': 'impressions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': e2e_ms / K, 'h2d_only_ms_per_step': h2d_ms,
                 'host_cpu_binding': (f'{len(cpus)} cores local to the GPU (NVML affinity)' if cpus else 'none')},
+        'e2e_compact': e2ec,
         'gpu_launches': int(launches) * K, 'gpu_launches_per_step': int(launches),
         'module_path': {'value': world * B * K / (mod_ms / 1e3), 'unit': 'impressions/s', 'ms_per_step': mod_ms / K,
                         'note': 'drop-in nn.Module path driven like train.py:69-75 (autograd + FusedAdam), device-resident'},

@@ -221,6 +221,21 @@ size_t nrm_rank_strings_capacity(int B, int C);
 int nrm_rank_strings(const long long* impression_id, const int* ranks, const long long* empty_num, int B, int C,
                      long long* offsets, char* out, long long capacity, void* stream);
 
+/* ---- compact wire format (additional entry point; tool/process_data.py:195-252 defines the packed one) -------- */
+/* Rebuilds the reference's packed float64 inputs in device memory from an article table and per-impression ids:
+ *   articles     float32 [n_articles, 80]: pca 64 | category | sub-category 5 | sentiment 3 | type | total_inviews,
+ *                total_pageviews, total_read_time | 3 pad floats; row 0 all-zero = the pad article (ids out of range read it)
+ *   hist_article int32 [B,H];  hist_time uint32 [B,H] = years | months << 12 | days << 16 | hours << 21
+ *                (the four integers of tool/normalization.py:31-39);  hist_click float32 [B,H,2] = read_time, scroll
+ *   cand_article int32 [B,C];  cand_time uint32 [B,C];  label32 float32 [B,C] (may be null)
+ * Outputs (all contiguous, 16-byte aligned): x_history float64 [B,H,80], x_target float64 [B,C,78], x_global float64
+ * [B,C,3], label64 float64 [B,C] (when label32 is given).  The model reads its inputs as float32
+ * (user_invariant_interest_model.py:74-75), so nrm_forward on these tensors equals nrm_forward on the ETL's own. */
+int nrm_expand_compact(const float* articles, int n_articles, const int* hist_article, const unsigned* hist_time,
+                       const float* hist_click, const int* cand_article, const unsigned* cand_time, const float* label32,
+                       int B, int H, int C, double* x_history, double* x_target, double* x_global, double* label64,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,9 @@ class _Slot:
         self.graph_fb: Optional[torch.cuda.CUDAGraph] = None
         self.graph_adam: Optional[torch.cuda.CUDAGraph] = None
         self.used = False
+        self.compact = None                    # device CompactBatch staging buffers (wire.py), allocated on first use
+        self.wire = 'packed'                   # what the last load() put into this slot
+        self.graph_wire = None                 # wire format the captured graph was recorded for
 
 
 class LossHandle:
@@ -56,8 +59,11 @@ class LossHandle:
 
 class FusedTrainStep:
     def __init__(self, model, B: int, H: int, C: int, *, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5,
-                 alpha=0.95, use_graph=True, ring=8, nslots=2):
+                 alpha=0.95, use_graph=True, ring=8, nslots=2, articles=None):
+        """`articles`: a device `wire.ArticleTable`; with it `load()` also accepts `wire.CompactBatch`es (ids instead of
+        packed float64 rows) and the step starts with the expansion kernel."""
         self.model, self.B, self.H, self.C, self.alpha = model, B, H, C, float(alpha)
+        self.articles = articles
         self.flat = model.flat_parameters()
         dev = self.flat.device
         self.dev, self.lib = dev, _lib.load()
@@ -136,10 +142,37 @@ class FusedTrainStep:
                    'nrm_adam_step_device')
 
     # ---- pipeline -------------------------------------------------------------------------
+    def _load_compact(self, s: _Slot, batch):
+        from . import wire
+        if self.articles is None:
+            raise _lib.NrmError('FusedTrainStep: pass articles=ArticleTable to feed CompactBatches')
+        if batch.shape != (self.B, self.H, self.C):
+            raise ValueError('CompactBatch shape does not match this step')
+        if s.compact is None:
+            s.compact = wire.CompactBatch(*[torch.zeros_like(getattr(batch, f), device=self.dev) for f in batch.__dataclass_fields__])
+            self._expand(s)                                  # first launch of the kernel outside any graph capture
+        with torch.cuda.stream(self.copy_stream):
+            if s.used:
+                self.copy_stream.wait_event(s.consumed)
+            for f in ('hist_article', 'hist_time', 'hist_click', 'cand_article', 'cand_time', 'label'):
+                getattr(s.compact, f).copy_(getattr(batch, f), non_blocking=True)
+            s.uid.copy_(batch.user_id, non_blocking=True)
+            s.ready.record(self.copy_stream)
+        s.wire = 'compact'
+        return s
+
+    def _expand(self, s: _Slot):
+        from . import wire
+        wire.expand_into(self.articles, s.compact, s.xh, s.xt, s.xg, s.label)
+
     def load(self, batch) -> _Slot:
-        """Enqueue the H2D copy of a (pinned) host batch into the next slot (round robin)."""
+        """Enqueue the H2D copy of a (pinned) host batch into the next slot (round robin).  `batch` is a packed
+        `synthetic.Batch`-like object (x_history, x_target, x_global, label, user_id) or a `wire.CompactBatch`."""
         s = self.slots[self.loaded % len(self.slots)]
         self.loaded += 1
+        if hasattr(batch, 'hist_article'):
+            return self._load_compact(s, batch)
+        s.wire = 'packed'
         with torch.cuda.stream(self.copy_stream):
             if s.used:
                 self.copy_stream.wait_event(s.consumed)      # do not overwrite a slot still being read
@@ -157,12 +190,15 @@ class FusedTrainStep:
         k = self.count % self.ring
         loss_out = self.loss_dev[k:k + 1]
         if self.use_graph:
-            if s.graph_fb is None:
+            if s.graph_fb is None or s.graph_wire != s.wire:
                 # eager warm-up pass is NOT wanted (it would be an extra optimizer step): capture directly
                 s.graph_fb = torch.cuda.CUDAGraph()
                 s.loss_slot = self.loss_dev.new_zeros(())
                 with torch.cuda.graph(s.graph_fb):
+                    if s.wire == 'compact':
+                        self._expand(s)
                     self._forward_backward(s, s.loss_slot)
+                s.graph_wire = s.wire
                 s.graph_adam = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(s.graph_adam):
                     self._adam()
@@ -173,6 +209,8 @@ class FusedTrainStep:
             s.graph_adam.replay()
             loss_out = s.loss_slot.view(1)
         else:
+            if s.wire == 'compact':
+                self._expand(s)
             self._forward_backward(s, loss_out)
             if self.dp is not None:
                 self.dp.buckets.reduce(self.grads, 0, self.grads.numel())

@@ -1,0 +1,61 @@
+"""Host side of the compact wire format (wire.py): record conversion, time packing, batching.  No GPU needed: the packed
+tensors are rebuilt with the test-only restatement oracle/wire_port.py."""
+import numpy as np
+import pytest
+import torch
+
+from news_recommendation_model_b200 import wire
+from news_recommendation_model_b200.synthetic import make_batch
+from oracle.wire_port import expand_reference, unpack_time
+
+
+def records_of(b):
+    return [[b.impression_id[i].numpy(), b.user_id[i].numpy(), b.x_history[i].numpy(), b.x_target[i].numpy(), b.x_global[i].numpy(),
+             b.label[i].numpy(), b.label_id[i].numpy(), b.empty_num[i].numpy()] for i in range(b.x_history.shape[0])]
+
+
+def test_pack_time_roundtrip_and_range_checks():
+    t = np.array([[0, 0, 0, 0], [3000, 12, 30, 23], [4095, 15, 31, 31], [1, 2, 3, 4]])
+    assert np.array_equal(unpack_time(wire.pack_time(t)), t.astype(np.float64))
+    for bad in ([4096, 0, 0, 0], [0, 16, 0, 0], [0, 0, 32, 0], [0, 0, 0, 32], [-1, 0, 0, 0], [0.5, 0, 0, 0]):
+        with pytest.raises(ValueError):
+            wire.pack_time(np.array([bad]))
+
+
+@pytest.mark.parametrize('exact', [True, False])
+def test_from_records_rebuilds_the_packed_tensors(exact):
+    b = make_batch(12, 30, 11, seed=8, user_num=50, variable_history=True, variable_candidates=True, fp32_exact=exact)
+    # repeat some articles so that de-duplication has something to do
+    b.x_history[3, :5, 4:78] = b.x_history[0, :5, 4:78]
+    b.x_target[2, 0, 4:78] = b.x_history[0, 0, 4:78]
+    ds = wire.from_records(records_of(b))
+    d = ds.data
+    assert ds.table.rows.dtype == torch.float32 and ds.table.rows.shape[1] == wire.ARTICLE_COLS
+    assert not ds.table.rows[0].any() and ds.table.rows[1:].any(dim=1).all()
+    assert int(d.hist_article.max()) < ds.table.n and int(d.hist_article.min()) >= 0
+    assert d.hist_article[3, 0] == d.hist_article[0, 0]
+    xh, xt, xg = expand_reference(ds.table.rows.numpy(), d.hist_article.numpy(), d.hist_time.numpy(), d.hist_click.numpy(),
+                                  d.cand_article.numpy(), d.cand_time.numpy())
+    # the model reads x.to(float32) (user_invariant_interest_model.py:74-75): equality is required after that cast
+    assert torch.equal(xh.float(), b.x_history.float()) and torch.equal(xt.float(), b.x_target.float())
+    assert torch.equal(xg.float(), b.x_global.float())
+    if exact:
+        assert torch.equal(xh, b.x_history) and torch.equal(xt, b.x_target) and torch.equal(xg, b.x_global)
+    assert torch.equal(d.label.double(), b.label) and torch.equal(d.empty_num, b.empty_num)
+    assert torch.equal(d.user_id, b.user_id) and torch.equal(d.impression_id, b.impression_id)
+    # pad rows / pad candidates point at the pad article
+    assert ((b.x_history.abs().sum(-1) == 0) == (d.hist_article == 0)).all()
+    assert ((b.x_target.abs().sum(-1) == 0) == (d.cand_article == 0)).all()
+
+
+def test_compact_dataset_batches_cover_every_impression_once():
+    t = wire.make_article_table(500, seed=1)
+    full = wire.make_compact_batch(t, 23, 7, 5, seed=2, variable_history=True)
+    ds = wire.CompactDataset(t, full)
+    seen = []
+    for cb in ds.batches(8, shuffle=True, seed=3, pin=False):
+        assert cb.shape[1:] == (7, 5)
+        seen += cb.impression_id.tolist()
+    assert sorted(seen) == sorted(full.impression_id.tolist())
+    assert sum(1 for _ in ds.batches(8, drop_last=True, pin=False)) == 2
+    assert full.input_bytes() == 23 * (7 * 16 + 5 * 12 + 8)
