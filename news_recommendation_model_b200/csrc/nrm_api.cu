@@ -66,7 +66,7 @@ KernelTimer::~KernelTimer() {
 // on the side stream), so its four small launches run under the attention / head kernels instead of after them.
 // Fork and join are ordinary stream events, so the pattern is also valid inside a CUDA-graph capture of the caller's
 // stream.  One side stream + two events per device, created on first use and kept for the life of the process.
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2; bool made; };
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join_tp; bool made; };
 static SideStream g_side[64];
 static SideStream* side_stream() {
   int dev = 0;
@@ -78,6 +78,8 @@ static SideStream* side_stream() {
     if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join_tp, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ss.made = true;
   }
   return &ss;
@@ -202,21 +204,49 @@ static int get_workspace(const char* fn, Workspace& w, void* ws, size_t ws_bytes
 }
 
 static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, int mode, int precision, cudaStream_t s) {
+  SideStream* ss = side_stream();
+  if (ss == nullptr) { set_error("encoder_forward: cannot create the side stream"); return NRM_ECUDA; }
+  const bool tc = precision != NRM_PRECISION_FP32;
+  static const bool inline_prep = getenv("NRM_INLINE_PREP") != nullptr;       // A/B switch: weight preparation on the caller's stream
+  if (inline_prep) {
+    if (tc) NRM_TRY(launch_attention_prep(P, w, s));
+    NRM_TRY(launch_head_transpose(P, w, s));
+    { KernelTimer t("embed_rows", s); NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
+    if (mode & NRM_MODE_KEEP_FOR_BWD) {
+      NRM_CUDA(cudaEventRecord(ss->fork, s));
+      NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+      NRM_TRY(launch_table_sort(w, ss->stream));
+      NRM_CUDA(cudaEventRecord(ss->join, ss->stream));
+    }
+    { KernelTimer t("w1_forward", s); NRM_TRY(launch_w1_forward(P, w, s)); }
+    if (tc) NRM_TRY(launch_candidate_tp(P, w, s));
+    KernelTimer t("attention_forward", s);
+    NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s));
+    NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s));
+    return NRM_OK;
+  }
+  // fork 0: what depends on the weights only (derived attention matrices, transposed head matrices) runs on the side
+  // stream under the embedding kernel
+  NRM_CUDA(cudaEventRecord(ss->fork0, s));
+  NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork0, 0));
+  if (tc) NRM_TRY(launch_attention_prep(P, w, ss->stream));
+  NRM_TRY(launch_head_transpose(P, w, ss->stream));
   { KernelTimer t("embed_rows", s);
     NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
+  // fork: the per-candidate vectors tp (they need the candidate rows of e) run under the w1 projection; then, for the
+  // backward's table gradients, the sort of the table ids (joined in encoder_backward)
+  NRM_CUDA(cudaEventRecord(ss->fork, s));
+  NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  if (tc) NRM_TRY(launch_candidate_tp(P, w, ss->stream));
+  NRM_CUDA(cudaEventRecord(ss->join_tp, ss->stream));
   if (mode & NRM_MODE_KEEP_FOR_BWD) {
-    // fork: sort the table ids for the backward's table gradients on the side stream (joined in encoder_backward)
-    SideStream* ss = side_stream();
-    if (ss == nullptr) { set_error("encoder_forward: cannot create the side stream"); return NRM_ECUDA; }
-    NRM_CUDA(cudaEventRecord(ss->fork, s));
-    NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
     NRM_TRY(launch_table_sort(w, ss->stream));
     NRM_CUDA(cudaEventRecord(ss->join, ss->stream));
   }
   // xh = w1(xin_h)   (user_invariant_interest_model.py:78)
   { KernelTimer t("w1_forward", s); NRM_TRY(launch_w1_forward(P, w, s)); }
-  if (precision != NRM_PRECISION_FP32) NRM_TRY(launch_attention_prep(P, w, s));
-  if (precision == NRM_PRECISION_FP32) {
+  NRM_CUDA(cudaStreamWaitEvent(s, ss->join_tp, 0));          // join: derived weights, transposed head matrices, tp
+  if (!tc) {
     { KernelTimer t("attention_forward_label", s); NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s)); }
     { KernelTimer t("attention_forward_textimg", s); NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s)); }
   } else {

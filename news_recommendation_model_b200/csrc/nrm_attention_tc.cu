@@ -41,12 +41,13 @@
 
 namespace nrm {
 
-// Optional phase timing (make EXTRA=-DNRM_TC_PROFILE): CTA 0 / thread 0 accumulates clock64 deltas per phase of the
-// forward kernel into g_tcprof; nrm_debug_tcprof() returns and clears them.  Compiled out by default.
+// Optional phase timing (make EXTRA=-DNRM_TC_PROFILE): in CTA 0, thread 0 (the warp that issues the MMAs) and thread 32
+// (a warp that does not) accumulate clock64 deltas per phase into g_tcprof[i] / g_tcprof[16 + i]; nrm_debug_tcprof()
+// returns and clears them.  Compiled out by default.
 #ifdef NRM_TC_PROFILE
-__device__ long long g_tcprof[16];
+__device__ long long g_tcprof[32];
 #define TCPROF_DECL long long tcp_t = clock64();
-#define TCPROF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n__ = clock64(); g_tcprof[i] += n__ - tcp_t; tcp_t = n__; } } while (0)
+#define TCPROF(i) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32)) { const long long n__ = clock64(); g_tcprof[(i) + (threadIdx.x ? 16 : 0)] += n__ - tcp_t; tcp_t = n__; } } while (0)
 #else
 #define TCPROF_DECL
 #define TCPROF(i) do { } while (0)
@@ -425,6 +426,7 @@ template <int NP, int NBD>
 struct TcSmemBwd {
   __align__(128) unsigned char opA[2][TileBytes<NP>::T64];   // history tiles [h][k]
   __align__(128) unsigned char opBD[NBD][2][TileBytes<NP>::T64];   // [0][q]: W_c [j][k] of item q;  [NBD-1][q]: dhid [h][j] of item q
+  __align__(128) unsigned char opW2[2][NBD == 2 ? TileBytes<NP>::T64 : 128];   // label branch: W_c of the odd candidates (software pipeline)
   __align__(128) unsigned char opP[2][TileBytes<NP>::T8];    // dP [c][k] per impression (B operand of the ds product)
   __align__(128) unsigned char ones[T8_BYTES];               // [8][64] ones (B operand of the Gt product)
   float ds[2][TC_MAXC][64];                                  // [impression][candidate][history row]
@@ -435,10 +437,12 @@ struct TcSmemBwd {
   __align__(16) float tt[2][2 * 128];                        // [buffer][item q][t 64 | tp 64]
   float w2[64];
   uint64_t mbar;
+  uint64_t mbar_h;                                           // hid products of the pipelined (label) kernel
   uint32_t tmem_base;
 };
 
-// TMEM columns: [0,64) hid, then Gt in [0,8);  [64,128) ds in [64,72), then S^T;  [128,192) dH;  [192,256) dA^T (text/img)
+// TMEM columns: [0,64) hid, then Gt in [0,8) (text/img);  [64,128) ds in [64,72), then S^T;  [128,192) dH (label);
+// [192,256) dA^T (text/img), Gt in [192,200) (label)
 constexpr uint32_t BWD_TMEM_COLS = 256, BWD_COL_HID = 0, BWD_COL_S = 64, BWD_COL_DH = 128, BWD_COL_DA = 192;
 // per-CTA partial sums (floats): dA^T [64 k][64 j] | dWd^T [64][64] | dw2 [64] | db2 [1] (+3 pad)
 constexpr int TCP_DA = 0, TCP_DWD = 4096, TCP_DW2 = 2 * 4096, TCP_DB2 = 2 * 4096 + 64, TC_PARTIAL = ATT_TC_PARTIAL;
@@ -455,6 +459,13 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   // dA^T = sum over items of S^T: the label kernel (one CTA per SM, registers to spare) adds the S^T it reads anyway in
   // registers; the text/img kernel (128 registers per thread) lets the tensor core accumulate it in TMEM with a second product
   constexpr bool DA_IN_REGS = INPUT_GRADS;
+  // Software pipeline (label kernel: one CTA per SM, nobody else hides its tensor-core latency): while the second group
+  // of products of candidate c (S^T, dH, Gt) runs, the CTA builds W_c of candidate c + 1 in a second buffer and queues its
+  // hid product behind them, so that product runs under epilogue 2 of candidate c.  hid is then only ever read by
+  // epilogue 1, and Gt moves out of its columns into the (unused, dA^T lives in registers) [192, 200).
+  constexpr bool PIPE = INPUT_GRADS;
+  constexpr uint32_t COL_GT = PIPE ? BWD_COL_DA : BWD_COL_HID;
+  static_assert(!PIPE || DA_IN_REGS, "the pipelined kernel parks Gt in the dA^T columns");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmemBwd<NP, NBD>& sm = *reinterpret_cast<TcSmemBwd<NP, NBD>*>(smem_raw);
   constexpr AttOffsets off = BRANCH == 0 ? ATT_LABEL : ATT_TI;
@@ -465,6 +476,15 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   constexpr uint32_t IDESC_ST = umma::make_idesc_bf16(64, 64, true, true);    // H^T dhid
   constexpr uint32_t IDESC_DH = umma::make_idesc_bf16(64, 64, false, true);   // dhid W_c
   constexpr uint32_t IDESC_GT = umma::make_idesc_bf16(64, 8, true, false);    // dhid^T ones
+#ifdef NRM_TC_PROFILE_BWD
+#ifndef PROF_BRANCH
+#define PROF_BRANCH 0
+#endif
+  TCPROF_DECL
+#define BPROF(i) do { if (BRANCH == PROF_BRANCH) TCPROF(i); } while (0)
+#else
+#define BPROF(i) do { } while (0)
+#endif
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* der = der_all + (long long)BRANCH * DER_SIZE;
   const float* Wd_rm = P + off.fc1_w + 192;            // Wd[j][k] = fc1.weight[j][192 + k]
@@ -475,13 +495,13 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
   for (int i = tid; i < (int)T8_BYTES / 2; i += TC_THREADS) reinterpret_cast<__nv_bfloat16*>(sm.ones)[i] = __float2bfloat16_rn(1.0f);
   const float b2 = __ldg(der + DER_B2);
   if (warp == 0) umma::tmem_alloc(&sm.tmem_base, BWD_TMEM_COLS);
-  if (tid == 0) umma::mbar_init(&sm.mbar, 1);
+  if (tid == 0) { umma::mbar_init(&sm.mbar, 1); umma::mbar_init(&sm.mbar_h, 1); }
   umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase_h = 0;
 
   // thread = (column half ch, TMEM sub-partition sp, impression half, row): every epilogue handles the 32 accumulator
   // columns [32 ch, 32 ch + 32) of its row
@@ -502,17 +522,12 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 
   const int npairs_b = (B + 1) / 2;
   int u0, u1;
-#ifdef NRM_TC_PROFILE_BWD
-  TCPROF_DECL
-#define BPROF(i) TCPROF(i)
-#else
-#define BPROF(i) do { } while (0)
-#endif
   // A pair's candidates may be split between two CTAs unless its outputs are accumulated in global memory over
   // history tiles or candidate chunks.  With the label branch a split pair has exactly two contributors to dxh
   // (ranges are at least C units long), each adding its finished partial sum once to a zeroed destination:
   // 0 + a + b == 0 + b + a bit for bit, so the result does not depend on which CTA gets there first.
   unit_range(npairs_b, C, H > 64 || (INPUT_GRADS && C > TC_MAXC), u0, u1);
+  BPROF(9);
   for (int u = u0; u < u1;) {
     const int pb = u / C, ca = u - pb * C, cend = min(C, ca + (u1 - u));   // candidates [ca, cend) of pair pb
     u += cend - ca;
@@ -574,25 +589,42 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         park_pair_vec(sm.tt[0], load_pair_vec(e, tpg, b0, C, c0, TOFF, nimp));
         __syncthreads();                                 // ds and the first pair's vectors visible
         BPROF(2);
+        // W_c tiles of candidate c: the pipelined kernel alternates between two buffers
+        auto wc_tile = [&](int c, int q) -> unsigned char* { return (PIPE && (c & 1)) ? sm.opW2[q] : sm.opBD[0][q]; };
+        auto issue_hid = [&](int c, uint64_t* bar) {
+          if (warp == 0 && umma::elect_one()) {
+            umma::fence_after_sync();
+            for (int q = 0; q < nimp; ++q)
+              umma::mma_product<SPLIT, 4>(tmem + BWD_COL_HID + half_off[q], umma::op_tile64_k(umma::smem_u32(sm.opA[q])),
+                                          umma::op_tile64_k(umma::smem_u32(wc_tile(c, q))), IDESC_HID, false);
+            umma::mma_commit(bar);
+          }
+        };
+        if (PIPE) {                                        // prologue: hid product of the chunk's first candidate
+          build_Wc_pair<NP>(sm.wda, sm.tt[0], nimp, wc_tile(0, 0), wc_tile(0, 1));
+          umma::fence_async_smem();
+          umma::fence_before_sync();
+          __syncthreads();
+          issue_hid(0, &sm.mbar_h);
+        }
         for (int c = 0; c < nc; ++c) {
           const long long rcm = bmine * C + c0 + c;
           const float* tt = sm.tt[c & 1];
           PairVec nxt{0.f, 0.f};
           if (c + 1 < nc) nxt = load_pair_vec(e, tpg, b0, C, c0 + c + 1, TOFF, nimp);     // one pair ahead
-          build_Wc_pair<NP>(sm.wda, tt, nimp, sm.opBD[0][0], sm.opBD[0][1]);
-          BPROF(3);
-          umma::fence_async_smem();
-          umma::fence_before_sync();
-          __syncthreads();                               // (1) operands visible; previous S^T / Gt reads done
-          if (warp == 0 && umma::elect_one()) {
-            umma::fence_after_sync();
-            for (int q = 0; q < nimp; ++q)
-              umma::mma_product<SPLIT, 4>(tmem + BWD_COL_HID + half_off[q], umma::op_tile64_k(umma::smem_u32(sm.opA[q])),
-                                          umma::op_tile64_k(umma::smem_u32(sm.opBD[0][q])), IDESC_HID, false);
-            umma::mma_commit(&sm.mbar);
+          if (!PIPE) {
+            build_Wc_pair<NP>(sm.wda, tt, nimp, sm.opBD[0][0], sm.opBD[0][1]);
+            BPROF(3);
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();                               // (1) operands visible; previous S^T / Gt reads done
+            issue_hid(c, &sm.mbar);
+            umma::mbar_wait(&sm.mbar, phase);
+            phase ^= 1;
+          } else {
+            umma::mbar_wait(&sm.mbar_h, phase_h);          // issued one candidate ago, ran under epilogue 2
+            phase_h ^= 1;
           }
-          umma::mbar_wait(&sm.mbar, phase);
-          phase ^= 1;
           umma::fence_after_sync();
           BPROF(4);
           // ---- epilogue 1: thread = (column half, impression half, history row)
@@ -633,7 +665,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
               const umma::Operand h_mn = umma::op_tile64_mn(umma::smem_u32(sm.opA[q]));
               const umma::Operand d_mn = umma::op_tile64_mn(umma::smem_u32(sm.opBD[DH][q]));
               const umma::Operand d_k = umma::op_tile64_k(umma::smem_u32(sm.opBD[DH][q]));
-              const umma::Operand w_mn = umma::op_tile64_mn(umma::smem_u32(sm.opBD[0][q]));
+              const umma::Operand w_mn = umma::op_tile64_mn(umma::smem_u32(wc_tile(c, q)));
               umma::mma_product<SPLIT, 4>(tmem + BWD_COL_S + half_off[q], h_mn, d_mn, IDESC_ST, false);
               if (!DA_IN_REGS) umma::mma_product<SPLIT, 4>(tmem + BWD_COL_DA + half_off[q], h_mn, d_mn, IDESC_ST, da_started[q]);
               if (INPUT_GRADS) umma::mma_product<SPLIT, 4>(tmem + BWD_COL_DH + half_off[q], d_k, w_mn, IDESC_DH, dh_started);
@@ -644,7 +676,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
                 for (int t = 0; t < NP; ++t)
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks)
-                    umma::mma_bf16(tmem + BWD_COL_HID + half_off[q], d_mn.desc + (uint64_t)(t * d_mn.part16 + ks * d_mn.kstep16),
+                    umma::mma_bf16(tmem + COL_GT + half_off[q], d_mn.desc + (uint64_t)(t * d_mn.part16 + ks * d_mn.kstep16),
                                    one.desc + (uint64_t)(ks * one.kstep16), IDESC_GT, (t > 0 || ks > 0) ? 1u : 0u);
               }
             }
@@ -652,6 +684,15 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
           }
           dh_started = true;
           for (int q = 0; q < nimp; ++q) da_started[q] = true;
+          if (PIPE && c + 1 < nc) {
+            // under the products just issued: W_c of the next candidate into the other buffer, its hid product queued
+            build_Wc_pair<NP>(sm.wda, sm.tt[(c + 1) & 1], nimp, wc_tile(c + 1, 0), wc_tile(c + 1, 1));
+            BPROF(3);
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();
+            issue_hid(c + 1, &sm.mbar_h);
+          }
           umma::mbar_wait(&sm.mbar, phase);
           phase ^= 1;
           umma::fence_after_sync();
@@ -683,7 +724,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
               }
             }
             if (ch == 0) {
-              const float gt = umma::tmem_ld1(my_tmem + BWD_COL_HID);
+              const float gt = umma::tmem_ld1(my_tmem + COL_GT);
               if (act) {
                 float* gdst = dtp + rcm * 64 + row;
                 if (r0 == 0) *gdst = gt; else *gdst += gt;
@@ -719,14 +760,22 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
         umma::tmem_ld32(my_tmem + BWD_COL_DH + cb * 32, v);
         if (act && r0 + row < H) {
           float* dstf = dxh + (bmine * H + r0 + row) * 64 + cb * 32;
+          // attention scores of this row (both column halves), once
+          float srow[TC_MAXC];
+#pragma unroll
+          for (int c = 0; c < TC_MAXC; ++c)
+            srow[c] = (single_chunk && c < ncs) ? sm.sc[((0 * 2 + half) * TC_MAXC + c) * 64 + row] + sm.sc[((1 * 2 + half) * TC_MAXC + c) * 64 + row] : 0.f;
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
             float4 a = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
             if (single_chunk) {
-              for (int c = 0; c < ncs; ++c) {
-                const float s = sm.sc[((0 * 2 + half) * TC_MAXC + c) * 64 + row] + sm.sc[((1 * 2 + half) * TC_MAXC + c) * 64 + row];
-                const float4 dp = *reinterpret_cast<const float4*>(sm.dpf + (half * TC_MAXC + c) * 64 + cb * 32 + 4 * k4);
-                a.x = fmaf(s, dp.x, a.x); a.y = fmaf(s, dp.y, a.y); a.z = fmaf(s, dp.z, a.z); a.w = fmaf(s, dp.w, a.w);
+#pragma unroll
+              for (int c = 0; c < TC_MAXC; ++c) {
+                if (c < ncs) {
+                  const float s = srow[c];
+                  const float4 dp = *reinterpret_cast<const float4*>(sm.dpf + (half * TC_MAXC + c) * 64 + cb * 32 + 4 * k4);
+                  a.x = fmaf(s, dp.x, a.x); a.y = fmaf(s, dp.y, a.y); a.z = fmaf(s, dp.z, a.z); a.w = fmaf(s, dp.w, a.w);
+                }
               }
             } else {
               const float4 g = *reinterpret_cast<float4*>(dstf + 4 * k4);
@@ -804,6 +853,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
     }
   }
   __syncthreads();
+  BPROF(10);
   if (warp == 0) umma::tmem_dealloc(tmem, BWD_TMEM_COLS);
 }
 
@@ -1027,9 +1077,14 @@ umma_selftest_kernel(const float* __restrict__ a0, const float* __restrict__ a1,
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
+// weights only (no dependence on the batch)
 int launch_attention_prep(const float* P, Workspace& w, cudaStream_t s) {
   att_prep_kernel<<<dim3(4, 2), 256, 0, s>>>(P, w.att_derived);
   NRM_LAUNCH_CHECK("att_prep_kernel");
+  return NRM_OK;
+}
+// needs the candidate rows of e written by embed_rows_kernel
+int launch_candidate_tp(const float* P, Workspace& w, cudaStream_t s) {
   candidate_tp_kernel<<<dim3((unsigned)((w.R + 31) / 32), 2), 256, 0, s>>>(P, w.e, w.R, w.tp);
   NRM_LAUNCH_CHECK("candidate_tp_kernel");
   return NRM_OK;
@@ -1205,15 +1260,15 @@ extern "C" int nrm_debug_mma_microbench(long long* out, int variant, int reps, i
   return NRM_OK;
 }
 
-extern "C" int nrm_debug_tcprof(long long* host_out16) {
+extern "C" int nrm_debug_tcprof(long long* host_out32) {
 #ifdef NRM_TC_PROFILE
-  long long zero[16] = {0};
+  long long zero[32] = {0};
   NRM_CUDA(cudaDeviceSynchronize());
-  NRM_CUDA(cudaMemcpyFromSymbol(host_out16, nrm::g_tcprof, sizeof(zero)));
+  NRM_CUDA(cudaMemcpyFromSymbol(host_out32, nrm::g_tcprof, sizeof(zero)));
   NRM_CUDA(cudaMemcpyToSymbol(nrm::g_tcprof, zero, sizeof(zero)));
   return NRM_OK;
 #else
-  (void)host_out16;
+  (void)host_out32;
   set_error("nrm_debug_tcprof: library built without -DNRM_TC_PROFILE");
   return NRM_EUNSUPPORTED;
 #endif

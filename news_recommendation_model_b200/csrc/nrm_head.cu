@@ -65,18 +65,27 @@ bn_finalize_kernel(const double* __restrict__ sums, long long rows, int training
 __global__ void __launch_bounds__(256)
 bn_bwd_combine_kernel(const float* __restrict__ dz, const float* __restrict__ e, const float* __restrict__ mean,
                       const float* __restrict__ rstd, const float* __restrict__ gamma, const double* __restrict__ sums,
-                      long long rows, int training, long long total, float* __restrict__ de) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= total) return;
-  const int n = (int)(i % E);
-  const float rs = rstd[n], g = gamma[n];
-  float v = dz[i];
-  if (training) {
-    const float m1 = (float)(sums[n] / (double)rows), m2 = (float)(sums[E + n] / (double)rows);
-    const float xh = (e[i] - mean[n]) * rs;
-    v = v - m1 - xh * m2;
+                      long long rows, int training, long long total4, float* __restrict__ de) {
+  // four consecutive columns per thread (264 = 66 x 4: a float4 never straddles a row)
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total4; i += (long long)gridDim.x * 256) {
+    const int n = (int)(i % (E / 4)) * 4;
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + n), g = __ldg(reinterpret_cast<const float4*>(gamma + n));
+    float4 v = __ldg(reinterpret_cast<const float4*>(dz) + i);
+    if (training) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(e) + i), mu = *reinterpret_cast<const float4*>(mean + n);
+      const float m1[4] = {(float)(sums[n] / (double)rows), (float)(sums[n + 1] / (double)rows), (float)(sums[n + 2] / (double)rows),
+                           (float)(sums[n + 3] / (double)rows)};
+      const float m2[4] = {(float)(sums[E + n] / (double)rows), (float)(sums[E + n + 1] / (double)rows),
+                           (float)(sums[E + n + 2] / (double)rows), (float)(sums[E + n + 3] / (double)rows)};
+      v.x = v.x - m1[0] - (x.x - mu.x) * rs.x * m2[0];
+      v.y = v.y - m1[1] - (x.y - mu.y) * rs.y * m2[1];
+      v.z = v.z - m1[2] - (x.z - mu.z) * rs.z * m2[2];
+      v.w = v.w - m1[3] - (x.w - mu.w) * rs.w * m2[3];
+    }
+    float4 d = reinterpret_cast<float4*>(de)[i];
+    d.x += rs.x * g.x * v.x; d.y += rs.y * g.y * v.y; d.z += rs.z * g.z * v.z; d.w += rs.w * g.w * v.w;
+    reinterpret_cast<float4*>(de)[i] = d;
   }
-  de[i] += rs * g * v;
 }
 
 // ---------------------------------------------------------------------------------
@@ -107,9 +116,10 @@ int launch_head_backward(const float* P, Workspace& w, const float* dlogits, flo
 
 int launch_bn_backward_combine(const float* P, Workspace& w, int training, const double* bn_bwd_sums,
                                long long global_rows, cudaStream_t s) {
-  const long long total = w.R * E;
-  bn_bwd_combine_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(w.dz, w.e, w.mean, w.rstd, P + P_BN_W, bn_bwd_sums,
-                                                                  global_rows, training, total, w.de);
+  const long long total4 = w.R * (E / 4);
+  const long long blocks = min((total4 + 255) / 256, (long long)sm_count() * 8);
+  bn_bwd_combine_kernel<<<(int)blocks, 256, 0, s>>>(w.dz, w.e, w.mean, w.rstd, P + P_BN_W, bn_bwd_sums,
+                                                   global_rows, training, total4, w.de);
   NRM_LAUNCH_CHECK("bn_bwd_combine_kernel");
   return NRM_OK;
 }

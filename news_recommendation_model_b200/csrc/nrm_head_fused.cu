@@ -19,11 +19,16 @@ constexpr int LDW = 268;           // row stride of the 264-wide shared buffers 
 constexpr int LDN = 68;            // row stride of the 66-wide shared buffers
 
 constexpr int WCHUNK = 64 * HID;   // floats per staged weight chunk: 64 contraction rows x 66 or 16 x 264
+constexpr int W_STAGES = 3;        // ring depth: chunk g is multiplied while g + 1 and g + 2 are in flight
+constexpr int W_LAYER_CHUNKS = 5;  // ceil(264 / 64) = ceil(66 / 16) = 5 chunks per layer
+constexpr int W_CHUNKS = 5 * W_LAYER_CHUNKS;
 struct HeadSmem {
   __align__(16) float w0[HT_ROWS * LDW];
   __align__(16) float w1[HT_ROWS * LDW];   // forward: the e tile; backward: cross row-group reduction scratch [4][2][264]
   __align__(16) float nb[HT_ROWS * LDN];
-  __align__(16) float wbuf[2][WCHUNK];   // double-buffered weight chunks (cp.async)
+  __align__(16) float wbuf[W_STAGES][WCHUNK];   // ring of weight chunks (cp.async, two chunks in flight)
+  const float* csrc[W_CHUNKS];           // global source of weight chunk g (all five layers of the kernel, in order)
+  int cfloats[W_CHUNKS];                 // its size
 };
 
 // Transposed copies of the five matrices for the forward pass: wt = [G1^T | G2^T | M1^T | M2^T | O1^T], each stored
@@ -52,31 +57,54 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// acc[i][q] += sum_k in[(rg*8+i)][k] * W[k][n + 66 q]   (W = [K][66 NQ] in global memory, output index contiguous).
-// The weight rows stream through shared memory in chunks of KC contraction rows (16.9 KB), double-buffered with
-// cp.async so that the next chunk lands while the current one is multiplied.  Called by EVERY thread of the CTA
-// (it synchronises); threads with work == false only help with the copies.
+// The weights of the five layers a kernel walks through stream through shared memory as ONE sequence of 25 chunks
+// (64 x 66 or 16 x 264 floats, 16.9 KB): chunk g lands in ring slot g % 3 while chunks g + 1 and g + 2 are in flight,
+// across layer boundaries, so a layer never starts with a cold fetch.  weight_stream_init() fills the chunk table from
+// the five (matrix, K, NOUT) triples and issues the first two chunks.
+struct HeadLayerDesc { const float* W; int K; int nout; };
+
+__device__ __forceinline__ void weight_chunk_issue(HeadSmem& sm, int g) {
+  if (g < W_CHUNKS) {
+    const float* src = sm.csrc[g];
+    float* dst = sm.wbuf[g % W_STAGES];
+    const int n4 = sm.cfloats[g] >> 2;
+    for (int i = threadIdx.x; i < n4; i += HT_THREADS) cp_async16(dst + 4 * i, src + 4 * i);
+  }
+  cp_async_commit();                                       // every thread commits one group per chunk index
+}
+
+__device__ __forceinline__ void weight_stream_init(HeadSmem& sm, const HeadLayerDesc (&layers)[5]) {
+  if (threadIdx.x < W_CHUNKS) {
+    const int l = threadIdx.x / W_LAYER_CHUNKS, c = threadIdx.x - l * W_LAYER_CHUNKS;
+    const int kc = WCHUNK / layers[l].nout;
+    const int rows = min(kc, layers[l].K - c * kc);
+    sm.csrc[threadIdx.x] = layers[l].W + (long long)c * kc * layers[l].nout;
+    sm.cfloats[threadIdx.x] = rows * layers[l].nout;
+  }
+  __syncthreads();
+  weight_chunk_issue(sm, 0);
+  weight_chunk_issue(sm, 1);
+}
+
+// acc[i][q] += sum_k in[(rg*9+i)][k] * W[k][n + 66 q]   (W = [K][66 NQ], output index contiguous), W = layer `layer` of the
+// kernel's weight stream.  Called by EVERY thread of the CTA (it synchronises); threads with work == false only help
+// with the copies.  One __syncthreads per chunk: it publishes chunk g and retires chunk g - 1, whose slot the chunk
+// issued right after it (g + 2) overwrites.
 template <int K, int NQ, int LDI>
-__device__ __forceinline__ void head_layer(const float* in, const float* __restrict__ W, float (*wbuf)[WCHUNK], bool work, int rg, int n,
-                                           float acc[HT_RPT][NQ]) {
+__device__ __forceinline__ void head_layer(const float* in, HeadSmem& sm, int layer, bool work, int rg, int n, float acc[HT_RPT][NQ]) {
   constexpr int NOUT = HID * NQ;
   constexpr int KC = WCHUNK / NOUT;                      // 64 (NQ = 1) or 16 (NQ = 4)
   constexpr int NCH = (K + KC - 1) / KC;
+  static_assert(NCH == W_LAYER_CHUNKS, "chunk table assumes five chunks per layer");
   const float* inr = in + rg * HT_RPT * LDI;
-  auto prefetch = [&](int c) {
-    const int rows = (K - c * KC) < KC ? (K - c * KC) : KC;
-    const float* src = W + (long long)c * KC * NOUT;
-    float* dst = wbuf[c & 1];
-    for (int i = threadIdx.x; i < rows * NOUT / 4; i += HT_THREADS) cp_async16(dst + 4 * i, src + 4 * i);
-    cp_async_commit();
-  };
-  prefetch(0);
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
-    if (c + 1 < NCH) { prefetch(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();                                     // chunk c visible to every thread
+    const int g = layer * W_LAYER_CHUNKS + c;
+    cp_async_wait<1>();                                  // chunk g has landed (g + 1 may still be in flight)
+    __syncthreads();
+    weight_chunk_issue(sm, g + 2);
     if (work) {
-      const float* wb = wbuf[c & 1];
+      const float* wb = sm.wbuf[g % W_STAGES];
       const int kc = (K - c * KC) < KC ? (K - c * KC) : KC;
       const int kc4 = kc & ~3;
       const float* inc = inr + c * KC;
@@ -111,7 +139,6 @@ __device__ __forceinline__ void head_layer(const float* in, const float* __restr
         }
       }
     }
-    __syncthreads();                                     // chunk buffer (c & 1) free for chunk c + 2
   }
 }
 
@@ -136,6 +163,10 @@ head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean,
   const int tid = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * HT_ROWS;
   const int nr = (int)min((long long)HT_ROWS, R - r0);
+  {
+    const HeadLayerDesc layers[5] = {{wt + WT_G1, E, HID}, {wt + WT_G2, HID, E}, {wt + WT_M1, E, HID}, {wt + WT_M2, HID, E}, {wt + WT_O1, E, HID}};
+    weight_stream_init(sm, layers);
+  }
   // e tile -> w1 (kept for the gating product), z = BatchNorm(e) -> w0.  All loads of the tile are issued first.
   {
     constexpr int NV = HT_ROWS * (E / 4), IT = (NV + HT_THREADS - 1) / HT_THREADS;
@@ -180,13 +211,13 @@ head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean,
 
   {  // gate.fc1
     float acc[HT_RPT][1]; zero_acc<1>(acc);
-    head_layer<E, 1, LDW>(sm.w0, wt + WT_G1, sm.wbuf, work, rg, n, acc);
+    head_layer<E, 1, LDW>(sm.w0, sm, 0, work, rg, n, acc);
     if (work) narrow_out(acc, P + P_GATE_FC1_B, a1g);
   }
   __syncthreads();
   {  // gate.fc2; x = gate * e -> w0
     float acc[HT_RPT][4]; zero_acc<4>(acc);
-    head_layer<HID, 4, LDN>(sm.nb, wt + WT_G2, sm.wbuf, work, rg, n, acc);
+    head_layer<HID, 4, LDN>(sm.nb, sm, 1, work, rg, n, acc);
     if (work) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -204,13 +235,13 @@ head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean,
   __syncthreads();
   {  // mlp.fc1
     float acc[HT_RPT][1]; zero_acc<1>(acc);
-    head_layer<E, 1, LDW>(sm.w0, wt + WT_M1, sm.wbuf, work, rg, n, acc);
+    head_layer<E, 1, LDW>(sm.w0, sm, 2, work, rg, n, acc);
     if (work) narrow_out(acc, P + P_MLP_FC1_B, a2g);
   }
   __syncthreads();
   {  // mlp.fc2 -> y -> w0
     float acc[HT_RPT][4]; zero_acc<4>(acc);
-    head_layer<HID, 4, LDN>(sm.nb, wt + WT_M2, sm.wbuf, work, rg, n, acc);
+    head_layer<HID, 4, LDN>(sm.nb, sm, 3, work, rg, n, acc);
     if (work) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -228,7 +259,7 @@ head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean,
   __syncthreads();
   {  // out_mlp.fc1
     float acc[HT_RPT][1]; zero_acc<1>(acc);
-    head_layer<E, 1, LDW>(sm.w0, wt + WT_O1, sm.wbuf, work, rg, n, acc);
+    head_layer<E, 1, LDW>(sm.w0, sm, 4, work, rg, n, acc);
     if (work) narrow_out(acc, P + P_OUT_FC1_B, a3g);
   }
   __syncthreads();
@@ -266,6 +297,12 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
   const int rg = work ? tid / HID : 0, n = work ? tid % HID : 0;
   const int rb = rg * HT_RPT;
   float* red = sm.w1;
+  {
+    // data-gradient chain: the nn.Linear weights in their natural [out][in] layout (the contraction runs over `out`)
+    const HeadLayerDesc layers[5] = {{P + P_OUT_FC1_W, HID, E}, {P + P_MLP_FC2_W, E, HID}, {P + P_MLP_FC1_W, HID, E},
+                                     {P + P_GATE_FC2_W, E, HID}, {P + P_GATE_FC1_W, HID, E}};
+    weight_stream_init(sm, layers);
+  }
 
   // da3 = dr * O2 * gelu'(a3) -> nb; dO2 / do2 partial sums
   if (work) {
@@ -294,7 +331,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
 
   {  // dy = da3 O1 -> w0
     float acc[HT_RPT][4]; zero_acc<4>(acc);
-    head_layer<HID, 4, LDN>(sm.nb, P + P_OUT_FC1_W, sm.wbuf, work, rg, n, acc);
+    head_layer<HID, 4, LDN>(sm.nb, sm, 0, work, rg, n, acc);
     if (work) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -309,7 +346,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
   __syncthreads();
   {  // da2 = (dy M2) * gelu'(a2) -> nb
     float acc[HT_RPT][1]; zero_acc<1>(acc);
-    head_layer<E, 1, LDW>(sm.w0, P + P_MLP_FC2_W, sm.wbuf, work, rg, n, acc);
+    head_layer<E, 1, LDW>(sm.w0, sm, 1, work, rg, n, acc);
     if (work) {
 #pragma unroll
       for (int i = 0; i < HT_RPT; ++i) {
@@ -325,7 +362,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
   __syncthreads();
   {  // dx = da2 M1;  dgate = dx * e -> w0;  de (direct path) = dx * gate
     float acc[HT_RPT][4]; zero_acc<4>(acc);
-    head_layer<HID, 4, LDN>(sm.nb, P + P_MLP_FC1_W, sm.wbuf, work, rg, n, acc);
+    head_layer<HID, 4, LDN>(sm.nb, sm, 2, work, rg, n, acc);
     if (work) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -346,7 +383,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
   __syncthreads();
   {  // da1 = (dgate G2) * gelu'(a1) -> nb
     float acc[HT_RPT][1]; zero_acc<1>(acc);
-    head_layer<E, 1, LDW>(sm.w0, P + P_GATE_FC2_W, sm.wbuf, work, rg, n, acc);
+    head_layer<E, 1, LDW>(sm.w0, sm, 3, work, rg, n, acc);
     if (work) {
 #pragma unroll
       for (int i = 0; i < HT_RPT; ++i) {
@@ -362,7 +399,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
   __syncthreads();
   {  // dz = da1 G1; BatchNorm partial sums of dz and dz * xhat over this tile's rows
     float acc[HT_RPT][4]; zero_acc<4>(acc);
-    head_layer<HID, 4, LDN>(sm.nb, P + P_GATE_FC1_W, sm.wbuf, work, rg, n, acc);
+    head_layer<HID, 4, LDN>(sm.nb, sm, 4, work, rg, n, acc);
     if (work) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -573,6 +610,13 @@ int head_wgrad_chunks(long long R) {
   return n < 1 ? 1 : n;
 }
 
+// transposed copies of the five matrices for the forward kernel: weights only, enqueued ahead of the encoder
+int launch_head_transpose(const float* P, Workspace& w, cudaStream_t s) {
+  head_transpose_kernel<<<dim3(8, 5), 256, 0, s>>>(P, w.head_wt);
+  NRM_LAUNCH_CHECK("head_transpose_kernel");
+  return NRM_OK;
+}
+
 int launch_head_forward_fused(const float* P, Workspace& w, int keep, float* logits, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
@@ -580,8 +624,6 @@ int launch_head_forward_fused(const float* P, Workspace& w, int keep, float* log
     NRM_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     configured = true;
   }
-  head_transpose_kernel<<<dim3(8, 5), 256, 0, s>>>(P, w.head_wt);
-  NRM_LAUNCH_CHECK("head_transpose_kernel");
   head_forward_kernel<<<head_tiles(w.R), HT_THREADS, sizeof(HeadSmem), s>>>(w.e, w.mean, w.rstd, P, w.head_wt, w.R, keep, w.a1, w.gate, w.a2,
                                                                           w.y, w.a3, logits);
   NRM_LAUNCH_CHECK("head_forward_kernel");

@@ -26,12 +26,14 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
 int launch_attention_finish(const float* P, Workspace& w, int branch, int precision, float* grads, cudaStream_t s);
 
 // nrm_attention_tc.cu  (precision = bf16 / bf16x3: tcgen05 tensor-core tiles)
-int launch_attention_prep(const float* P, Workspace& w, cudaStream_t s);          // derived weights -> w.att_derived
+int launch_attention_prep(const float* P, Workspace& w, cudaStream_t s);          // derived weights -> w.att_derived (weights only)
+int launch_candidate_tp(const float* P, Workspace& w, cudaStream_t s);            // per-candidate tp -> w.tp (needs w.e target rows)
 int launch_attention_forward_tc(const BatchPtrs& in, Workspace& w, int branch, int precision, cudaStream_t s);
 int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
 int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaStream_t s);   // both branches
 
 // nrm_head_fused.cu
+int launch_head_transpose(const float* P, Workspace& w, cudaStream_t s);          // transposed head matrices -> w.head_wt (weights only)
 int launch_head_forward_fused(const float* P, Workspace& w, int keep, float* logits, cudaStream_t s);
 int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogits, float* grads, cudaStream_t s);   // -> w.bn_bwd_sums, w.dz, w.de
 

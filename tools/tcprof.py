@@ -15,13 +15,13 @@ for prec in sys.argv[1:] or ['bf16x3', 'bf16']:
     model = nrm.UserModel(1000); model.load_state_dict(load_weights('train'), strict=False)
     model.to('cuda').eval().set_precision(prec)
     b = make_batch(1024, 50, 5, seed=1, user_num=1000).to('cuda')
-    buf = (ctypes.c_longlong * 16)()
+    buf = (ctypes.c_longlong * 32)()
     with torch.no_grad():
         model(b.x_history, b.x_target, b.x_global)
         lib.nrm_debug_tcprof(buf)
         model(b.x_history, b.x_target, b.x_global)
     _lib.check(lib.nrm_debug_tcprof(buf), 'tcprof')
-    tot = sum(buf)
+    tot = sum(buf[:16])
     print(f'{prec}: CTA 0, both branches, {tot} cycles total')
     for i, n in enumerate(names):
         print(f'   {n:32s} {buf[i]:9d}  {100.0 * buf[i] / max(tot, 1):5.1f}%')
