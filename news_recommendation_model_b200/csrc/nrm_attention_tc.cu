@@ -860,9 +860,9 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 // Sum the per-CTA partials (fixed order) and write the attention-MLP gradients that do not depend on tp:
 //   fc1.weight grad blocks: [:, 0:64] = dA, [:, 192:256] = dWd   (the Bm-dependent blocks are completed by
 //   attention_tp_grad_kernel); fc2.weight = dw2; fc2.bias = db2.   Partials are transposed ([k][j]).
-__global__ void __launch_bounds__(1024)
-attention_tc_compose_kernel(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads,
-                            float* __restrict__ dA_all) {
+__device__ __forceinline__ void
+attention_tc_compose_block(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads,
+                           float* __restrict__ dA_all) {
   const int branch = blockIdx.y;
   const AttOffsets off = branch == 0 ? ATT_LABEL : ATT_TI;
   const float* part = part_all + (long long)branch * ATT_TC_PARTS_MAX * TC_PARTIAL;
@@ -914,9 +914,9 @@ attention_tc_compose_kernel(const float* __restrict__ part_all, int nparts0, int
 // The tp = Bm t + b1 path, over the R candidate rows: dBm[j][k] = sum_r dtp[r][j] t[r][k], db1[j] = sum_r dtp[r][j],
 // and (label branch) dxt[r][k] += sum_j dtp[r][j] Bm[j][k].  32 rows per CTA -> partials, summed by the finish kernel.
 constexpr int TPG_ROWS = 32, TPG_PART = 4096 + 64;
-__global__ void __launch_bounds__(256)
-attention_tp_grad_kernel(const float* __restrict__ dtp_all, const float* __restrict__ e, long long R,
-                         const float* __restrict__ P, float* __restrict__ dxt, float* __restrict__ part_all, int nparts) {
+__device__ __forceinline__ void
+attention_tp_grad_block(int block, const float* __restrict__ dtp_all, const float* __restrict__ e, long long R,
+                        const float* __restrict__ P, float* __restrict__ dxt, float* __restrict__ part_all, int nparts) {
   const int branch = blockIdx.y;
   const float* dtp = dtp_all + (long long)branch * R * 64;
   const int toff = branch == 0 ? E_XT : E_PCAT;
@@ -927,7 +927,7 @@ attention_tp_grad_kernel(const float* __restrict__ dtp_all, const float* __restr
   __shared__ float st[TPG_ROWS][64];    // t rows
   __shared__ float sB[64][65];          // Bm[j][k] = Wb + Wc
   const int tid = threadIdx.x;
-  const long long r0 = (long long)blockIdx.x * TPG_ROWS;
+  const long long r0 = (long long)block * TPG_ROWS;
   const int nr = (int)min((long long)TPG_ROWS, R - r0);
   for (int i = tid; i < TPG_ROWS * 64; i += 256) {
     const int r = i >> 6, k = i & 63;
@@ -961,7 +961,7 @@ attention_tp_grad_kernel(const float* __restrict__ dtp_all, const float* __restr
         for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], tv[b], acc[a][b]);
       }
     }
-    float* out = part + (long long)blockIdx.x * TPG_PART;
+    float* out = part + (long long)block * TPG_PART;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       *reinterpret_cast<float4*>(out + (4 * tj + a) * 64 + 4 * tk) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
@@ -982,6 +982,21 @@ attention_tp_grad_kernel(const float* __restrict__ dtp_all, const float* __restr
 #pragma unroll
       for (int i = 0; i < 8; ++i) dxt[(r0 + r) * 64 + kq + 8 * i] += v[i];
     }
+  }
+}
+
+// One launch for the two independent reductions: blocks [0, 129) sum the per-CTA partials of the backward kernels,
+// blocks [129, 129 + nparts) (their first 256 threads) take 32 candidate rows each through the tp path.
+constexpr int COMPOSE_BLOCKS = 129;
+__global__ void __launch_bounds__(1024)
+attention_finish_kernel(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads, float* __restrict__ dA_all,
+                        const float* __restrict__ dtp_all, const float* __restrict__ e, long long R, const float* __restrict__ P,
+                        float* __restrict__ dxt, float* __restrict__ tp_part, int nparts) {
+  if (blockIdx.x < COMPOSE_BLOCKS) {
+    attention_tc_compose_block(part_all, nparts0, nparts1, grads, dA_all);
+  } else {
+    if (threadIdx.x >= 256) return;
+    attention_tp_grad_block(blockIdx.x - COMPOSE_BLOCKS, dtp_all, e, R, P, dxt, tp_part, nparts);
   }
 }
 
@@ -1145,11 +1160,10 @@ int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace&
 
 // both branches at once (after both backward kernels)
 int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaStream_t s) {
-  attention_tc_compose_kernel<<<dim3(129, 2), 1024, 0, s>>>(w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA);
-  NRM_LAUNCH_CHECK("attention_tc_compose_kernel");
   const int nparts = (int)((w.R + TPG_ROWS - 1) / TPG_ROWS);
-  attention_tp_grad_kernel<<<dim3(nparts, 2), 256, 0, s>>>(w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
-  NRM_LAUNCH_CHECK("attention_tp_grad_kernel");
+  attention_finish_kernel<<<dim3(COMPOSE_BLOCKS + nparts, 2), 1024, 0, s>>>(w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA,
+                                                                             w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
+  NRM_LAUNCH_CHECK("attention_finish_kernel");
   attention_tp_finish_kernel<<<dim3(TPG_PART / 64, 2), 256, 0, s>>>(w.tp_part, nparts, w.att_dA, grads);
   NRM_LAUNCH_CHECK("attention_tp_finish_kernel");
   return NRM_OK;

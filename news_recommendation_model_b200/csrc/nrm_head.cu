@@ -21,43 +21,18 @@ bn_partial_kernel(const float* __restrict__ e, long long R, int rows_per_chunk, 
   part[((long long)blockIdx.x * 2 + 1) * E + n] = q;
 }
 
-// sums[i] = sum over parts of part[p][i], i < 2*264; block = 66 entries x 4 interleaved groups of partials combined in
-// group order (8 blocks)
-__global__ void __launch_bounds__(264)
+// sums[i] = sum over parts of part[p][i], i < 2*264: one warp per sum, lane l adds parts l, l + 32, ... (all loads in
+// flight at once), then a fixed shuffle tree.
+__global__ void __launch_bounds__(256)
 bn_partial_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ sums) {
-  __shared__ double red[4][66];
-  const int lane = threadIdx.x % 66, grp = threadIdx.x / 66;
-  const int i = blockIdx.x * 66 + lane;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= 2 * E) return;
   double s = 0.0;
-#pragma unroll 4
-  for (int p = grp; p < nparts; p += 4) s += part[(long long)p * 2 * E + i];
-  red[grp][lane] = s;
-  __syncthreads();
-  if (grp == 0) sums[i] = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
-}
-
-// training: batch mean / biased variance from (global) sums; running stats with momentum
-// 0.1 and the unbiased variance (nn.BatchNorm1d);  eval: running statistics.
-__global__ void __launch_bounds__(E)
-bn_finalize_kernel(const double* __restrict__ sums, long long rows, int training, float* __restrict__ run_mean,
-                   float* __restrict__ run_var, long long* __restrict__ nbt, float* __restrict__ mean,
-                   float* __restrict__ rstd) {
-  const int n = threadIdx.x;
-  float m, v;
-  if (training) {
-    const double dm = sums[n] / (double)rows;
-    double dv = sums[E + n] / (double)rows - dm * dm;
-    if (dv < 0.0) dv = 0.0;
-    m = (float)dm; v = (float)dv;
-    const double unbiased = rows > 1 ? dv * (double)rows / (double)(rows - 1) : dv;
-    run_mean[n] = (1.f - BN_MOMENTUM) * run_mean[n] + BN_MOMENTUM * m;
-    run_var[n] = (1.f - BN_MOMENTUM) * run_var[n] + BN_MOMENTUM * (float)unbiased;
-    if (n == 0) *nbt += 1;
-  } else {
-    m = run_mean[n]; v = run_var[n];
-  }
-  mean[n] = m;
-  rstd[n] = 1.0f / sqrtf(v + BN_EPS);
+#pragma unroll 8
+  for (int p = lane; p < nparts; p += 32) s += part[(long long)p * 2 * E + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) sums[i] = s;
 }
 
 // de += rstd * gamma * (dz - mean_r(dz) - xhat * mean_r(dz * xhat))      (training)
@@ -98,16 +73,15 @@ int launch_bn_partial_sums(Workspace& w, cudaStream_t s) {
   const int rp = stat_rows(w.R), nch = stat_chunks(w.R);
   bn_partial_kernel<<<nch, E, 0, s>>>(w.e, w.R, rp, w.stat_part);
   NRM_LAUNCH_CHECK("bn_partial_kernel");
-  bn_partial_reduce_kernel<<<2 * E / 66, 264, 0, s>>>(w.stat_part, nch, w.bn_sums);
+  bn_partial_reduce_kernel<<<(2 * E + 7) / 8, 256, 0, s>>>(w.stat_part, nch, w.bn_sums);
   NRM_LAUNCH_CHECK("bn_partial_reduce_kernel");
   return NRM_OK;
 }
 
 int launch_head_forward(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt, int training, int keep,
                         const double* bn_sums, long long global_rows, float* logits, cudaStream_t s) {
-  bn_finalize_kernel<<<1, E, 0, s>>>(bn_sums, global_rows, training, run_mean, run_var, nbt, w.mean, w.rstd);
-  NRM_LAUNCH_CHECK("bn_finalize_kernel");
-  return launch_head_forward_fused(P, w, keep, logits, s);
+  // the BatchNorm finalisation (batch / running statistics, running-statistics update) is the prologue of the fused kernel
+  return launch_head_forward_fused(P, w, run_mean, run_var, nbt, training, keep, bn_sums, global_rows, logits, s);
 }
 
 int launch_head_backward(const float* P, Workspace& w, const float* dlogits, float* G, cudaStream_t s) {

@@ -154,7 +154,9 @@ __device__ __forceinline__ void zero_acc(float acc[HT_RPT][NQ]) {
 // forward
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(HT_THREADS, 1)
-head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd,
+head_forward_kernel(const float* __restrict__ e, const double* __restrict__ bn_sums, long long bn_rows, int training,
+                    float* __restrict__ run_mean, float* __restrict__ run_var, long long* __restrict__ nbt,
+                    float* __restrict__ mean_out, float* __restrict__ rstd_out,
                     const float* __restrict__ P, const float* __restrict__ wt, long long R, int keep,
                     float* __restrict__ a1g, float* __restrict__ gateg, float* __restrict__ a2g, float* __restrict__ yg,
                     float* __restrict__ a3g, float* __restrict__ logits) {
@@ -177,6 +179,33 @@ head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean,
       ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < NV && r < nr) ev[u] = __ldg(reinterpret_cast<const float4*>(e + (r0 + r) * E) + c4);
     }
+    // BatchNorm1d statistics (models/user_model.py:18,32), every CTA for itself: training = batch mean / biased variance
+    // from the (global) column sums; eval = running statistics.  CTA 0 also publishes them for the backward kernels and
+    // updates the running statistics (momentum 0.1, unbiased variance) as nn.BatchNorm1d does.
+    float* mean = sm.nb;
+    float* rstd = sm.nb + E;
+    if (tid < E) {
+      const int n = tid;
+      float m, v;
+      if (training) {
+        const double dm = bn_sums[n] / (double)bn_rows;
+        double dv = bn_sums[E + n] / (double)bn_rows - dm * dm;
+        if (dv < 0.0) dv = 0.0;
+        m = (float)dm; v = (float)dv;
+        if (blockIdx.x == 0) {
+          const double unbiased = bn_rows > 1 ? dv * (double)bn_rows / (double)(bn_rows - 1) : dv;
+          run_mean[n] = (1.f - BN_MOMENTUM) * run_mean[n] + BN_MOMENTUM * m;
+          run_var[n] = (1.f - BN_MOMENTUM) * run_var[n] + BN_MOMENTUM * (float)unbiased;
+          if (n == 0) *nbt += 1;
+        }
+      } else {
+        m = run_mean[n]; v = run_var[n];
+      }
+      const float rs = 1.0f / sqrtf(v + BN_EPS);
+      mean[n] = m; rstd[n] = rs;
+      if (blockIdx.x == 0) { mean_out[n] = m; rstd_out[n] = rs; }
+    }
+    __syncthreads();
 #pragma unroll
     for (int u = 0; u < IT; ++u) {
       const int i = tid + u * HT_THREADS, r = i / (E / 4), c4 = i - r * (E / 4);
@@ -184,7 +213,7 @@ head_forward_kernel(const float* __restrict__ e, const float* __restrict__ mean,
       const float4 v = ev[u];
       float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nr) {
-        const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+        const float4 mu = reinterpret_cast<const float4*>(mean)[c4], rs = reinterpret_cast<const float4*>(rstd)[c4];
         const float4 ga = __ldg(reinterpret_cast<const float4*>(P + P_BN_W) + c4), be = __ldg(reinterpret_cast<const float4*>(P + P_BN_B) + c4);
         z.x = (v.x - mu.x) * rs.x * ga.x + be.x; z.y = (v.y - mu.y) * rs.y * ga.y + be.y;
         z.z = (v.z - mu.z) * rs.z * ga.z + be.z; z.w = (v.w - mu.w) * rs.w * ga.w + be.w;
@@ -617,15 +646,17 @@ int launch_head_transpose(const float* P, Workspace& w, cudaStream_t s) {
   return NRM_OK;
 }
 
-int launch_head_forward_fused(const float* P, Workspace& w, int keep, float* logits, cudaStream_t s) {
+int launch_head_forward_fused(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt, int training, int keep,
+                              const double* bn_sums, long long bn_rows, float* logits, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     NRM_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     NRM_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     configured = true;
   }
-  head_forward_kernel<<<head_tiles(w.R), HT_THREADS, sizeof(HeadSmem), s>>>(w.e, w.mean, w.rstd, P, w.head_wt, w.R, keep, w.a1, w.gate, w.a2,
-                                                                          w.y, w.a3, logits);
+  head_forward_kernel<<<head_tiles(w.R), HT_THREADS, sizeof(HeadSmem), s>>>(w.e, bn_sums, bn_rows, training, run_mean, run_var, nbt, w.mean,
+                                                                          w.rstd, P, w.head_wt, w.R, keep, w.a1, w.gate, w.a2, w.y, w.a3,
+                                                                          logits);
   NRM_LAUNCH_CHECK("head_forward_kernel");
   return NRM_OK;
 }

@@ -9,37 +9,40 @@
 
 namespace nrm {
 
-constexpr int W1_ROWS = 128, W1_THREADS = 256;
+constexpr int W1_ROWS = 128, W1_THREADS = 256;     // backward tiles
+constexpr int W1F_ROWS = 64, W1F_THREADS = 128;     // forward tiles: 34 KB of shared memory, six CTAs per SM, the whole grid resident
 constexpr int W1_PART = 64 * XIN + 64;          // dW1 [64][66] | db1 [64]
 
 // Asynchronous tile copy (cp.async, 16 bytes per request): every request of the tile is in flight at once; the caller
 // waits with copy_wait() before the __syncthreads() that publishes the tile.
+template <int THREADS = W1_THREADS>
 __device__ __forceinline__ void copy_tile(float* dst, const float* __restrict__ src, int nfloats) {
-  // src is 16-byte aligned (tile starts are multiples of 128 rows); nfloats is a multiple of 2
+  // src is 16-byte aligned (tile starts are multiples of 64 rows); nfloats is a multiple of 2
   const int n4 = nfloats >> 2;
-  for (int i = threadIdx.x; i < n4; i += W1_THREADS) {
+  for (int i = threadIdx.x; i < n4; i += THREADS) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 4 * i);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + 4 * i) : "memory");
   }
-  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += W1_THREADS) dst[i] = __ldg(src + i);
+  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += THREADS) dst[i] = __ldg(src + i);
 }
 __device__ __forceinline__ void copy_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-struct W1SmemFwd { __align__(16) float xs[W1_ROWS * XIN]; __align__(16) float wt[XIN * 64]; };
+struct W1SmemFwd { __align__(16) float xs[W1F_ROWS * XIN]; __align__(16) float wt[XIN * 64]; };
 
-__global__ void __launch_bounds__(W1_THREADS, 2)
+__global__ void __launch_bounds__(W1F_THREADS, 6)
 w1_forward_kernel(const float* __restrict__ xin, const float* __restrict__ P, float* __restrict__ xh, long long NH) {
   extern __shared__ __align__(16) unsigned char w1_raw[];
   W1SmemFwd& sm = *reinterpret_cast<W1SmemFwd*>(w1_raw);
   const int tid = threadIdx.x, rg = tid >> 4, cg = tid & 15;
-  for (int i = tid; i < 64 * XIN; i += W1_THREADS) { const int j = i / XIN, k = i - j * XIN; sm.wt[k * 64 + j] = __ldg(P + P_W1_W + i); }
+  const long long ntiles = (NH + W1F_ROWS - 1) / W1F_ROWS;
+  long long tile = blockIdx.x;
+  if (tile < ntiles) copy_tile<W1F_THREADS>(sm.xs, xin + tile * W1F_ROWS * XIN, (int)min((long long)W1F_ROWS, NH - tile * W1F_ROWS) * XIN);
+  // W1^T while the first tile is in flight
+  for (int i = tid; i < 64 * XIN; i += W1F_THREADS) { const int j = i / XIN, k = i - j * XIN; sm.wt[k * 64 + j] = __ldg(P + P_W1_W + i); }
   const float4 bias = __ldg(reinterpret_cast<const float4*>(P + P_W1_B) + cg);
-  const long long ntiles = (NH + W1_ROWS - 1) / W1_ROWS;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long r0 = tile * W1_ROWS;
-    const int nr = (int)min((long long)W1_ROWS, NH - r0);
-    __syncthreads();
-    copy_tile(sm.xs, xin + r0 * XIN, nr * XIN);
+  for (; tile < ntiles; tile += gridDim.x) {
+    const long long r0 = tile * W1F_ROWS;
+    const int nr = (int)min((long long)W1F_ROWS, NH - r0);
     copy_wait();
     __syncthreads();
     float acc[8][4];
@@ -56,6 +59,9 @@ w1_forward_kernel(const float* __restrict__ xin, const float* __restrict__ P, fl
         acc[i][2] = fmaf(a, w.z, acc[i][2]); acc[i][3] = fmaf(a, w.w, acc[i][3]);
       }
     }
+    __syncthreads();                                  // tile consumed
+    const long long nt = tile + gridDim.x;
+    if (nt < ntiles) copy_tile<W1F_THREADS>(sm.xs, xin + nt * W1F_ROWS * XIN, (int)min((long long)W1F_ROWS, NH - nt * W1F_ROWS) * XIN);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (rg * 8 + i < nr)
@@ -174,9 +180,9 @@ int launch_w1_forward(const float* P, Workspace& w, cudaStream_t s) {
     NRM_CUDA(cudaFuncSetAttribute(w1_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(W1SmemBwd)));
     configured = true;
   }
-  const long long ntiles = (w.NH + W1_ROWS - 1) / W1_ROWS;
-  const int grid = (int)min(ntiles, (long long)4 * sm_count());
-  w1_forward_kernel<<<grid, W1_THREADS, sizeof(W1SmemFwd), s>>>(w.xin_h, P, w.xh, w.NH);
+  const long long ntiles = (w.NH + W1F_ROWS - 1) / W1F_ROWS;
+  const int grid = (int)min(ntiles, (long long)6 * sm_count());
+  w1_forward_kernel<<<grid, W1F_THREADS, sizeof(W1SmemFwd), s>>>(w.xin_h, P, w.xh, w.NH);
   NRM_LAUNCH_CHECK("w1_forward_kernel");
   return NRM_OK;
 }
