@@ -1205,12 +1205,12 @@ mma_microbench_kernel(long long* __restrict__ out, int variant, int reps, int nk
   extern __shared__ __align__(128) unsigned char mb_raw[];
   unsigned char* opA = mb_raw;                       // 128 x 64 bf16 = 16 KB
   unsigned char* opB = mb_raw + 16384;               // 64 x 64 bf16 = 8 KB
-  __shared__ uint64_t mbar;
+  __shared__ uint64_t mbar, mbar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (16384 + 8192) / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(mb_raw)[i] = 0x3c003c00u;
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
-  if (tid == 0) umma::mbar_init(&mbar, 1);
+  if (tid == 0) { umma::mbar_init(&mbar, 1); umma::mbar_init(&mbar2, 1); }
   umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
@@ -1246,6 +1246,26 @@ mma_microbench_kernel(long long* __restrict__ out, int variant, int reps, int nk
       out[0] = t1 - t0; out[1] = t2 - t0;
     }
     umma::mbar_wait(&mbar, 0);
+  } else if (variant == 5) {
+    // two issuing threads (warps 0 and 4), M64 N64 K-major each, disjoint accumulator columns
+    if ((warp == 0 || warp == 4) && umma::elect_one()) {
+      const uint32_t aa = umma::smem_u32(opA), bb = umma::smem_u32(opB);
+      const uint64_t a_k = umma::make_desc(aa, 1024, 128), b_k = umma::make_desc(bb, 1024, 128);
+      uint64_t* bar = warp == 0 ? &mbar : &mbar2;
+      const uint32_t acc = tmem + (warp == 0 ? 0u : 64u);
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll 4
+        for (int ks = 0; ks < nk; ++ks) umma::mma_bf16(acc, a_k + (uint64_t)((ks & 3) * 128), b_k + (uint64_t)((ks & 3) * 128), umma::make_idesc_bf16(64, 64), ks > 0);
+      }
+      t1 = clock64();
+      umma::mma_commit(bar);
+      umma::mbar_wait(bar, 0);
+      t2 = clock64();
+      out[warp == 0 ? 0 : 2] = t1 - t0; out[warp == 0 ? 1 : 3] = t2 - t0;
+    }
+    umma::mbar_wait(&mbar, 0);
+    umma::mbar_wait(&mbar2, 0);
   } else {
     umma::fence_after_sync();
     float acc = 0.f;
@@ -1267,7 +1287,7 @@ mma_microbench_kernel(long long* __restrict__ out, int variant, int reps, int nk
 }  // namespace nrm
 
 extern "C" int nrm_debug_mma_microbench(long long* out, int variant, int reps, int nk, void* stream) {
-  if (!out || variant < 0 || variant > 4 || reps < 1 || nk < 1) { set_error("nrm_debug_mma_microbench: bad argument"); return NRM_EINVAL; }
+  if (!out || variant < 0 || variant > 5 || reps < 1 || nk < 1) { set_error("nrm_debug_mma_microbench: bad argument"); return NRM_EINVAL; }
   const size_t smem = 16384 + 8192;
   mma_microbench_kernel<<<1, TC_THREADS, smem, (cudaStream_t)stream>>>(out, variant, reps, nk);
   NRM_LAUNCH_CHECK("mma_microbench_kernel");
