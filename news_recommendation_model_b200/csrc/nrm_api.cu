@@ -66,7 +66,7 @@ KernelTimer::~KernelTimer() {
 // on the side stream), so its four small launches run under the attention / head kernels instead of after them.
 // Fork and join are ordinary stream events, so the pattern is also valid inside a CUDA-graph capture of the caller's
 // stream.  One side stream + two events per device, created on first use and kept for the life of the process.
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join_tp; bool made; };
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp; bool made; };
 static SideStream g_side[64];
 static SideStream* side_stream() {
   int dev = 0;
@@ -80,6 +80,7 @@ static SideStream* side_stream() {
     if (cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.fork0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.join_tp, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ss.made = true;
   }
   return &ss;
@@ -152,7 +153,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   w.a2 = (float*)take(f * R * HID);
   w.y = (float*)take(f * R * E);
   w.a3 = (float*)take(f * R * HID);
-  w.head_wt = (float*)take(f * 5 * HID * E);
+  w.head_wt = (float*)take(f * (HEAD_WT_W1T + 64 * XIN));
   w.att_derived = (float*)take(f * 2 * 12420);
   w.tp = (float*)take(f * 2 * R * 64);
   if (training) {
@@ -209,8 +210,8 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   const bool tc = precision != NRM_PRECISION_FP32;
   static const bool inline_prep = getenv("NRM_INLINE_PREP") != nullptr;       // A/B switch: weight preparation on the caller's stream
   if (inline_prep) {
-    if (tc) NRM_TRY(launch_attention_prep(P, w, s));
     NRM_TRY(launch_head_transpose(P, w, s));
+    if (tc) NRM_TRY(launch_attention_prep(P, w, s));
     { KernelTimer t("embed_rows", s); NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
     if (mode & NRM_MODE_KEEP_FOR_BWD) {
       NRM_CUDA(cudaEventRecord(ss->fork, s));
@@ -229,8 +230,9 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   // stream under the embedding kernel
   NRM_CUDA(cudaEventRecord(ss->fork0, s));
   NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork0, 0));
+  NRM_TRY(launch_head_transpose(P, w, ss->stream));          // includes w1^T for the history projection below
+  NRM_CUDA(cudaEventRecord(ss->join0, ss->stream));
   if (tc) NRM_TRY(launch_attention_prep(P, w, ss->stream));
-  NRM_TRY(launch_head_transpose(P, w, ss->stream));
   { KernelTimer t("embed_rows", s);
     NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
   // fork: the per-candidate vectors tp (they need the candidate rows of e) run under the w1 projection; then, for the
@@ -244,6 +246,7 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
     NRM_CUDA(cudaEventRecord(ss->join, ss->stream));
   }
   // xh = w1(xin_h)   (user_invariant_interest_model.py:78)
+  NRM_CUDA(cudaStreamWaitEvent(s, ss->join0, 0));            // w1^T ready
   { KernelTimer t("w1_forward", s); NRM_TRY(launch_w1_forward(P, w, s)); }
   NRM_CUDA(cudaStreamWaitEvent(s, ss->join_tp, 0));          // join: derived weights, transposed head matrices, tp
   if (!tc) {

@@ -120,6 +120,7 @@ constexpr int ATT_TC_PARTS_MAX = 512; // CTAs of the tensor-core attention backw
 constexpr int ATT_TC_PARTIAL = 2 * 4096 + 68;   // dA^T | dWd^T | dw2 | db2 floats per CTA
 constexpr int HEAD_WG_CHUNKS_MAX = 64; // row chunks of the head weight-gradient kernel
 constexpr int STAT_BLOCKS = 256;       // row chunks of the column-statistics kernels
+constexpr int HEAD_WT_W1T = 5 * HID * E;      // offset of w1.weight^T [66][64] in Workspace::head_wt (after the five head matrices)
 constexpr int W1_SPLITS = 256;         // most CTAs (= partials) of the w1 backward
 
 struct Workspace {

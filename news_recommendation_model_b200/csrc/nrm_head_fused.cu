@@ -34,13 +34,14 @@ struct HeadSmem {
 // Transposed copies of the five matrices for the forward pass: wt = [G1^T | G2^T | M1^T | M2^T | O1^T], each stored
 // [contraction index][output index] (output contiguous), same element count as the original.
 constexpr int WT_G1 = 0, WT_G2 = HID * E, WT_M1 = 2 * HID * E, WT_M2 = 3 * HID * E, WT_O1 = 4 * HID * E, WT_TOTAL = 5 * HID * E;
+static_assert(WT_TOTAL == HEAD_WT_W1T, "w1^T follows the five head matrices in the transposed-weights buffer");
 
 __global__ void __launch_bounds__(256)
 head_transpose_kernel(const float* __restrict__ P, float* __restrict__ wt) {
-  const int m = blockIdx.y;                                  // matrix
-  const long long src_off[5] = {P_GATE_FC1_W, P_GATE_FC2_W, P_MLP_FC1_W, P_MLP_FC2_W, P_OUT_FC1_W};
-  const int rows = (m == 1 || m == 3) ? E : HID;             // source is [rows][cols] = [out][in]
-  const int cols = (m == 1 || m == 3) ? HID : E;
+  const int m = blockIdx.y;                                  // matrix; 5 = w1.weight [64][66] of the history projection
+  const long long src_off[6] = {P_GATE_FC1_W, P_GATE_FC2_W, P_MLP_FC1_W, P_MLP_FC2_W, P_OUT_FC1_W, P_W1_W};
+  const int rows = m == 5 ? 64 : (m == 1 || m == 3) ? E : HID;             // source is [rows][cols] = [out][in]
+  const int cols = m == 5 ? XIN : (m == 1 || m == 3) ? HID : E;
   const float* src = P + src_off[m];
   float* dst = wt + (long long)m * HID * E;                  // [cols][rows]
   for (int i = blockIdx.x * 256 + threadIdx.x; i < rows * cols; i += gridDim.x * 256) {
@@ -641,7 +642,7 @@ int head_wgrad_chunks(long long R) {
 
 // transposed copies of the five matrices for the forward kernel: weights only, enqueued ahead of the encoder
 int launch_head_transpose(const float* P, Workspace& w, cudaStream_t s) {
-  head_transpose_kernel<<<dim3(8, 5), 256, 0, s>>>(P, w.head_wt);
+  head_transpose_kernel<<<dim3(8, 6), 256, 0, s>>>(P, w.head_wt);
   NRM_LAUNCH_CHECK("head_transpose_kernel");
   return NRM_OK;
 }

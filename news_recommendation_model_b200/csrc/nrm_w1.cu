@@ -30,15 +30,16 @@ __device__ __forceinline__ void copy_wait() { asm volatile("cp.async.wait_all;\n
 struct W1SmemFwd { __align__(16) float xs[W1F_ROWS * XIN]; __align__(16) float wt[XIN * 64]; };
 
 __global__ void __launch_bounds__(W1F_THREADS, 6)
-w1_forward_kernel(const float* __restrict__ xin, const float* __restrict__ P, float* __restrict__ xh, long long NH) {
+w1_forward_kernel(const float* __restrict__ xin, const float* __restrict__ P, const float* __restrict__ w1t, float* __restrict__ xh,
+                  long long NH) {
   extern __shared__ __align__(16) unsigned char w1_raw[];
   W1SmemFwd& sm = *reinterpret_cast<W1SmemFwd*>(w1_raw);
   const int tid = threadIdx.x, rg = tid >> 4, cg = tid & 15;
   const long long ntiles = (NH + W1F_ROWS - 1) / W1F_ROWS;
   long long tile = blockIdx.x;
   if (tile < ntiles) copy_tile<W1F_THREADS>(sm.xs, xin + tile * W1F_ROWS * XIN, (int)min((long long)W1F_ROWS, NH - tile * W1F_ROWS) * XIN);
-  // W1^T while the first tile is in flight
-  for (int i = tid; i < 64 * XIN; i += W1F_THREADS) { const int j = i / XIN, k = i - j * XIN; sm.wt[k * 64 + j] = __ldg(P + P_W1_W + i); }
+  // W1^T [66][64] (transposed once per step by head_transpose_kernel): a straight copy, in flight with the first tile
+  copy_tile<W1F_THREADS>(sm.wt, w1t, XIN * 64);
   const float4 bias = __ldg(reinterpret_cast<const float4*>(P + P_W1_B) + cg);
   for (; tile < ntiles; tile += gridDim.x) {
     const long long r0 = tile * W1F_ROWS;
@@ -182,7 +183,7 @@ int launch_w1_forward(const float* P, Workspace& w, cudaStream_t s) {
   }
   const long long ntiles = (w.NH + W1F_ROWS - 1) / W1F_ROWS;
   const int grid = (int)min(ntiles, (long long)6 * sm_count());
-  w1_forward_kernel<<<grid, W1F_THREADS, sizeof(W1SmemFwd), s>>>(w.xin_h, P, w.xh, w.NH);
+  w1_forward_kernel<<<grid, W1F_THREADS, sizeof(W1SmemFwd), s>>>(w.xin_h, P, w.head_wt + HEAD_WT_W1T, w.xh, w.NH);
   NRM_LAUNCH_CHECK("w1_forward_kernel");
   return NRM_OK;
 }
