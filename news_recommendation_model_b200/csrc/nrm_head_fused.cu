@@ -469,7 +469,8 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
 constexpr int WG_THREADS = 320, WG_TILE = 32, WG_PART = HID * E + E;
 constexpr int WG_LDP = 72;          // row stride of the narrow-side tile (66 padded to 9 groups of 8)
 
-// thread (ng, kg) owns the 8 x 8 block dW[8 ng .. +8][8 kg .. +8]: per row two 16-byte reads of each operand feed 64 FMAs
+// thread (ng, kg) owns the 8 x 8 block dW[8 ng .. +8][{4 kg .. +4} u {132 + 4 kg .. +4}] (two 4-wide column groups, so
+// that the lanes of a warp read consecutive 16-byte words of the wide tile): per row two 16-byte reads of each operand feed 64 FMAs
 __global__ void __launch_bounds__(WG_THREADS, 1)
 head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd,
                   const float* __restrict__ P, long long R, int rows_per_chunk,
@@ -544,7 +545,7 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
 #pragma unroll 4
       for (int r = 0; r < WG_TILE; ++r) {
         const float4 p0 = *reinterpret_cast<const float4*>(&sp[r][8 * ng]), p1 = *reinterpret_cast<const float4*>(&sp[r][8 * ng + 4]);
-        const float4 q0 = *reinterpret_cast<const float4*>(&sq[r][8 * kg]), q1 = *reinterpret_cast<const float4*>(&sq[r][8 * kg + 4]);
+        const float4 q0 = *reinterpret_cast<const float4*>(&sq[r][4 * kg]), q1 = *reinterpret_cast<const float4*>(&sq[r][E / 2 + 4 * kg]);
         const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
         const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
@@ -567,14 +568,14 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
     for (int a = 0; a < 8; ++a) {
       const int nn = 8 * ng + a;
       if (nn < HID) {
-        *reinterpret_cast<float4*>(out + nn * E + 8 * kg) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-        *reinterpret_cast<float4*>(out + nn * E + 8 * kg + 4) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+        *reinterpret_cast<float4*>(out + nn * E + 4 * kg) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        *reinterpret_cast<float4*>(out + nn * E + E / 2 + 4 * kg) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
       }
     }
     if (wide_bias) {
       if (ng == 0) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) out[HID * E + 8 * kg + b] = bsum[b];
+        for (int b = 0; b < 8; ++b) out[HID * E + (b < 4 ? 4 * kg + b : E / 2 + 4 * kg + b - 4)] = bsum[b];
       }
     } else if (kg == 0) {
 #pragma unroll
