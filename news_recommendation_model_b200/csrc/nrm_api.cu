@@ -86,6 +86,11 @@ static SideStream* side_stream() {
   return &ss;
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("NRM_NO_PDL") == nullptr;
+  return on;
+}
+
 struct LayoutEntry { const char* name; long long offset; long long numel; };
 #define II "invariant_interest_model."
 static const LayoutEntry kLayout[] = {

@@ -140,6 +140,8 @@ template <int BRANCH>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_forward_kernel(const double* __restrict__ xh, const float* __restrict__ xhp, int B, int H, int C,
                          const float* __restrict__ P, float* __restrict__ e) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttSmemFwd& sm = *reinterpret_cast<AttSmemFwd*>(smem_raw);
   constexpr AttOffsets off = BRANCH == 0 ? ATT_LABEL : ATT_TI;
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_backward_kernel(const double* __restrict__ xh, const float* __restrict__ xhp, int B, int H, int C,
                           const float* __restrict__ P, const float* __restrict__ e, const float* __restrict__ de,
                           float* __restrict__ dxh, float* __restrict__ dxt, float* __restrict__ part) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttSmemBwd& sm = *reinterpret_cast<AttSmemBwd*>(smem_raw);
   constexpr AttOffsets off = BRANCH == 0 ? ATT_LABEL : ATT_TI;
@@ -447,6 +451,8 @@ attention_backward_kernel(const double* __restrict__ xh, const float* __restrict
 // fc1.weight grad [64,256] = [dA | dBm | dBm - dA | dWd]; fc1.bias = db1; fc2.weight = dw2; fc2.bias = db2.
 __global__ void __launch_bounds__(256)
 attention_compose_kernel(const float* __restrict__ part, int nparts, AttOffsets off, float* __restrict__ grads) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   // block = 64 consecutive (j,k) entries x 4 interleaved groups of partials, combined in group order
   __shared__ float red[4][3][64];
   const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -495,10 +501,10 @@ int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, 
   const size_t smem = sizeof(AttSmemFwd);
   if (branch == 0) {
     NRM_CUDA(cudaFuncSetAttribute(attention_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_forward_kernel<0><<<w.B, ATT_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, P, w.e);
+    launch_pdl(attention_forward_kernel<0>, dim3(w.B), dim3(ATT_THREADS), smem, s, in.xh, w.xh, w.B, w.H, w.C, P, w.e);
   } else {
     NRM_CUDA(cudaFuncSetAttribute(attention_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_forward_kernel<1><<<w.B, ATT_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, P, w.e);
+    launch_pdl(attention_forward_kernel<1>, dim3(w.B), dim3(ATT_THREADS), smem, s, in.xh, w.xh, w.B, w.H, w.C, P, w.e);
   }
   NRM_LAUNCH_CHECK("attention_forward_kernel");
   return NRM_OK;
@@ -512,10 +518,10 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
   float* part = w.att_part + (long long)branch * ATT_BWD_CTAS_MAX * ATT_PARTIAL;
   if (branch == 0) {
     NRM_CUDA(cudaFuncSetAttribute(attention_backward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_backward_kernel<0><<<grid, ATT_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, P, w.e, w.de, w.dxh, w.dxt, part);
+    launch_pdl(attention_backward_kernel<0>, dim3(grid), dim3(ATT_THREADS), smem, s, in.xh, w.xh, w.B, w.H, w.C, P, w.e, w.de, w.dxh, w.dxt, part);
   } else {
     NRM_CUDA(cudaFuncSetAttribute(attention_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_backward_kernel<1><<<grid, ATT_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, P, w.e, w.de, w.dxh, w.dxt, part);
+    launch_pdl(attention_backward_kernel<1>, dim3(grid), dim3(ATT_THREADS), smem, s, in.xh, w.xh, w.B, w.H, w.C, P, w.e, w.de, w.dxh, w.dxt, part);
   }
   NRM_LAUNCH_CHECK("attention_backward_kernel");
   return NRM_OK;
@@ -524,7 +530,7 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
 int launch_attention_finish(const float* P, Workspace& w, int branch, int precision, float* grads, cudaStream_t s) {
   if (precision != NRM_PRECISION_FP32) return branch == 1 ? launch_attention_finish_tc(P, w, grads, s) : NRM_OK;   // one pass for both branches
   const float* part = w.att_part + (long long)branch * ATT_BWD_CTAS_MAX * ATT_PARTIAL;
-  attention_compose_kernel<<<64, 256, 0, s>>>(part, att_bwd_grid(w.B), branch == 0 ? ATT_LABEL : ATT_TI, grads);
+  launch_pdl(attention_compose_kernel, dim3(64), dim3(256), 0, s, part, att_bwd_grid(w.B), branch == 0 ? ATT_LABEL : ATT_TI, grads);
   NRM_LAUNCH_CHECK("attention_compose_kernel");
   return NRM_OK;
 }

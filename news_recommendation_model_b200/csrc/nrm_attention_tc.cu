@@ -65,6 +65,8 @@ __host__ __device__ constexpr int wda_index(int j, int k) { return (((k >> 3) * 
 
 __global__ void __launch_bounds__(256)
 att_prep_kernel(const float* __restrict__ P, float* __restrict__ der) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const AttOffsets off = blockIdx.y == 0 ? ATT_LABEL : ATT_TI;
   float* d = der + (long long)blockIdx.y * DER_SIZE;
   const float* W = P + off.fc1_w;
@@ -84,6 +86,8 @@ att_prep_kernel(const float* __restrict__ P, float* __restrict__ der) {
 // features / PCA vector inside e_concat).  32 rows per CTA, blockIdx.y = branch.
 __global__ void __launch_bounds__(256)
 candidate_tp_kernel(const float* __restrict__ P, const float* __restrict__ e, long long R, float* __restrict__ tp_all) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   __shared__ float st[32][65];          // t rows
   __shared__ float sBT[64][65];         // Bm^T: [k][j]
   const AttOffsets off = blockIdx.y == 0 ? ATT_LABEL : ATT_TI;
@@ -413,6 +417,8 @@ template <int SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attention_forward_tc_kernel(const double* __restrict__ xh, const float* __restrict__ xhp, int B, int H, int C,
                             const float* __restrict__ der_all, const float* __restrict__ tp_all, float* __restrict__ e) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   if (blockIdx.y == 0) attention_forward_tc_body<0, SPLIT>(xh, xhp, B, H, C, der_all, tp_all, e);
   else attention_forward_tc_body<1, SPLIT>(xh, xhp, B, H, C, der_all, tp_all, e);
 }
@@ -453,6 +459,8 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
                              const float* __restrict__ der_all, const float* __restrict__ tp_all, const float* __restrict__ P,
                              const float* __restrict__ e, const float* __restrict__ de, float* __restrict__ dxh, float* __restrict__ dxt,
                              float* __restrict__ dtp, float* __restrict__ part) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   constexpr int NP = SPLIT == 3 ? 2 : 1;
   constexpr bool INPUT_GRADS = (BRANCH == 0);
   constexpr int NBD = INPUT_GRADS ? 2 : 1, DH = NBD - 1;
@@ -992,6 +1000,8 @@ __global__ void __launch_bounds__(1024)
 attention_finish_kernel(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads, float* __restrict__ dA_all,
                         const float* __restrict__ dtp_all, const float* __restrict__ e, long long R, const float* __restrict__ P,
                         float* __restrict__ dxt, float* __restrict__ tp_part, int nparts) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   if (blockIdx.x < COMPOSE_BLOCKS) {
     attention_tc_compose_block(part_all, nparts0, nparts1, grads, dA_all);
   } else {
@@ -1005,6 +1015,8 @@ attention_finish_kernel(const float* __restrict__ part_all, int nparts0, int npa
 __global__ void __launch_bounds__(256)
 attention_tp_finish_kernel(const float* __restrict__ part_all, int nparts, const float* __restrict__ dA_all,
                            float* __restrict__ grads) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const int branch = blockIdx.y;
   const AttOffsets off = branch == 0 ? ATT_LABEL : ATT_TI;
   const float* part = part_all + (long long)branch * nparts * TPG_PART;
@@ -1094,13 +1106,13 @@ umma_selftest_kernel(const float* __restrict__ a0, const float* __restrict__ a1,
 // ---------------------------------------------------------------------------------
 // weights only (no dependence on the batch)
 int launch_attention_prep(const float* P, Workspace& w, cudaStream_t s) {
-  att_prep_kernel<<<dim3(4, 2), 256, 0, s>>>(P, w.att_derived);
+  launch_pdl(att_prep_kernel, dim3(dim3(4, 2)), dim3(256), 0, s, P, w.att_derived);
   NRM_LAUNCH_CHECK("att_prep_kernel");
   return NRM_OK;
 }
 // needs the candidate rows of e written by embed_rows_kernel
 int launch_candidate_tp(const float* P, Workspace& w, cudaStream_t s) {
-  candidate_tp_kernel<<<dim3((unsigned)((w.R + 31) / 32), 2), 256, 0, s>>>(P, w.e, w.R, w.tp);
+  launch_pdl(candidate_tp_kernel, dim3(dim3((unsigned)((w.R + 31) / 32), 2)), dim3(256), 0, s, P, w.e, w.R, w.tp);
   NRM_LAUNCH_CHECK("candidate_tp_kernel");
   return NRM_OK;
 }
@@ -1121,7 +1133,7 @@ static int launch_fwd_both(const BatchPtrs& in, Workspace& w, cudaStream_t s) {
   if (smem > 227 * 1024) { set_error("attention forward: shared memory"); return NRM_EUNSUPPORTED; }
   const int grid = min((w.B + 1) / 2, per_sm * sm_count());
   NRM_CUDA(cudaFuncSetAttribute(attention_forward_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_forward_tc_kernel<SPLIT><<<dim3(grid, 2), TC_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, w.att_derived, w.tp, w.e);
+  launch_pdl(attention_forward_tc_kernel<SPLIT>, dim3(dim3(grid, 2)), dim3(TC_THREADS), smem, s, in.xh, w.xh, w.B, w.H, w.C, w.att_derived, w.tp, w.e);
   NRM_LAUNCH_CHECK("attention_forward_tc_kernel");
   return NRM_OK;
 }
@@ -1147,8 +1159,7 @@ static int launch_bwd(const BatchPtrs& in, const float* P, Workspace& w, cudaStr
   float* part = w.att_part + (long long)BRANCH * ATT_TC_PARTS_MAX * TC_PARTIAL;
   float* dtp = w.dtp + (long long)BRANCH * w.R * 64;
   NRM_CUDA(cudaFuncSetAttribute(attention_backward_tc_kernel<BRANCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_backward_tc_kernel<BRANCH, SPLIT><<<grid, TC_THREADS, smem, s>>>(in.xh, w.xh, w.B, w.H, w.C, w.att_derived, w.tp, P, w.e, w.de,
-                                                                            w.dxh, w.dxt, dtp, part);
+  launch_pdl(attention_backward_tc_kernel<BRANCH, SPLIT>, dim3(grid), dim3(TC_THREADS), smem, s, in.xh, w.xh, w.B, w.H, w.C, w.att_derived, w.tp, P, w.e, w.de, w.dxh, w.dxt, dtp, part);
   NRM_LAUNCH_CHECK("attention_backward_tc_kernel");
   return NRM_OK;
 }
@@ -1161,10 +1172,9 @@ int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace&
 // both branches at once (after both backward kernels)
 int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaStream_t s) {
   const int nparts = (int)((w.R + TPG_ROWS - 1) / TPG_ROWS);
-  attention_finish_kernel<<<dim3(COMPOSE_BLOCKS + nparts, 2), 1024, 0, s>>>(w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA,
-                                                                             w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
+  launch_pdl(attention_finish_kernel, dim3(dim3(COMPOSE_BLOCKS + nparts, 2)), dim3(1024), 0, s, w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA, w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
   NRM_LAUNCH_CHECK("attention_finish_kernel");
-  attention_tp_finish_kernel<<<dim3(TPG_PART / 64, 2), 256, 0, s>>>(w.tp_part, nparts, w.att_dA, grads);
+  launch_pdl(attention_tp_finish_kernel, dim3(dim3(TPG_PART / 64, 2)), dim3(256), 0, s, w.tp_part, nparts, w.att_dA, grads);
   NRM_LAUNCH_CHECK("attention_tp_finish_kernel");
   return NRM_OK;
 }

@@ -92,6 +92,34 @@ int cuda_fail(cudaError_t e, const char* what);
     cudaError_t e__ = cudaGetLastError();                           \
     if (e__ != cudaSuccess) return ::nrm::cuda_fail(e__, name);     \
   } while (0)
+// ----------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with launch_pdl() may begin (block scheduling, its code up to
+// pdl_wait()) while the kernel in front of it on the stream is still draining, provided that kernel has executed
+// pdl_trigger() in every block; pdl_wait() then blocks until the kernel in front has completed and its writes are
+// visible.  Rules used here: every kernel launched with launch_pdl() executes pdl_wait() as its FIRST statement (so it
+// never touches memory early) and pdl_trigger() right after it (the next kernel only ever waits at its own first
+// statement).  Kernels in front that never trigger (torch's, memsets, NCCL) simply give the ordinary stream order.
+// Works under stream capture (the edge becomes a programmatic graph dependency).  NRM_NO_PDL=1 disables the attribute.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+#ifdef NRM_PDL_EARLY_TRIGGER
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_trigger() {}      // implicit trigger when the block exits
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define NRM_TRY(expr)            \
   do {                           \
     int rc__ = (expr);           \

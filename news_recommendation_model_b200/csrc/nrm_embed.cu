@@ -19,6 +19,8 @@ embed_rows_kernel(const double* __restrict__ xh, const double* __restrict__ xt, 
                   const double* __restrict__ xg, long long xg_bs, int H, int C, long long NH, long long N,
                   const float* __restrict__ P, float* __restrict__ xin_h, float* __restrict__ e,
                   int* __restrict__ keys32, int* __restrict__ keys8) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
   const int q = threadIdx.x & 7;
   if (row >= N) return;
@@ -123,6 +125,8 @@ struct SortPair { SortStream s[2]; };
 
 __global__ void __launch_bounds__(1024)
 sort_hist_kernel(const SortPair sp) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   extern __shared__ int hist[];
   const int st = blockIdx.x < sp.s[0].nchunks ? 0 : 1;
   const SortStream& S = sp.s[st];
@@ -140,6 +144,8 @@ sort_hist_kernel(const SortPair sp) {
 // Per key (one warp each): exclusive scan of the chunk histograms over chunks, in place, and the key's total.
 __global__ void __launch_bounds__(256)
 sort_colscan_kernel(const SortPair sp) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   int key = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int st = key < sp.s[0].nkeys ? 0 : 1;
   const SortStream& S = sp.s[st];
@@ -165,6 +171,8 @@ sort_colscan_kernel(const SortPair sp) {
 // SEG_GROUP-sized groups -> group starts; also the group -> key map.
 __global__ void __launch_bounds__(1024)
 sort_keyscan_kernel(const SortPair sp) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   __shared__ int warp_off[2][32];
   __shared__ int block_tot[2];
   __shared__ int carry[2];
@@ -223,6 +231,8 @@ sort_keyscan_kernel(const SortPair sp) {
 // the shared counter.  The walk touches shared memory and registers only.
 __global__ void __launch_bounds__(128)
 sort_scatter_kernel(const SortPair sp) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   extern __shared__ int ssm[];                      // keys[SORT_CHUNK] | pos[nkeys] | segment starts[nkeys]
   const int st = blockIdx.x < sp.s[0].nchunks ? 0 : 1;
   const SortStream& S = sp.s[st];
@@ -348,6 +358,8 @@ __device__ __forceinline__ void table_grad_l1(const SortStream& S, int g, const 
 __global__ void __launch_bounds__(256)
 table_grad_l1_kernel(const SortPair sp, int warps0, const float* __restrict__ dxin_h, const float* __restrict__ dxt,
                      long long NH, float* __restrict__ gpart32, float* __restrict__ gpart8) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (w < warps0) {
     const SortStream& S = sp.s[0];
@@ -366,6 +378,8 @@ table_grad_l1_kernel(const SortPair sp, int warps0, const float* __restrict__ dx
 __global__ void __launch_bounds__(128)
 table_grad_l2_kernel(const SortPair sp, const float* __restrict__ gpart32, const float* __restrict__ gpart8,
                      float* __restrict__ grads) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   __shared__ float red[4][32];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x < NKEY32) {
@@ -424,6 +438,8 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
                          const float* __restrict__ xin_h, const float* __restrict__ e,
                          const float* __restrict__ dxin_h, const float* __restrict__ dxt, const float* __restrict__ de,
                          float* __restrict__ part) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   __shared__ float red[8][96];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float as[16][4], ai[8][4];
@@ -514,6 +530,8 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
 // memory (deterministic) and the scatter of the [96] vector into the flat gradient entries.
 __global__ void __launch_bounds__(256)
 small_linear_grad_finish_kernel(const float* __restrict__ part, int nparts, float* __restrict__ grads) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   __shared__ float red[256];
   const int k = blockIdx.x, t = threadIdx.x;
   float acc = 0.f;
@@ -542,8 +560,7 @@ small_linear_grad_finish_kernel(const float* __restrict__ part, int nparts, floa
 // ---------------------------------------------------------------------------------
 int launch_embed_rows(const BatchPtrs& in, const float* P, Workspace& w, bool with_keys, cudaStream_t s) {
   const int grid = (int)((w.N + 31) / 32);
-  embed_rows_kernel<<<grid, 256, 0, s>>>(in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.H, w.C, w.NH, w.N, P, w.xin_h, w.e,
-                                         with_keys ? w.keys32 : nullptr, with_keys ? w.keys8 : nullptr);
+  launch_pdl(embed_rows_kernel, dim3(grid), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.H, w.C, w.NH, w.N, P, w.xin_h, w.e, with_keys ? w.keys32 : nullptr, with_keys ? w.keys8 : nullptr);
   NRM_LAUNCH_CHECK("embed_rows_kernel");
   return NRM_OK;
 }
@@ -565,13 +582,13 @@ int launch_table_sort(Workspace& w, cudaStream_t s) {
     NRM_CUDA(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (SORT_CHUNK + 2 * NKEY32))));
     configured = true;
   }
-  sort_hist_kernel<<<nch, 1024, NKEY32 * sizeof(int), s>>>(sp);
+  launch_pdl(sort_hist_kernel, dim3(nch), dim3(1024), NKEY32 * sizeof(int), s, sp);
   NRM_LAUNCH_CHECK("sort_hist_kernel");
-  sort_colscan_kernel<<<(NKEY32 + NKEY8 + 7) / 8, 256, 0, s>>>(sp);
+  launch_pdl(sort_colscan_kernel, dim3((NKEY32 + NKEY8 + 7) / 8), dim3(256), 0, s, sp);
   NRM_LAUNCH_CHECK("sort_colscan_kernel");
-  sort_keyscan_kernel<<<2, 1024, 0, s>>>(sp);
+  launch_pdl(sort_keyscan_kernel, dim3(2), dim3(1024), 0, s, sp);
   NRM_LAUNCH_CHECK("sort_keyscan_kernel");
-  sort_scatter_kernel<<<nch, 128, sizeof(int) * (SORT_CHUNK + 2 * NKEY32), s>>>(sp);
+  launch_pdl(sort_scatter_kernel, dim3(nch), dim3(128), sizeof(int) * (SORT_CHUNK + 2 * NKEY32), s, sp);
   NRM_LAUNCH_CHECK("sort_scatter_kernel");
   return NRM_OK;
 }
@@ -580,10 +597,10 @@ int launch_table_grads(Workspace& w, float* grads, cudaStream_t s) {
   const SortPair sp = make_sort_pair(w);
   const long long g32 = sp.s[0].n / SEG_GROUP + NKEY32 + 1, g8 = sp.s[1].n / SEG_GROUP + NKEY8 + 1;   // upper bounds
   { KernelTimer t("table_l1", s);
-  table_grad_l1_kernel<<<(int)((g32 + g8 + 7) / 8), 256, 0, s>>>(sp, (int)g32, w.dxin_h, w.dxt, w.NH, w.gpart32, w.gpart8);
+  launch_pdl(table_grad_l1_kernel, dim3((int)((g32 + g8 + 7) / 8)), dim3(256), 0, s, sp, (int)g32, w.dxin_h, w.dxt, w.NH, w.gpart32, w.gpart8);
   NRM_LAUNCH_CHECK("table_grad_l1_kernel"); }
   { KernelTimer t("table_l2", s);
-  table_grad_l2_kernel<<<NKEY32 + (NKEY8 + 15) / 16, 128, 0, s>>>(sp, w.gpart32, w.gpart8, grads);
+  launch_pdl(table_grad_l2_kernel, dim3(NKEY32 + (NKEY8 + 15) / 16), dim3(128), 0, s, sp, w.gpart32, w.gpart8, grads);
   NRM_LAUNCH_CHECK("table_grad_l2_kernel"); }
   return NRM_OK;
 }
@@ -592,10 +609,9 @@ int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, c
   // one row per lane and pass: enough CTAs to cover the rows once, at most one wave of 2 CTAs per SM
   int nparts = (int)((w.N + 255) / 256);
   nparts = max(1, min(nparts, min(1024, 2 * sm_count())));
-  small_linear_grad_kernel<<<nparts, 256, 0, s>>>(in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.C, w.NH, w.N, w.xin_h, w.e,
-                                                  w.dxin_h, w.dxt, w.de, w.small_part);
+  launch_pdl(small_linear_grad_kernel, dim3(nparts), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.C, w.NH, w.N, w.xin_h, w.e, w.dxin_h, w.dxt, w.de, w.small_part);
   NRM_LAUNCH_CHECK("small_linear_grad_kernel");
-  small_linear_grad_finish_kernel<<<96, 256, 0, s>>>(w.small_part, nparts, grads);
+  launch_pdl(small_linear_grad_finish_kernel, dim3(96), dim3(256), 0, s, w.small_part, nparts, grads);
   NRM_LAUNCH_CHECK("small_linear_grad_finish_kernel");
   return NRM_OK;
 }

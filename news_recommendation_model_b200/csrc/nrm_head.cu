@@ -11,6 +11,8 @@ namespace nrm {
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(E)
 bn_partial_kernel(const float* __restrict__ e, long long R, int rows_per_chunk, double* __restrict__ part) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const int n = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
   const long long r1 = min(R, r0 + rows_per_chunk);
@@ -25,6 +27,8 @@ bn_partial_kernel(const float* __restrict__ e, long long R, int rows_per_chunk, 
 // flight at once), then a fixed shuffle tree.
 __global__ void __launch_bounds__(256)
 bn_partial_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ sums) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= 2 * E) return;
   double s = 0.0;
@@ -41,6 +45,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_combine_kernel(const float* __restrict__ dz, const float* __restrict__ e, const float* __restrict__ mean,
                       const float* __restrict__ rstd, const float* __restrict__ gamma, const double* __restrict__ sums,
                       long long rows, int training, long long total4, float* __restrict__ de) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   // four consecutive columns per thread (264 = 66 x 4: a float4 never straddles a row)
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total4; i += (long long)gridDim.x * 256) {
     const int n = (int)(i % (E / 4)) * 4;
@@ -71,9 +77,9 @@ static inline int stat_chunks(long long R) { const int rp = stat_rows(R); return
 
 int launch_bn_partial_sums(Workspace& w, cudaStream_t s) {
   const int rp = stat_rows(w.R), nch = stat_chunks(w.R);
-  bn_partial_kernel<<<nch, E, 0, s>>>(w.e, w.R, rp, w.stat_part);
+  launch_pdl(bn_partial_kernel, dim3(nch), dim3(E), 0, s, w.e, w.R, rp, w.stat_part);
   NRM_LAUNCH_CHECK("bn_partial_kernel");
-  bn_partial_reduce_kernel<<<(2 * E + 7) / 8, 256, 0, s>>>(w.stat_part, nch, w.bn_sums);
+  launch_pdl(bn_partial_reduce_kernel, dim3((2 * E + 7) / 8), dim3(256), 0, s, w.stat_part, nch, w.bn_sums);
   NRM_LAUNCH_CHECK("bn_partial_reduce_kernel");
   return NRM_OK;
 }
@@ -92,8 +98,7 @@ int launch_bn_backward_combine(const float* P, Workspace& w, int training, const
                                long long global_rows, cudaStream_t s) {
   const long long total4 = w.R * (E / 4);
   const long long blocks = min((total4 + 255) / 256, (long long)sm_count() * 8);
-  bn_bwd_combine_kernel<<<(int)blocks, 256, 0, s>>>(w.dz, w.e, w.mean, w.rstd, P + P_BN_W, bn_bwd_sums,
-                                                   global_rows, training, total4, w.de);
+  launch_pdl(bn_bwd_combine_kernel, dim3((int)blocks), dim3(256), 0, s, w.dz, w.e, w.mean, w.rstd, P + P_BN_W, bn_bwd_sums, global_rows, training, total4, w.de);
   NRM_LAUNCH_CHECK("bn_bwd_combine_kernel");
   return NRM_OK;
 }

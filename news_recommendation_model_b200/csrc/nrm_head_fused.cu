@@ -38,6 +38,8 @@ static_assert(WT_TOTAL == HEAD_WT_W1T, "w1^T follows the five head matrices in t
 
 __global__ void __launch_bounds__(256)
 head_transpose_kernel(const float* __restrict__ P, float* __restrict__ wt) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const int m = blockIdx.y;                                  // matrix; 5 = w1.weight [64][66] of the history projection
   const long long src_off[6] = {P_GATE_FC1_W, P_GATE_FC2_W, P_MLP_FC1_W, P_MLP_FC2_W, P_OUT_FC1_W, P_W1_W};
   const int rows = m == 5 ? 64 : (m == 1 || m == 3) ? E : HID;             // source is [rows][cols] = [out][in]
@@ -161,6 +163,8 @@ head_forward_kernel(const float* __restrict__ e, const double* __restrict__ bn_s
                     const float* __restrict__ P, const float* __restrict__ wt, long long R, int keep,
                     float* __restrict__ a1g, float* __restrict__ gateg, float* __restrict__ a2g, float* __restrict__ yg,
                     float* __restrict__ a3g, float* __restrict__ logits) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char hs_raw[];
   HeadSmem& sm = *reinterpret_cast<HeadSmem*>(hs_raw);
   const int tid = threadIdx.x;
@@ -318,6 +322,8 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
                      float* __restrict__ da3g, float* __restrict__ dyg, float* __restrict__ da2g, float* __restrict__ dgateg,
                      float* __restrict__ da1g, float* __restrict__ dzg, float* __restrict__ deg,
                      float* __restrict__ part_f, double* __restrict__ part_bn) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char hs_raw[];
   HeadSmem& sm = *reinterpret_cast<HeadSmem*>(hs_raw);
   const int tid = threadIdx.x;
@@ -478,6 +484,8 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
                   const float* __restrict__ yg, const float* __restrict__ da3g, const float* __restrict__ dyg,
                   const float* __restrict__ da2g, const float* __restrict__ dgateg, const float* __restrict__ da1g,
                   float* __restrict__ part) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   __shared__ __align__(16) float sp[WG_TILE][WG_LDP];
   __shared__ __align__(16) float sq[WG_TILE][E];
   const int layer = blockIdx.y, tid = threadIdx.x;
@@ -589,6 +597,8 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
 __global__ void __launch_bounds__(256)
 head_grad_finish_kernel(const float* __restrict__ part, int nchunks, const float* __restrict__ part_f, int ntiles,
                         const double* __restrict__ part_bn, float* __restrict__ grads, double* __restrict__ bn_bwd_sums) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const int layer = blockIdx.y;
   if (layer < 5) {
     const long long w_off[5] = {P_OUT_FC1_W, P_MLP_FC2_W, P_MLP_FC1_W, P_GATE_FC2_W, P_GATE_FC1_W};
@@ -643,7 +653,7 @@ int head_wgrad_chunks(long long R) {
 
 // transposed copies of the five matrices for the forward kernel: weights only, enqueued ahead of the encoder
 int launch_head_transpose(const float* P, Workspace& w, cudaStream_t s) {
-  head_transpose_kernel<<<dim3(8, 6), 256, 0, s>>>(P, w.head_wt);
+  launch_pdl(head_transpose_kernel, dim3(dim3(8, 6)), dim3(256), 0, s, P, w.head_wt);
   NRM_LAUNCH_CHECK("head_transpose_kernel");
   return NRM_OK;
 }
@@ -656,9 +666,7 @@ int launch_head_forward_fused(const float* P, Workspace& w, float* run_mean, flo
     NRM_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     configured = true;
   }
-  head_forward_kernel<<<head_tiles(w.R), HT_THREADS, sizeof(HeadSmem), s>>>(w.e, bn_sums, bn_rows, training, run_mean, run_var, nbt, w.mean,
-                                                                          w.rstd, P, w.head_wt, w.R, keep, w.a1, w.gate, w.a2, w.y, w.a3,
-                                                                          logits);
+  launch_pdl(head_forward_kernel, dim3(head_tiles(w.R)), dim3(HT_THREADS), sizeof(HeadSmem), s, w.e, bn_sums, bn_rows, training, run_mean, run_var, nbt, w.mean, w.rstd, P, w.head_wt, w.R, keep, w.a1, w.gate, w.a2, w.y, w.a3, logits);
   NRM_LAUNCH_CHECK("head_forward_kernel");
   return NRM_OK;
 }
@@ -670,17 +678,15 @@ int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogit
     configured = true;
   }
   const int ntiles = head_tiles(w.R);
-  head_backward_kernel<<<ntiles, HT_THREADS, sizeof(HeadSmem), s>>>(w.e, w.mean, w.rstd, P, w.R, dlogits, w.a1, w.gate, w.a2, w.a3, w.da3, w.dy,
-                                                                  w.da2, w.dgate, w.da1, w.dz, w.de, w.head_part_f, w.head_part_bn);
+  launch_pdl(head_backward_kernel, dim3(ntiles), dim3(HT_THREADS), sizeof(HeadSmem), s, w.e, w.mean, w.rstd, P, w.R, dlogits, w.a1, w.gate, w.a2, w.a3, w.da3, w.dy, w.da2, w.dgate, w.da1, w.dz, w.de, w.head_part_f, w.head_part_bn);
   NRM_LAUNCH_CHECK("head_backward_kernel");
   const int nch = head_wgrad_chunks(w.R);
   int rpc = (int)((w.R + nch - 1) / nch);
   rpc = (rpc + WG_TILE - 1) / WG_TILE * WG_TILE;
   const int nchunks = (int)((w.R + rpc - 1) / rpc);
-  head_wgrad_kernel<<<dim3(nchunks, 5), WG_THREADS, 0, s>>>(w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2,
-                                                            w.dgate, w.da1, w.head_part_w);
+  launch_pdl(head_wgrad_kernel, dim3(dim3(nchunks, 5)), dim3(WG_THREADS), 0, s, w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2, w.dgate, w.da1, w.head_part_w);
   NRM_LAUNCH_CHECK("head_wgrad_kernel");
-  head_grad_finish_kernel<<<dim3(70, 7), 256, 0, s>>>(w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums);
+  launch_pdl(head_grad_finish_kernel, dim3(dim3(70, 7)), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums);
   NRM_LAUNCH_CHECK("head_grad_finish_kernel");
   return NRM_OK;
 }

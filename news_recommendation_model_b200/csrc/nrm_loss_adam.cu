@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(256)
 loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ delta, const long long* __restrict__ uid,
                     const double* __restrict__ label, int B, int C, float alpha, float* __restrict__ dlog,
                     float* __restrict__ drow, double* __restrict__ lpart) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   __shared__ double red[8][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float invN = 1.0f / ((float)B * (float)C);
@@ -98,6 +100,8 @@ loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ 
 
 __global__ void loss_finalize_kernel(const double* __restrict__ lpart, int nblocks, int B, int C, float alpha,
                                      float* __restrict__ loss) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double s1 = 0.0, s2 = 0.0;
   for (int i = 0; i < nblocks; ++i) { s1 += lpart[i * 2]; s2 += lpart[i * 2 + 1]; }
@@ -108,6 +112,8 @@ __global__ void loss_finalize_kernel(const double* __restrict__ lpart, int nbloc
 
 __global__ void __launch_bounds__(256)
 loss_scale_kernel(const float* __restrict__ dlog, const float* __restrict__ grad_loss, long long n, float* __restrict__ out) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i < n) out[i] = dlog[i] * __ldg(grad_loss);
 }
@@ -118,6 +124,8 @@ loss_scale_kernel(const float* __restrict__ dlog, const float* __restrict__ grad
 __global__ void __launch_bounds__(256)
 delta_grad_kernel(const long long* __restrict__ uid, const float* __restrict__ drow, int B,
                   const float* __restrict__ grad_loss, float* __restrict__ ddelta, long long delta_numel) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -152,6 +160,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long n, AdamArgs a) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * 256;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
@@ -170,6 +180,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void __launch_bounds__(256)
 adam_scalar_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                    long long n, AdamArgs a) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   const long long stride = (long long)gridDim.x * 256;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) adam_one(p[i], g[i], m[i], v[i], a);
 }
@@ -183,6 +195,8 @@ struct AdamDeviceState {          // mirrored by FusedTrainStep (python): 1 x in
 static_assert(sizeof(AdamDeviceState) == 40, "AdamDeviceState layout is part of the C ABI");
 
 __global__ void adam_prepare_kernel(AdamDeviceState* st) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const long long t = ++st->step;
   const double bc1 = 1.0 - pow((double)st->beta1, (double)t);
@@ -194,6 +208,8 @@ __global__ void adam_prepare_kernel(AdamDeviceState* st) {
 __global__ void __launch_bounds__(256)
 adam_device_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                    long long n, const AdamDeviceState* __restrict__ st) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   AdamArgs a;
   a.step_size = st->step_size; a.bc2_sqrt = st->bc2_sqrt; a.beta1 = st->beta1; a.beta2 = st->beta2;
   a.eps = st->eps; a.wd = st->wd; a.grad_scale = st->grad_scale;
@@ -224,14 +240,14 @@ extern "C" int nrm_adam_step_device(float* param, const float* grad, float* exp_
   }
   cudaStream_t s = (cudaStream_t)stream;
   AdamDeviceState* st = (AdamDeviceState*)adam_state;
-  adam_prepare_kernel<<<1, 32, 0, s>>>(st);
+  launch_pdl(adam_prepare_kernel, dim3(1), dim3(32), 0, s, st);
   NRM_LAUNCH_CHECK("adam_prepare_kernel");
   if (n == 0) return NRM_OK;
   long long blocks = ((n + 3) / 4 + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   KernelTimer t("adam", s);
-  adam_device_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, st);
+  launch_pdl(adam_device_kernel, dim3((int)blocks), dim3(256), 0, s, param, grad, exp_avg, exp_avg_sq, n, st);
   NRM_LAUNCH_CHECK("adam_device_kernel");
   return NRM_OK;
 }
@@ -250,9 +266,9 @@ extern "C" int nrm_loss_forward(const float* logits, const float* delta, const l
   if (carve_loss(ls, scratch, B, C) > scratch_bytes) { set_error("nrm_loss_forward: scratch too small"); return NRM_EWORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = min(LOSS_BLOCKS, (B + 7) / 8);
-  loss_forward_kernel<<<blocks, 256, 0, s>>>(logits, delta, user_id, label, B, C, alpha, ls.dlog, ls.drow, ls.lpart);
+  launch_pdl(loss_forward_kernel, dim3(blocks), dim3(256), 0, s, logits, delta, user_id, label, B, C, alpha, ls.dlog, ls.drow, ls.lpart);
   NRM_LAUNCH_CHECK("loss_forward_kernel");
-  loss_finalize_kernel<<<1, 32, 0, s>>>(ls.lpart, blocks, B, C, alpha, loss);
+  launch_pdl(loss_finalize_kernel, dim3(1), dim3(32), 0, s, ls.lpart, blocks, B, C, alpha, loss);
   NRM_LAUNCH_CHECK("loss_finalize_kernel");
   return NRM_OK;
 }
@@ -266,11 +282,11 @@ extern "C" int nrm_loss_backward(const long long* user_id, int B, int C, const f
   if (carve_loss(ls, const_cast<void*>(scratch), B, C) > scratch_bytes) { set_error("nrm_loss_backward: scratch too small"); return NRM_EWORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = (long long)B * C;
-  loss_scale_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(ls.dlog, grad_loss, n, dlogits);
+  launch_pdl(loss_scale_kernel, dim3((int)((n + 255) / 256)), dim3(256), 0, s, ls.dlog, grad_loss, n, dlogits);
   NRM_LAUNCH_CHECK("loss_scale_kernel");
   if (ddelta != nullptr && delta_numel > 0) {
     NRM_CUDA(cudaMemsetAsync(ddelta, 0, sizeof(float) * (size_t)delta_numel, s));
-    delta_grad_kernel<<<(B + 7) / 8, 256, 0, s>>>(user_id, ls.drow, B, grad_loss, ddelta, delta_numel);
+    launch_pdl(delta_grad_kernel, dim3((B + 7) / 8), dim3(256), 0, s, user_id, ls.drow, B, grad_loss, ddelta, delta_numel);
     NRM_LAUNCH_CHECK("delta_grad_kernel");
   }
   return NRM_OK;
@@ -294,8 +310,8 @@ extern "C" int nrm_adam_step(float* param, const float* grad, float* exp_avg, fl
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   KernelTimer t("adam", s);
-  if (aligned) adam_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, a);
-  else adam_scalar_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, a);
+  if (aligned) launch_pdl(adam_kernel, dim3((int)blocks), dim3(256), 0, s, param, grad, exp_avg, exp_avg_sq, n, a);
+  else launch_pdl(adam_scalar_kernel, dim3((int)blocks), dim3(256), 0, s, param, grad, exp_avg, exp_avg_sq, n, a);
   NRM_LAUNCH_CHECK("adam_kernel");
   return NRM_OK;
 }

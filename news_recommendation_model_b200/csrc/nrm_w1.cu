@@ -32,6 +32,8 @@ struct W1SmemFwd { __align__(16) float xs[W1F_ROWS * XIN]; __align__(16) float w
 __global__ void __launch_bounds__(W1F_THREADS, 6)
 w1_forward_kernel(const float* __restrict__ xin, const float* __restrict__ P, const float* __restrict__ w1t, float* __restrict__ xh,
                   long long NH) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char w1_raw[];
   W1SmemFwd& sm = *reinterpret_cast<W1SmemFwd*>(w1_raw);
   const int tid = threadIdx.x, rg = tid >> 4, cg = tid & 15;
@@ -75,6 +77,8 @@ struct W1SmemBwd { __align__(16) float ds[W1_ROWS * 64]; __align__(16) float xs[
 __global__ void __launch_bounds__(W1_THREADS, 2)
 w1_backward_kernel(const float* __restrict__ xin, const float* __restrict__ dxh, const float* __restrict__ P,
                    float* __restrict__ dxin, long long NH, float* __restrict__ part) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char w1_raw[];
   W1SmemBwd& sm = *reinterpret_cast<W1SmemBwd*>(w1_raw);
   const int tid = threadIdx.x, rg = tid >> 4, cg = tid & 15;
@@ -161,6 +165,8 @@ w1_backward_kernel(const float* __restrict__ xin, const float* __restrict__ dxh,
 // w1.weight / w1.bias are adjacent in the flat layout: one pass over W1_PART entries
 __global__ void __launch_bounds__(256)
 w1_finish_kernel(const float* __restrict__ part, int nparts, float* __restrict__ grads) {
+  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
+  pdl_trigger();
   __shared__ float red[4][64];
   const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int i = blockIdx.x * 64 + lane;
@@ -183,7 +189,7 @@ int launch_w1_forward(const float* P, Workspace& w, cudaStream_t s) {
   }
   const long long ntiles = (w.NH + W1F_ROWS - 1) / W1F_ROWS;
   const int grid = (int)min(ntiles, (long long)6 * sm_count());
-  w1_forward_kernel<<<grid, W1F_THREADS, sizeof(W1SmemFwd), s>>>(w.xin_h, P, w.head_wt + HEAD_WT_W1T, w.xh, w.NH);
+  launch_pdl(w1_forward_kernel, dim3(grid), dim3(W1F_THREADS), sizeof(W1SmemFwd), s, w.xin_h, P, w.head_wt + HEAD_WT_W1T, w.xh, w.NH);
   NRM_LAUNCH_CHECK("w1_forward_kernel");
   return NRM_OK;
 }
@@ -196,9 +202,9 @@ int launch_w1_backward(const float* P, Workspace& w, float* G, cudaStream_t s) {
   }
   const long long ntiles = (w.NH + W1_ROWS - 1) / W1_ROWS;
   const int grid = (int)min(ntiles, (long long)min(2 * sm_count(), W1_SPLITS));
-  w1_backward_kernel<<<grid, W1_THREADS, sizeof(W1SmemBwd), s>>>(w.xin_h, w.dxh, P, w.dxin_h, w.NH, w.splitk);
+  launch_pdl(w1_backward_kernel, dim3(grid), dim3(W1_THREADS), sizeof(W1SmemBwd), s, w.xin_h, w.dxh, P, w.dxin_h, w.NH, w.splitk);
   NRM_LAUNCH_CHECK("w1_backward_kernel");
-  w1_finish_kernel<<<(W1_PART + 63) / 64, 256, 0, s>>>(w.splitk, grid, G);
+  launch_pdl(w1_finish_kernel, dim3((W1_PART + 63) / 64), dim3(256), 0, s, w.splitk, grid, G);
   NRM_LAUNCH_CHECK("w1_finish_kernel");
   return NRM_OK;
 }
