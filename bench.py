@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='FusedTrainStep issues the C-ABI calls eagerly instead of replaying a CUDA graph')
     ap.add_argument('--cpu-steps', type=int, default=8)
+    ap.add_argument('--no-scoring', action='store_true', help='skip the scoring (configs[2]) leg')
     ap.add_argument('--no-affinity', action='store_true', help='do not bind each rank to the CPU cores local to its GPU')
     return ap.parse_args()
 
@@ -356,6 +357,75 @@ def run_ours(args):
             roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
                         'traffic': traffic, 'peak_source': pk['source'], 'algorithmic_bytes_per_launch': work, 'launch_ms': dur * 1e3}
 
+    # ---- D. scoring (BASELINE configs[2]; test.py:31-74 + 118-132): 2-model ensemble (train + validation checkpoints), eval mode,
+    #         H = 200 (the ETL's pad length), ragged candidate lists padded to the batch maximum, pads trimmed per batch as
+    #         test.py:52-56, epilogue + stable ranks + submission text on the GPU (scoring.py).  Batch 80 as test.py:138 and a
+    #         large-batch variant; resident inputs and end to end (pinned host float64 inputs in, text bytes out).
+    scoring = None
+    if not args.no_scoring:
+        from fixtures import load_weights as lw
+        model.set_precision(args.precision)
+        m_val = nrm.UserModel(args.user_num)
+        m_val.load_state_dict(lw('validation'), strict=False)
+        m_val.to(dev).eval().set_precision(args.precision)
+        model.eval()
+        ens = [model, m_val]
+        scoring = {'unit': 'impressions/s', 'config': 'eval, 2-model ensemble, H=200 (variable length), candidates ~ clipped lognormal [5,100] padded to the '
+                   'batch maximum, softmax / pad re-softmax / stable ranks / submission text on the GPU'}
+        for Bs, reps in ((80, 20), (1024, 4)):
+            hb = [make_batch(Bs, 200, 100, seed=777 + 31 * rank + i, user_num=args.user_num, variable_history=True, variable_candidates=True).pin()
+                  for i in range(2)]
+            trims = [int(b.empty_num.min()) for b in hb]
+            db = [b.to(dev) for b in hb]
+
+            def score(b, trim, text):
+                keep = b.x_target.shape[1] - trim
+                with torch.no_grad():
+                    sc, rk = nrm.scoring.ensemble_scores(ens, b.x_history, b.x_target[:, :keep], b.x_global[:, :keep], b.empty_num - trim)
+                return nrm.scoring.submission_text(b.impression_id, rk, b.empty_num - trim) if text else sc
+            for i in range(2):
+                score(db[i], trims[i], False)
+            barrier()
+            e0.record()
+            for i in range(reps):
+                score(db[i % 2], trims[i % 2], False)
+            e1.record()
+            barrier()
+            ms_res = max_over_ranks(e0.elapsed_time(e1)) / reps
+            # end to end: batch i + 1 travels on a copy stream while batch i is scored; the text bytes come back every batch
+            cs = torch.cuda.Stream(dev)
+
+            def fetch(i):
+                with torch.cuda.stream(cs):
+                    t = hb[i % 2].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(cs)
+                return t, ev
+
+            def e2e_scoring(n):
+                total = 0
+                nxt = fetch(0)
+                for i in range(n):
+                    cur, ev = nxt
+                    if i + 1 < n:
+                        nxt = fetch(i + 1)
+                    torch.cuda.current_stream(dev).wait_event(ev)
+                    total += len(score(cur, trims[i % 2], True))
+                    for f in cur.__dataclass_fields__:
+                        getattr(cur, f).record_stream(torch.cuda.current_stream(dev))
+                return total
+            e2e_scoring(2)
+            barrier()
+            e0.record()
+            nbytes = e2e_scoring(reps)
+            e1.record()
+            barrier()
+            ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / reps
+            scoring[f'batch_{Bs}'] = {'value': world * Bs / (ms_res / 1e3), 'ms_per_batch': ms_res,
+                                      'e2e': {'value': world * Bs / (ms_e2e / 1e3), 'ms_per_batch': ms_e2e,
+                                              'h2d_bytes_per_batch': hb[0].input_bytes(), 'd2h_bytes_per_batch': nbytes // reps},
+                                      'candidate_columns': hb[0].x_target.shape[1] - trims[0]}
+        model.train()
+
     # short resident runs of the other precisions (same step, same data), for context
     variants = {}
     if not args.no_variants:
@@ -404,7 +474,7 @@ def run_ours(args):
                         'note': 'drop-in nn.Module path driven like train.py:69-75 (autograd + FusedAdam), device-resident'},
         'api': 'FusedTrainStep (CUDA-graph replay of the 5 C-ABI calls)' if not args.no_graph else 'FusedTrainStep (eager C-ABI calls)',
         'roofline': roofline, 'kernels_ms_per_step': {k: round(v['ms_per_step'], 4) for k, v in kern.items()},
-        'cpu_baseline': cpu, 'precision_variants': variants,
+        'cpu_baseline': cpu, 'precision_variants': variants, 'scoring': scoring,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

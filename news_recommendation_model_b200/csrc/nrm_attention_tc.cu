@@ -320,7 +320,9 @@ __device__ __forceinline__ void attention_forward_tc_body(const double* __restri
   const int npairs_b = (B + 1) / 2;
   int u0, u1;
   TCPROF_DECL
-  unit_range(npairs_b, C, H > 64, u0, u1);            // pooled sums over history tiles stay inside one CTA
+  // a (pair, candidate) unit accumulates its own pooled vector over the history tiles, so a pair's candidates may be
+  // dealt to several CTAs (each re-stages the pair's history tiles): long candidate lists fill the machine even with few pairs
+  unit_range(npairs_b, C, false, u0, u1);
   for (int u = u0; u < u1;) {
     const int pb = u / C, ca = u - pb * C, cend = min(C, ca + (u1 - u));   // candidates [ca, cend) of pair pb
     u += cend - ca;
@@ -1131,7 +1133,9 @@ static int launch_fwd_both(const BatchPtrs& in, Workspace& w, cudaStream_t s) {
   const int per_sm = 2;
   const size_t smem = padded_smem(sizeof(TcSmemFwd<NP>), per_sm);
   if (smem > 227 * 1024) { set_error("attention forward: shared memory"); return NRM_EUNSUPPORTED; }
-  const int grid = min((w.B + 1) / 2, per_sm * sm_count());
+  // one CTA per pair or per candidate chunk of TC_MAXC units, whichever gives more CTAs; never more than fit at once
+  const long long npairs = (w.B + 1) / 2, units = npairs * w.C;
+  const int grid = (int)min(max(npairs, (units + TC_MAXC - 1) / TC_MAXC), (long long)per_sm * sm_count());
   NRM_CUDA(cudaFuncSetAttribute(attention_forward_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   launch_pdl(attention_forward_tc_kernel<SPLIT>, dim3(dim3(grid, 2)), dim3(TC_THREADS), smem, s, in.xh, w.xh, w.B, w.H, w.C, w.att_derived, w.tp, w.e);
   NRM_LAUNCH_CHECK("attention_forward_tc_kernel");

@@ -60,10 +60,53 @@ def score_epilogue(logits: torch.Tensor, empty_num: Optional[torch.Tensor] = Non
 
 
 @torch.no_grad()
-def ensemble_scores(model_list: Sequence[torch.nn.Module], x_history, x_inview, x_global, empty_num=None, want_ranks: bool = True):
-    """`test.py:58-70` for one batch: every model's eval forward, then the fused epilogue."""
-    outs = [m(x_history, x_inview, x_global) for m in model_list]
-    return score_epilogue(torch.stack(outs, 0), empty_num, want_ranks)
+def ensemble_logits(model_list: Sequence[torch.nn.Module], x_history, x_inview, x_global, empty_num=None, groups: int = 8,
+                    min_group: int = 128) -> torch.Tensor:
+    """Eval-mode logits [M,B,C] of every ensemble member, as `model(x_history, x_inview, x_global)` gives them.
+
+    Pad candidates are all-zero rows (`process_data.py:214-222`), so all pads of an impression have the SAME logit, and
+    candidate lists are ragged (median 11, maximum ~100): computing every column of the batch spends most of the time on
+    copies of one number.  With `empty_num` given, the impressions are therefore sorted by their number of real candidates
+    and scored in up to `groups` groups, each only as wide as its longest list plus one pad column; the pad logit is then
+    replicated into the remaining columns.  The result is bit-identical to scoring the full rectangle (rows are independent
+    in eval mode; `tests/test_gpu_scoring.py` checks it), so `test.py`'s softmax-over-pads quirk is reproduced exactly."""
+    B, C = int(x_inview.shape[0]), int(x_inview.shape[1])
+    M = len(model_list)
+    dev = x_history.device
+    if empty_num is None or B < 2 * min_group or C < 8:
+        return torch.stack([m(x_history, x_inview, x_global) for m in model_list], 0)
+    n = (C - empty_num.detach().to('cpu', torch.int64)).clamp_(0, C)                # real candidates per impression
+    order = torch.argsort(n, descending=True, stable=True)
+    G = max(1, min(groups, B // min_group))
+    edges = [((B * g // G) + 1) // 2 * 2 for g in range(G)] + [B]                  # even starts: the kernels work on pairs
+    out = torch.empty(M, B, C, dtype=torch.float32, device=dev)
+    for g in range(G):
+        lo, hi = edges[g], edges[g + 1]
+        if hi <= lo:
+            continue
+        idx_cpu = order[lo:hi]
+        cg = min(C, int(n[idx_cpu].max()) + 1)
+        idx = idx_cpu.to(dev)
+        xh_g = x_history.index_select(0, idx)
+        xt_g = x_inview.index_select(0, idx)[:, :cg]
+        xg_g = x_global.index_select(0, idx)[:, :cg]
+        if cg < C:
+            pad_col = n[idx_cpu].to(dev).unsqueeze(1)                               # first pad column of every impression (< cg)
+        for mi, m in enumerate(model_list):
+            lg = m(xh_g, xt_g, xg_g)
+            if cg < C:
+                lg = torch.cat((lg, lg.gather(1, pad_col).expand(-1, C - cg)), 1)
+            out[mi].index_copy_(0, idx, lg)
+    return out
+
+
+@torch.no_grad()
+def ensemble_scores(model_list: Sequence[torch.nn.Module], x_history, x_inview, x_global, empty_num=None, want_ranks: bool = True,
+                    groups: int = 8):
+    """`test.py:58-70` for one batch: every model's eval forward (ragged-aware, see `ensemble_logits`), then the fused
+    epilogue.  `groups=1` scores the full rectangle."""
+    logits = ensemble_logits(model_list, x_history, x_inview, x_global, empty_num if groups > 1 else None, groups)
+    return score_epilogue(logits, empty_num, want_ranks)
 
 
 def submission_lines(impression_id: torch.Tensor, ranks: torch.Tensor, empty_num: Optional[torch.Tensor] = None
