@@ -172,3 +172,23 @@ def test_config5_training_step_runs_at_reduced_batch():
         rep = P.compare_step(model, p, b, training=True)
         assert rep['logits'] <= P.TOL_LOGITS and rep['loss'] <= P.TOL_LOSS, (prec, P.format_report(rep))
         assert not P.grad_failures(rep), (prec, P.format_report(rep))
+
+
+def test_config5_full_size_training_step_two_implementations_agree():
+    """B = 4096, H = 256 (four history tiles per impression, masked tails), one whole training step: the FFMA fp32 path and
+    the pipelined tcgen05 path agree within the fp32 tolerances, and the tensor-core path is run-to-run deterministic."""
+    b = make_batch(4096, 256, 5, seed=555, user_num=1000, variable_history=True).to('cuda')
+    res = {}
+    for prec in ('fp32', 'bf16x3'):
+        res[prec] = _train_step(_model('train', 1000, prec, train=True), b)
+    again = _train_step(_model('train', 1000, 'bf16x3', train=True), b)
+    assert torch.equal(res['bf16x3'][0], again[0]) and torch.equal(res['bf16x3'][1], again[1])
+    for k in again[2]:
+        assert torch.equal(res['bf16x3'][2][k], again[2][k]), k
+    (o32, l32, g32), (o3, l3, g3) = res['fp32'], res['bf16x3']
+    assert (o32 - o3).abs().max().item() <= 2 * P.TOL_LOGITS
+    assert abs(float(l32) - float(l3)) <= P.TOL_LOSS
+    for k in g32:
+        scale = g32[k].abs().max().item()
+        tol = P.TOL_GRAD_ABS if k in P.NOISE_KEYS else 2 * P.TOL_GRAD_REL * scale + P.TOL_GRAD_ABS
+        assert (g32[k] - g3[k]).abs().max().item() <= tol, (k, (g32[k] - g3[k]).abs().max().item(), scale)
