@@ -9,12 +9,14 @@
 // forms the five weight gradients dW = P^T Q over row chunks with one accumulator column per thread; a last
 // kernel adds the chunk partials in fixed order (deterministic, no atomics).
 #include "nrm_kernels.cuh"
+#include "nrm_umma.cuh"      // mbarrier helpers
 
 namespace nrm {
 
 constexpr int HT_ROWS = 36;        // candidate rows per tile: 5120 rows (B=1024, C=5) -> 143 tiles, one wave of 148 SMs
 constexpr int HT_RPT = 9;          // rows per thread (4 row groups)
-constexpr int HT_THREADS = 288;    // 4 x 66 = 264 working threads, 9 warps
+constexpr int HT_CONSUMERS = 288;  // 4 x 66 = 264 working threads, 9 warps: the layers
+constexpr int HT_THREADS = 320;    // + warp 9: its first lane streams the weight chunks with bulk async copies (TMA engine)
 constexpr int LDW = 268;           // row stride of the 264-wide shared buffers (16-byte aligned rows)
 constexpr int LDN = 68;            // row stride of the 66-wide shared buffers
 
@@ -27,8 +29,8 @@ struct HeadSmem {
   __align__(16) float w1[HT_ROWS * LDW];   // forward: the e tile; backward: cross row-group reduction scratch [4][2][264]
   __align__(16) float nb[HT_ROWS * LDN];
   __align__(16) float wbuf[W_STAGES][WCHUNK];   // ring of weight chunks (cp.async, two chunks in flight)
-  const float* csrc[W_CHUNKS];           // global source of weight chunk g (all five layers of the kernel, in order)
-  int cfloats[W_CHUNKS];                 // its size
+  uint64_t full[W_STAGES];               // chunk landed in the slot (complete_tx of the bulk copy)
+  uint64_t empty[W_STAGES];              // the nine consumer warps have finished with the slot
 };
 
 // Transposed copies of the five matrices for the forward pass: wt = [G1^T | G2^T | M1^T | M2^T | O1^T], each stored
@@ -52,47 +54,35 @@ head_transpose_kernel(const float* __restrict__ P, float* __restrict__ wt) {
   }
 }
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 // The weights of the five layers a kernel walks through stream through shared memory as ONE sequence of 25 chunks
-// (64 x 66 or 16 x 264 floats, 16.9 KB): chunk g lands in ring slot g % 3 while chunks g + 1 and g + 2 are in flight,
-// across layer boundaries, so a layer never starts with a cold fetch.  weight_stream_init() fills the chunk table from
-// the five (matrix, K, NOUT) triples and issues the first two chunks.
+// (64 x 66 or 16 x 264 floats, 16.9 KB) in a three-slot ring, across layer boundaries, so a layer never starts with a cold
+// fetch.  Producer / consumer pipeline: the first lane of warp 9 issues one bulk async copy per chunk
+// (cp.async.bulk ... mbarrier::complete_tx: the TMA engine moves the 16.9 KB, no thread touches the data), arming the
+// slot's `full` barrier with the byte count; the nine consumer warps wait on `full`, multiply, and arrive on the slot's
+// `empty` barrier (one arrival per warp), which the producer waits for before refilling the slot.  No CTA-wide barrier
+// per chunk: the consumer warps drift apart by up to the ring depth.
 struct HeadLayerDesc { const float* W; int K; int nout; };
 
-__device__ __forceinline__ void weight_chunk_issue(HeadSmem& sm, int g) {
-  if (g < W_CHUNKS) {
-    const float* src = sm.csrc[g];
-    float* dst = sm.wbuf[g % W_STAGES];
-    const int n4 = sm.cfloats[g] >> 2;
-    for (int i = threadIdx.x; i < n4; i += HT_THREADS) cp_async16(dst + 4 * i, src + 4 * i);
-  }
-  cp_async_commit();                                       // every thread commits one group per chunk index
-}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(HT_CONSUMERS) : "memory"); }
 
-__device__ __forceinline__ void weight_stream_init(HeadSmem& sm, const HeadLayerDesc (&layers)[5]) {
-  if (threadIdx.x < W_CHUNKS) {
-    const int l = threadIdx.x / W_LAYER_CHUNKS, c = threadIdx.x - l * W_LAYER_CHUNKS;
+__device__ __forceinline__ void weight_producer(HeadSmem& sm, const HeadLayerDesc (&layers)[5]) {
+  for (int g = 0; g < W_CHUNKS; ++g) {
+    const int l = g / W_LAYER_CHUNKS, c = g - l * W_LAYER_CHUNKS;
     const int kc = WCHUNK / layers[l].nout;
     const int rows = min(kc, layers[l].K - c * kc);
-    sm.csrc[threadIdx.x] = layers[l].W + (long long)c * kc * layers[l].nout;
-    sm.cfloats[threadIdx.x] = rows * layers[l].nout;
+    const float* src = layers[l].W + (long long)c * kc * layers[l].nout;
+    const uint32_t bytes = (uint32_t)(rows * layers[l].nout * sizeof(float));
+    const int slot = g % W_STAGES, use = g / W_STAGES;
+    if (use > 0) umma::mbar_wait(&sm.empty[slot], (uint32_t)((use - 1) & 1));
+    const uint32_t bar = umma::smem_u32(&sm.full[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     umma::smem_u32(sm.wbuf[slot])), "l"(src), "r"(bytes), "r"(bar) : "memory");
   }
-  __syncthreads();
-  weight_chunk_issue(sm, 0);
-  weight_chunk_issue(sm, 1);
 }
 
 // acc[i][q] += sum_k in[(rg*9+i)][k] * W[k][n + 66 q]   (W = [K][66 NQ], output index contiguous), W = layer `layer` of the
-// kernel's weight stream.  Called by EVERY thread of the CTA (it synchronises); threads with work == false only help
-// with the copies.  One __syncthreads per chunk: it publishes chunk g and retires chunk g - 1, whose slot the chunk
-// issued right after it (g + 2) overwrites.
+// kernel's weight stream.  Called by every CONSUMER thread (threads with work == false only take part in the barriers).
 template <int K, int NQ, int LDI>
 __device__ __forceinline__ void head_layer(const float* in, HeadSmem& sm, int layer, bool work, int rg, int n, float acc[HT_RPT][NQ]) {
   constexpr int NOUT = HID * NQ;
@@ -103,11 +93,10 @@ __device__ __forceinline__ void head_layer(const float* in, HeadSmem& sm, int la
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     const int g = layer * W_LAYER_CHUNKS + c;
-    cp_async_wait<1>();                                  // chunk g has landed (g + 1 may still be in flight)
-    __syncthreads();
-    weight_chunk_issue(sm, g + 2);
+    const int slot = g % W_STAGES;
+    umma::mbar_wait(&sm.full[slot], (uint32_t)((g / W_STAGES) & 1));      // chunk g has landed
     if (work) {
-      const float* wb = sm.wbuf[g % W_STAGES];
+      const float* wb = sm.wbuf[slot];
       const int kc = (K - c * KC) < KC ? (K - c * KC) : KC;
       const int kc4 = kc & ~3;
       const float* inc = inr + c * KC;
@@ -142,6 +131,8 @@ __device__ __forceinline__ void head_layer(const float* in, HeadSmem& sm, int la
         }
       }
     }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) umma::mbar_arrive(&sm.empty[slot]);       // this warp is done with the slot
   }
 }
 
@@ -172,15 +163,23 @@ head_forward_kernel(const float* __restrict__ e, const double* __restrict__ bn_s
   const int nr = (int)min((long long)HT_ROWS, R - r0);
   {
     const HeadLayerDesc layers[5] = {{wt + WT_G1, E, HID}, {wt + WT_G2, HID, E}, {wt + WT_M1, E, HID}, {wt + WT_M2, HID, E}, {wt + WT_O1, E, HID}};
-    weight_stream_init(sm, layers);
+    // barriers of the weight ring, then the roles split: warp 9 streams the weights and leaves
+    if (tid == 0) {
+      for (int j = 0; j < W_STAGES; ++j) { umma::mbar_init(&sm.full[j], 1); umma::mbar_init(&sm.empty[j], HT_CONSUMERS / 32); }
+    }
+    __syncthreads();
+    if (tid >= HT_CONSUMERS) {
+      if (tid == HT_CONSUMERS) weight_producer(sm, layers);
+      return;
+    }
   }
   // e tile -> w1 (kept for the gating product), z = BatchNorm(e) -> w0.  All loads of the tile are issued first.
   {
-    constexpr int NV = HT_ROWS * (E / 4), IT = (NV + HT_THREADS - 1) / HT_THREADS;
+    constexpr int NV = HT_ROWS * (E / 4), IT = (NV + HT_CONSUMERS - 1) / HT_CONSUMERS;
     float4 ev[IT];
 #pragma unroll
     for (int u = 0; u < IT; ++u) {
-      const int i = tid + u * HT_THREADS, r = i / (E / 4), c4 = i - r * (E / 4);
+      const int i = tid + u * HT_CONSUMERS, r = i / (E / 4), c4 = i - r * (E / 4);
       ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < NV && r < nr) ev[u] = __ldg(reinterpret_cast<const float4*>(e + (r0 + r) * E) + c4);
     }
@@ -210,10 +209,10 @@ head_forward_kernel(const float* __restrict__ e, const double* __restrict__ bn_s
       mean[n] = m; rstd[n] = rs;
       if (blockIdx.x == 0) { mean_out[n] = m; rstd_out[n] = rs; }
     }
-    __syncthreads();
+    consumer_sync();
 #pragma unroll
     for (int u = 0; u < IT; ++u) {
-      const int i = tid + u * HT_THREADS, r = i / (E / 4), c4 = i - r * (E / 4);
+      const int i = tid + u * HT_CONSUMERS, r = i / (E / 4), c4 = i - r * (E / 4);
       if (i >= NV) continue;
       const float4 v = ev[u];
       float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -227,7 +226,7 @@ head_forward_kernel(const float* __restrict__ e, const double* __restrict__ bn_s
       *reinterpret_cast<float4*>(sm.w0 + r * LDW + 4 * c4) = z;
     }
   }
-  __syncthreads();
+  consumer_sync();
   const bool work = tid < 4 * HID;
   const int rg = work ? tid / HID : 0, n = work ? tid % HID : 0;
   const int rb = rg * HT_RPT;
@@ -248,7 +247,7 @@ head_forward_kernel(const float* __restrict__ e, const double* __restrict__ bn_s
     head_layer<E, 1, LDW>(sm.w0, sm, 0, work, rg, n, acc);
     if (work) narrow_out(acc, P + P_GATE_FC1_B, a1g);
   }
-  __syncthreads();
+  consumer_sync();
   {  // gate.fc2; x = gate * e -> w0
     float acc[HT_RPT][4]; zero_acc<4>(acc);
     head_layer<HID, 4, LDN>(sm.nb, sm, 1, work, rg, n, acc);
@@ -266,13 +265,13 @@ head_forward_kernel(const float* __restrict__ e, const double* __restrict__ bn_s
       }
     }
   }
-  __syncthreads();
+  consumer_sync();
   {  // mlp.fc1
     float acc[HT_RPT][1]; zero_acc<1>(acc);
     head_layer<E, 1, LDW>(sm.w0, sm, 2, work, rg, n, acc);
     if (work) narrow_out(acc, P + P_MLP_FC1_B, a2g);
   }
-  __syncthreads();
+  consumer_sync();
   {  // mlp.fc2 -> y -> w0
     float acc[HT_RPT][4]; zero_acc<4>(acc);
     head_layer<HID, 4, LDN>(sm.nb, sm, 3, work, rg, n, acc);
@@ -290,15 +289,15 @@ head_forward_kernel(const float* __restrict__ e, const double* __restrict__ bn_s
       }
     }
   }
-  __syncthreads();
+  consumer_sync();
   {  // out_mlp.fc1
     float acc[HT_RPT][1]; zero_acc<1>(acc);
     head_layer<E, 1, LDW>(sm.w0, sm, 4, work, rg, n, acc);
     if (work) narrow_out(acc, P + P_OUT_FC1_B, a3g);
   }
-  __syncthreads();
+  consumer_sync();
   // out_mlp.fc2: one warp per row
-  for (int r = tid >> 5; r < nr; r += HT_THREADS / 32) {
+  for (int r = tid >> 5; r < nr; r += HT_CONSUMERS / 32) {
     const int lane = tid & 31;
     float acc = 0.f;
     for (int c = lane; c < HID; c += 32) acc = fmaf(sm.nb[r * LDN + c], __ldg(P + P_OUT_FC2_W + c), acc);
@@ -337,7 +336,15 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
     // data-gradient chain: the nn.Linear weights in their natural [out][in] layout (the contraction runs over `out`)
     const HeadLayerDesc layers[5] = {{P + P_OUT_FC1_W, HID, E}, {P + P_MLP_FC2_W, E, HID}, {P + P_MLP_FC1_W, HID, E},
                                      {P + P_GATE_FC2_W, E, HID}, {P + P_GATE_FC1_W, HID, E}};
-    weight_stream_init(sm, layers);
+    // barriers of the weight ring, then the roles split: warp 9 streams the weights and leaves
+    if (tid == 0) {
+      for (int j = 0; j < W_STAGES; ++j) { umma::mbar_init(&sm.full[j], 1); umma::mbar_init(&sm.empty[j], HT_CONSUMERS / 32); }
+    }
+    __syncthreads();
+    if (tid >= HT_CONSUMERS) {
+      if (tid == HT_CONSUMERS) weight_producer(sm, layers);
+      return;
+    }
   }
 
   // da3 = dr * O2 * gelu'(a3) -> nb; dO2 / do2 partial sums
@@ -361,7 +368,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
     red[rg * 2 * E + n] = dw;
     if (n == 0) red[rg * 2 * E + E] = db;
   }
-  __syncthreads();
+  consumer_sync();
   if (tid < HID) part_f[(long long)blockIdx.x * HB_F + tid] = ((red[tid] + red[2 * E + tid]) + red[4 * E + tid]) + red[6 * E + tid];
   if (tid == HID) part_f[(long long)blockIdx.x * HB_F + HID] = ((red[E] + red[2 * E + E]) + red[4 * E + E]) + red[6 * E + E];
 
@@ -379,7 +386,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
         }
     }
   }
-  __syncthreads();
+  consumer_sync();
   {  // da2 = (dy M2) * gelu'(a2) -> nb
     float acc[HT_RPT][1]; zero_acc<1>(acc);
     head_layer<E, 1, LDW>(sm.w0, sm, 1, work, rg, n, acc);
@@ -395,7 +402,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
       }
     }
   }
-  __syncthreads();
+  consumer_sync();
   {  // dx = da2 M1;  dgate = dx * e -> w0;  de (direct path) = dx * gate
     float acc[HT_RPT][4]; zero_acc<4>(acc);
     head_layer<HID, 4, LDN>(sm.nb, sm, 2, work, rg, n, acc);
@@ -416,7 +423,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
         }
     }
   }
-  __syncthreads();
+  consumer_sync();
   {  // da1 = (dgate G2) * gelu'(a1) -> nb
     float acc[HT_RPT][1]; zero_acc<1>(acc);
     head_layer<E, 1, LDW>(sm.w0, sm, 3, work, rg, n, acc);
@@ -432,7 +439,7 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
       }
     }
   }
-  __syncthreads();
+  consumer_sync();
   {  // dz = da1 G1; BatchNorm partial sums of dz and dz * xhat over this tile's rows
     float acc[HT_RPT][4]; zero_acc<4>(acc);
     head_layer<HID, 4, LDN>(sm.nb, sm, 4, work, rg, n, acc);
@@ -457,8 +464,8 @@ head_backward_kernel(const float* __restrict__ e, const float* __restrict__ mean
       }
     }
   }
-  __syncthreads();
-  for (int i = tid; i < 2 * E; i += HT_THREADS)
+  consumer_sync();
+  for (int i = tid; i < 2 * E; i += HT_CONSUMERS)
     part_bn[(long long)blockIdx.x * 2 * E + i] = ((double)red[i] + (double)red[2 * E + i]) + ((double)red[4 * E + i] + (double)red[6 * E + i]);
 }
 
