@@ -238,10 +238,6 @@ __device__ __forceinline__ void park_pair_vec(float* tt, const PairVec v) {
   tt[q * 128 + i] = v.t;
   tt[q * 128 + 64 + i] = v.tp;
 }
-__device__ __forceinline__ void stage_weights(const float* __restrict__ der, float* wda) {
-  for (int i = threadIdx.x; i < 8192 / 4; i += TC_THREADS)
-    reinterpret_cast<float4*>(wda)[i] = __ldg(reinterpret_cast<const float4*>(der) + i);
-}
 
 __device__ __forceinline__ void st_bf16(unsigned char* p, float v) {
   *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
@@ -280,6 +276,7 @@ struct TcSmemFwd {
   __align__(16) float tt[2][2 * 128];                        // [buffer][item q][t 64 | tp 64]
   float w2[64];
   uint64_t mbar;
+  uint64_t wbar;                                             // bulk copy of the derived weights has landed
   uint32_t tmem_base;
 };
 
@@ -302,13 +299,17 @@ __device__ __forceinline__ void attention_forward_tc_body(const double* __restri
 
   const float* tpg = tp_all + (long long)BRANCH * B * C * 64;
   if (tid < 64) sm.w2[tid] = __ldg(der + DER_W2 + tid);
-  stage_weights(der, sm.wda);
+  if (tid == 0) {                                      // Wd | A (32 KB): one bulk copy by the TMA engine, under the rest of the prologue
+    umma::mbar_init(&sm.mbar, 1);
+    umma::mbar_init(&sm.wbar, 1);
+    umma::bulk_load(sm.wda, der, 8192 * sizeof(float), &sm.wbar);
+  }
   const float b2 = __ldg(der + DER_B2);
   if (warp == 0) umma::tmem_alloc(&sm.tmem_base, FWD_TMEM_COLS);
-  if (tid == 0) umma::mbar_init(&sm.mbar, 1);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  umma::mbar_wait(&sm.wbar, 0);
   const uint32_t tmem = sm.tmem_base;
   uint32_t phase = 0;
 
@@ -446,6 +447,7 @@ struct TcSmemBwd {
   float w2[64];
   uint64_t mbar;
   uint64_t mbar_h;                                           // hid products of the pipelined (label) kernel
+  uint64_t wbar;                                             // bulk copy of the derived weights has landed
   uint32_t tmem_base;
 };
 
@@ -501,15 +503,19 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 
   const float* tpg = tp_all + (long long)BRANCH * B * C * 64;
   if (tid < 64) sm.w2[tid] = __ldg(der + DER_W2 + tid);
-  stage_weights(der, sm.wda);
+  if (tid == 0) {                                      // Wd | A (32 KB): one bulk copy by the TMA engine, under the rest of the prologue
+    umma::mbar_init(&sm.mbar, 1); umma::mbar_init(&sm.mbar_h, 1);
+    umma::mbar_init(&sm.wbar, 1);
+    umma::bulk_load(sm.wda, der, 8192 * sizeof(float), &sm.wbar);
+  }
   for (int i = tid; i < (int)T8_BYTES / 2; i += TC_THREADS) reinterpret_cast<__nv_bfloat16*>(sm.ones)[i] = __float2bfloat16_rn(1.0f);
   const float b2 = __ldg(der + DER_B2);
   if (warp == 0) umma::tmem_alloc(&sm.tmem_base, BWD_TMEM_COLS);
-  if (tid == 0) { umma::mbar_init(&sm.mbar, 1); umma::mbar_init(&sm.mbar_h, 1); }
   umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  umma::mbar_wait(&sm.wbar, 0);
   const uint32_t tmem = sm.tmem_base;
   uint32_t phase = 0, phase_h = 0;
 
