@@ -47,7 +47,7 @@ def parse():
     ap.add_argument('--sync-bn', action='store_true', help='all-reduce BatchNorm statistics across ranks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='FusedTrainStep issues the C-ABI calls eagerly instead of replaying a CUDA graph')
-    ap.add_argument('--cpu-steps', type=int, default=8)
+    ap.add_argument('--cpu-steps', type=int, default=60, help='train steps of the CPU port timed for cpu_baseline (about 15 s on 16 cores)')
     ap.add_argument('--no-scoring', action='store_true', help='skip the scoring (configs[2]) leg')
     ap.add_argument('--no-affinity', action='store_true', help='do not bind each rank to the CPU cores local to its GPU')
     return ap.parse_args()
@@ -147,7 +147,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, min(args.steps, 100)), max(1, min(args.warmup, 5))
     rate, ms, cores = cpu_reference_rate(args, steps, warmup)
     line = {
         'impl': 'reference', 'metric': 'train_impressions_per_sec', 'value': rate, 'unit': 'impressions/s',
