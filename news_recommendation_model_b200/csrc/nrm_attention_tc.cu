@@ -877,7 +877,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 //   fc1.weight grad blocks: [:, 0:64] = dA, [:, 192:256] = dWd   (the Bm-dependent blocks are completed by
 //   attention_tp_grad_kernel); fc2.weight = dw2; fc2.bias = db2.   Partials are transposed ([k][j]).
 __device__ __forceinline__ void
-attention_tc_compose_block(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads,
+attention_tc_compose_block(int block, const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads,
                            float* __restrict__ dA_all) {
   const int branch = blockIdx.y;
   const AttOffsets off = branch == 0 ? ATT_LABEL : ATT_TI;
@@ -887,8 +887,8 @@ attention_tc_compose_block(const float* __restrict__ part_all, int nparts0, int 
   // block = 32 consecutive (k,j) entries x 32 interleaved groups of partials, combined in group order; grid.x = 128 (+1)
   __shared__ float red[32][2][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  if (blockIdx.x < 128) {
-    const int i = blockIdx.x * 32 + lane;              // k*64 + j
+  if (block < 128) {
+    const int i = block * 32 + lane;              // k*64 + j
     float dA = 0.f, dWd = 0.f;
 #pragma unroll 4
     for (int p = grp; p < nparts; p += 32) {
@@ -929,9 +929,15 @@ attention_tc_compose_block(const float* __restrict__ part_all, int nparts0, int 
 
 // The tp = Bm t + b1 path, over the R candidate rows: dBm[j][k] = sum_r dtp[r][j] t[r][k], db1[j] = sum_r dtp[r][j],
 // and (label branch) dxt[r][k] += sum_j dtp[r][j] Bm[j][k].  32 rows per CTA -> partials, summed by the finish kernel.
-constexpr int TPG_ROWS = 32, TPG_PART = 4096 + 64;
+constexpr int TPG_ROWS = 32, TPG_PART = 4096 + 64, TPG_SUB = 4;
+struct TpgSmem {
+  float sB[64][65];                   // Bm[j][k] = Wb + Wc (shared by the block's four tiles)
+  float sd[TPG_SUB][TPG_ROWS][65];    // dtp rows
+  float st[TPG_SUB][TPG_ROWS][64];    // t rows
+};
+// 1024 threads = four groups of 256, each taking one 32-row tile (partial number block * 4 + group)
 __device__ __forceinline__ void
-attention_tp_grad_block(int block, const float* __restrict__ dtp_all, const float* __restrict__ e, long long R,
+attention_tp_grad_block(int block, TpgSmem& sm, const float* __restrict__ dtp_all, const float* __restrict__ e, long long R,
                         const float* __restrict__ P, float* __restrict__ dxt, float* __restrict__ part_all, int nparts) {
   const int branch = blockIdx.y;
   const float* dtp = dtp_all + (long long)branch * R * 64;
@@ -939,23 +945,24 @@ attention_tp_grad_block(int block, const float* __restrict__ dtp_all, const floa
   const float* W = P + (branch == 0 ? ATT_LABEL.fc1_w : ATT_TI.fc1_w);     // fc1.weight [64,256]
   const int input_grads = branch == 0;
   float* part = part_all + (long long)branch * nparts * TPG_PART;
-  __shared__ float sd[TPG_ROWS][65];    // dtp rows
-  __shared__ float st[TPG_ROWS][64];    // t rows
-  __shared__ float sB[64][65];          // Bm[j][k] = Wb + Wc
-  const int tid = threadIdx.x;
-  const long long r0 = (long long)block * TPG_ROWS;
-  const int nr = (int)min((long long)TPG_ROWS, R - r0);
+  const int sub = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  const int tile = block * TPG_SUB + sub;
+  float (*sd)[65] = sm.sd[sub];
+  float (*st)[64] = sm.st[sub];
+  const long long r0 = (long long)tile * TPG_ROWS;
+  const int nr = (int)max(0LL, min((long long)TPG_ROWS, R - r0));
   for (int i = tid; i < TPG_ROWS * 64; i += 256) {
     const int r = i >> 6, k = i & 63;
     sd[r][k] = r < nr ? __ldg(dtp + (r0 + r) * 64 + k) : 0.f;
     st[r][k] = r < nr ? __ldg(e + (r0 + r) * E + toff + k) : 0.f;
   }
   if (input_grads)
-    for (int i = tid; i < 64 * 64; i += 256) {
+    for (int i = threadIdx.x; i < 64 * 64; i += 1024) {
       const int j = i >> 6, k = i & 63;
-      sB[j][k] = __ldg(W + j * 256 + 64 + k) + __ldg(W + j * 256 + 128 + k);
+      sm.sB[j][k] = __ldg(W + j * 256 + 64 + k) + __ldg(W + j * 256 + 128 + k);
     }
   __syncthreads();
+  if (tile >= nparts) return;
   {
     // dBm partial: thread (tj, tk) owns a 4 x 4 block of [j][k]
     const int tj = tid >> 4, tk = tid & 15;
@@ -977,7 +984,7 @@ attention_tp_grad_block(int block, const float* __restrict__ dtp_all, const floa
         for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], tv[b], acc[a][b]);
       }
     }
-    float* out = part + (long long)block * TPG_PART;
+    float* out = part + (long long)tile * TPG_PART;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       *reinterpret_cast<float4*>(out + (4 * tj + a) * 64 + 4 * tk) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
@@ -992,7 +999,7 @@ attention_tp_grad_block(int block, const float* __restrict__ dtp_all, const floa
     for (int j = 0; j < 64; ++j) {
       const float d = sd[r][j];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaf(d, sB[j][kq + 8 * i], v[i]);
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(d, sm.sB[j][kq + 8 * i], v[i]);
     }
     if (r < nr) {
 #pragma unroll
@@ -1001,8 +1008,9 @@ attention_tp_grad_block(int block, const float* __restrict__ dtp_all, const floa
   }
 }
 
-// One launch for the two independent reductions: blocks [0, 129) sum the per-CTA partials of the backward kernels,
-// blocks [129, 129 + nparts) (their first 256 threads) take 32 candidate rows each through the tp path.
+// One launch for the two independent reductions: the first ceil(nparts / 4) blocks take 4 x 32 candidate rows each through
+// the tp path (they are the longer ones, so they are scheduled first), the next 129 sum the per-CTA partials of the
+// backward kernels.
 constexpr int COMPOSE_BLOCKS = 129;
 __global__ void __launch_bounds__(1024)
 attention_finish_kernel(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads, float* __restrict__ dA_all,
@@ -1010,11 +1018,12 @@ attention_finish_kernel(const float* __restrict__ part_all, int nparts0, int npa
                         float* __restrict__ dxt, float* __restrict__ tp_part, int nparts) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
-  if (blockIdx.x < COMPOSE_BLOCKS) {
-    attention_tc_compose_block(part_all, nparts0, nparts1, grads, dA_all);
+  extern __shared__ __align__(16) unsigned char fin_raw[];
+  const int tp_blocks = (nparts + TPG_SUB - 1) / TPG_SUB;
+  if ((int)blockIdx.x < tp_blocks) {
+    attention_tp_grad_block(blockIdx.x, *reinterpret_cast<TpgSmem*>(fin_raw), dtp_all, e, R, P, dxt, tp_part, nparts);
   } else {
-    if (threadIdx.x >= 256) return;
-    attention_tp_grad_block(blockIdx.x - COMPOSE_BLOCKS, dtp_all, e, R, P, dxt, tp_part, nparts);
+    attention_tc_compose_block(blockIdx.x - tp_blocks, part_all, nparts0, nparts1, grads, dA_all);
   }
 }
 
@@ -1182,7 +1191,12 @@ int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace&
 // both branches at once (after both backward kernels)
 int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaStream_t s) {
   const int nparts = (int)((w.R + TPG_ROWS - 1) / TPG_ROWS);
-  launch_pdl(attention_finish_kernel, dim3(dim3(COMPOSE_BLOCKS + nparts, 2)), dim3(1024), 0, s, w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA, w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
+  static bool configured = false;
+  if (!configured) {
+    NRM_CUDA(cudaFuncSetAttribute(attention_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TpgSmem)));
+    configured = true;
+  }
+  launch_pdl(attention_finish_kernel, dim3(COMPOSE_BLOCKS + (nparts + TPG_SUB - 1) / TPG_SUB, 2), dim3(1024), sizeof(TpgSmem), s, w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA, w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
   NRM_LAUNCH_CHECK("attention_finish_kernel");
   launch_pdl(attention_tp_finish_kernel, dim3(dim3(TPG_PART / 64, 2)), dim3(256), 0, s, w.tp_part, nparts, w.att_dA, grads);
   NRM_LAUNCH_CHECK("attention_tp_finish_kernel");
