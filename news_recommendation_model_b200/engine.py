@@ -80,6 +80,8 @@ class FlatParams:
                 p.data = view
                 self.slots.append((name, off, n, p.shape))
         self.bn_weight_off = next(off for name, off, _, _ in self.slots if name == 'bn.weight')
+        # the Parameter objects in layout order (without delta): the autograd inputs of every forward
+        self.params = [named[name] for name, _, _, _ in self.slots if name != 'delta']
 
     def is_current(self, named: Dict[str, torch.nn.Parameter]) -> bool:
         base = self.buf.data_ptr()

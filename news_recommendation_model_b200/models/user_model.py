@@ -90,9 +90,9 @@ class UserModel(nn.Module):
     def forward(self, x_history, x_target, x_global):
         flat = self.flat_parameters()
         mode = engine.MODE_BN_BATCH_STATS if self.training else engine.MODE_EVAL
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        params = flat.params
+        if torch.is_grad_enabled() and (self.delta.requires_grad or any(p.requires_grad for p in params)):
             mode |= engine.MODE_KEEP_FOR_BWD
-            params = [getattr_path(self, name) for name, _, _, _ in flat.slots if name != 'delta']
             return engine._ForwardFn.apply(self, x_history, x_target, x_global, mode, *params)
         rt = self._runtime()
         logits, _ = engine.forward_logits(rt, flat, self.bn.running_mean, self.bn.running_var,

@@ -21,6 +21,12 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError('invalid Adam hyper-parameter')
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale))
         self._flat_state = {}     # id(group) -> (base_ptr, numel, exp_avg, exp_avg_sq)
+        self._plan = {}           # id(group) -> cached layout of the flat fast path (see _step_cached)
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._plan.clear()                 # the loaded per-tensor state is re-packed into flat buffers by the next step
+        self._flat_state.clear()
 
     @staticmethod
     def _flat_span(plist):
@@ -42,6 +48,8 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for group in self.param_groups:
+            if self._step_cached(group):
+                continue
             plist = [p for p in group['params'] if p.grad is not None]
             if not plist:
                 continue
@@ -57,6 +65,10 @@ class FusedAdam(torch.optim.Optimizer):
                      all(p.grad.data_ptr() - gspan[0] == p.data_ptr() - pspan[0] for p in plist))
             if fused:
                 self._step_flat(group, plist, pspan, gspan, kw)
+                first = min(range(len(plist)), key=lambda i: plist[i].data_ptr())
+                gbase = plist[first].grad.data_ptr()
+                self._plan[id(group)] = dict(pptrs=[p.data_ptr() for p in plist], goffs=[p.grad.data_ptr() - gbase for p in plist],
+                                             first=first, n=pspan[1], pflat=_span_tensor(plist[first], pspan[1]))
             else:
                 for p in plist:
                     st = self.state[p]
@@ -68,6 +80,35 @@ class FusedAdam(torch.optim.Optimizer):
                     g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                     engine.adam_step(p, g, st['exp_avg'], st['exp_avg_sq'], step=st['step'], **kw)
         return loss
+
+    def _step_cached(self, group) -> bool:
+        """Fast path for the steady state of a training loop: same parameter tensors as in the last fused step, and
+        gradients that are again views of ONE flat buffer at the same offsets (what the hand-written backward hands to
+        autograd every step).  Only pointers are compared; anything else falls back to the full analysis."""
+        plan = self._plan.get(id(group))
+        if plan is None:
+            return False
+        params = group['params']
+        if len(params) != len(plan['pptrs']):
+            return False
+        g0 = params[plan['first']].grad
+        if g0 is None:
+            return False
+        gbase = g0.data_ptr()
+        goffs = plan['goffs']
+        for i, p in enumerate(params):
+            g = p.grad
+            if g is None or p.data_ptr() != plan['pptrs'][i] or g.data_ptr() - gbase != goffs[i]:
+                return False
+        fs = self._flat_state[id(group)]
+        state = self.state
+        step = state[params[0]]['step'] + 1
+        for p in params:
+            state[p]['step'] = step
+        b1, b2 = group['betas']
+        engine.adam_step(plan['pflat'], _span_tensor(g0, plan['n']), fs[2], fs[3], step=step, lr=group['lr'], beta1=b1, beta2=b2,
+                         eps=group['eps'], weight_decay=group['weight_decay'], grad_scale=group['grad_scale'])
+        return True
 
     def _step_flat(self, group, plist, pspan, gspan, kw):
         base, n = pspan
