@@ -92,7 +92,25 @@ class FlatParams:
         return True
 
     def grad_views(self, gbuf: torch.Tensor, skip_delta: bool) -> List[torch.Tensor]:
-        return [gbuf[off:off + n].view(shape) for name, off, n, shape in self.slots
+        """Views of the flat gradient buffer with the parameters' shapes, in layout order: ONE split call (sizes include
+        the alignment gaps between entries) instead of a slice per tensor."""
+        plan = self.__dict__.get('_split_plan')
+        if plan is None:
+            sizes, pick, pos = [], [], 0
+            for name, off, n, shape in self.slots:
+                if off > pos:
+                    sizes.append(off - pos)
+                pick.append((len(sizes), name, shape if len(shape) != 1 else None))
+                sizes.append(n)
+                pos = off + n
+            if self.total > pos:
+                sizes.append(self.total - pos)
+            plan = self._split_plan = (sizes, pick)
+        sizes, pick = plan
+        if gbuf.numel() != self.total:
+            return [gbuf[off:off + n].view(shape) for name, off, n, shape in self.slots if not (skip_delta and name == 'delta')]
+        parts = gbuf.split_with_sizes(sizes)
+        return [parts[i] if shape is None else parts[i].view(shape) for i, name, shape in pick
                 if not (skip_delta and name == 'delta')]
 
 
