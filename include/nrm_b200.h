@@ -163,7 +163,9 @@ int nrm_backward_encoder(const double* x_history, const double* x_target, long l
 /* ---- UserModel.loss (user_model.py:37-43) ---------------------------------------- */
 /* loss = (1-alpha) BCE(softmax(out), y) + alpha BCE(softmax(out + delta[id]), y), mean
  * over B*C, log clamped at -100 (nn.BCELoss).  Writes *loss (float32) and keeps the unit
- * gradients in `scratch` (>= nrm_loss_scratch_bytes(B,C)). */
+ * gradients in `scratch` (>= nrm_loss_scratch_bytes(B,C)).  `scratch` must be ZERO-FILLED ONCE
+ * before its first use (it holds the arrival counter with which the last block of the forward
+ * kernel adds the block sums in fixed order; every call leaves the counter at zero again). */
 size_t nrm_loss_scratch_bytes(int B, int C);
 int nrm_loss_forward(const float* logits, const float* delta, const long long* user_id,
                      const double* label, int B, int C, float alpha,

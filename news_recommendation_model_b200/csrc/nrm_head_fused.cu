@@ -599,49 +599,65 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
   }
 }
 
-// Sum the chunk partials in chunk order and write the head gradients (transposing layers 1 and 3, whose weights
-// are [264][66]); also out_mlp.fc2 from the tile partials of kernel A and the BatchNorm sums.
+// Sum the chunk partials and write the head gradients (transposing layers 1 and 3, whose weights are [264][66]); also
+// out_mlp.fc2 from the tile partials of kernel A and the BatchNorm sums.  Block = 64 consecutive entries x 4 interleaved
+// groups of partials (group g adds partials g, g + 4, ... in order; the four group sums are combined in group order):
+// fixed summation order, chains a quarter as long.
+constexpr int GF_ENT = 64;
 __global__ void __launch_bounds__(256)
 head_grad_finish_kernel(const float* __restrict__ part, int nchunks, const float* __restrict__ part_f, int ntiles,
                         const double* __restrict__ part_bn, float* __restrict__ grads, double* __restrict__ bn_bwd_sums) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
+  __shared__ double red[4][GF_ENT];
   const int layer = blockIdx.y;
-  if (layer < 5) {
-    const long long w_off[5] = {P_OUT_FC1_W, P_MLP_FC2_W, P_MLP_FC1_W, P_GATE_FC2_W, P_GATE_FC1_W};
-    const long long b_off[5] = {P_OUT_FC1_B, P_MLP_FC2_B, P_MLP_FC1_B, P_GATE_FC2_B, P_GATE_FC1_B};
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < WG_PART; i += gridDim.x * 256) {
+  const int lane = threadIdx.x & (GF_ENT - 1), grp = threadIdx.x >> 6;
+  const int i = blockIdx.x * GF_ENT + lane;
+  const int nent = layer < 5 ? WG_PART : layer == 5 ? HID + 1 : 2 * E;
+  if (blockIdx.x * GF_ENT >= nent) return;
+  double s = 0.0;
+  if (i < nent) {
+    if (layer < 5) {
       const float* src = part + (long long)layer * nchunks * WG_PART + i;
-      float s = 0.f;
-#pragma unroll 8
-      for (int c = 0; c < nchunks; ++c) s += src[(long long)c * WG_PART];
+      float f = 0.f;
+#pragma unroll 4
+      for (int c = grp; c < nchunks; c += 4) f += src[(long long)c * WG_PART];
+      s = (double)f;
+    } else if (layer == 5) {
+      float f = 0.f;
+#pragma unroll 4
+      for (int t = grp; t < ntiles; t += 4) f += part_f[(long long)t * HB_F + i];
+      s = (double)f;
+    } else {
+#pragma unroll 4
+      for (int t = grp; t < ntiles; t += 4) s += part_bn[(long long)t * 2 * E + i];
+    }
+  }
+  red[grp][lane] = s;
+  __syncthreads();
+  if (grp != 0 || i >= nent) return;
+  if (layer < 6) {
+    const float v = (((float)red[0][lane] + (float)red[1][lane]) + (float)red[2][lane]) + (float)red[3][lane];
+    if (layer < 5) {
+      const long long w_off[5] = {P_OUT_FC1_W, P_MLP_FC2_W, P_MLP_FC1_W, P_GATE_FC2_W, P_GATE_FC1_W};
+      const long long b_off[5] = {P_OUT_FC1_B, P_MLP_FC2_B, P_MLP_FC1_B, P_GATE_FC2_B, P_GATE_FC1_B};
       if (i < HID * E) {
         const int nn = i / E, kq = i - nn * E;
-        if (layer == 1 || layer == 3) grads[w_off[layer] + (long long)kq * HID + nn] = s;
-        else grads[w_off[layer] + (long long)nn * E + kq] = s;
+        if (layer == 1 || layer == 3) grads[w_off[layer] + (long long)kq * HID + nn] = v;
+        else grads[w_off[layer] + (long long)nn * E + kq] = v;
       } else {
-        const int b = i - HID * E;
+        const int bi = i - HID * E;
         const int nb = (layer == 1 || layer == 3) ? E : HID;
-        if (b < nb) grads[b_off[layer] + b] = s;
+        if (bi < nb) grads[b_off[layer] + bi] = v;
       }
-    }
-  } else if (layer == 5) {
-    // out_mlp.fc2 weight / bias from the tile partials
-    for (int i = blockIdx.x * 256 + threadIdx.x; i <= HID; i += gridDim.x * 256) {
-      float s = 0.f;
-#pragma unroll 8
-      for (int t = 0; t < ntiles; ++t) s += part_f[(long long)t * HB_F + i];
-      if (i < HID) grads[P_OUT_FC2_W + i] = s; else grads[P_OUT_FC2_B] = s;
+    } else {
+      if (i < HID) grads[P_OUT_FC2_W + i] = v; else grads[P_OUT_FC2_B] = v;
     }
   } else {
     // BatchNorm: column sums of dz and dz * xhat (this rank's rows), bn.weight / bn.bias gradients
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < 2 * E; i += gridDim.x * 256) {
-      double s = 0.0;
-#pragma unroll 8
-      for (int t = 0; t < ntiles; ++t) s += part_bn[(long long)t * 2 * E + i];
-      bn_bwd_sums[i] = s;
-      if (i < E) grads[P_BN_B + i] = (float)s; else grads[P_BN_W + (i - E)] = (float)s;
-    }
+    const double v = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
+    bn_bwd_sums[i] = v;
+    if (i < E) grads[P_BN_B + i] = (float)v; else grads[P_BN_W + (i - E)] = (float)v;
   }
 }
 
@@ -693,7 +709,7 @@ int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogit
   const int nchunks = (int)((w.R + rpc - 1) / rpc);
   launch_pdl(head_wgrad_kernel, dim3(dim3(nchunks, 5)), dim3(WG_THREADS), 0, s, w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2, w.dgate, w.da1, w.head_part_w);
   NRM_LAUNCH_CHECK("head_wgrad_kernel");
-  launch_pdl(head_grad_finish_kernel, dim3(dim3(70, 7)), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums);
+  launch_pdl(head_grad_finish_kernel, dim3((WG_PART + GF_ENT - 1) / GF_ENT, 7), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums);
   NRM_LAUNCH_CHECK("head_grad_finish_kernel");
   return NRM_OK;
 }

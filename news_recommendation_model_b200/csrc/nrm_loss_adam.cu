@@ -10,6 +10,7 @@ struct LossScratch {
   float* dlog;      // [B*C]  d loss / d logits for grad_loss == 1
   float* drow;      // [B]    d loss / d delta[user_id[b]] contribution of impression b
   double* lpart;    // [LOSS_BLOCKS][2]
+  unsigned* ticket; // arrival counter of the forward kernel's blocks (zero between calls)
 };
 static size_t carve_loss(LossScratch& ls, void* base, int B, int C) {
   size_t off = 0;
@@ -17,6 +18,7 @@ static size_t carve_loss(LossScratch& ls, void* base, int B, int C) {
   ls.dlog = (float*)take(sizeof(float) * (size_t)B * C);
   ls.drow = (float*)take(sizeof(float) * (size_t)B);
   ls.lpart = (double*)take(sizeof(double) * LOSS_BLOCKS * 2);
+  ls.ticket = (unsigned*)take(sizeof(unsigned));
   return off;
 }
 
@@ -69,7 +71,7 @@ __device__ __forceinline__ float bce_softmax_term(const float* __restrict__ out,
 __global__ void __launch_bounds__(256)
 loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ delta, const long long* __restrict__ uid,
                     const double* __restrict__ label, int B, int C, float alpha, float* __restrict__ dlog,
-                    float* __restrict__ drow, double* __restrict__ lpart) {
+                    float* __restrict__ drow, double* __restrict__ lpart, unsigned* __restrict__ ticket, float* __restrict__ loss) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
   __shared__ double red[8][2];
@@ -95,38 +97,35 @@ loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ 
     double s1 = 0.0, s2 = 0.0;
     for (int i = 0; i < 8; ++i) { s1 += red[i][0]; s2 += red[i][1]; }
     lpart[blockIdx.x * 2 + 0] = s1; lpart[blockIdx.x * 2 + 1] = s2;
+    // the block that arrives last adds the block sums in block order (deterministic) and leaves the counter at zero
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      s1 = 0.0; s2 = 0.0;
+      for (unsigned i = 0; i < gridDim.x; ++i) { s1 += __ldcg(lpart + i * 2); s2 += __ldcg(lpart + i * 2 + 1); }
+      const double n = (double)B * (double)C;
+      const float a = (float)(s1 / n), c = (float)(s2 / n);
+      *loss = (1.f - alpha) * a + alpha * c;
+      *ticket = 0u;
+    }
   }
 }
 
-__global__ void loss_finalize_kernel(const double* __restrict__ lpart, int nblocks, int B, int C, float alpha,
-                                     float* __restrict__ loss) {
-  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
-  pdl_trigger();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < nblocks; ++i) { s1 += lpart[i * 2]; s2 += lpart[i * 2 + 1]; }
-  const double n = (double)B * (double)C;
-  const float a = (float)(s1 / n), c = (float)(s2 / n);
-  *loss = (1.f - alpha) * a + alpha * c;
-}
-
+// One launch for the loss backward: blocks [0, nscale) scale the unit gradients by the upstream gradient, the others give
+// ddelta[user] = grad_loss * sum of drow over the impressions of that user, in batch order.  One warp per impression:
+// it owns the sum iff no earlier impression has the same user id (no atomics, deterministic).
 __global__ void __launch_bounds__(256)
-loss_scale_kernel(const float* __restrict__ dlog, const float* __restrict__ grad_loss, long long n, float* __restrict__ out) {
+loss_backward_kernel(const float* __restrict__ dlog, const float* __restrict__ grad_loss, long long n, int nscale, float* __restrict__ out,
+                     const long long* __restrict__ uid, const float* __restrict__ drow, int B, float* __restrict__ ddelta,
+                     long long delta_numel) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i < n) out[i] = dlog[i] * __ldg(grad_loss);
-}
-
-// ddelta[user] = grad_loss * sum of drow over the impressions of that user, in batch order.
-// One warp per impression: it owns the sum iff no earlier impression has the same user id
-// (no atomics, deterministic).
-__global__ void __launch_bounds__(256)
-delta_grad_kernel(const long long* __restrict__ uid, const float* __restrict__ drow, int B,
-                  const float* __restrict__ grad_loss, float* __restrict__ ddelta, long long delta_numel) {
-  pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
-  pdl_trigger();
-  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if ((int)blockIdx.x < nscale) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = dlog[i] * __ldg(grad_loss);
+    return;
+  }
+  const int b = (blockIdx.x - nscale) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const long long id = uid[b];
@@ -266,10 +265,9 @@ extern "C" int nrm_loss_forward(const float* logits, const float* delta, const l
   if (carve_loss(ls, scratch, B, C) > scratch_bytes) { set_error("nrm_loss_forward: scratch too small"); return NRM_EWORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = min(LOSS_BLOCKS, (B + 7) / 8);
-  launch_pdl(loss_forward_kernel, dim3(blocks), dim3(256), 0, s, logits, delta, user_id, label, B, C, alpha, ls.dlog, ls.drow, ls.lpart);
+  launch_pdl(loss_forward_kernel, dim3(blocks), dim3(256), 0, s, logits, delta, user_id, label, B, C, alpha, ls.dlog, ls.drow, ls.lpart,
+             ls.ticket, loss);
   NRM_LAUNCH_CHECK("loss_forward_kernel");
-  launch_pdl(loss_finalize_kernel, dim3(1), dim3(32), 0, s, ls.lpart, blocks, B, C, alpha, loss);
-  NRM_LAUNCH_CHECK("loss_finalize_kernel");
   return NRM_OK;
 }
 
@@ -282,13 +280,12 @@ extern "C" int nrm_loss_backward(const long long* user_id, int B, int C, const f
   if (carve_loss(ls, const_cast<void*>(scratch), B, C) > scratch_bytes) { set_error("nrm_loss_backward: scratch too small"); return NRM_EWORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = (long long)B * C;
-  launch_pdl(loss_scale_kernel, dim3((int)((n + 255) / 256)), dim3(256), 0, s, ls.dlog, grad_loss, n, dlogits);
-  NRM_LAUNCH_CHECK("loss_scale_kernel");
-  if (ddelta != nullptr && delta_numel > 0) {
-    NRM_CUDA(cudaMemsetAsync(ddelta, 0, sizeof(float) * (size_t)delta_numel, s));
-    launch_pdl(delta_grad_kernel, dim3((B + 7) / 8), dim3(256), 0, s, user_id, ls.drow, B, grad_loss, ddelta, delta_numel);
-    NRM_LAUNCH_CHECK("delta_grad_kernel");
-  }
+  const int nscale = (int)((n + 255) / 256);
+  const bool want_delta = ddelta != nullptr && delta_numel > 0;
+  if (want_delta) NRM_CUDA(cudaMemsetAsync(ddelta, 0, sizeof(float) * (size_t)delta_numel, s));
+  launch_pdl(loss_backward_kernel, dim3(nscale + (want_delta ? (B + 7) / 8 : 0)), dim3(256), 0, s, ls.dlog, grad_loss, n, nscale, dlogits,
+             user_id, ls.drow, B, ddelta, delta_numel);
+  NRM_LAUNCH_CHECK("loss_backward_kernel");
   return NRM_OK;
 }
 

@@ -139,6 +139,7 @@ class Runtime:
         self.train_ws: Optional[torch.Tensor] = None
         self.train_ws_token: Optional[StepToken] = None
         self.loss_scratch: Optional[torch.Tensor] = None
+        self.loss_scratch_busy = False
 
     def workspace(self, B, H, C, mode, device) -> torch.Tensor:
         need = int(_lib.load().nrm_workspace_bytes(B, H, C, mode))
@@ -284,7 +285,14 @@ class _LossFn(torch.autograd.Function):
         B, C = out.shape
         dev = out.device
         need = int(lib.nrm_loss_scratch_bytes(B, C))
-        scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+        # zero-filled once (it holds an arrival counter); reused from step to step unless a backward is still pending on it
+        scratch = rt.loss_scratch
+        if scratch is None or scratch.numel() != need or scratch.device != dev or rt.loss_scratch_busy:
+            scratch = torch.zeros(need, dtype=torch.uint8, device=dev)
+            if not rt.loss_scratch_busy:
+                rt.loss_scratch = scratch
+        if scratch is rt.loss_scratch and any(ctx.needs_input_grad):
+            rt.loss_scratch_busy = True                    # until the backward has been enqueued
         loss = torch.empty((), dtype=torch.float32, device=dev)
         uid = user_id.to(device=dev, dtype=torch.int64).contiguous()
         lab = label.to(device=dev, dtype=torch.float64).contiguous()
@@ -311,6 +319,9 @@ class _LossFn(torch.autograd.Function):
             ddelta = torch.empty(ctx.delta_numel, dtype=torch.float32, device=dev)
         _lib.check(lib.nrm_loss_backward(_ptr(ctx.uid), B, C, _ptr(gl), _ptr(dlogits), _ptr(ddelta), ctx.delta_numel,
                                          _ptr(ctx.scratch), ctx.scratch.numel(), _stream(dev)), 'nrm_loss_backward')
+        rt = ctx.model._runtime()
+        if ctx.scratch is rt.loss_scratch:
+            rt.loss_scratch_busy = False
         return None, None, None, None, None, dlogits, ddelta
 
 

@@ -81,7 +81,7 @@ class FusedTrainStep:
         ws_bytes = int(self.lib.nrm_workspace_bytes(B, H, C, self.mode))
         self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         ls_bytes = int(self.lib.nrm_loss_scratch_bytes(B, C))
-        self.loss_scratch = torch.empty(ls_bytes, dtype=torch.uint8, device=dev)
+        self.loss_scratch = torch.zeros(ls_bytes, dtype=torch.uint8, device=dev)    # zero once: holds an arrival counter
         self.logits = torch.empty(B, C, dtype=torch.float32, device=dev)
         self.dlogits = torch.empty(B, C, dtype=torch.float32, device=dev)
         self.one = torch.ones((), dtype=torch.float32, device=dev)
