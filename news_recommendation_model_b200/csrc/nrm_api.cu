@@ -66,7 +66,7 @@ KernelTimer::~KernelTimer() {
 // on the side stream), so its four small launches run under the attention / head kernels instead of after them.
 // Fork and join are ordinary stream events, so the pattern is also valid inside a CUDA-graph capture of the caller's
 // stream.  One side stream + two events per device, created on first use and kept for the life of the process.
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp; bool made; };
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp, fork3, join3; bool made; };
 static SideStream g_side[64];
 static SideStream* side_stream() {
   int dev = 0;
@@ -81,6 +81,8 @@ static SideStream* side_stream() {
     if (cudaEventCreateWithFlags(&ss.fork0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.join_tp, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.join0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ss.made = true;
   }
   return &ss;
@@ -213,24 +215,6 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   SideStream* ss = side_stream();
   if (ss == nullptr) { set_error("encoder_forward: cannot create the side stream"); return NRM_ECUDA; }
   const bool tc = precision != NRM_PRECISION_FP32;
-  static const bool inline_prep = getenv("NRM_INLINE_PREP") != nullptr;       // A/B switch: weight preparation on the caller's stream
-  if (inline_prep) {
-    NRM_TRY(launch_head_transpose(P, w, s));
-    if (tc) NRM_TRY(launch_attention_prep(P, w, s));
-    { KernelTimer t("embed_rows", s); NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
-    if (mode & NRM_MODE_KEEP_FOR_BWD) {
-      NRM_CUDA(cudaEventRecord(ss->fork, s));
-      NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-      NRM_TRY(launch_table_sort(w, ss->stream));
-      NRM_CUDA(cudaEventRecord(ss->join, ss->stream));
-    }
-    { KernelTimer t("w1_forward", s); NRM_TRY(launch_w1_forward(P, w, s)); }
-    if (tc) NRM_TRY(launch_candidate_tp(P, w, s));
-    KernelTimer t("attention_forward", s);
-    NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s));
-    NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s));
-    return NRM_OK;
-  }
   // fork 0: what depends on the weights only (derived attention matrices, transposed head matrices) runs on the side
   // stream under the embedding kernel
   NRM_CUDA(cudaEventRecord(ss->fork0, s));
@@ -282,10 +266,16 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
     NRM_TRY(launch_attention_finish(P, w, 0, precision, G, s));
     NRM_TRY(launch_attention_finish(P, w, 1, precision, G, s)); }
   NRM_CUDA(cudaStreamWaitEvent(s, ss->join2, 0));          // join: dxin_h ready
-  { KernelTimer t("small_linear_grads", s); NRM_TRY(launch_small_linear_grads(in, w, G, s)); }
+  // fork: the sentiment / instant Linear gradients (side stream) next to the table gradients (two latency-bound kernel
+  // pairs that write disjoint gradient ranges)
+  NRM_CUDA(cudaEventRecord(ss->fork3, s));
+  NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork3, 0));
+  { KernelTimer t("small_linear_grads", ss->stream); NRM_TRY(launch_small_linear_grads(in, w, G, ss->stream)); }
+  NRM_CUDA(cudaEventRecord(ss->join3, ss->stream));
   // join: the id sort enqueued by the forward (same workspace) must have finished
   NRM_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
   NRM_TRY(launch_table_grads(w, G, s));
+  NRM_CUDA(cudaStreamWaitEvent(s, ss->join3, 0));
   return NRM_OK;
 }
 
