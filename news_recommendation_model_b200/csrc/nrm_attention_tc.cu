@@ -876,6 +876,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 // Sum the per-CTA partials (fixed order) and write the attention-MLP gradients that do not depend on tp:
 //   fc1.weight grad blocks: [:, 0:64] = dA, [:, 192:256] = dWd   (the Bm-dependent blocks are completed by
 //   attention_tp_grad_kernel); fc2.weight = dw2; fc2.bias = db2.   Partials are transposed ([k][j]).
+constexpr int COMPOSE_BLOCKS = 65;      // 64 blocks of 64 (k,j) entries + one for fc2
 __device__ __forceinline__ void
 attention_tc_compose_block(int block, const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads,
                            float* __restrict__ dA_all) {
@@ -884,25 +885,27 @@ attention_tc_compose_block(int block, const float* __restrict__ part_all, int np
   const float* part = part_all + (long long)branch * ATT_TC_PARTS_MAX * TC_PARTIAL;
   const int nparts = branch == 0 ? nparts0 : nparts1;
   float* dA_out = dA_all + branch * 4096;
-  // block = 32 consecutive (k,j) entries x 32 interleaved groups of partials, combined in group order; grid.x = 128 (+1)
-  __shared__ float red[32][2][32];
+  // block = 64 consecutive (k,j) entries (two per lane) x 32 interleaved groups of partials, combined in group order;
+  // 64 such blocks (+1) per branch, so that the whole finish kernel is one wave
+  __shared__ float red[32][4][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  if (block < 128) {
-    const int i = block * 32 + lane;              // k*64 + j
-    float dA = 0.f, dWd = 0.f;
+  if (block < COMPOSE_BLOCKS - 1) {
+    const int i = block * 64 + lane;              // k*64 + j; the lane's second entry is i + 32
+    float dA0 = 0.f, dWd0 = 0.f, dA1 = 0.f, dWd1 = 0.f;
 #pragma unroll 4
     for (int p = grp; p < nparts; p += 32) {
       const float* q = part + (long long)p * TC_PARTIAL;
-      dA += q[TCP_DA + i];
-      dWd += q[TCP_DWD + i];
+      dA0 += q[TCP_DA + i]; dA1 += q[TCP_DA + i + 32];
+      dWd0 += q[TCP_DWD + i]; dWd1 += q[TCP_DWD + i + 32];
     }
-    red[grp][0][lane] = dA; red[grp][1][lane] = dWd;
+    red[grp][0][lane] = dA0; red[grp][1][lane] = dWd0; red[grp][2][lane] = dA1; red[grp][3][lane] = dWd1;
     __syncthreads();
-    if (grp == 0) {
-      dA = red[0][0][lane]; dWd = red[0][1][lane];
+    if (grp < 2) {                                     // warp 0 finishes entry i, warp 1 entry i + 32
+      float dA = red[0][2 * grp][lane], dWd = red[0][2 * grp + 1][lane];
 #pragma unroll
-      for (int g = 1; g < 32; ++g) { dA += red[g][0][lane]; dWd += red[g][1][lane]; }
-      const int k = i >> 6, j = i & 63;
+      for (int g = 1; g < 32; ++g) { dA += red[g][2 * grp][lane]; dWd += red[g][2 * grp + 1][lane]; }
+      const int ii = i + 32 * grp;
+      const int k = ii >> 6, j = ii & 63;
       float* rowp = grads + off.fc1_w + j * 256;
       rowp[k] = dA; rowp[192 + k] = dWd;
       dA_out[j * 64 + k] = dA;
@@ -1009,9 +1012,9 @@ attention_tp_grad_block(int block, TpgSmem& sm, const float* __restrict__ dtp_al
 }
 
 // One launch for the two independent reductions: the first ceil(nparts / 4) blocks take 4 x 32 candidate rows each through
-// the tp path (they are the longer ones, so they are scheduled first), the next 129 sum the per-CTA partials of the
+// the tp path (they are the longer ones, so they are scheduled first), the next 65 sum the per-CTA partials of the
 // backward kernels.
-constexpr int COMPOSE_BLOCKS = 129;
+
 __global__ void __launch_bounds__(1024)
 attention_finish_kernel(const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads, float* __restrict__ dA_all,
                         const float* __restrict__ dtp_all, const float* __restrict__ e, long long R, const float* __restrict__ P,
