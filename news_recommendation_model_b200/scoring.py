@@ -59,6 +59,24 @@ def score_epilogue(logits: torch.Tensor, empty_num: Optional[torch.Tensor] = Non
     return scores, ranks
 
 
+def bucket_plan(n: torch.Tensor, C: int, groups: int = 8, min_group: int = 128):
+    """Host-side plan of `ensemble_logits`: `n` [B] = real candidates per impression (CPU int64), C = columns of the batch.
+    Returns [(indices, width)]: the impressions sorted by candidate count (stable, descending) cut into up to `groups`
+    groups with even boundaries (the kernels work on impression pairs); `width` = longest list of the group + 1 pad column,
+    capped at C.  Every impression appears exactly once; an impression with pads always has a pad column inside `width`."""
+    B = int(n.numel())
+    order = torch.argsort(n, descending=True, stable=True)
+    G = max(1, min(int(groups), B // max(1, int(min_group))))
+    edges = [((B * g // G) + 1) // 2 * 2 for g in range(G)] + [B]
+    plan = []
+    for g in range(G):
+        lo, hi = edges[g], edges[g + 1]
+        if hi > lo:
+            idx = order[lo:hi]
+            plan.append((idx, min(int(C), int(n[idx].max()) + 1)))
+    return plan
+
+
 @torch.no_grad()
 def ensemble_logits(model_list: Sequence[torch.nn.Module], x_history, x_inview, x_global, empty_num=None, groups: int = 8,
                     min_group: int = 128) -> torch.Tensor:
@@ -76,16 +94,8 @@ def ensemble_logits(model_list: Sequence[torch.nn.Module], x_history, x_inview, 
     if empty_num is None or B < 2 * min_group or C < 8:
         return torch.stack([m(x_history, x_inview, x_global) for m in model_list], 0)
     n = (C - empty_num.detach().to('cpu', torch.int64)).clamp_(0, C)                # real candidates per impression
-    order = torch.argsort(n, descending=True, stable=True)
-    G = max(1, min(groups, B // min_group))
-    edges = [((B * g // G) + 1) // 2 * 2 for g in range(G)] + [B]                  # even starts: the kernels work on pairs
     out = torch.empty(M, B, C, dtype=torch.float32, device=dev)
-    for g in range(G):
-        lo, hi = edges[g], edges[g + 1]
-        if hi <= lo:
-            continue
-        idx_cpu = order[lo:hi]
-        cg = min(C, int(n[idx_cpu].max()) + 1)
+    for idx_cpu, cg in bucket_plan(n, C, groups, min_group):
         idx = idx_cpu.to(dev)
         xh_g = x_history.index_select(0, idx)
         xt_g = x_inview.index_select(0, idx)[:, :cg]

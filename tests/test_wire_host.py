@@ -59,3 +59,24 @@ def test_compact_dataset_batches_cover_every_impression_once():
     assert sorted(seen) == sorted(full.impression_id.tolist())
     assert sum(1 for _ in ds.batches(8, drop_last=True, pin=False)) == 2
     assert full.input_bytes() == 23 * (7 * 16 + 5 * 12 + 8)
+
+
+def test_scoring_bucket_plan_covers_every_impression_with_a_pad_column():
+    """Host logic of the ragged-aware scoring (scoring.bucket_plan): groups are disjoint, cover the batch, start on even
+    positions of the sorted order, and are wide enough for every member's real candidates plus one pad."""
+    from news_recommendation_model_b200.scoring import bucket_plan
+    g = torch.Generator().manual_seed(5)
+    for B, C, groups, min_group in ((1024, 94, 8, 128), (81, 40, 8, 16), (300, 7, 4, 16), (5, 20, 8, 128), (64, 100, 3, 10)):
+        n = torch.randint(0, C + 1, (B,), generator=g)
+        n[0] = C
+        plan = bucket_plan(n, C, groups, min_group)
+        seen = torch.cat([idx for idx, _ in plan])
+        assert sorted(seen.tolist()) == list(range(B))
+        assert len(plan) <= max(1, min(groups, B // min_group))
+        pos, prev_max = 0, C
+        for idx, width in plan:
+            assert pos % 2 == 0 and 1 <= width <= C
+            assert int(n[idx].max()) <= prev_max              # sorted by candidate count, descending
+            prev_max = int(n[idx].min())
+            assert bool(((n[idx] < width) | (n[idx] == C)).all())   # a pad column inside the width unless the row has no pads
+            pos += idx.numel()
