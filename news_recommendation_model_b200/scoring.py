@@ -191,6 +191,37 @@ def model_test(model_list, test_data, device='cuda', prediction_queue=None, id_l
     return prediction_queue, id_list
 
 
+@torch.no_grad()
+def model_validation(model_list, validation_data, device='cuda', batch_size=1):
+    """Mirror of `verify.py:model_validation` (`verify.py:19-42`): returns `[auc, tpr]` = mean per-impression ROC AUC
+    (`tool/evaluation.py:3-5`, ties averaged) of the ensemble scores and the fraction of impressions whose best-scored
+    candidate is the clicked one (`verify.py:32`, `tool/evaluation.py:16-17`).  Scores, AUC and hits are computed on the
+    GPU per batch (`ensemble_scores`, `metrics.batch_metrics`); one number pair comes back at the end instead of one
+    sklearn call per impression."""
+    from . import metrics
+    loader = torch.utils.data.DataLoader(dataset=validation_data, batch_size=batch_size, shuffle=False)
+    for model in model_list:
+        model.eval()
+        model.to(device)
+    auc_sum = torch.zeros((), dtype=torch.float64, device=device)
+    hit_sum = torch.zeros((), dtype=torch.float64, device=device)
+    count = 0
+    for data in loader:
+        _, _, x_history, x_inview, x_global, label, _, empty_num = data
+        trim = int(torch.min(empty_num))
+        x_history, x_inview, x_global, label = x_history.to(device), x_inview.to(device), x_global.to(device), label.to(device)
+        if trim > 0:                                               # test.py:52-56
+            x_inview, x_global, label = x_inview[:, 0:-trim], x_global[:, 0:-trim], label[:, 0:-trim]
+            empty_num = empty_num - trim
+        scores, _ = ensemble_scores(model_list, x_history, x_inview, x_global, empty_num, want_ranks=False)
+        n_valid = (scores.shape[1] - empty_num).to(device)
+        m = metrics.batch_metrics(scores, label, n_valid)
+        auc_sum += m['auc'].double().sum()
+        hit_sum += m['hit'].double().sum()
+        count += int(scores.shape[0])
+    return [float(auc_sum) / max(count, 1), float(hit_sum) / max(count, 1)]
+
+
 def write_submission_file(text_chunks: Sequence[bytes], path: str, name: str = 'predictions') -> str:
     """`test.py:write_submission_file` (`test.py:76-116`) for text that `model_test(text_sink=...)` already formatted:
     writes `path + "predictions.txt"` and zips it to `path + name + ".zip"`."""
