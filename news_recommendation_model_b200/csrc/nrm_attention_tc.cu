@@ -875,7 +875,7 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
 
 // Sum the per-CTA partials (fixed order) and write the attention-MLP gradients that do not depend on tp:
 //   fc1.weight grad blocks: [:, 0:64] = dA, [:, 192:256] = dWd   (the Bm-dependent blocks are completed by
-//   attention_tp_grad_kernel); fc2.weight = dw2; fc2.bias = db2.   Partials are transposed ([k][j]).
+//   the tp-path blocks of attention_finish_kernel + attention_tp_finish_kernel); fc2.weight = dw2; fc2.bias = db2.   Partials are transposed ([k][j]).
 constexpr int COMPOSE_BLOCKS = 65;      // 64 blocks of 64 (k,j) entries + one for fc2
 __device__ __forceinline__ void
 attention_tc_compose_block(int block, const float* __restrict__ part_all, int nparts0, int nparts1, float* __restrict__ grads,

@@ -6,8 +6,8 @@
 // Backward: kernel A walks the same tile backwards through the data-gradient chain (it reads the nn.Linear
 // weights in their natural [out][in] layout: every contraction here has the output index contiguous), writes the
 // per-layer gradients of the pre-activations and per-tile partial sums for BatchNorm and out_mlp.fc2; kernel B
-// forms the five weight gradients dW = P^T Q over row chunks with one accumulator column per thread; a last
-// kernel adds the chunk partials in fixed order (deterministic, no atomics).
+// forms the five weight gradients dW = P^T Q over row chunks with 8 x 8 register tiles; a last kernel adds the chunk
+// partials in fixed order (deterministic, no atomics).
 #include "nrm_kernels.cuh"
 #include "nrm_umma.cuh"      // mbarrier helpers
 
