@@ -47,7 +47,8 @@ class _Slot:
 
 
 class LossHandle:
-    """Result of one step; `.item()` waits for that step only."""
+    """Result of one step; `.item()` waits for that step only.  The values live in a pinned ring of `ring` (default 8)
+    entries: read a handle before `ring` more steps have been enqueued."""
 
     def __init__(self, host_slot: torch.Tensor, event: torch.cuda.Event):
         self._host, self._event = host_slot, event
@@ -198,15 +199,18 @@ class FusedTrainStep:
                     if s.wire == 'compact':
                         self._expand(s)
                     self._forward_backward(s, s.loss_slot)
+                    if self.dp is None:
+                        self._adam()                     # single process: the whole step is ONE graph
                 s.graph_wire = s.wire
-                s.graph_adam = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(s.graph_adam):
-                    self._adam()
+                if self.dp is not None:                  # data parallel: the gradient all-reduce sits between two graphs
+                    s.graph_adam = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(s.graph_adam):
+                        self._adam()
             s.graph_fb.replay()
             if self.dp is not None:
                 self.dp.buckets.reduce(self.grads, 0, self.grads.numel())
                 self.dp.buckets.wait()
-            s.graph_adam.replay()
+                s.graph_adam.replay()
             loss_out = s.loss_slot.view(1)
         else:
             if s.wire == 'compact':

@@ -203,8 +203,13 @@ def test_fused_train_step_is_bitwise_reproducible_over_many_graph_replays():
     for run in range(2):
         m = _model('train', 200, 'bf16x3', train=True)
         tr = nrm.FusedTrainStep(m, B, H, C, lr=1e-3, weight_decay=1e-5)
-        losses = [tr.step(batches[i % 3]) for i in range(60)]
-        vals = [h.item() for h in losses]
+        vals, prev = [], None
+        for i in range(60):                       # loss of step i is read after step i + 1 has been enqueued (the result ring
+            h = tr.step(batches[i % 3])           # holds 8 steps: a handle must be read before it is 8 steps old)
+            if prev is not None:
+                vals.append(prev.item())
+            prev = h
+        vals.append(prev.item())
         torch.cuda.synchronize()
         finals.append((vals, m.flat_parameters().buf.clone(), m.bn.running_var.clone()))
     assert finals[0][0] == finals[1][0]
