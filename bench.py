@@ -420,9 +420,28 @@ def run_ours(args):
             e1.record()
             barrier()
             ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / reps
+            # the same loop fed in the compact wire format (ids into the resident article table, wire.expand on the GPU)
+            hc = [wire.make_compact_batch(table_host, Bs, 200, 100, seed=555 + 31 * rank + i, user_num=args.user_num, variable_history=True,
+                                          variable_candidates=True).pin() for i in range(2)]
+            trims_c = [int(b.empty_num.min()) for b in hc]
+
+            def e2e_scoring_compact(n):
+                total = 0
+                for i in range(n):
+                    total += len(score(wire.expand(table, hc[i % 2].to(dev, non_blocking=True)), trims_c[i % 2], True))
+                return total
+            e2e_scoring_compact(2)
+            barrier()
+            e0.record()
+            e2e_scoring_compact(reps)
+            e1.record()
+            barrier()
+            ms_e2ec = max_over_ranks(e0.elapsed_time(e1)) / reps
             scoring[f'batch_{Bs}'] = {'value': world * Bs / (ms_res / 1e3), 'ms_per_batch': ms_res,
                                       'e2e': {'value': world * Bs / (ms_e2e / 1e3), 'ms_per_batch': ms_e2e,
                                               'h2d_bytes_per_batch': hb[0].input_bytes(), 'd2h_bytes_per_batch': nbytes // reps},
+                                      'e2e_compact': {'value': world * Bs / (ms_e2ec / 1e3), 'ms_per_batch': ms_e2ec,
+                                                      'h2d_bytes_per_batch': hc[0].input_bytes()},
                                       'candidate_columns': hb[0].x_target.shape[1] - trims[0]}
         model.train()
 
