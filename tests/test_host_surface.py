@@ -157,3 +157,31 @@ def test_models_shim_shadows_the_reference_package():
             "assert UserModel is n.UserModel and MLP is n.MLP and config['pca_vector'] == 64; print('ok')") % (os.path.join(ROOT, 'shim'), ROOT)
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
     assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
+
+
+def test_flat_params_views_and_gradient_split_plan_on_cpu():
+    """engine.FlatParams is plain tensor plumbing (no kernels): the parameters become views of ONE buffer in layout order,
+    and grad_views() (one split_with_sizes call) returns exactly the slices the layout describes."""
+    import torch
+    import news_recommendation_model_b200 as nrm
+    from news_recommendation_model_b200 import engine
+    m = nrm.UserModel(7)
+    named = dict(m.named_parameters())
+    flat = engine.FlatParams(named)
+    assert flat.is_current(named) and flat.total % 4 == 0
+    base = flat.buf.data_ptr()
+    for name, off, n, shape in flat.slots:
+        p = named[name]
+        assert p.data_ptr() == base + 4 * off and p.numel() == n and tuple(p.shape) == tuple(shape)
+    assert [id(p) for p in flat.params] == [id(named[name]) for name, _, _, _ in flat.slots if name != 'delta']
+    g = torch.arange(flat.total, dtype=torch.float32)
+    for skip in (False, True):
+        views = flat.grad_views(g, skip)
+        slots = [sl for sl in flat.slots if not (skip and sl[0] == 'delta')]
+        assert len(views) == len(slots)
+        for v, (name, off, n, shape) in zip(views, slots):
+            assert tuple(v.shape) == tuple(shape) and v.data_ptr() == g.data_ptr() + 4 * off
+            assert float(v.reshape(-1)[0]) == float(off) and float(v.reshape(-1)[-1]) == float(off + n - 1)
+    # a buffer of another length falls back to plain slicing
+    g2 = torch.zeros(flat.total + 8)
+    assert len(flat.grad_views(g2, False)) == len(flat.slots)
