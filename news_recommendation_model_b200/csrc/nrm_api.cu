@@ -66,7 +66,7 @@ KernelTimer::~KernelTimer() {
 // on the side stream), so its four small launches run under the attention / head kernels instead of after them.
 // Fork and join are ordinary stream events, so the pattern is also valid inside a CUDA-graph capture of the caller's
 // stream.  One side stream + two events per device, created on first use and kept for the life of the process.
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp, fork3, join3; bool made; };
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp, fork3, join3, fork4, join4; bool made; };
 static SideStream g_side[64];
 static SideStream* side_stream() {
   int dev = 0;
@@ -83,6 +83,8 @@ static SideStream* side_stream() {
     if (cudaEventCreateWithFlags(&ss.join0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.fork3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.join3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork4, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join4, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ss.made = true;
   }
   return &ss;
@@ -403,7 +405,26 @@ extern "C" int nrm_backward_encoder(const double* x_history, const double* x_tar
 extern "C" int nrm_backward(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
                             long long xg_bs, int B, int H, int C, const float* params, int mode, int precision,
                             const float* dlogits, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
-  NRM_TRY(nrm_backward_head(B, H, C, params, dlogits, grads, nullptr, workspace, workspace_bytes, stream));
-  return nrm_backward_encoder(x_history, x_target, xt_bs, x_global, xg_bs, B, H, C, params, mode, precision, nullptr, 0,
-                              grads, workspace, workspace_bytes, stream);
+  // Head and encoder backward in one call: the head's weight gradients (only the optimizer needs them) run on the side
+  // stream beside the BatchNorm path and the start of the encoder backward instead of in front of them.
+  const int training = mode & NRM_MODE_BN_BATCH_STATS;
+  NRM_TRY(check_shape("nrm_backward", B, H, C));
+  if (!x_history || !x_target || !x_global || !params || !dlogits || !grads) { set_error("nrm_backward: null pointer"); return NRM_EINVAL; }
+  Workspace w;
+  NRM_TRY(get_workspace("nrm_backward", w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
+  cudaStream_t s = (cudaStream_t)stream;
+  SideStream* ss = side_stream();
+  if (ss == nullptr) { set_error("nrm_backward: cannot create the side stream"); return NRM_ECUDA; }
+  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
+  { KernelTimer t("head_backward", s);
+    NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
+    NRM_CUDA(cudaEventRecord(ss->fork4, s));
+    NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork4, 0));
+    NRM_TRY(launch_head_backward_wgrad(params, w, grads, ss->stream));
+    NRM_CUDA(cudaEventRecord(ss->join4, ss->stream));
+    NRM_TRY(launch_head_backward_bn(w, grads, s)); }
+  NRM_TRY(launch_bn_backward_combine(params, w, training, w.bn_bwd_sums, w.R, s));
+  NRM_TRY(encoder_backward(in, params, w, precision, grads, s));
+  NRM_CUDA(cudaStreamWaitEvent(s, ss->join4, 0));          // join: head weight gradients written
+  return NRM_OK;
 }

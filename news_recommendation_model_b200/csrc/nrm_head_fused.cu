@@ -606,11 +606,11 @@ head_wgrad_kernel(const float* __restrict__ e, const float* __restrict__ mean, c
 constexpr int GF_ENT = 64;
 __global__ void __launch_bounds__(256)
 head_grad_finish_kernel(const float* __restrict__ part, int nchunks, const float* __restrict__ part_f, int ntiles,
-                        const double* __restrict__ part_bn, float* __restrict__ grads, double* __restrict__ bn_bwd_sums) {
+                        const double* __restrict__ part_bn, float* __restrict__ grads, double* __restrict__ bn_bwd_sums, int layer_base) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
   __shared__ double red[4][GF_ENT];
-  const int layer = blockIdx.y;
+  const int layer = layer_base + blockIdx.y;           // 0-4 weight gradients, 5 out_mlp.fc2, 6 BatchNorm sums
   const int lane = threadIdx.x & (GF_ENT - 1), grp = threadIdx.x >> 6;
   const int i = blockIdx.x * GF_ENT + lane;
   const int nent = layer < 5 ? WG_PART : layer == 5 ? HID + 1 : 2 * E;
@@ -694,24 +694,50 @@ int launch_head_forward_fused(const float* P, Workspace& w, float* run_mean, flo
   return NRM_OK;
 }
 
-int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogits, float* G, cudaStream_t s) {
+// The head backward in three parts, so that a caller may run the weight gradients beside what follows:
+//   dgrad : the data-gradient chain (-> da*, dy, dgate, dz, de and the per-tile partials)
+//   bn    : BatchNorm sums from the tile partials (-> w.bn_bwd_sums, bn.weight / bn.bias gradients): needed by the encoder backward
+//   wgrad : the five weight gradients + out_mlp.fc2 (only the optimizer needs them)
+static void head_wgrad_shape(const Workspace& w, int& rpc, int& nchunks) {
+  const int nch = head_wgrad_chunks(w.R);
+  rpc = (int)((w.R + nch - 1) / nch);
+  rpc = (rpc + WG_TILE - 1) / WG_TILE * WG_TILE;
+  nchunks = (int)((w.R + rpc - 1) / rpc);
+}
+
+int launch_head_backward_dgrad(const float* P, Workspace& w, const float* dlogits, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     NRM_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     configured = true;
   }
-  const int ntiles = head_tiles(w.R);
-  launch_pdl(head_backward_kernel, dim3(ntiles), dim3(HT_THREADS), sizeof(HeadSmem), s, w.e, w.mean, w.rstd, P, w.R, dlogits, w.a1, w.gate, w.a2, w.a3, w.da3, w.dy, w.da2, w.dgate, w.da1, w.dz, w.de, w.head_part_f, w.head_part_bn);
+  launch_pdl(head_backward_kernel, dim3(head_tiles(w.R)), dim3(HT_THREADS), sizeof(HeadSmem), s, w.e, w.mean, w.rstd, P, w.R, dlogits, w.a1, w.gate, w.a2, w.a3, w.da3, w.dy, w.da2, w.dgate, w.da1, w.dz, w.de, w.head_part_f, w.head_part_bn);
   NRM_LAUNCH_CHECK("head_backward_kernel");
-  const int nch = head_wgrad_chunks(w.R);
-  int rpc = (int)((w.R + nch - 1) / nch);
-  rpc = (rpc + WG_TILE - 1) / WG_TILE * WG_TILE;
-  const int nchunks = (int)((w.R + rpc - 1) / rpc);
-  launch_pdl(head_wgrad_kernel, dim3(dim3(nchunks, 5)), dim3(WG_THREADS), 0, s, w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2, w.dgate, w.da1, w.head_part_w);
-  NRM_LAUNCH_CHECK("head_wgrad_kernel");
-  launch_pdl(head_grad_finish_kernel, dim3((WG_PART + GF_ENT - 1) / GF_ENT, 7), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums);
+  return NRM_OK;
+}
+
+int launch_head_backward_bn(Workspace& w, float* G, cudaStream_t s) {
+  int rpc, nchunks;
+  head_wgrad_shape(w, rpc, nchunks);
+  launch_pdl(head_grad_finish_kernel, dim3((2 * E + GF_ENT - 1) / GF_ENT, 1), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, head_tiles(w.R), w.head_part_bn, G, w.bn_bwd_sums, 6);
   NRM_LAUNCH_CHECK("head_grad_finish_kernel");
   return NRM_OK;
+}
+
+int launch_head_backward_wgrad(const float* P, Workspace& w, float* G, cudaStream_t s) {
+  int rpc, nchunks;
+  head_wgrad_shape(w, rpc, nchunks);
+  launch_pdl(head_wgrad_kernel, dim3(nchunks, 5), dim3(WG_THREADS), 0, s, w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2, w.dgate, w.da1, w.head_part_w);
+  NRM_LAUNCH_CHECK("head_wgrad_kernel");
+  launch_pdl(head_grad_finish_kernel, dim3((WG_PART + GF_ENT - 1) / GF_ENT, 6), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, head_tiles(w.R), w.head_part_bn, G, w.bn_bwd_sums, 0);
+  NRM_LAUNCH_CHECK("head_grad_finish_kernel");
+  return NRM_OK;
+}
+
+int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogits, float* G, cudaStream_t s) {
+  NRM_TRY(launch_head_backward_dgrad(P, w, dlogits, s));
+  NRM_TRY(launch_head_backward_bn(w, G, s));
+  return launch_head_backward_wgrad(P, w, G, s);
 }
 
 }  // namespace nrm

@@ -36,6 +36,9 @@ int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaS
 int launch_head_transpose(const float* P, Workspace& w, cudaStream_t s);          // transposed head matrices -> w.head_wt (weights only)
 int launch_head_forward_fused(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt, int training, int keep,
                               const double* bn_sums, long long bn_rows, float* logits, cudaStream_t s);
+int launch_head_backward_dgrad(const float* P, Workspace& w, const float* dlogits, cudaStream_t s);
+int launch_head_backward_bn(Workspace& w, float* grads, cudaStream_t s);                   // -> w.bn_bwd_sums, bn.weight / bn.bias gradients
+int launch_head_backward_wgrad(const float* P, Workspace& w, float* grads, cudaStream_t s);   // weight gradients of the five Linear layers + out_mlp.fc2
 int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogits, float* grads, cudaStream_t s);   // -> w.bn_bwd_sums, w.dz, w.de
 
 // nrm_head.cu
