@@ -2,7 +2,7 @@
 """Headline benchmark: training-step throughput of the EB-NeRD recommender hot path.
 
   python bench.py --gpus 1 --steps K --warmup W            (our CUDA path)
-  python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, oracle port)
+  python bench.py --impl reference --steps K --warmup W    (the unmodified reference's CPU path from baseline/_ref)
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (data parallel)
 
 One "step" = train.py:69-75 on one batch of synthetic EB-NeRD-shaped impressions:
@@ -49,6 +49,7 @@ def parse():
     ap.add_argument('--no-graph', action='store_true', help='FusedTrainStep issues the C-ABI calls eagerly instead of replaying a CUDA graph')
     ap.add_argument('--cpu-steps', type=int, default=60, help='train steps of the CPU port timed for cpu_baseline (about 15 s on 16 cores)')
     ap.add_argument('--no-scoring', action='store_true', help='skip the scoring (configs[2]) leg')
+    ap.add_argument('--no-dp-check', action='store_true', help='skip the N-rank vs single-process numerical pre-flight (world > 1)')
     ap.add_argument('--no-affinity', action='store_true', help='do not bind each rank to the CPU cores local to its GPU')
     return ap.parse_args()
 
@@ -117,30 +118,60 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm: the oracle port of the reference's CPU path (oracle/reference_port.py)
+# reference arm: the reference's own CPU path (baseline/_ref; oracle/reference_port.py only when that copy is absent)
 # ------------------------------------------------------------------------------------------
 def cpu_reference_rate(args, steps, warmup):
-    from oracle import reference_port as O
+    """Time train.py:69-75 on the host cores.  Preferred: the UNMODIFIED reference `models.user_model.UserModel`
+    from baseline/_ref (byte copy made by oracle/make_ref.py; kind "reference").  Fallback when that copy is absent:
+    the oracle port (kind "port").  -> (impressions/s, ms/step, cores, kind)"""
     from news_recommendation_model_b200.synthetic import make_batch
+    from oracle.make_ref import reference_modules, reference_root
     torch.set_num_threads(os.cpu_count())
-    p = O.load_params(load_weights(), user_num=args.user_num)
-    leaves = [p[k].requires_grad_(True) for k in O.TRAINABLE_KEYS + ('delta',)]
-    opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-5)
     batches = [make_batch(args.batch, args.history, args.candidates, seed=100 + i, user_num=args.user_num) for i in range(2)]
     times = []
-    for i in range(warmup + steps):
-        b = batches[i % len(batches)]
-        t0 = time.perf_counter()
-        out = O.user_model_forward(p, b.x_history, b.x_target, b.x_global, training=True)
-        loss = O.user_model_loss(p['delta'], b.user_id, out, b.label)
-        loss.backward()
-        opt.step()
-        opt.zero_grad()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
+    if reference_root() is not None:
+        kind = 'reference'
+        with reference_modules(with_scripts=False) as ref:
+            model = ref.UserModel(args.user_num)               # train.py:46
+            model.load_state_dict(load_weights(), strict=False)
+            model.train()
+            opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)   # train.py:48
+            for i in range(warmup + steps):
+                b = batches[i % len(batches)]
+                t0 = time.perf_counter()
+                out = model(b.x_history, b.x_target, b.x_global)                 # train.py:69
+                loss = model.loss(b.user_id, out, b.label)                         # train.py:71
+                loss.backward()                                                    # train.py:73-75
+                opt.step()
+                opt.zero_grad()
+                dt = time.perf_counter() - t0
+                if i >= warmup:
+                    times.append(dt)
+    else:
+        kind = 'port'
+        from oracle import reference_port as O
+        p = O.load_params(load_weights(), user_num=args.user_num)
+        leaves = [p[k].requires_grad_(True) for k in O.TRAINABLE_KEYS + ('delta',)]
+        opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-5)
+        for i in range(warmup + steps):
+            b = batches[i % len(batches)]
+            t0 = time.perf_counter()
+            out = O.user_model_forward(p, b.x_history, b.x_target, b.x_global, training=True)
+            loss = O.user_model_loss(p['delta'], b.user_id, out, b.label)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
     total = float(np.sum(times))
-    return args.batch * steps / total, total / steps * 1e3, os.cpu_count()
+    return args.batch * steps / total, total / steps * 1e3, os.cpu_count(), kind
+
+
+def _cpu_sample_text(kind, steps, warmup, batch):
+    what = ('the unmodified reference models.user_model.UserModel (baseline/_ref, byte copy of /root/reference) driven as train.py:69-75'
+            if kind == 'reference' else 'oracle/reference_port.py (baseline/_ref absent)')
+    return f'{steps} full train steps (B={batch}) of {what} on the host CPU, {warmup} warm-up'
 
 
 def run_reference(args):
@@ -148,15 +179,14 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 100)), max(1, min(args.warmup, 5))
-    rate, ms, cores = cpu_reference_rate(args, steps, warmup)
+    rate, ms, cores, kind = cpu_reference_rate(args, steps, warmup)
     line = {
         'impl': 'reference', 'metric': 'train_impressions_per_sec', 'value': rate, 'unit': 'impressions/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, 1),
-        'cpu_baseline': {'value': rate, 'unit': 'impressions/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{steps} full train steps (B={args.batch}) of oracle/reference_port.py on the host CPU, '
-                                   f'{warmup} warm-up'},
+        'cpu_baseline': {'value': rate, 'unit': 'impressions/s', 'cores': cores, 'kind': kind,
+                         'sample': _cpu_sample_text(kind, steps, warmup, args.batch)},
         'e2e': {'value': rate, 'unit': 'impressions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -198,6 +228,13 @@ def run_ours(args):
     model.set_precision(args.precision)
     if world > 1:
         DataParallel(model, sync_bn=args.sync_bn)
+
+    # pre-flight under data parallelism: N ranks vs one process on the same batch, identical replicas (tests/dp_check.py)
+    dp_parity = None
+    if world > 1 and not args.no_dp_check:
+        import dp_check
+        ok, rep = dp_check.run_check(dev, rank, world, precision=args.precision)
+        dp_parity = {'status': 'ok' if ok else 'FAILED', **{k: (round(v, 9) if isinstance(v, float) else v) for k, v in rep.items()}}
 
     B, H, C = args.batch, args.history, args.candidates
     host = [make_batch(B, H, C, seed=1234 + 97 * rank + i, user_num=args.user_num).pin() for i in range(N_POOL)]
@@ -475,9 +512,9 @@ def run_ours(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, ms, cores = cpu_reference_rate(args, args.cpu_steps, 2)
-        cpu = {'value': rate, 'unit': 'impressions/s', 'cores': cores, 'kind': 'port', 'ms_per_step': ms,
-               'sample': f'{args.cpu_steps} full train steps (B={B}) of oracle/reference_port.py, 2 warm-up'}
+        rate, ms, cores, kind = cpu_reference_rate(args, args.cpu_steps, 2)
+        cpu = {'value': rate, 'unit': 'impressions/s', 'cores': cores, 'kind': kind, 'ms_per_step': ms,
+               'sample': _cpu_sample_text(kind, args.cpu_steps, 2, B)}
     line = {
         'metric': 'train_impressions_per_sec', 'value': value, 'unit': 'impressions/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -493,7 +530,7 @@ def run_ours(args):
                         'note': 'drop-in nn.Module path driven like train.py:69-75 (autograd + FusedAdam), device-resident'},
         'api': 'FusedTrainStep (CUDA-graph replay of the 5 C-ABI calls)' if not args.no_graph else 'FusedTrainStep (eager C-ABI calls)',
         'roofline': roofline, 'kernels_ms_per_step': {k: round(v['ms_per_step'], 4) for k, v in kern.items()},
-        'cpu_baseline': cpu, 'precision_variants': variants, 'scoring': scoring,
+        'cpu_baseline': cpu, 'precision_variants': variants, 'scoring': scoring, 'dp_parity': dp_parity,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

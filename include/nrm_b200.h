@@ -165,10 +165,12 @@ int nrm_backward_encoder(const double* x_history, const double* x_target, long l
  * over B*C, log clamped at -100 (nn.BCELoss).  Writes *loss (float32) and keeps the unit
  * gradients in `scratch` (>= nrm_loss_scratch_bytes(B,C)).  `scratch` must be ZERO-FILLED ONCE
  * before its first use (it holds the arrival counter with which the last block of the forward
- * kernel adds the block sums in fixed order; every call leaves the counter at zero again). */
+ * kernel adds the block sums in fixed order; every call leaves the counter at zero again).
+ * delta has delta_numel = user_num + 1 entries (user_model.py:23).  A user id outside [0, delta_numel) makes the reference
+ * raise IndexError; here the loss of that step is NaN (no host synchronisation) and the backward ignores the id. */
 size_t nrm_loss_scratch_bytes(int B, int C);
-int nrm_loss_forward(const float* logits, const float* delta, const long long* user_id,
-                     const double* label, int B, int C, float alpha,
+int nrm_loss_forward(const float* logits, const float* delta, long long delta_numel,
+                     const long long* user_id, const double* label, int B, int C, float alpha,
                      float* loss, void* scratch, size_t scratch_bytes, void* stream);
 /* grad_loss: device scalar dL/dloss.  dlogits [B,C]; ddelta: dense [delta_numel],
  * overwritten (zeros + per-user sums, duplicates combined in batch order). */

@@ -42,7 +42,7 @@ SIGNATURES = {
     'nrm_backward_head': (i32, [i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
     'nrm_backward_encoder': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, ll, vp, vp, sz, vp]),
     'nrm_loss_scratch_bytes': (sz, [i32, i32]),
-    'nrm_loss_forward': (i32, [vp, vp, vp, vp, i32, i32, f32, vp, vp, sz, vp]),
+    'nrm_loss_forward': (i32, [vp, vp, ll, vp, vp, i32, i32, f32, vp, vp, sz, vp]),
     'nrm_loss_backward': (i32, [vp, i32, i32, vp, vp, vp, ll, vp, sz, vp]),
     'nrm_adam_step': (i32, [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, ll, f32, vp]),
     'nrm_adam_step_device': (i32, [vp, vp, vp, vp, ll, vp, vp]),

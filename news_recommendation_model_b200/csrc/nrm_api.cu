@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "nrm_kernels.cuh"
 
@@ -20,15 +22,20 @@ int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return NRM_ECUDA;
 }
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-    else n = 148;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
+int sm_count() {                      // per device (a process may drive several GPUs)
+  static int n[64] = {};
+  const int dev = current_device();
+  int v = __atomic_load_n(&n[dev], __ATOMIC_RELAXED);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    __atomic_store_n(&n[dev], v, __ATOMIC_RELAXED);
   }
-  return n;
+  return v;
 }
 
 // ---- launch counter and optional per-kernel event timing ------------------------------
@@ -40,9 +47,11 @@ struct TimerSlot { const char* name; cudaEvent_t beg[kTimerRing], end[kTimerRing
 static TimerSlot g_timers[kTimerSlots];
 static int g_ntimers = 0;
 static bool g_timing = false;
+static std::mutex g_timer_mu;          // g_timers / g_ntimers (launches may come from several host threads)
 
 KernelTimer::KernelTimer(const char* name, cudaStream_t stream) : slot_(-1), stream_(stream) {
   if (!g_timing) return;
+  std::lock_guard<std::mutex> lock(g_timer_mu);
   int s = -1;
   for (int i = 0; i < g_ntimers; ++i) if (strcmp(g_timers[i].name, name) == 0) { s = i; break; }
   if (s < 0) { if (g_ntimers == kTimerSlots) return; s = g_ntimers++; g_timers[s].name = name; g_timers[s].used = 0; g_timers[s].made = false; }
@@ -54,6 +63,7 @@ KernelTimer::KernelTimer(const char* name, cudaStream_t stream) : slot_(-1), str
 }
 KernelTimer::~KernelTimer() {
   if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lock(g_timer_mu);
   TimerSlot& t = g_timers[slot_];
   cudaEventRecord(t.end[t.used], stream_);
   t.used++;
@@ -65,29 +75,30 @@ KernelTimer::~KernelTimer() {
 // embedding kernel (fork: event on the caller's stream) and joined just before the table-gradient kernels (join: event
 // on the side stream), so its four small launches run under the attention / head kernels instead of after them.
 // Fork and join are ordinary stream events, so the pattern is also valid inside a CUDA-graph capture of the caller's
-// stream.  One side stream + two events per device, created on first use and kept for the life of the process.
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp, fork3, join3, fork4, join4; bool made; };
-static SideStream g_side[64];
-static SideStream* side_stream() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStream& ss = g_side[dev];
-  if (!ss.made) {
-    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.fork0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.join_tp, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.join0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.fork3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.join3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.fork4, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.join4, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    ss.made = true;
-  }
-  return &ss;
+// stream.
+struct SideStream {
+  int dev; cudaStream_t caller;
+  cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp, fork3, join3, fork4, join4;
+};
+// One side stream + event set per (device, caller stream): two models / threads that drive different streams of one device
+// never share fork / join events (a wait can only ever bind to its own caller's record).  Created under a mutex on first use
+// and kept for the life of the process (a caller that churns through streams leaks one small entry per stream).
+static std::mutex g_side_mu;
+static std::vector<SideStream*> g_sides;
+static SideStream* side_stream(cudaStream_t caller) {
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  for (SideStream* p : g_sides)
+    if (p->dev == dev && p->caller == caller) return p;
+  SideStream* ss = new SideStream();
+  ss->dev = dev; ss->caller = caller;
+  bool ok = cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking) == cudaSuccess;
+  cudaEvent_t* evs[] = {&ss->fork, &ss->join, &ss->fork2, &ss->join2, &ss->fork0, &ss->join0, &ss->join_tp, &ss->fork3, &ss->join3,
+                        &ss->fork4, &ss->join4};
+  for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { delete ss; return nullptr; }
+  g_sides.push_back(ss);
+  return ss;
 }
 
 bool pdl_enabled() {
@@ -214,7 +225,7 @@ static int get_workspace(const char* fn, Workspace& w, void* ws, size_t ws_bytes
 }
 
 static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, int mode, int precision, cudaStream_t s) {
-  SideStream* ss = side_stream();
+  SideStream* ss = side_stream(s);
   if (ss == nullptr) { set_error("encoder_forward: cannot create the side stream"); return NRM_ECUDA; }
   const bool tc = precision != NRM_PRECISION_FP32;
   // fork 0: what depends on the weights only (derived attention matrices, transposed head matrices) runs on the side
@@ -249,11 +260,15 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
     NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s));
     NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s));
   }
+  // join: the id sort (long finished: it ran under the w1 / attention kernels) comes back to the caller's stream HERE, so a
+  // training-mode forward that is never followed by a backward (validation with gradients enabled, a graph capture of the
+  // forward alone) leaves no unjoined side-stream work, and the workspace may be reused or freed in stream order
+  if (mode & NRM_MODE_KEEP_FOR_BWD) NRM_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
   return NRM_OK;
 }
 
 static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, int precision, float* G, cudaStream_t s) {
-  SideStream* ss = side_stream();
+  SideStream* ss = side_stream(s);
   if (ss == nullptr) { set_error("encoder_backward: cannot create the side stream"); return NRM_ECUDA; }
   { KernelTimer t("attention_backward_label", s); NRM_TRY(launch_attention_backward(in, P, w, 0, precision, s)); }
   // fork: the w1 backward only needs dxh (label attention); it runs on the side stream under the text/img attention
@@ -274,8 +289,7 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
   NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork3, 0));
   { KernelTimer t("small_linear_grads", ss->stream); NRM_TRY(launch_small_linear_grads(in, w, G, ss->stream)); }
   NRM_CUDA(cudaEventRecord(ss->join3, ss->stream));
-  // join: the id sort enqueued by the forward (same workspace) must have finished
-  NRM_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+  // (the id sort enqueued by the forward was joined at the end of that forward)
   NRM_TRY(launch_table_grads(w, G, s));
   NRM_CUDA(cudaStreamWaitEvent(s, ss->join3, 0));
   return NRM_OK;
@@ -288,6 +302,7 @@ using namespace nrm;
 extern "C" int nrm_version(void) { return 100; }
 extern "C" unsigned long long nrm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" void nrm_timing_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_timer_mu);
   g_timing = on != 0;
   for (int i = 0; i < g_ntimers; ++i) g_timers[i].used = 0;
 }
@@ -296,6 +311,7 @@ extern "C" int nrm_timing_report(char* buf, size_t buf_bytes) {
   if (!buf || buf_bytes == 0) { set_error("nrm_timing_report: bad buffer"); return NRM_EINVAL; }
   size_t off = 0;
   buf[0] = 0;
+  std::lock_guard<std::mutex> lock(g_timer_mu);
   for (int i = 0; i < g_ntimers; ++i) {
     TimerSlot& t = g_timers[i];
     double total = 0.0;
@@ -413,7 +429,7 @@ extern "C" int nrm_backward(const double* x_history, const double* x_target, lon
   Workspace w;
   NRM_TRY(get_workspace("nrm_backward", w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
   cudaStream_t s = (cudaStream_t)stream;
-  SideStream* ss = side_stream();
+  SideStream* ss = side_stream(s);
   if (ss == nullptr) { set_error("nrm_backward: cannot create the side stream"); return NRM_ECUDA; }
   const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
   { KernelTimer t("head_backward", s);

@@ -1194,10 +1194,9 @@ int launch_attention_backward_tc(const BatchPtrs& in, const float* P, Workspace&
 // both branches at once (after both backward kernels)
 int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaStream_t s) {
   const int nparts = (int)((w.R + TPG_ROWS - 1) / TPG_ROWS);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;                          // function attributes are per device
+  if (configured.first_time()) {
     NRM_CUDA(cudaFuncSetAttribute(attention_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TpgSmem)));
-    configured = true;
   }
   launch_pdl(attention_finish_kernel, dim3(COMPOSE_BLOCKS + (nparts + TPG_SUB - 1) / TPG_SUB, 2), dim3(1024), sizeof(TpgSmem), s, w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA, w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
   NRM_LAUNCH_CHECK("attention_finish_kernel");

@@ -126,8 +126,22 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     if (rc__ != NRM_OK) return rc__; \
   } while (0)
 
-int sm_count();
+int sm_count();                      // of the current device
+int current_device();
 void count_launch();
+
+// "Once per device" guard for cudaFuncSetAttribute-style set-up (function attributes are per device; a process may
+// drive several GPUs from several threads).  first_time() is true for the callers that find the current device's flag clear;
+// the flag is set right away, so two racing threads may both run the (idempotent) set-up, never neither.
+struct DeviceOnce {
+  unsigned char done[64] = {};
+  bool first_time() {
+    const int d = current_device();
+    if (__atomic_load_n(&done[d], __ATOMIC_ACQUIRE)) return false;
+    __atomic_store_n(&done[d], (unsigned char)1, __ATOMIC_RELEASE);
+    return true;
+  }
+};
 
 // Optional per-kernel device timing (nrm_timing_enable): brackets the launches issued
 // during its lifetime with CUDA events on `stream`.  A no-op unless enabled.

@@ -577,10 +577,9 @@ static SortPair make_sort_pair(Workspace& w) {
 int launch_table_sort(Workspace& w, cudaStream_t s) {
   const SortPair sp = make_sort_pair(w);
   const int nch = sp.s[0].nchunks + sp.s[1].nchunks;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;                          // function attributes are per device
+  if (configured.first_time()) {
     NRM_CUDA(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (SORT_CHUNK + 2 * NKEY32))));
-    configured = true;
   }
   launch_pdl(sort_hist_kernel, dim3(nch), dim3(1024), NKEY32 * sizeof(int), s, sp);
   NRM_LAUNCH_CHECK("sort_hist_kernel");

@@ -683,11 +683,10 @@ int launch_head_transpose(const float* P, Workspace& w, cudaStream_t s) {
 
 int launch_head_forward_fused(const float* P, Workspace& w, float* run_mean, float* run_var, long long* nbt, int training, int keep,
                               const double* bn_sums, long long bn_rows, float* logits, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;                          // function attributes are per device
+  if (configured.first_time()) {
     NRM_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     NRM_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
-    configured = true;
   }
   launch_pdl(head_forward_kernel, dim3(head_tiles(w.R)), dim3(HT_THREADS), sizeof(HeadSmem), s, w.e, bn_sums, bn_rows, training, run_mean, run_var, nbt, w.mean, w.rstd, P, w.head_wt, w.R, keep, w.a1, w.gate, w.a2, w.y, w.a3, logits);
   NRM_LAUNCH_CHECK("head_forward_kernel");
@@ -706,10 +705,9 @@ static void head_wgrad_shape(const Workspace& w, int& rpc, int& nchunks) {
 }
 
 int launch_head_backward_dgrad(const float* P, Workspace& w, const float* dlogits, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;                          // function attributes are per device
+  if (configured.first_time()) {
     NRM_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
-    configured = true;
   }
   launch_pdl(head_backward_kernel, dim3(head_tiles(w.R)), dim3(HT_THREADS), sizeof(HeadSmem), s, w.e, w.mean, w.rstd, P, w.R, dlogits, w.a1, w.gate, w.a2, w.a3, w.da3, w.dy, w.da2, w.dgate, w.da1, w.dz, w.de, w.head_part_f, w.head_part_bn);
   NRM_LAUNCH_CHECK("head_backward_kernel");

@@ -70,7 +70,7 @@ __device__ __forceinline__ float bce_softmax_term(const float* __restrict__ out,
 
 __global__ void __launch_bounds__(256)
 loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ delta, const long long* __restrict__ uid,
-                    const double* __restrict__ label, int B, int C, float alpha, float* __restrict__ dlog,
+                    const double* __restrict__ label, int B, int C, long long delta_numel, float alpha, float* __restrict__ dlog,
                     float* __restrict__ drow, double* __restrict__ lpart, unsigned* __restrict__ ticket, float* __restrict__ loss) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
@@ -82,7 +82,12 @@ loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ 
     const float* o = logits + (long long)b * C;
     const double* y = label + (long long)b * C;
     float* dl = dlog + (long long)b * C;
-    const float sh = delta[uid[b]];
+    // user id outside delta[0 .. user_num]: the reference raises IndexError (user_model.py:38).  A kernel cannot raise, so the
+    // step's loss becomes NaN (loud, no host sync) and the row's shift is 0; the backward skips such ids.
+    const long long id = uid[b];
+    const bool id_ok = id >= 0 && id < delta_numel;
+    const float sh = id_ok ? delta[id] : 0.f;
+    if (!id_ok) l2 = __longlong_as_double(0x7ff8000000000000LL);
     float rs1, rs2;
     const float a = bce_softmax_term(o, y, C, 0.f, invN, 1.f - alpha, dl, false, &rs1);
     __syncwarp();
@@ -256,16 +261,17 @@ extern "C" size_t nrm_loss_scratch_bytes(int B, int C) {
   return carve_loss(ls, nullptr, B > 0 ? B : 1, C > 0 ? C : 1);
 }
 
-extern "C" int nrm_loss_forward(const float* logits, const float* delta, const long long* user_id, const double* label,
-                                int B, int C, float alpha, float* loss, void* scratch, size_t scratch_bytes, void* stream) {
-  if (!logits || !delta || !user_id || !label || !loss || !scratch || B <= 0 || C <= 0) {
+extern "C" int nrm_loss_forward(const float* logits, const float* delta, long long delta_numel, const long long* user_id,
+                                const double* label, int B, int C, float alpha, float* loss, void* scratch, size_t scratch_bytes,
+                                void* stream) {
+  if (!logits || !delta || delta_numel <= 0 || !user_id || !label || !loss || !scratch || B <= 0 || C <= 0) {
     set_error("nrm_loss_forward: bad argument"); return NRM_EINVAL;
   }
   LossScratch ls;
   if (carve_loss(ls, scratch, B, C) > scratch_bytes) { set_error("nrm_loss_forward: scratch too small"); return NRM_EWORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = min(LOSS_BLOCKS, (B + 7) / 8);
-  launch_pdl(loss_forward_kernel, dim3(blocks), dim3(256), 0, s, logits, delta, user_id, label, B, C, alpha, ls.dlog, ls.drow, ls.lpart,
+  launch_pdl(loss_forward_kernel, dim3(blocks), dim3(256), 0, s, logits, delta, user_id, label, B, C, delta_numel, alpha, ls.dlog, ls.drow, ls.lpart,
              ls.ticket, loss);
   NRM_LAUNCH_CHECK("loss_forward_kernel");
   return NRM_OK;

@@ -181,11 +181,10 @@ w1_finish_kernel(const float* __restrict__ part, int nparts, float* __restrict__
 static_assert(P_W1_B == P_W1_W + 64 * XIN, "w1.weight / w1.bias must be contiguous in the flat layout");
 
 int launch_w1_forward(const float* P, Workspace& w, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;                          // function attributes are per device
+  if (configured.first_time()) {
     NRM_CUDA(cudaFuncSetAttribute(w1_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(W1SmemFwd)));
     NRM_CUDA(cudaFuncSetAttribute(w1_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(W1SmemBwd)));
-    configured = true;
   }
   const long long ntiles = (w.NH + W1F_ROWS - 1) / W1F_ROWS;
   const int grid = (int)min(ntiles, (long long)6 * sm_count());
@@ -195,10 +194,9 @@ int launch_w1_forward(const float* P, Workspace& w, cudaStream_t s) {
 }
 
 int launch_w1_backward(const float* P, Workspace& w, float* G, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;                          // function attributes are per device
+  if (configured.first_time()) {
     NRM_CUDA(cudaFuncSetAttribute(w1_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(W1SmemBwd)));
-    configured = true;
   }
   const long long ntiles = (w.NH + W1_ROWS - 1) / W1_ROWS;
   const int grid = (int)min(ntiles, (long long)min(2 * sm_count(), W1_SPLITS));

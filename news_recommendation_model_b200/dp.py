@@ -87,6 +87,7 @@ class DataParallel:
         self.buckets = GradientBuckets(group)
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self._head_begin = None
+        self._rows_checked = None
         model._dp = self
         if broadcast:
             flat = model.flat_parameters()
@@ -96,8 +97,18 @@ class DataParallel:
 
     # ---- BatchNorm statistics -----------------------------------------------------------
     def all_reduce_stats(self, sums: torch.Tensor, local_rows: int) -> int:
+        """Sum the BatchNorm statistics over the ranks; returns the global row count.  Shards must be equal (the gradient
+        average weights every rank the same): checked with one small all-reduce whenever the local row count changes."""
+        if local_rows != self._rows_checked:
+            t = torch.tensor([local_rows, -local_rows], dtype=torch.int64, device=sums.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            hi, lo = int(t[0]), -int(t[1])
+            if hi != lo:
+                raise RuntimeError(f'DataParallel(sync_bn=True): ranks hold between {lo} and {hi} candidate rows; shard the global '
+                                   'batch evenly (drop or pad the ragged tail) -- unequal shards would bias the averaged gradients')
+            self._rows_checked = local_rows
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
-        return local_rows * self.world       # equal shards (bench / tests); ragged shards all-reduce the count too
+        return local_rows * self.world
 
     # ---- gradient buckets ---------------------------------------------------------------
     def _split(self, flat):
@@ -114,8 +125,20 @@ class DataParallel:
             fn()
 
     def reduce_head_bucket(self, g: torch.Tensor, flat):
+        # [bn.weight .. out_mlp.fc2.bias]; delta (behind it in the layout) is averaged by the loss backward (reduce_delta)
         hb = self._split(flat)
-        self._on_comm_stream(lambda: self.buckets.reduce(g, hb, g.numel()))
+        self._on_comm_stream(lambda: self.buckets.reduce(g, hb, flat.fixed))
+
+    def reduce_delta(self, ddelta: torch.Tensor):
+        """Average the per-user bias gradient across ranks, in stream order on the caller's stream (the result is handed to
+        autograd right away, see engine._LossFn.backward)."""
+        if ddelta.numel() == 0:
+            return
+        if self.buckets._avg:
+            dist.all_reduce(ddelta, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(ddelta, op=dist.ReduceOp.SUM, group=self.group)
+            ddelta.div_(self.world)
 
     def reduce_encoder_bucket(self, g: torch.Tensor, flat):
         hb = self._split(flat)

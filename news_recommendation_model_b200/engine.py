@@ -297,7 +297,7 @@ class _LossFn(torch.autograd.Function):
         uid = user_id.to(device=dev, dtype=torch.int64).contiguous()
         lab = label.to(device=dev, dtype=torch.float64).contiguous()
         o = out.detach().contiguous()
-        _lib.check(lib.nrm_loss_forward(_ptr(o), _ptr(delta.detach()), _ptr(uid), _ptr(lab), B, C, float(alpha), _ptr(loss),
+        _lib.check(lib.nrm_loss_forward(_ptr(o), _ptr(delta.detach()), delta.numel(), _ptr(uid), _ptr(lab), B, C, float(alpha), _ptr(loss),
                                         _ptr(scratch), need, _stream(dev)), 'nrm_loss_forward')
         ctx.model, ctx.token, ctx.uid, ctx.scratch, ctx.shape = model, token, uid, scratch, (B, C)
         ctx.delta_numel = delta.numel()
@@ -322,6 +322,14 @@ class _LossFn(torch.autograd.Function):
         rt = ctx.model._runtime()
         if ctx.scratch is rt.loss_scratch:
             rt.loss_scratch_busy = False
+        dp = ctx.model._dp
+        if dp is not None:
+            # Data parallel: average the delta gradient HERE, before autograd sees it.  AccumulateGrad(delta) runs as soon as
+            # this function returns -- a view that is all-reduced later (with the head bucket) would be accumulated into an
+            # existing .grad (zero_grad(set_to_none=False), gradient accumulation) with its un-reduced, rank-local values and
+            # the replicas would drift apart.  The head bucket therefore ends in front of delta (dp.reduce_head_bucket), and
+            # the gradient stays the flat buffer's view so that FusedAdam keeps its one-launch path.
+            dp.reduce_delta(ddelta)                            # in place, in stream order: still the flat buffer's view
         return None, None, None, None, None, dlogits, ddelta
 
 

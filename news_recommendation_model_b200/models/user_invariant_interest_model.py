@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from .. import engine
-from ..config import config as model_config, GLOBAL_COLS
+from ..config import config as model_config, GLOBAL_COLS, HIST_COLS, TGT_COLS
 from .attention_model import PointwiseAttentionExpanded
 
 
@@ -41,3 +41,40 @@ class UserInvariantInterestModel(nn.Module):
         named = {'invariant_interest_model.' + k: p for k, p in self.named_parameters()}
         e = engine.standalone_encoder(named, x_history, x_target, xg)
         return e[:, :, 0:128], e[:, :, 136:264]
+
+    # ---- the reference's helper methods (:50-71), same signatures and results -------------------------------------------
+    def slice_x(self, x, n):
+        """Column groups of packed rows (:50-56): views, no arithmetic."""
+        out, start = [], 0
+        for i in range(n):
+            out.append(x[:, :, start:start + self.slice_len_list[i]])
+            start += self.slice_len_list[i]
+        return out
+
+    def _embed_rows(self, rows):
+        """Run the fused row-embedding kernel on packed candidate rows [B,L,78] (float64) -> x_label_t [B,L,64] =
+        [feature_embedding 56 | time_embedding 8] (the `ec` columns 136:200 of e_concat); one dummy history row per
+        impression keeps the encoder's shape contract."""
+        B = rows.shape[0]
+        xh = torch.zeros(B, 1, HIST_COLS, dtype=torch.float64, device=rows.device)
+        xg = torch.zeros(B, rows.shape[1], GLOBAL_COLS, dtype=torch.float64, device=rows.device)
+        named = {'invariant_interest_model.' + k: p for k, p in self.named_parameters()}
+        e = engine.standalone_encoder(named, xh, rows, xg)
+        return e[:, :, 136:200]
+
+    def feature_embedding(self, category, sub_category, sentiment, type):
+        """(:58-64) category [.,.,1], sub_category [.,.,5], sentiment [.,.,3], type [.,.,1] -> [.,.,56]."""
+        B, L = category.shape[0], category.shape[1]
+        rows = torch.zeros(B, L, TGT_COLS, dtype=torch.float64, device=category.device)
+        rows[:, :, 68:69] = category.to(torch.float64)
+        rows[:, :, 69:74] = sub_category.to(torch.float64)
+        rows[:, :, 74:77] = sentiment.to(torch.float64)
+        rows[:, :, 77:78] = type.to(torch.float64)
+        return self._embed_rows(rows)[:, :, 0:56].contiguous()
+
+    def time_embedding(self, time):
+        """(:66-71) [years, months, days, hours] buckets [.,.,4] -> [.,.,8] (sum of the four lookups)."""
+        B, L = time.shape[0], time.shape[1]
+        rows = torch.zeros(B, L, TGT_COLS, dtype=torch.float64, device=time.device)
+        rows[:, :, 0:4] = time.to(torch.float64)
+        return self._embed_rows(rows)[:, :, 56:64].contiguous()

@@ -34,7 +34,9 @@ class UserModel(nn.Module):
         # runtime state (flat buffers, workspaces, data-parallel hooks): not part of state_dict
         self._rt = None
         self._dp = None
-        self.precision = 'fp32'
+        # pair products on the tensor cores with hi/lo split operands: meets the fp32 tolerances (tests/test_gpu_tensorcore.py),
+        # so the unmodified train.py / test.py get the fast path; 'fp32' selects the strict FFMA kernels
+        self.precision = 'bf16x3'
 
     # ---- runtime plumbing --------------------------------------------------------------
     def __getstate__(self):
@@ -52,7 +54,7 @@ class UserModel(nn.Module):
         return engine.PRECISION[self.precision]
 
     def set_precision(self, precision: str):
-        """'fp32' (default, FFMA), 'bf16x3' (tcgen05 tiles, hi/lo split operands, fp32-grade) or 'bf16' (tcgen05 tiles)."""
+        """'bf16x3' (default: tcgen05 tiles, hi/lo split operands, fp32-grade), 'fp32' (strict FFMA) or 'bf16' (tcgen05 tiles)."""
         if precision not in engine.PRECISION:
             raise ValueError(f'precision must be one of {sorted(engine.PRECISION)}')
         self.precision = precision

@@ -43,6 +43,7 @@ class _Slot:
         self.used = False
         self.compact = None                    # device CompactBatch staging buffers (wire.py), allocated on first use
         self.wire = 'packed'                   # what the last load() put into this slot
+        self.rows = B                          # impressions the last load() put into this slot (< B: ragged last batch)
         self.graph_wire = None                 # wire format the captured graph was recorded for
 
 
@@ -94,6 +95,7 @@ class FusedTrainStep:
         self.copy_stream = torch.cuda.Stream(dev)
         self.use_graph = use_graph
         self.world = world
+        self._tail_scratch = {}
         self._warmup()
 
     def _warmup(self):
@@ -118,21 +120,24 @@ class FusedTrainStep:
         torch.cuda.synchronize(self.dev)
 
     # ---- the five C-ABI calls of one step (train.py:69-75) --------------------------------
-    def _forward_backward(self, s: _Slot, loss_out: torch.Tensor):
+    def _forward_backward(self, s: _Slot, loss_out: torch.Tensor, B: Optional[int] = None, loss_scratch: Optional[torch.Tensor] = None):
+        """B < self.B: a ragged last batch in the first B rows of the slot (eager only; its own zeroed loss scratch)."""
         lib, m, f = self.lib, self.model, self.flat
         st = engine._stream(self.dev)
-        B, H, C = self.B, self.H, self.C
+        H, C = self.H, self.C
+        B = self.B if B is None else B
+        loss_scratch = self.loss_scratch if loss_scratch is None else loss_scratch
         if self.dp is not None and self.dp.sync_bn:
             raise _lib.NrmError('FusedTrainStep: sync_bn needs the two-phase calls; use model.forward/backward')
         _lib.check(lib.nrm_forward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf),
                                    _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked), self.mode,
                                    self.precision, _p(self.logits), _p(self.ws), self.ws.numel(), st), 'nrm_forward')
         delta = f.buf[f.fixed:f.fixed + f.delta_numel]
-        _lib.check(lib.nrm_loss_forward(_p(self.logits), _p(delta), _p(s.uid), _p(s.label), B, C, self.alpha, _p(loss_out),
-                                        _p(self.loss_scratch), self.loss_scratch.numel(), st), 'nrm_loss_forward')
+        _lib.check(lib.nrm_loss_forward(_p(self.logits), _p(delta), f.delta_numel, _p(s.uid), _p(s.label), B, C, self.alpha, _p(loss_out),
+                                        _p(loss_scratch), loss_scratch.numel(), st), 'nrm_loss_forward')
         ddelta = self.grads[f.fixed:f.fixed + f.delta_numel]
         _lib.check(lib.nrm_loss_backward(_p(s.uid), B, C, _p(self.one), _p(self.dlogits), _p(ddelta), f.delta_numel,
-                                         _p(self.loss_scratch), self.loss_scratch.numel(), st), 'nrm_loss_backward')
+                                         _p(loss_scratch), loss_scratch.numel(), st), 'nrm_loss_backward')
         _lib.check(lib.nrm_backward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
                                     self.precision, _p(self.dlogits), _p(self.grads), _p(self.ws), self.ws.numel(), st),
                    'nrm_backward')
@@ -141,6 +146,43 @@ class FusedTrainStep:
         _lib.check(self.lib.nrm_adam_step_device(_p(self.flat.buf), _p(self.grads), _p(self.exp_avg), _p(self.exp_avg_sq),
                                                  self.flat.total, _p(self.adam_state), engine._stream(self.dev)),
                    'nrm_adam_step_device')
+
+    # ---- optimizer state: what torch.optim.Adam + LambdaLR give the reference loop (train.py:48-49) --------------------
+    _ADAM_FIELDS = ('lr', 'beta1', 'beta2', 'eps', 'weight_decay', 'grad_scale')
+
+    def _adam_host(self):
+        step, lr, b1, b2, eps, wd, gs, _, _ = struct.unpack('<q8f', bytes(self.adam_state.cpu().numpy().tobytes()))
+        return {'step': step, 'lr': lr, 'beta1': b1, 'beta2': b2, 'eps': eps, 'weight_decay': wd, 'grad_scale': gs}
+
+    def set_hyper(self, **kw):
+        """Change lr / beta1 / beta2 / eps / weight_decay / grad_scale between steps (e.g. the 0.65 ** epoch schedule of
+        train.py:49).  The captured graphs stay valid: the Adam kernel reads these values from device memory; the new values
+        are written with one small async copy on the current stream, i.e. in order with the steps."""
+        unknown = set(kw) - set(self._ADAM_FIELDS)
+        if unknown:
+            raise ValueError(f'unknown Adam hyper-parameter(s): {sorted(unknown)}')
+        cur = self._adam_host() if len(kw) < len(self._ADAM_FIELDS) else {}
+        cur.update({k: float(v) for k, v in kw.items()})
+        raw = struct.pack('<6f', *[cur[k] for k in self._ADAM_FIELDS])
+        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        self.adam_state[8:32].copy_(host.to(self.dev, non_blocking=False))
+
+    def set_lr(self, lr: float):
+        self.set_hyper(lr=lr)
+
+    def state_dict(self):
+        """Optimizer state for checkpoint / resume: flat moments (same layout as the flat parameter buffer), step and the
+        hyper-parameters.  Model weights and BatchNorm buffers are in model.state_dict() as usual."""
+        torch.cuda.current_stream(self.dev).synchronize()
+        return {'exp_avg': self.exp_avg.detach().clone(), 'exp_avg_sq': self.exp_avg_sq.detach().clone(), **self._adam_host(),
+                'layout': [(name, off, n) for name, off, n, _ in self.flat.slots]}
+
+    def load_state_dict(self, sd):
+        if [tuple(x) for x in sd['layout']] != [(name, off, n) for name, off, n, _ in self.flat.slots]:
+            raise _lib.NrmError('FusedTrainStep.load_state_dict: the saved moments use another parameter layout (user_num?)')
+        self.exp_avg.copy_(sd['exp_avg']); self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+        raw = struct.pack('<q8f', int(sd['step']), sd['lr'], sd['beta1'], sd['beta2'], sd['eps'], sd['weight_decay'], sd['grad_scale'], 0.0, 0.0)
+        self.adam_state.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev))
 
     # ---- pipeline -------------------------------------------------------------------------
     def _load_compact(self, s: _Slot, batch):
@@ -160,6 +202,7 @@ class FusedTrainStep:
             s.uid.copy_(batch.user_id, non_blocking=True)
             s.ready.record(self.copy_stream)
         s.wire = 'compact'
+        s.rows = self.B
         return s
 
     def _expand(self, s: _Slot):
@@ -174,14 +217,19 @@ class FusedTrainStep:
         if hasattr(batch, 'hist_article'):
             return self._load_compact(s, batch)
         s.wire = 'packed'
+        b = int(batch.x_history.shape[0])
+        if b > self.B or tuple(batch.x_history.shape[1:]) != (self.H, HIST_COLS) or tuple(batch.x_target.shape[1:]) != (self.C, TGT_COLS):
+            raise ValueError(f'batch of shape {tuple(batch.x_history.shape)} / {tuple(batch.x_target.shape)} does not fit this step '
+                             f'(B <= {self.B}, H = {self.H}, C = {self.C})')
+        s.rows = b                                           # b < B: the ragged last batch of DataLoader(..., drop_last=False), train.py:40
         with torch.cuda.stream(self.copy_stream):
             if s.used:
                 self.copy_stream.wait_event(s.consumed)      # do not overwrite a slot still being read
-            s.xh.copy_(batch.x_history, non_blocking=True)
-            s.xt.copy_(batch.x_target, non_blocking=True)
-            s.xg.copy_(batch.x_global, non_blocking=True)
-            s.label.copy_(batch.label, non_blocking=True)
-            s.uid.copy_(batch.user_id, non_blocking=True)
+            s.xh[:b].copy_(batch.x_history, non_blocking=True)
+            s.xt[:b].copy_(batch.x_target, non_blocking=True)
+            s.xg[:b].copy_(batch.x_global, non_blocking=True)
+            s.label[:b].copy_(batch.label, non_blocking=True)
+            s.uid[:b].copy_(batch.user_id, non_blocking=True)
             s.ready.record(self.copy_stream)
         return s
 
@@ -190,7 +238,18 @@ class FusedTrainStep:
         cur.wait_event(s.ready)
         k = self.count % self.ring
         loss_out = self.loss_dev[k:k + 1]
-        if self.use_graph:
+        if s.rows != self.B:
+            # ragged last batch: the same five calls with the smaller B, eagerly (a graph per tail size would never be replayed)
+            if self.dp is not None:
+                raise _lib.NrmError('FusedTrainStep: ragged batches under data parallelism would bias the gradient average; '
+                                    'drop or pad the tail')
+            scratch = self._tail_scratch.get(s.rows)
+            if scratch is None:
+                scratch = self._tail_scratch[s.rows] = torch.zeros(int(self.lib.nrm_loss_scratch_bytes(s.rows, self.C)),
+                                                                   dtype=torch.uint8, device=self.dev)
+            self._forward_backward(s, loss_out, B=s.rows, loss_scratch=scratch)
+            self._adam()
+        elif self.use_graph:
             if s.graph_fb is None or s.graph_wire != s.wire:
                 # eager warm-up pass is NOT wanted (it would be an extra optimizer step): capture directly
                 s.graph_fb = torch.cuda.CUDAGraph()

@@ -1,10 +1,17 @@
 #!/usr/bin/env python
-"""Multi-GPU check, run under torchrun on N GPUs of one box:
+"""Multi-GPU numerical check, run under torchrun on N GPUs of one box:
 
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dp_check.py
 
-N ranks x (B/N impressions) with synchronised BatchNorm statistics must reproduce one process
-on the whole batch: same logits, same averaged gradients, same weights after Adam."""
+`run_check()` is also what `bench.py --gpus N` calls as its pre-flight (result in the JSON line as `dp_parity`) and what
+tests/test_gpu_dp.py launches when the box shows >= 2 GPUs.
+
+1. module path, synchronised BatchNorm statistics: N ranks x (B/N impressions) must reproduce one process on the whole
+   batch -- same logits, same averaged gradients, same BatchNorm buffers;
+2. the `delta` gradient (averaged inside the loss backward, engine._LossFn.backward) is bit-identical on every rank, also when
+   it is accumulated into an existing .grad (zero_grad(set_to_none=False) + a second micro-batch);
+3. FusedTrainStep (the path bench.py measures): three steps on rank-local shards leave bit-identical weights on every rank, and
+   they equal a single-process FusedTrainStep on the whole batch within the fp32 tolerances when sync_bn is on."""
 import os
 import sys
 
@@ -22,11 +29,16 @@ from news_recommendation_model_b200.synthetic import make_batch, Batch   # noqa:
 from fixtures import load_weights                      # noqa: E402
 
 
-def main():
-    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    dist.init_process_group('nccl', device_id=dev)
+def _same_on_all_ranks(t: torch.Tensor) -> bool:
+    """True when `t` holds the same bits on every rank."""
+    lo, hi = t.detach().clone(), t.detach().clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi))
+
+
+def run_check(dev, rank: int, world: int, precision: str = 'bf16x3', fused: bool = True):
+    """-> (ok, report dict).  Needs an initialised NCCL process group with one rank per GPU."""
     B, H, C, U = 64 * world, 50, 5, 100
     full = make_batch(B, H, C, seed=7, user_num=U)
     delta0 = torch.from_numpy(np.random.default_rng(2).normal(0, 0.3, U + 1).astype(np.float32))
@@ -36,9 +48,10 @@ def main():
         m.load_state_dict(load_weights('train'), strict=False)
         with torch.no_grad():
             m.delta.copy_(delta0)
-        return m.to(dev).train()
+        return m.to(dev).train().set_precision(precision)
 
-    # single-process reference on the whole batch (every rank computes it redundantly)
+    rep = {}
+    # ---- 1. module path vs one process on the whole batch (every rank computes the reference redundantly)
     ref = fresh()
     d = full.to(dev)
     out = ref(d.x_history, d.x_target, d.x_global)
@@ -46,33 +59,82 @@ def main():
     ref_grads = {k: p.grad.clone() for k, p in ref.named_parameters()}
     ref_out = out.detach()
 
-    # data parallel: this rank's shard
     lo, hi = shard_range(B, rank, world)
-    shard = Batch(*[getattr(full, f)[lo:hi] for f in full.__dataclass_fields__]).to(dev)
+    shard_host = Batch(*[getattr(full, f)[lo:hi] for f in full.__dataclass_fields__])
+    shard = shard_host.to(dev)
     m = fresh()
     DataParallel(m, sync_bn=True)
     o = m(shard.x_history, shard.x_target, shard.x_global)
     m.loss(shard.user_id, o, shard.label).backward()
     torch.cuda.synchronize()
-    err_logits = (o.detach() - ref_out[lo:hi]).abs().max().item()
+    rep['logits_err'] = (o.detach() - ref_out[lo:hi]).abs().max().item()
     worst = ('', 0.0)
     for k, p in m.named_parameters():
-        if k in ('delta', 'out_mlp.fc2.bias'):
+        if k in ('delta', 'out_mlp.fc2.bias'):       # pure rounding noise (softmax shift invariance): compared in absolute terms below
             continue
         scale = ref_grads[k].abs().max().item()
         err = (p.grad - ref_grads[k]).abs().max().item() / max(scale, 1e-12)
         if err > worst[1]:
             worst = (k, err)
-    bn_err = (m.bn.running_mean - ref.bn.running_mean).abs().max().item()
-    ok = err_logits <= 1e-4 and worst[1] <= 5e-4 and bn_err <= 1e-5
+    rep['worst_grad_rel_err'], rep['worst_grad'] = worst[1], worst[0]
+    rep['bn_running_mean_err'] = (m.bn.running_mean - ref.bn.running_mean).abs().max().item()
+    rep['delta_grad_abs_err'] = (m.delta.grad - ref_grads['delta']).abs().max().item()
+    ok = rep['logits_err'] <= 1e-4 and worst[1] <= 5e-4 and rep['bn_running_mean_err'] <= 1e-5 and rep['delta_grad_abs_err'] <= 1e-6
+
+    # ---- 2. every gradient identical on every rank, also after accumulating a second micro-batch into existing .grad
+    same = all(_same_on_all_ranks(p.grad) for p in m.parameters())
+    o2 = m(shard.x_history, shard.x_target, shard.x_global)
+    (2.0 * m.loss(shard.user_id, o2, shard.label)).backward()            # accumulates into the .grad of the first pass
+    torch.cuda.synchronize()
+    same_acc = all(_same_on_all_ranks(p.grad) for p in m.parameters())
+    rep['grads_identical_on_all_ranks'], rep['accumulated_grads_identical_on_all_ranks'] = same, same_acc
+    ok = ok and same and same_acc
+
+    # ---- 3. the fused path bench.py measures
+    if fused:
+        for sync_bn in ((False, True) if getattr(nrm.FusedTrainStep, 'SYNC_BN', False) else (False,)):
+            mf = fresh()
+            DataParallel(mf, sync_bn=sync_bn)
+            tr = nrm.FusedTrainStep(mf, hi - lo, H, C, lr=1e-3, weight_decay=1e-5)
+            pinned = shard_host.pin()
+            for _ in range(3):
+                h = tr.step(pinned)
+            h.item()
+            torch.cuda.synchronize()
+            rep[f'fused_weights_identical_sync_bn_{int(sync_bn)}'] = _same_on_all_ranks(mf.flat_parameters().buf)
+            ok = ok and rep[f'fused_weights_identical_sync_bn_{int(sync_bn)}']
+            if sync_bn:
+                m1 = fresh()
+                tr1 = nrm.FusedTrainStep(m1, B, H, C, lr=1e-3, weight_decay=1e-5)
+                fp = full.pin()
+                for _ in range(3):
+                    h1 = tr1.step(fp)
+                h1.item()
+                torch.cuda.synchronize()
+                a, b = mf.flat_parameters(), m1.flat_parameters()
+                # three Adam steps move a weight by up to 3e-3; elements with ~zero gradients follow the sign of rounding noise
+                # (delta, out_mlp.fc2.bias): compare the fixed part without those two
+                skip = {'delta', 'out_mlp.fc2.bias'}
+                werr = max((a.buf[off:off + n] - b.buf[off:off + n]).abs().max().item() for name, off, n, _ in a.slots if name not in skip)
+                rep['fused_sync_bn_vs_single_process_weight_err'] = werr
+                rep['fused_sync_bn_vs_single_process_loss_err'] = abs(h.item() - h1.item())
+                ok = ok and werr <= 1.5e-4 and rep['fused_sync_bn_vs_single_process_loss_err'] <= 1e-5
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item() == 1.0), rep
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    ok, rep = run_check(dev, rank, world)
     if rank == 0:
-        print(f'dp_check world={world}: logits err {err_logits:.2e}, worst grad rel err {worst[1]:.2e} ({worst[0]}), '
-              f'bn running_mean err {bn_err:.2e} -> {"OK" if flag.item() == 1.0 else "FAILED"}', flush=True)
+        print(f'dp_check world={world}: {rep} -> {"OK" if ok else "FAILED"}', flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1.0 else 1)
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == '__main__':

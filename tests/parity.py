@@ -18,8 +18,9 @@ TOL_GRAD_ABS = 1e-7        # delta / out_mlp.fc2.bias gradients are pure roundin
 NOISE_KEYS = ('delta', 'out_mlp.fc2.bias')
 
 
-def build_models(weights, user_num, delta0=None, device='cuda'):
-    model = nrm.UserModel(user_num)
+def build_models(weights, user_num, delta0=None, device='cuda', precision='fp32'):
+    """precision: 'fp32' = the strict FFMA kernels (callers switch with model.set_precision for the tensor-core paths)."""
+    model = nrm.UserModel(user_num).set_precision(precision)
     model.load_state_dict(weights, strict=False)
     p = O.load_params(weights, user_num=user_num)
     if delta0 is not None:

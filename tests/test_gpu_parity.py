@@ -215,3 +215,42 @@ def test_fused_train_step_equals_module_path(use_graph):
         assert torch.equal(pa, pb), k
     for k in ('running_mean', 'running_var', 'num_batches_tracked'):
         assert torch.equal(getattr(ma.bn, k), getattr(mb.bn, k)), k
+
+
+def test_helper_methods_of_the_invariant_interest_model_match_the_oracle():
+    """slice_x / feature_embedding / time_embedding (user_invariant_interest_model.py:50-71) keep the reference's signatures;
+    the embeddings run through the fused row kernel."""
+    b = make_batch(5, 9, 4, seed=17, user_num=10)
+    model, p = P.build_models(load_weights('train'), 10)
+    inv = model.invariant_interest_model
+    xt = b.x_target.to('cuda')
+    parts = inv.slice_x(xt.to(torch.float32), 6)
+    ref_parts = O.split_row(b.x_target.to(torch.float32), 6)
+    assert [tuple(a.shape) for a in parts] == [tuple(r.shape) for r in ref_parts]
+    for a, r in zip(parts, ref_parts):
+        assert torch.equal(a.cpu(), r)
+    t, _, cat, sub, sent, typ = parts
+    rt, _, rcat, rsub, rsent, rtyp = ref_parts
+    with torch.no_grad():
+        fe = inv.feature_embedding(cat, sub, sent, typ).cpu()
+        te = inv.time_embedding(t).cpu()
+    assert fe.shape == (5, 4, 56) and te.shape == (5, 4, 8)
+    assert (fe - O.feature_embedding(p, rcat, rsub, rsent, rtyp)).abs().max().item() <= 1e-6
+    assert (te - O.time_embedding(p, rt)).abs().max().item() <= 1e-6
+
+
+def test_out_of_range_user_id_gives_a_nan_loss_instead_of_reading_out_of_bounds():
+    """The reference raises IndexError for delta[id] with id > user_num (user_model.py:38); the kernel cannot raise, so the loss
+    of that step is NaN and nothing is read outside delta."""
+    b = make_batch(8, 5, 3, seed=3, user_num=10)
+    model, _ = P.build_models(load_weights('train'), 10)
+    model.train()
+    d = b.to('cuda')
+    out = model(d.x_history, d.x_target, d.x_global)
+    good = model.loss(d.user_id, out, d.label)
+    uid = d.user_id.clone()
+    uid[3] = 11
+    bad = model.loss(uid, out, d.label)
+    uid[3] = -1
+    bad2 = model.loss(uid, out, d.label)
+    assert torch.isfinite(good) and torch.isnan(bad) and torch.isnan(bad2)
