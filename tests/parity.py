@@ -78,3 +78,25 @@ def format_report(rep) -> str:
     for k, (err, scale) in rep['grads'].items():
         lines.append(f"  {k:58s} err {err:.3e}  max|g| {scale:.3e}  rel {err / max(scale, 1e-30):.2e}")
     return '\n'.join(lines)
+
+
+def assert_weights_follow(named_params, ref, steps, lr=1e-3):
+    """Weights after `steps` Adam steps against a reference trajectory.  Adam moves every element by ~lr per step whatever the
+    size of its gradient, so an element whose gradient is far below its tensor's largest one (a nearly dead ReLU channel of the
+    instant-interest Linear, say) follows the SIGN of fp32 re-association noise and can drift by a few lr between two correct
+    implementations.  Hence two bounds: 99.9 % of all elements within 1 % of the steps * lr a weight can travel (at least 2e-5),
+    and no element further than a quarter of it.  delta / out_mlp.fc2.bias (pure-noise gradients) are left out."""
+    errs, worst = [], ('', 0.0)
+    for k, v in named_params:
+        if k in NOISE_KEYS:
+            continue
+        e = (v.detach().cpu().float() - ref[k].detach().float()).abs().flatten()
+        errs.append(e)
+        if e.numel() and e.max().item() > worst[1]:
+            worst = (k, e.max().item())
+    errs = torch.cat(errs)
+    pick = torch.randperm(errs.numel(), generator=torch.Generator().manual_seed(0))[:200000]
+    q999 = torch.quantile(errs[pick].double(), 0.999).item()
+    travel = steps * lr
+    assert q999 <= max(2e-5, 0.01 * travel), ('99.9 % quantile', q999, worst)
+    assert worst[1] <= 0.25 * travel, ('max', worst)
