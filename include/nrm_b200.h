@@ -111,6 +111,9 @@ long long   nrm_layout_fixed_floats(void);            /* floats before delta (16
  * NRM_MODE_KEEP_FOR_BWD in `mode` it is sized for forward + backward (activations are kept
  * between the two calls). */
 size_t nrm_workspace_bytes(int B, int H, int C, int mode);
+/* byte offset of e_concat [B*C,264] (= [eu_H 128 | eu_L 8 | ec 128], user_model.py:31) inside that workspace: the output of
+ * nrm_forward_encoder (UserInvariantInterestModel.forward + UserInstantInterestModel.forward) */
+size_t nrm_workspace_e_offset(int B, int H, int C, int mode);
 
 /* ---- UserModel.forward (user_model.py:27-35) ------------------------------------- */
 /* mode & NRM_MODE_BN_BATCH_STATS: BatchNorm uses batch statistics, updates

@@ -35,6 +35,7 @@ SIGNATURES = {
     'nrm_layout_numel': (ll, [i32]),
     'nrm_layout_fixed_floats': (ll, []),
     'nrm_workspace_bytes': (sz, [i32, i32, i32, i32]),
+    'nrm_workspace_e_offset': (sz, [i32, i32, i32, i32]),
     'nrm_forward': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp]),
     'nrm_forward_encoder': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, vp, sz, vp]),
     'nrm_forward_head': (i32, [i32, i32, i32, vp, vp, vp, vp, i32, vp, ll, vp, vp, sz, vp]),

@@ -101,6 +101,13 @@ static SideStream* side_stream(cudaStream_t caller) {
   return ss;
 }
 
+// NRM_ATT_ITEM_TILES=1 selects the previous per-(pair, candidate) M = 64 tensor-core kernels (nrm_attention_tc.cu) instead of the
+// row-stacked ones (nrm_attention_rs.cu); kept as the second tensor-core implementation for A/B tests.
+bool use_rowstacked() {
+  static const bool on = getenv("NRM_ATT_ITEM_TILES") == nullptr;
+  return on;
+}
+
 bool pdl_enabled() {
   static const bool on = getenv("NRM_NO_PDL") == nullptr;
   return on;
@@ -163,6 +170,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   const size_t NH = (size_t)w.NH, R = (size_t)w.R, N = (size_t)w.N;
   w.xin_h = (float*)take(f * NH * XIN);
   w.xh = (float*)take(f * NH * 64);
+  w.pca_h = (float*)take(f * NH * 64);
   w.e = (float*)take(f * R * E);
   w.mean = (float*)take(f * E);
   w.rstd = (float*)take(f * E);
@@ -176,6 +184,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   w.head_wt = (float*)take(f * (HEAD_WT_W1T + 64 * XIN));
   w.att_derived = (float*)take(f * 2 * 12420);
   w.tp = (float*)take(f * 2 * R * 64);
+  w.att_rs_img = (float*)take(attention_rs_image_bytes());
   if (training) {
     w.da3 = (float*)take(f * R * HID); w.da2 = (float*)take(f * R * HID); w.da1 = (float*)take(f * R * HID);
     w.dy = (float*)take(f * R * E);
@@ -234,7 +243,7 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork0, 0));
   NRM_TRY(launch_head_transpose(P, w, ss->stream));          // includes w1^T for the history projection below
   NRM_CUDA(cudaEventRecord(ss->join0, ss->stream));
-  if (tc) NRM_TRY(launch_attention_prep(P, w, ss->stream));
+  if (tc) { NRM_TRY(launch_attention_prep(P, w, ss->stream)); NRM_TRY(launch_attention_prep_rs(P, w, ss->stream)); }
   { KernelTimer t("embed_rows", s);
     NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
   // fork: the per-candidate vectors tp (they need the candidate rows of e) run under the w1 projection; then, for the
@@ -257,8 +266,12 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   } else {
     // tensor-core path: one launch covers both branches
     KernelTimer t("attention_forward", s);
-    NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s));
-    NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s));
+    if (use_rowstacked()) {
+      NRM_TRY(launch_attention_forward_rs(in, w, precision, s));
+    } else {
+      NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s));
+      NRM_TRY(launch_attention_forward(in, P, w, 1, precision, s));
+    }
   }
   // join: the id sort (long finished: it ran under the w1 / attention kernels) comes back to the caller's stream HERE, so a
   // training-mode forward that is never followed by a backward (validation with gradients enabled, a graph capture of the
@@ -338,6 +351,15 @@ extern "C" size_t nrm_workspace_bytes(int B, int H, int C, int mode) {
   if (B <= 0 || H <= 0 || C <= 0) return 0;
   Workspace w;
   return carve_workspace(w, nullptr, B, H, C, mode);
+}
+
+// Byte offset of e_concat [R,264] inside a workspace carved for (B, H, C, mode): lets a caller of nrm_forward_encoder read the
+// encoder output (eu_H | eu_L | ec) without knowing the carve order.
+extern "C" size_t nrm_workspace_e_offset(int B, int H, int C, int mode) {
+  if (B <= 0 || H <= 0 || C <= 0) return 0;
+  Workspace w;
+  carve_workspace(w, reinterpret_cast<void*>(uintptr_t(256)), B, H, C, mode);
+  return (size_t)(reinterpret_cast<uintptr_t>(w.e) - 256);
 }
 
 extern "C" int nrm_forward_encoder(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,

@@ -172,6 +172,7 @@ struct Workspace {
   // forward (always)
   float* xin_h;        // [NH,66]   embedded history rows (w1 input)
   float* xh;           // [NH,64]   w1 output
+  float* pca_h;        // [NH,64]   text/img PCA slice of the history rows as fp32
   float* e;            // [R,264]   e_concat
   float* mean;         // [264]
   float* rstd;         // [264]
@@ -188,6 +189,7 @@ struct Workspace {
   float* head_part_w;  // [5][chunks][66*264+264] weight-gradient partials
   float* att_derived;  // [2][12420] derived attention weights (tensor-core paths)
   float* tp;           // [2][R,64]  tp = (Wb + Wc) t + b1 per candidate row and branch (tensor-core paths)
+  float* att_rs_img;   // weight image of the row-stacked attention kernels (nrm_attention_rs.cu): bf16 operand tiles, hi | lo
   // backward (training only)
   float* da3; float* da2; float* da1;   // [R,66]
   float* dy;           // [R,264]

@@ -17,7 +17,7 @@ namespace nrm {
 __global__ void __launch_bounds__(256)
 embed_rows_kernel(const double* __restrict__ xh, const double* __restrict__ xt, long long xt_bs,
                   const double* __restrict__ xg, long long xg_bs, int H, int C, long long NH, long long N,
-                  const float* __restrict__ P, float* __restrict__ xin_h, float* __restrict__ e,
+                  const float* __restrict__ P, float* __restrict__ xin_h, float* __restrict__ e, float* __restrict__ pca_h,
                   int* __restrict__ keys32, int* __restrict__ keys8) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
@@ -82,6 +82,15 @@ embed_rows_kernel(const double* __restrict__ xh, const double* __restrict__ xt, 
   dst[56 + q] = tm;
   if (is_hist) {
     if (q < 2) dst[64 + q] = (float)src[78 + q];
+    if (pca_h != nullptr) {
+      // text/img PCA slice as fp32 [NH, 64] (what `x_history.to(float32)` gives the reference, user_invariant_interest_model.py:74):
+      // the attention kernels of both branches then stage plain fp32 rows, and the float64 rows are read exactly once per step
+      const double2* ps = reinterpret_cast<const double2*>(src + 4 + q * 8);
+      const double2 a = ps[0], b = ps[1], c2 = ps[2], d = ps[3];
+      float4* pd = reinterpret_cast<float4*>(pca_h + row * 64 + q * 8);
+      pd[0] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+      pd[1] = make_float4((float)c2.x, (float)c2.y, (float)d.x, (float)d.y);
+    }
   } else {
     const long long r = row - NH;
     float* er = e + r * E;
@@ -560,7 +569,7 @@ small_linear_grad_finish_kernel(const float* __restrict__ part, int nparts, floa
 // ---------------------------------------------------------------------------------
 int launch_embed_rows(const BatchPtrs& in, const float* P, Workspace& w, bool with_keys, cudaStream_t s) {
   const int grid = (int)((w.N + 31) / 32);
-  launch_pdl(embed_rows_kernel, dim3(grid), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.H, w.C, w.NH, w.N, P, w.xin_h, w.e, with_keys ? w.keys32 : nullptr, with_keys ? w.keys8 : nullptr);
+  launch_pdl(embed_rows_kernel, dim3(grid), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.H, w.C, w.NH, w.N, P, w.xin_h, w.e, w.pca_h, with_keys ? w.keys32 : nullptr, with_keys ? w.keys8 : nullptr);
   NRM_LAUNCH_CHECK("embed_rows_kernel");
   return NRM_OK;
 }

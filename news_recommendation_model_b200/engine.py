@@ -365,8 +365,7 @@ def standalone_encoder(named: Dict[str, torch.Tensor], x_history, x_target, x_gl
     xg_bs = xg.stride(0) if B > 1 else C * GLOBAL_COLS
     _lib.check(lib.nrm_forward_encoder(_ptr(xh), _ptr(xt), xt_bs, _ptr(xg), xg_bs, B, H, C, _ptr(buf), MODE_EVAL, 0, None,
                                        _ptr(ws), need, _stream(dev)), 'nrm_forward_encoder')
-    # e_concat is the third buffer of the workspace carve (csrc/nrm_api.cu: xin_h, xh, e)
-    off_e = _round256(4 * B * H * 66) + _round256(4 * B * H * 64)
+    off_e = int(lib.nrm_workspace_e_offset(B, H, C, MODE_EVAL))
     e = ws[off_e:off_e + 4 * B * C * E_DIM].view(torch.float32).view(B, C, E_DIM)
     return e.clone()
 
