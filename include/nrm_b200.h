@@ -97,6 +97,7 @@ int         nrm_debug_mma_microbench(long long* out, int variant, int reps, int 
 
 /* Phase cycle counters of the tensor-core attention forward (only in a -DNRM_TC_PROFILE build; otherwise returns
  * NRM_EUNSUPPORTED): 16 host int64 = clock64 cycles accumulated by CTA 0 per phase since the last call. */
+int         nrm_debug_rsprof(long long* host_out64);   /* row-stacked attention kernels: per-role wait cycles (-DNRM_RS_PROFILE builds) */
 int         nrm_debug_tcprof(long long* host_out32);
 
 /* ---- flat parameter layout (reference state_dict order) ---- */

@@ -29,6 +29,7 @@ SIGNATURES = {
     'nrm_debug_umma_selftest': (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
     'nrm_debug_mma_microbench': (i32, [vp, i32, i32, i32, vp]),
     'nrm_debug_tcprof': (i32, [vp]),
+    'nrm_debug_rsprof': (i32, [vp]),
     'nrm_layout_entries': (i32, []),
     'nrm_layout_name': (C.c_char_p, [i32]),
     'nrm_layout_offset': (ll, [i32]),

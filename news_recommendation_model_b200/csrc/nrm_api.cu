@@ -340,6 +340,8 @@ extern "C" int nrm_timing_report(char* buf, size_t buf_bytes) {
   }
   return NRM_OK;
 }
+// per-role wait cycles of the row-stacked attention kernels (development builds with -DNRM_RS_PROFILE); reads and clears
+extern "C" int nrm_debug_rsprof(long long* host_out64) { return rsprof_read(host_out64); }
 extern "C" const char* nrm_last_error(void) { return g_err; }
 extern "C" int nrm_layout_entries(void) { return kLayoutEntries; }
 extern "C" const char* nrm_layout_name(int i) { return (i >= 0 && i < kLayoutEntries) ? kLayout[i].name : nullptr; }

@@ -33,8 +33,22 @@
 namespace nrm {
 namespace rs {
 
-constexpr int THREADS = 448;                 // 14 warps
-constexpr int W_PROD = 0, W_EPI = 4, W_MMA = 12, W_LOAD = 13;   // first warp of each role (producers 0-3, epilogue 4-11)
+// Optional per-role wait accounting (make EXTRA=-DNRM_RS_PROFILE; tools/rs_roleprof.py): in CTA 0, lane 0 of one warp per role
+// adds the clock64 cycles it spends inside each kind of mbarrier wait to g_rsprof[role * 8 + kind]; slot 7 = the role's total.
+#ifdef NRM_RS_PROFILE
+__device__ long long g_rsprof[64];
+#define RSPROF_WAIT(role, kind, stmt) do { const long long t__ = clock64(); stmt; if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_rsprof[(role) * 8 + (kind)] += clock64() - t__; } while (0)
+#define RSPROF_TOTAL_BEGIN const long long rsprof_t0 = clock64();
+#define RSPROF_TOTAL_END(role) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_rsprof[(role) * 8 + 7] += clock64() - rsprof_t0; } while (0)
+#else
+#define RSPROF_WAIT(role, kind, stmt) do { stmt; } while (0)
+#define RSPROF_TOTAL_BEGIN
+#define RSPROF_TOTAL_END(role) do { } while (0)
+#endif
+
+constexpr int THREADS = 832;                 // 26 warps
+constexpr int N_PROD = 8, N_EPI = 16;        // producer warps (sub-partition x K half), epilogue warps (sub-partition x column quarter)
+constexpr int W_PROD = 0, W_EPI = 8, W_MMA = 24, W_LOAD = 25;   // first warp of each role; warp % 4 = TMEM sub-partition for producers and epilogue
 constexpr int CG = 8;                        // candidates per unit
 constexpr int HCH = 64;                      // history rows per chunk
 constexpr int NSTAGE = 3;                    // history-chunk stages (the loader runs two chunks ahead)
@@ -89,21 +103,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {       // a -> 
   const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&p);
 }
-// hi / lo split of two floats -> packed bf16 pairs
+// hi / lo split of two floats -> packed bf16 pairs: hi = bf16_rn(v), lo = bf16_rn(v - hi).  The two hi values come back as floats
+// with one shift and one mask of the packed word (6 instructions per pair).
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const float2 hf = __bfloat1622float2(h);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = pack_bf16(a - hf.x, b - hf.y);
+  hi = pack_bf16(a, b);
+  lo = pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
+
+// ---- packed fp32 pairs (Blackwell fma.rn.f32x2 / mul / add): one issue slot for two lanes' worth of FP32 work -----------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 struct Stage {
   float hf[HCH * HF_STRIDE];                       // fp32 history rows of the chunk (producers)
-  __align__(128) unsigned char hbf[2][8192];       // the same rows as a K-major bf16 tile [64 h][64 k], hi | lo (pooling operand A, read MN-major;
-                                                   // producers copy the h half of their operand row from here)
+  __align__(128) unsigned char hbf[2][8192];       // the same rows as a K-major bf16 tile [64 h][64 k], hi | lo: operand A of the pooling product
+                                                   // (read MN-major), published by the producer threads of the chunk's first candidate
   __align__(16) float tv[CG][64];                  // candidate vectors t_c
   __align__(16) float tpv[CG][64];                 // tp_c = (Wb + Wc) t_c + b1
-  __align__(128) unsigned char s2[2][2048];        // scores [16 slots = candidate + 8 * column half][64 h] K-major bf16, hi | lo
+  __align__(128) unsigned char s2[2][4096];        // scores [32 slots = candidate + 8 * column quarter][64 h] K-major bf16, hi | lo
 };
 
 template <int NP>
@@ -112,6 +133,7 @@ struct Smem {
   Stage st[NSTAGE];
   float w2[2][64];
   float b2[2];
+  __align__(16) float zrow[64];                    // a zero history row: what the producer threads of rows past the chunk's end read
   uint64_t stage_full[NSTAGE], stage_empty[NSTAGE], s_full[NSTAGE], a_full[2], a_empty[2], d_full[2], d_empty[2], pool_full[2], pool_empty[2], wbar;
   uint32_t tmem_base;
 };
@@ -119,7 +141,7 @@ struct Smem {
 // TMEM columns
 constexpr uint32_t COL_D = 0;          // 2 x 64   hid accumulators
 constexpr uint32_t COL_A = 128;        // 2 x (64 hi + 64 lo)   operand rows, K = 128 bf16 = 64 columns per part
-constexpr uint32_t COL_POOL = 384;     // 2 x 16   pooled^T partials
+constexpr uint32_t COL_POOL = 384;     // 2 x 32   pooled^T partials (candidate + 8 * column quarter)
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Geo {
@@ -167,23 +189,6 @@ __device__ __forceinline__ void issue_stage(Stage& st, const float* __restrict__
   }
   cp_async_commit();
 }
-// fp32 rows (landed) -> K-major bf16 tile(s), rows >= hl zero.  Item = (row, 8-column block); a warp pass covers 16 rows x 2 blocks.
-template <int NP>
-__device__ __forceinline__ void build_hbf(Stage& st, int hl) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int w = 0; w < 16; ++w) {
-    const int row = (w & 3) * 16 + (lane & 15), kb = (w >> 2) * 2 + (lane >> 4);
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (row < hl) {
-      const float4 a = *reinterpret_cast<const float4*>(&st.hf[row * HF_STRIDE + kb * 8]);
-      const float4 c = *reinterpret_cast<const float4*>(&st.hf[row * HF_STRIDE + kb * 8 + 4]);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-    }
-    umma::store_operand8<NP>(st.hbf[0], umma::tile64_offset(row, kb), 8192, v);
-  }
-}
-
 // flattened (unit, chunk) sequence of a CTA
 struct ChunkIter {
   int u, ci, branch, b, c0, ncg, h0, hl, rows, ntiles;
@@ -213,16 +218,16 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
       umma::mbar_init(&sm.stage_full[i], 1);       // loader warp
-      umma::mbar_init(&sm.stage_empty[i], 5);      // 4 producer warps + the pooling product's commit
-      umma::mbar_init(&sm.s_full[i], 8);           // 8 epilogue warps
+      umma::mbar_init(&sm.stage_empty[i], N_PROD + 1);   // producer warps + the pooling product's commit
+      umma::mbar_init(&sm.s_full[i], N_EPI);             // epilogue warps
     }
     for (int i = 0; i < 2; ++i) {
-      umma::mbar_init(&sm.a_full[i], 4);           // 4 producer warps
+      umma::mbar_init(&sm.a_full[i], N_PROD);      // producer warps
       umma::mbar_init(&sm.a_empty[i], 1);          // commit of the hid product
       umma::mbar_init(&sm.d_full[i], 1);           // commit of the hid product
-      umma::mbar_init(&sm.d_empty[i], 8);          // 8 epilogue warps
+      umma::mbar_init(&sm.d_empty[i], N_EPI);      // epilogue warps
       umma::mbar_init(&sm.pool_full[i], 1);        // commit of the pooling product
-      umma::mbar_init(&sm.pool_empty[i], 4);       // the 4 epilogue warps of column half 0
+      umma::mbar_init(&sm.pool_empty[i], 4);       // the 4 epilogue warps of column quarter 0
     }
     umma::mbar_init(&sm.wbar, 1);
     // weights of both branches: bulk copies by the TMA engine, under the rest of the prologue
@@ -239,10 +244,11 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
     sm.w2[br][j] = __ldg(tail + j);
     if (j == 0) sm.b2[br] = __ldg(tail + 64);
   }
-  for (int i = tid; i < NSTAGE * 2 * 2048 / 4; i += THREADS) {     // score tiles start finite (stale entries meet zero history rows)
-    const int s = i / (2 * 2048 / 4), r = i - s * (2 * 2048 / 4);
+  for (int i = tid; i < NSTAGE * 2 * 4096 / 4; i += THREADS) {     // score tiles start finite (stale entries meet zero history rows)
+    const int s = i / (2 * 4096 / 4), r = i - s * (2 * 4096 / 4);
     reinterpret_cast<uint32_t*>(sm.st[s].s2[0])[r] = 0u;
   }
+  if (tid < 64) sm.zrow[tid] = 0.f;
   if (warp == 0) umma::tmem_alloc(&sm.tmem_base, TMEM_COLS);
   umma::fence_async_smem();
   umma::fence_before_sync();
@@ -258,12 +264,13 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
 
   if (warp == W_LOAD) {
     // =========================================== loader ===========================================
+    RSPROF_TOTAL_BEGIN
     const int total = (u1 - u0) * g.nchunks;
     ChunkIter it_issue, it_fin;
     int n_issued = 0;
     auto issue = [&]() {
       const int s = n_issued % NSTAGE;
-      umma::mbar_wait(&sm.stage_empty[s], ((n_issued / NSTAGE) & 1) ^ 1);
+      RSPROF_WAIT(0, 0, umma::mbar_wait(&sm.stage_empty[s], ((n_issued / NSTAGE) & 1) ^ 1));
       const int br = it_issue.branch;
       issue_stage(sm.st[s], br == 0 ? xhp : pca32, e, br == 0 ? E_XT : E_PCAT, tp_all + br * tp_branch, H, C, it_issue.b, it_issue.c0,
                   it_issue.ncg, it_issue.h0, it_issue.hl);
@@ -273,32 +280,31 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
     if (total > 0) { it_issue.set(g, u0, 0); it_fin.set(g, u0, 0); }
     while (n_issued < total && n_issued < NSTAGE - 1) issue();
     for (int k = 0; k < total; ++k) {
-      if (n_issued - k - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
-      __syncwarp();
+      RSPROF_WAIT(0, 1, if (n_issued - k - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>());
       const int s = k % NSTAGE;
-      build_hbf<NP>(sm.st[s], it_fin.hl);
-      umma::fence_async_smem();                          // hbf is read by the tensor core (async proxy)
-      arrive_warp(&sm.stage_full[s]);
+      arrive_warp(&sm.stage_full[s]);                    // every lane's copies have landed (wait_group above + the __syncwarp inside)
       if (k + 1 < total) it_fin.next(g);
       if (n_issued < total) issue();                     // into the stage chunk k - 1 used (its pooling product follows chunk k's first tile)
     }
+    RSPROF_TOTAL_END(0);
   } else if (warp == W_MMA) {
     // =========================================== MMA issuer ===========================================
     if (umma::elect_one()) {
       umma::mbar_wait(&sm.wbar, 0);
+      RSPROF_TOTAL_BEGIN
       constexpr uint32_t IDESC_HID = umma::make_idesc_bf16(128, 64);
-      constexpr uint32_t IDESC_POOL = umma::make_idesc_bf16(64, 16, true, false);
+      constexpr uint32_t IDESC_POOL = umma::make_idesc_bf16(64, 32, true, false);
       const uint64_t wdesc0 = umma::make_desc(umma::smem_u32(sm.W[0][0]), 1024, 128);      // + W_TILE / 16 per part, + 2 W_TILE / 16 per branch
       uint32_t chunk_seq = 0, tile_seq = 0, unit_seq = 0;
       // deferred pooling product of the previous chunk (issued after the next tile's hid product so that the tensor pipe
       // does not idle while the last epilogue of the chunk finishes)
       bool pend = false; uint32_t p_s = 0, p_ph = 0, p_ps = 0, p_pph = 0; bool p_first = false, p_last = false;
       auto do_pool = [&]() {
-        umma::mbar_wait(&sm.s_full[p_s], p_ph);
-        if (p_first) umma::mbar_wait(&sm.pool_empty[p_ps], p_pph ^ 1);
+        RSPROF_WAIT(1, 2, umma::mbar_wait(&sm.s_full[p_s], p_ph));
+        if (p_first) RSPROF_WAIT(1, 3, umma::mbar_wait(&sm.pool_empty[p_ps], p_pph ^ 1));
         umma::fence_after_sync();
-        umma::mma_product<SPLIT, 4>(tmem + COL_POOL + 16 * p_ps, umma::op_tile64_mn(umma::smem_u32(sm.st[p_s].hbf[0])),
-                                    umma::make_operand(umma::smem_u32(sm.st[p_s].s2[0]), 256, 128, 512, 2048), IDESC_POOL, !p_first);
+        umma::mma_product<SPLIT, 4>(tmem + COL_POOL + 32 * p_ps, umma::op_tile64_mn(umma::smem_u32(sm.st[p_s].hbf[0])),
+                                    umma::make_operand(umma::smem_u32(sm.st[p_s].s2[0]), 512, 128, 1024, 4096), IDESC_POOL, !p_first);
         umma::mma_commit(&sm.stage_empty[p_s]);
         if (p_last) umma::mma_commit(&sm.pool_full[p_ps]);
         pend = false;
@@ -309,8 +315,8 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
           int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
           for (int ti = 0; ti < ntiles; ++ti, ++tile_seq) {
             const uint32_t as = tile_seq & 1, aph = (tile_seq >> 1) & 1;
-            umma::mbar_wait(&sm.a_full[as], aph);
-            umma::mbar_wait(&sm.d_empty[as], aph ^ 1);
+            RSPROF_WAIT(1, 0, umma::mbar_wait(&sm.a_full[as], aph));
+            RSPROF_WAIT(1, 1, umma::mbar_wait(&sm.d_empty[as], aph ^ 1));
             umma::fence_after_sync();
             const uint32_t d = tmem + COL_D + 64 * as, a = tmem + COL_A + 128 * as;
 #pragma unroll
@@ -329,9 +335,11 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
         }
       }
       if (pend) do_pool();
+      RSPROF_TOTAL_END(1);
     }
   } else if (warp < W_EPI) {
     // =========================================== producers ===========================================
+    RSPROF_TOTAL_BEGIN
     const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
     uint32_t chunk_seq = 0, tile_seq = 0;
     for (int u = u0; u < u1; ++u) {
@@ -340,47 +348,61 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
         int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
         const uint32_t s = chunk_seq % NSTAGE, ph = (chunk_seq / NSTAGE) & 1;
         const Stage& st = sm.st[s];
-        umma::mbar_wait(&sm.stage_full[s], ph);
+        const float inv_hl = 1.0f / (float)hl;
+        RSPROF_WAIT(2, 0, umma::mbar_wait(&sm.stage_full[s], ph));
         for (int ti = 0; ti < ntiles; ++ti, ++tile_seq) {
           const uint32_t as = tile_seq & 1, aph = (tile_seq >> 1) & 1;
-          umma::mbar_wait(&sm.a_empty[as], aph ^ 1);
+          RSPROF_WAIT(2, 1, umma::mbar_wait(&sm.a_empty[as], aph ^ 1));
           umma::fence_after_sync();
           const int rg = ti * 128 + 32 * (warp & 3) + lane;
           const bool valid = rg < rows;
-          const int cl = valid ? rg / hl : 0, hloc = valid ? rg - cl * hl : 0;
+          const int cl = valid ? __float2int_rz(((float)rg + 0.5f) * inv_hl) : 0, hloc = valid ? rg - cl * hl : 0;   // exact: rg < 640, hl <= 64
           const uint32_t a_hi = tmem + COL_A + 128 * as + lane_sel, a_lo = a_hi + 64;
-          const float* hrow = &st.hf[hloc * HF_STRIDE];
+          const float* hrow = valid ? &st.hf[hloc * HF_STRIDE] : sm.zrow;       // rows past the end: zero operand row, no selects
           const float* trow = &st.tv[cl][0];
+          // The rows of the chunk's first candidate (cl == 0) cover every history row once: those threads also publish their
+          // h half (bf16 hi | lo) as the K-major tile the pooling product reads MN-major; rows the chunk does not have are zeroed
+          // by the threads of tile 0 that sit at those row numbers.
+          const bool own_h = valid && cl == 0;
+          const int zr = (ti == 0 && rg < HCH && rg >= hl) ? rg : -1;
+          unsigned char* hb_own = const_cast<unsigned char*>(st.hbf[0]) + (uint32_t)(hloc >> 3) * umma::TILE64_SBO + (uint32_t)(hloc & 7) * 16u;
+          const int khalf = warp >> 2;                    // this warp's half of the K range: passes kp = 2 khalf, 2 khalf + 1
 #pragma unroll
-          for (int kp = 0; kp < 4; ++kp) {                // two 8-column blocks (16 k) per pass
+          for (int kq = 0; kq < 2; ++kq) {                // two 8-column blocks (16 k) per pass
+            const int kp = 2 * khalf + kq;
             uint32_t ph_hi[8], ph_lo[8], hh[8], hl_[8];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const int kb = 2 * kp + q;
               const float4 h0v = *reinterpret_cast<const float4*>(hrow + 8 * kb), h1v = *reinterpret_cast<const float4*>(hrow + 8 * kb + 4);
               const float4 t0v = *reinterpret_cast<const float4*>(trow + 8 * kb), t1v = *reinterpret_cast<const float4*>(trow + 8 * kb + 4);
-              const float p[8] = {h0v.x * t0v.x, h0v.y * t0v.y, h0v.z * t0v.z, h0v.w * t0v.w, h1v.x * t1v.x, h1v.y * t1v.y, h1v.z * t1v.z, h1v.w * t1v.w};
+              const float hv[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+              const float tv8[8] = {t0v.x, t0v.y, t0v.z, t0v.w, t1v.x, t1v.y, t1v.z, t1v.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                if (NP == 2) split2(p[2 * i], p[2 * i + 1], ph_hi[4 * q + i], ph_lo[4 * q + i]);
-                else ph_hi[4 * q + i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+                if (NP == 2) {
+                  split2(hv[2 * i] * tv8[2 * i], hv[2 * i + 1] * tv8[2 * i + 1], ph_hi[4 * q + i], ph_lo[4 * q + i]);
+                  split2(hv[2 * i], hv[2 * i + 1], hh[4 * q + i], hl_[4 * q + i]);
+                } else {
+                  ph_hi[4 * q + i] = pack_bf16(hv[2 * i] * tv8[2 * i], hv[2 * i + 1] * tv8[2 * i + 1]);
+                  hh[4 * q + i] = pack_bf16(hv[2 * i], hv[2 * i + 1]);
+                }
               }
-              const uint32_t off = umma::tile64_offset(hloc, kb);
-              const uint4 a = *reinterpret_cast<const uint4*>(st.hbf[0] + off);
-              hh[4 * q] = a.x; hh[4 * q + 1] = a.y; hh[4 * q + 2] = a.z; hh[4 * q + 3] = a.w;
-              if (NP == 2) {
-                const uint4 c = *reinterpret_cast<const uint4*>(st.hbf[1] + off);
-                hl_[4 * q] = c.x; hl_[4 * q + 1] = c.y; hl_[4 * q + 2] = c.z; hl_[4 * q + 3] = c.w;
+              if (own_h) {
+                *reinterpret_cast<uint4*>(hb_own + kb * umma::TILE64_LBO) = make_uint4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
+                if (NP == 2) *reinterpret_cast<uint4*>(hb_own + 8192 + kb * umma::TILE64_LBO) = make_uint4(hl_[4 * q], hl_[4 * q + 1], hl_[4 * q + 2], hl_[4 * q + 3]);
               }
-            }
-            if (!valid) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { ph_hi[i] = 0u; ph_lo[i] = 0u; hh[i] = 0u; hl_[i] = 0u; }
+              if (zr >= 0) {
+                unsigned char* z = const_cast<unsigned char*>(st.hbf[0]) + umma::tile64_offset(zr, kb);
+                *reinterpret_cast<uint4*>(z) = make_uint4(0u, 0u, 0u, 0u);
+                if (NP == 2) *reinterpret_cast<uint4*>(z + 8192) = make_uint4(0u, 0u, 0u, 0u);
+              }
             }
             tmem_st8(a_hi + 8 * kp, ph_hi);               // k' = 16 kp .. 16 kp + 15  (t (.) h half)
             tmem_st8(a_hi + 32 + 8 * kp, hh);             // k' = 64 + 16 kp ..        (h half)
             if (NP == 2) { tmem_st8(a_lo + 8 * kp, ph_lo); tmem_st8(a_lo + 32 + 8 * kp, hl_); }
           }
+          umma::fence_async_smem();                        // the h tile is read by the tensor core (async proxy) in the pooling product
           tmem_st_wait();
           umma::fence_before_sync();
           arrive_warp(&sm.a_full[as]);
@@ -388,19 +410,21 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
         arrive_warp(&sm.stage_empty[s]);                   // done with hf / tv / hbf of this stage
       }
     }
+    if (warp == 0) RSPROF_TOTAL_END(2);
   } else {
     // =========================================== epilogue ===========================================
-    const int sp = warp & 3, ch = (warp - W_EPI) >> 2;
+    RSPROF_TOTAL_BEGIN
+    const int sp = warp & 3, cq = (warp - W_EPI) >> 2;     // TMEM sub-partition, quarter of the 64 hidden units
     const uint32_t lane_sel = (uint32_t)(32 * sp) << 16;
     uint32_t chunk_seq = 0, tile_seq = 0, unit_seq = 0;
     // deferred write-out of the previous unit's pooled vectors (its pooling product is issued one tile late)
     bool pend = false; uint32_t p_ps = 0, p_pph = 0; int p_branch = 0, p_b = 0, p_c0 = 0, p_ncg = 0;
     auto write_pooled = [&]() {
-      if (ch == 0) {
-        umma::mbar_wait(&sm.pool_full[p_ps], p_pph);
+      if (cq == 0) {
+        RSPROF_WAIT(3, 2, umma::mbar_wait(&sm.pool_full[p_ps], p_pph));
         umma::fence_after_sync();
-        float v[16];
-        umma::tmem_ld16(tmem + COL_POOL + 16 * p_ps + lane_sel, v);
+        float v[32];
+        umma::tmem_ld32(tmem + COL_POOL + 32 * p_ps + lane_sel, v);
         umma::fence_before_sync();
         arrive_warp(&sm.pool_empty[p_ps]);
         if (lane < 16) {                                   // an M = 64 accumulator occupies lanes 0-15 of each sub-partition: k = 16 sp + lane
@@ -408,7 +432,7 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
           float* dst = e + ((long long)p_b * C + p_c0) * E + poff + 16 * sp + lane;
 #pragma unroll
           for (int c = 0; c < CG; ++c)
-            if (c < p_ncg) dst[(long long)c * E] = v[c] + v[c + 8];
+            if (c < p_ncg) dst[(long long)c * E] = (v[c] + v[c + 8]) + (v[c + 16] + v[c + 24]);
         }
       }
       pend = false;
@@ -416,37 +440,72 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
     for (int u = u0; u < u1; ++u, ++unit_seq) {
       int branch, b, c0, ncg; g.unit(u, branch, b, c0, ncg);
       const float b2 = sm.b2[branch];
-      const float* w2 = &sm.w2[branch][32 * ch];
+      f32x2 w2p[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w2p[i] = pk(sm.w2[branch][16 * cq + 2 * i], sm.w2[branch][16 * cq + 2 * i + 1]);
       for (int ci = 0; ci < g.nchunks; ++ci, ++chunk_seq) {
         int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
         const uint32_t s = chunk_seq % NSTAGE, ph = (chunk_seq / NSTAGE) & 1;
         Stage& st = sm.st[s];
-        umma::mbar_wait(&sm.stage_full[s], ph);
+        const float inv_hl = 1.0f / (float)hl;
+        RSPROF_WAIT(3, 0, umma::mbar_wait(&sm.stage_full[s], ph));
         for (int ti = 0; ti < ntiles; ++ti, ++tile_seq) {
           const uint32_t ds = tile_seq & 1, dph = (tile_seq >> 1) & 1;
-          umma::mbar_wait(&sm.d_full[ds], dph);
+          RSPROF_WAIT(3, 1, umma::mbar_wait(&sm.d_full[ds], dph));
           umma::fence_after_sync();
-          float v[32];
-          umma::tmem_ld32(tmem + COL_D + 64 * ds + 32 * ch + lane_sel, v);
+          float x[16];
+          umma::tmem_ld16(tmem + COL_D + 64 * ds + 16 * cq + lane_sel, x);
           umma::fence_before_sync();
           arrive_warp(&sm.d_empty[ds]);                    // accumulator stage free: the next hid product may start
           const int rg = ti * 128 + 32 * sp + lane;
           const bool valid = rg < rows;
-          const int cl = valid ? rg / hl : 0, hloc = valid ? rg - cl * hl : 0;
-          const float* tp = &st.tpv[cl][32 * ch];
-          float acc = ch == 0 ? b2 : 0.f;
+          const int cl = valid ? __float2int_rz(((float)rg + 0.5f) * inv_hl) : 0, hloc = valid ? rg - cl * hl : 0;
+          const float* tp = &st.tpv[cl][16 * cq];
+          // Exact-erf GELU (nrm_common.cuh: gelu_f; Abramowitz-Stegun 7.1.26) on the 16 hidden units of this thread, as 8 packed
+          // pairs (fma.rn.f32x2: one issue slot per two FP32 operations -- the kernel is bound by issue slots) and written stage by
+          // stage so that the independent dependency chains interleave.   With half = 0.5 erfc(|x| / sqrt 2) = poly(t) exp(-x^2 / 2):
+          //     gelu(x) = x / 2 + |x| (1/2 - half)
+          f32x2 xp[8], q[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
+          for (int j4 = 0; j4 < 4; ++j4) {
             const float4 t4 = *reinterpret_cast<const float4*>(tp + 4 * j4);
-            const float4 w4 = *reinterpret_cast<const float4*>(w2 + 4 * j4);
-            acc = fmaf(gelu_f(v[4 * j4 + 0] + t4.x), w4.x, acc);
-            acc = fmaf(gelu_f(v[4 * j4 + 1] + t4.y), w4.y, acc);
-            acc = fmaf(gelu_f(v[4 * j4 + 2] + t4.z), w4.z, acc);
-            acc = fmaf(gelu_f(v[4 * j4 + 3] + t4.w), w4.w, acc);
+            xp[2 * j4] = add2(pk(x[4 * j4], x[4 * j4 + 1]), pk(t4.x, t4.y));
+            xp[2 * j4 + 1] = add2(pk(x[4 * j4 + 2], x[4 * j4 + 3]), pk(t4.z, t4.w));
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a, b, ta, tb, ea, eb;
+            upk(xp[i], a, b);
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ta) : "f"(fmaf(fabsf(a), 0.23164189f, 1.0f)));      // t = 1 / (1 + 0.3275911 |x| / sqrt 2)
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tb) : "f"(fmaf(fabsf(b), 0.23164189f, 1.0f)));
+            f32x2 ar = mul2(mul2(xp[i], xp[i]), pk(-0.72134752044448170368f, -0.72134752044448170368f));   // -x^2 log2(e) / 2
+            upk(ar, ea, eb);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(ea));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(eb));
+            const f32x2 t2 = pk(ta, tb);
+            f32x2 poly = fma2(t2, pk(0.5f * 1.061405429f, 0.5f * 1.061405429f), pk(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+            poly = fma2(t2, poly, pk(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+            poly = fma2(t2, poly, pk(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+            poly = fma2(t2, poly, pk(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+            poly = mul2(poly, t2);                                                                           // 0.5 erfc(z) / exp(-z^2)
+            q[i] = fma2(poly, mul2(pk(ea, eb), pk(-1.f, -1.f)), pk(0.5f, 0.5f));                             // 1/2 - half
+          }
+          f32x2 acc2 = pk(cq == 0 ? b2 : 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a, b, qa, qb, ha, hb;
+            upk(xp[i], a, b);
+            upk(q[i], qa, qb);
+            upk(mul2(xp[i], pk(0.5f, 0.5f)), ha, hb);
+            const float g0 = fmaf(fabsf(a), qa, ha), g1 = fmaf(fabsf(b), qb, hb);
+            acc2 = fma2(pk(g0, g1), w2p[i], acc2);
+          }
+          float acc, acc_hi;
+          upk(acc2, acc, acc_hi);
+          acc += acc_hi;
           if (valid) {
-            const int slot = cl + 8 * ch;
-            const uint32_t off = (uint32_t)(hloc >> 3) * 256u + (uint32_t)(slot >> 3) * 128u + (uint32_t)(slot & 7) * 16u + (uint32_t)(hloc & 7) * 2u;
+            const int slot = cl + 8 * cq;
+            const uint32_t off = (uint32_t)(hloc >> 3) * 512u + (uint32_t)(slot >> 3) * 128u + (uint32_t)(slot & 7) * 16u + (uint32_t)(hloc & 7) * 2u;
             const __nv_bfloat16 hi = __float2bfloat16_rn(acc);
             *reinterpret_cast<__nv_bfloat16*>(st.s2[0] + off) = hi;
             if (NP == 2) *reinterpret_cast<__nv_bfloat16*>(st.s2[1] + off) = __float2bfloat16_rn(acc - __bfloat162float(hi));
@@ -461,6 +520,7 @@ attention_forward_rs_kernel(const float* __restrict__ pca32, const float* __rest
       pend = true; p_ps = unit_seq & 1; p_pph = (unit_seq >> 1) & 1; p_branch = branch; p_b = b; p_c0 = c0; p_ncg = ncg;
     }
     if (pend) write_pooled();
+    if (warp == W_EPI) RSPROF_TOTAL_END(3);
   }
 
   umma::fence_before_sync();
@@ -495,5 +555,19 @@ int launch_attention_forward_rs(const BatchPtrs& in, Workspace& w, int precision
 }
 
 size_t attention_rs_image_bytes() { return (size_t)rs::img_bytes(); }
+
+int rsprof_read(long long* host_out64) {
+#ifdef NRM_RS_PROFILE
+  long long zero[64] = {0};
+  NRM_CUDA(cudaDeviceSynchronize());
+  NRM_CUDA(cudaMemcpyFromSymbol(host_out64, rs::g_rsprof, sizeof(zero)));
+  NRM_CUDA(cudaMemcpyToSymbol(rs::g_rsprof, zero, sizeof(zero)));
+  return NRM_OK;
+#else
+  (void)host_out64;
+  set_error("library built without -DNRM_RS_PROFILE");
+  return NRM_EUNSUPPORTED;
+#endif
+}
 
 }  // namespace nrm

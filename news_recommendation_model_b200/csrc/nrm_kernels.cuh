@@ -34,6 +34,7 @@ int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaS
 
 // nrm_attention_rs.cu  (row-stacked M = 128 formulation, operand rows in tensor memory; precision = bf16 / bf16x3)
 size_t attention_rs_image_bytes();
+int rsprof_read(long long* host_out64);                                         // -DNRM_RS_PROFILE builds only
 int launch_attention_prep_rs(const float* P, Workspace& w, cudaStream_t s);       // weight image -> w.att_rs_img (weights only)
 int launch_attention_forward_rs(const BatchPtrs& in, Workspace& w, int precision, cudaStream_t s);   // both branches, one launch
 

@@ -76,23 +76,25 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
 }
-// Spins on try_wait (a hardware-assisted, time-limited sleep).  A protocol error must never hang the GPU: after ~2 s of waiting
-// the thread traps, which surfaces as a launch failure on the host instead of a wedged device.
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait is a hardware-assisted sleep: the waiting warp is suspended until the phase completes or the time hint (in ns) runs out,
+// so a waiting role does not take issue slots from the working warps of its scheduler (with the default hint a waiter returns every
+// ~100 ns: in the warp-specialised kernels half of all issued instructions were wait loops).  A protocol error must never hang the
+// GPU: after ~4 s of waiting the thread traps, which surfaces as a launch failure on the host instead of a wedged device.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 1000000u) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t"
-      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  int spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) asm volatile("trap;\n");
+    if (++spins > 4000) asm volatile("trap;\n");        // 4000 x <= 1 ms
   }
 }
 
