@@ -189,20 +189,27 @@ class FusedTrainStep:
         from . import wire
         if self.articles is None:
             raise _lib.NrmError('FusedTrainStep: pass articles=ArticleTable to feed CompactBatches')
-        if batch.shape != (self.B, self.H, self.C):
-            raise ValueError('CompactBatch shape does not match this step')
+        b, bh, bc = batch.shape
+        if b > self.B or (bh, bc) != (self.H, self.C):
+            raise ValueError(f'CompactBatch of shape {batch.shape} does not fit this step (B <= {self.B}, H = {self.H}, C = {self.C})')
         if s.compact is None:
-            s.compact = wire.CompactBatch(*[torch.zeros_like(getattr(batch, f), device=self.dev) for f in batch.__dataclass_fields__])
+            s.compact = wire.CompactBatch(*[torch.zeros((self.B,) + tuple(getattr(batch, f).shape[1:]), dtype=getattr(batch, f).dtype, device=self.dev)
+                                            for f in batch.__dataclass_fields__])
             self._expand(s)                                  # first launch of the kernel outside any graph capture
         with torch.cuda.stream(self.copy_stream):
             if s.used:
                 self.copy_stream.wait_event(s.consumed)
             for f in ('hist_article', 'hist_time', 'hist_click', 'cand_article', 'cand_time', 'label'):
-                getattr(s.compact, f).copy_(getattr(batch, f), non_blocking=True)
-            s.uid.copy_(batch.user_id, non_blocking=True)
+                getattr(s.compact, f)[:b].copy_(getattr(batch, f), non_blocking=True)
+            s.uid[:b].copy_(batch.user_id, non_blocking=True)
             s.ready.record(self.copy_stream)
+        loader = getattr(batch, '_loader', None)
+        if loader is not None:                               # wire.PrefetchLoader: its pinned ring slot is free once these copies are done
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+            loader.release(batch, ev)
         s.wire = 'compact'
-        s.rows = self.B
+        s.rows = b                                           # b < B: ragged last batch (expanded whole, trained on its first b rows)
         return s
 
     def _expand(self, s: _Slot):
@@ -247,6 +254,8 @@ class FusedTrainStep:
             if scratch is None:
                 scratch = self._tail_scratch[s.rows] = torch.zeros(int(self.lib.nrm_loss_scratch_bytes(s.rows, self.C)),
                                                                    dtype=torch.uint8, device=self.dev)
+            if s.wire == 'compact':
+                self._expand(s)
             self._forward_backward(s, loss_out, B=s.rows, loss_scratch=scratch)
             self._adam()
         elif self.use_graph:

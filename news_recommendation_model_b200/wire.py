@@ -16,10 +16,13 @@ kernel behind `UserModel.forward` runs unchanged and produces bit-identical resu
 
 `from_records` converts the reference's own record lists (`process_data.py:252`, what `import_processed_data` returns)
 once, on the host, into a table + compact arrays in pinned memory; `CompactDataset.batches` then yields pre-batched
-pinned `CompactBatch`es (the data-loader row N4: no per-step collate of float64 `[B,200,80]`)."""
+pinned `CompactBatch`es; `PrefetchLoader` does the same from a background thread into a fixed pinned ring (the data-loader row N4:
+no per-step collate of float64 `[B,200,80]`, no per-batch pinning)."""
 from __future__ import annotations
 
 import ctypes
+import queue
+import threading
 from dataclasses import dataclass
 from typing import Iterator, List, Optional, Sequence
 
@@ -150,6 +153,118 @@ class CompactDataset:
                 return
             b = self.select(idx)
             yield b.pin() if pin else b
+
+
+class PrefetchLoader:
+    """The data-loader row N4 as a pipeline: a background thread gathers the next batches of a `CompactDataset` into a FIXED ring
+    of pinned host buffers (allocated once: no `cudaHostAlloc` per batch, the cost that makes `pin_memory()` per batch slower than
+    the training step itself) while the GPU trains on the current one.  Replaces `torch.utils.data.DataLoader(list, batch_size,
+    shuffle=True)` + default collate of float64 `[B,200,80]` records (train.py:37-40).
+
+        loader = PrefetchLoader(ds, batch_size, shuffle=True, seed=epoch)
+        for cb in loader:                       # cb: pinned CompactBatch view of a ring slot (the last one may be shorter)
+            handle = step.step(cb)              # FusedTrainStep.load enqueues the H2D copies and releases the slot when they are done
+
+    A slot is recycled once its consumer has released it: `FusedTrainStep.load` does so with the event of its copy stream;
+    any other consumer may call `loader.release(cb, event)` after enqueuing its copies, or do nothing, in which case the slot is
+    released when the NEXT batch is requested, with an event recorded on the current stream at that moment."""
+
+    def __init__(self, dataset: CompactDataset, batch_size: int, shuffle: bool = False, seed: int = 0, drop_last: bool = False,
+                 depth: int = 4, pin: bool = True):
+        if depth < 2:
+            raise ValueError('PrefetchLoader needs a ring of at least 2 slots')
+        self.ds, self.batch_size, self.shuffle, self.seed, self.drop_last, self.depth = dataset, batch_size, shuffle, seed, drop_last, depth
+        d = dataset.data
+        self.fields = list(d.__dataclass_fields__)
+        pin = pin and torch.cuda.is_available()               # CPU-only hosts (unit tests): plain buffers, same logic
+
+        def buf(f):
+            t = torch.empty((batch_size,) + tuple(getattr(d, f).shape[1:]), dtype=getattr(d, f).dtype)
+            return t.pin_memory() if pin else t
+        self.ring = [CompactBatch(*[buf(f) for f in self.fields]) for _ in range(depth)]
+        self._free: 'queue.Queue' = queue.Queue()
+        self._full: 'queue.Queue' = queue.Queue()
+        self._events = [None] * depth
+        self._thread: Optional[threading.Thread] = None
+        self._pending_slot: Optional[int] = None
+        self._lock = threading.Lock()
+
+    def __len__(self) -> int:
+        n = len(self.ds)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def _worker(self, order: torch.Tensor):
+        n = order.numel()
+        try:
+            for s in range(0, n, self.batch_size):
+                idx = order[s:s + self.batch_size]
+                if self.drop_last and idx.numel() < self.batch_size:
+                    break
+                slot = self._free.get()
+                if slot is None:
+                    return
+                ev = self._events[slot]
+                if ev is not None:
+                    ev.synchronize()                          # the consumer's H2D copies out of this slot have finished
+                    self._events[slot] = None
+                rows = int(idx.numel())
+                buf = self.ring[slot]
+                for f in self.fields:                         # gathers release the GIL; they write straight into pinned memory
+                    torch.index_select(getattr(self.ds.data, f), 0, idx, out=getattr(buf, f)[:rows])
+                self._full.put((slot, rows))
+        finally:
+            self._full.put(None)
+
+    def __iter__(self) -> Iterator[CompactBatch]:
+        if self._thread is not None:
+            raise RuntimeError('PrefetchLoader: one pass at a time')
+        n = len(self.ds)
+        order = torch.randperm(n, generator=torch.Generator().manual_seed(self.seed)) if self.shuffle else torch.arange(n)
+        while not self._free.empty():
+            self._free.get_nowait()
+        for i in range(self.depth):
+            self._free.put(i)
+        self._thread = threading.Thread(target=self._worker, args=(order,), daemon=True)
+        self._thread.start()
+        try:
+            while True:
+                item = self._full.get()
+                self._release_pending()
+                if item is None:
+                    break
+                slot, rows = item
+                buf = self.ring[slot]
+                cb = CompactBatch(*[getattr(buf, f)[:rows] for f in self.fields])
+                cb._loader, cb._slot = self, slot
+                self._pending_slot = slot
+                yield cb
+        finally:
+            self._release_pending()
+            self._free.put(None)                              # unblock a worker that waits for a slot
+            self._thread.join()
+            self._thread = None
+
+    def release(self, cb: CompactBatch, event=None) -> None:
+        """The copies out of `cb`'s pinned slot are covered by `event` (default: an event recorded now on the current stream)."""
+        slot = getattr(cb, '_slot', None)
+        if slot is None or getattr(cb, '_loader', None) is not self:
+            return
+        with self._lock:
+            if self._pending_slot != slot:
+                return                                        # already released
+            self._pending_slot = None
+        if event is None and torch.cuda.is_available():
+            event = torch.cuda.Event()
+            event.record()
+        self._events[slot] = event
+        self._free.put(slot)
+
+    def _release_pending(self):
+        slot = self._pending_slot
+        if slot is not None:
+            cb = CompactBatch(*[getattr(self.ring[slot], f) for f in self.fields])
+            cb._loader, cb._slot = self, slot
+            self.release(cb)
 
 
 def from_records(records: Sequence[Sequence], pin: bool = False) -> CompactDataset:

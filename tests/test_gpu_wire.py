@@ -93,3 +93,34 @@ def test_slot_recaptures_its_graph_when_the_wire_format_changes():
     b = tr.step(cb).item()
     c = tr.step(packed).item()
     assert a == b == c           # lr = 0: the same batch gives the same loss through either format (BN in batch-stat mode)
+
+
+def test_records_through_the_prefetch_loader_train_like_the_packed_path_bit_for_bit():
+    """The loader row N4 end to end: the reference's record list (tool/process_data.py:252 layout) -> wire.from_records ->
+    wire.PrefetchLoader (background thread, fixed pinned ring, ragged last batch) -> FusedTrainStep, against the same impressions
+    fed as packed float64 tensors in the same order: every loss and the final weights are bit-identical."""
+    from news_recommendation_model_b200.synthetic import Batch, make_batch
+    N, B, H, C, U = 40, 16, 50, 5, 60
+    full = make_batch(N, H, C, seed=808, user_num=U, fp32_exact=True, variable_history=True)
+    records = [[full.impression_id[i].numpy(), full.user_id[i].numpy(), full.x_history[i].numpy(), full.x_target[i].numpy(),
+                full.x_global[i].numpy(), full.label[i].numpy(), full.label_id[i].numpy(), full.empty_num[i].numpy()] for i in range(N)]
+    ds = wire.from_records(records, pin=True)
+
+    def fresh():
+        m = nrm.UserModel(U)
+        m.load_state_dict(load_weights('train'), strict=False)
+        return m.to('cuda').train()
+    ma, mb = fresh(), fresh()
+    ta = nrm.FusedTrainStep(ma, B, H, C, lr=1e-3, weight_decay=1e-5, articles=ds.table.to('cuda'))
+    tb = nrm.FusedTrainStep(mb, B, H, C, lr=1e-3, weight_decay=1e-5)
+    la = [ta.step(cb) for cb in wire.PrefetchLoader(ds, B, depth=2)]
+    la = None or la
+    lb = []
+    for s in range(0, N, B):
+        sl = Batch(*[getattr(full, f)[s:s + B] for f in full.__dataclass_fields__])
+        lb.append(tb.step(sl.pin()))
+    assert len(la) == len(lb) == 3
+    va, vb = [h.item() for h in la], [h.item() for h in lb]
+    assert va == vb, (va, vb)
+    assert torch.equal(ma.flat_parameters().buf, mb.flat_parameters().buf)
+    assert torch.equal(ma.bn.running_mean, mb.bn.running_mean)

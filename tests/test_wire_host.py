@@ -80,3 +80,25 @@ def test_scoring_bucket_plan_covers_every_impression_with_a_pad_column():
             prev_max = int(n[idx].min())
             assert bool(((n[idx] < width) | (n[idx] == C)).all())   # a pad column inside the width unless the row has no pads
             pos += idx.numel()
+
+
+def test_prefetch_loader_yields_the_same_batches_as_the_synchronous_generator():
+    """wire.PrefetchLoader (background thread, fixed ring, ragged last batch) against CompactDataset.batches on the same order."""
+    from news_recommendation_model_b200 import wire
+    table = wire.make_article_table(300, seed=3)
+    full = wire.make_compact_batch(table, 53, 7, 4, seed=5, user_num=20, variable_history=True)
+    ds = wire.CompactDataset(table, full)
+    for shuffle in (False, True):
+        ref = list(ds.batches(8, shuffle=shuffle, seed=11, pin=False))
+        loader = wire.PrefetchLoader(ds, 8, shuffle=shuffle, seed=11, depth=3)
+        assert len(loader) == len(ref) == 7
+        got = []
+        for cb in loader:
+            got.append(wire.CompactBatch(*[getattr(cb, f).clone() for f in cb.__dataclass_fields__]))   # the slot is recycled after the next request
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            for f in a.__dataclass_fields__:
+                assert torch.equal(getattr(a, f), getattr(b, f)), f
+        assert got[-1].shape[0] == 53 % 8
+    # a second pass over the same loader object works (one pass at a time)
+    assert sum(cb.shape[0] for cb in wire.PrefetchLoader(ds, 16, drop_last=True, depth=2)) == 48
