@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--no-graph', action='store_true', help='FusedTrainStep issues the C-ABI calls eagerly instead of replaying a CUDA graph')
     ap.add_argument('--cpu-steps', type=int, default=60, help='train steps of the CPU port timed for cpu_baseline (about 15 s on 16 cores)')
     ap.add_argument('--no-scoring', action='store_true', help='skip the scoring (configs[2]) leg')
+    ap.add_argument('--no-loader', action='store_true', help='skip the record-list -> loader -> loss leg')
+    ap.add_argument('--no-long-history', action='store_true', help='skip the configs[4] leg (B=4096, H=256)')
     ap.add_argument('--no-dp-check', action='store_true', help='skip the N-rank vs single-process numerical pre-flight (world > 1)')
     ap.add_argument('--no-affinity', action='store_true', help='do not bind each rank to the CPU cores local to its GPU')
     return ap.parse_args()
@@ -201,6 +203,119 @@ def workload_config(args, world):
             'l2_policy': f'{N_POOL} distinct input batches rotated (~{N_POOL * 36} MB of inputs > 126 MB L2)'}
 
 
+
+# ------------------------------------------------------------------------------------------
+# kernel timing + roofline helpers
+# ------------------------------------------------------------------------------------------
+def timed_kernels(lib, fn, n):
+    """Run fn(i) n times with the library's per-kernel-group CUDA events enabled (events on the launch stream of every group,
+    nrm_timing_enable); -> {group: ms per call of fn}."""
+    import ctypes
+    from news_recommendation_model_b200 import _lib
+    lib.nrm_timing_enable(1)
+    for i in range(n):
+        fn(i)
+    torch.cuda.synchronize()
+    cbuf = ctypes.create_string_buffer(16384)
+    _lib.check(lib.nrm_timing_report(cbuf, 16384), 'nrm_timing_report')
+    lib.nrm_timing_enable(0)
+    kern = {}
+    for ln in cbuf.value.decode().strip().splitlines():
+        name, cnt, tot = ln.split()
+        kern[name] = {'launch_groups': int(cnt), 'ms': float(tot) / n}
+    return kern
+
+
+def algorithmic_work(B, H, C, total_params):
+    """Algorithmic FLOPs / bytes of every timed kernel group of one training step (SURVEY 8d per-impression figures x B;
+    DESIGN.md section 4).  EVERY group is a roofline candidate: the dominant one is whichever takes longest."""
+    P, R, NH = B * C * H, B * C, B * H
+    N = NH + R
+    head = 2.0 * 87186 * R                                       # 5 x (264 x 66) + 66 MACs per candidate row
+    return {
+        'attention_forward_label': ('tensor', 2.0 * P * D * D), 'attention_forward_textimg': ('tensor', 2.0 * P * D * D),
+        'attention_forward': ('tensor', 2 * 2.0 * P * D * D),    # both branches in one launch (tensor-core paths)
+        'attention_backward_label': ('tensor', 3 * 2.0 * P * D * D), 'attention_backward_textimg': ('tensor', 2 * 2.0 * P * D * D),
+        'head_forward': ('tensor', head), 'head_backward': ('tensor', 2 * head),
+        'w1_backward': ('tensor', 2 * 2.0 * 66 * 64 * NH),
+        'embed_rows': ('hbm', 8.0 * (80 * NH + 81 * R) + 4.0 * (66 * NH + 64 * NH + 136 * R)),
+        'w1_forward': ('hbm', 4.0 * (66 + 64) * NH),
+        'bn_statistics': ('hbm', 4.0 * 264 * R),
+        'attention_finish': ('hbm', 4.0 * 2 * (64 + 64 + 264) * R),
+        'small_linear_grads': ('hbm', 4.0 * (19 + 16) * N + 8.0 * 6 * N),
+        'table_l1': ('hbm', 4.0 * (6 * 32 + 5 * 8) * N + 4.0 * 11 * N), 'table_l2': ('hbm', 4.0 * (6 * 32 + 5 * 8) * N / 128),
+        'adam': ('hbm', 28.0 * total_params),
+    }
+
+
+def pick_roofline(kern, work, pk, precision, traffic_table=None):
+    cand = {k: v for k, v in kern.items() if k in work}
+    if not cand:
+        return None
+    top = max(cand, key=lambda k: cand[k]['ms'])
+    bound, w = work[top]
+    dur = kern[top]['ms'] / 1e3
+    traffic = (traffic_table or {}).get(top)
+    if bound == 'tensor':
+        ach = w / dur / 1e12
+        return {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tensor'], 'unit': 'TFLOP/s', 'frac': ach / pk['tensor'],
+                'traffic': traffic, 'peak_source': pk['source'] + ' bf16 sustained (cuBLAS)', 'algorithmic_flops_per_launch': w,
+                'launch_ms': dur * 1e3,
+                'note': {'fp32': 'FFMA path: the products run on the CUDA cores',
+                         'bf16': 'tcgen05 tiles, bf16 operands',
+                         'bf16x3': 'attention: tcgen05 tiles, 3 MMAs issued per algorithmic product (hi/lo split); bound by the GELU / '
+                                   'operand-build work on the CUDA cores (issue slots), see DESIGN.md section 4.  head / w1: FFMA'}[precision]}
+    ach = w / dur / 1e9
+    return {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'], 'traffic': traffic,
+            'peak_source': pk['source'], 'algorithmic_bytes_per_launch': w, 'launch_ms': dur * 1e3}
+
+
+def all_fractions(kern, work, pk):
+    """{group: fraction of its roofline}: the whole table, so that a regression anywhere is visible."""
+    out = {}
+    for k, v in kern.items():
+        if k in work and v['ms'] > 0:
+            bound, w = work[k]
+            out[k] = round(w / (v['ms'] / 1e3) / (pk['tensor'] * 1e12 if bound == 'tensor' else pk['hbm'] * 1e9), 4)
+    return out
+
+
+def scoring_cpu_baseline(host_batch, user_num):
+    """The reference's own scoring loop (test.py:31-74 model_test, unmodified, baseline/_ref) on the host cores: one batch-80
+    sample of the bench's scoring workload, 2-model ensemble (test.py:150-152)."""
+    import queue
+    from fixtures import load_weights as lw
+    from oracle.make_ref import reference_modules, reference_root
+    if reference_root() is None:
+        return None
+    torch.set_num_threads(os.cpu_count())
+    b = host_batch
+    n = int(b.x_history.shape[0])
+    records = [[b.impression_id[i].numpy(), b.user_id[i].numpy(), b.x_history[i].numpy(), b.x_target[i].numpy(), b.x_global[i].numpy(),
+                b.label[i].numpy(), b.label_id[i].numpy(), b.empty_num[i].numpy()] for i in range(n)]
+    with reference_modules() as ref:
+        models = []
+        for name in ('train', 'validation'):
+            m = ref.UserModel(user_num)
+            m.load_state_dict(lw(name), strict=False)
+            models.append(m)
+        ref.model_test(models, records[:16], torch.device('cpu'), queue.Queue(), [], batch_size=16)     # warm-up
+        t0 = time.perf_counter()
+        ref.model_test(models, records, torch.device('cpu'), queue.Queue(), [], batch_size=80)          # test.py:138 batch size
+        dt = time.perf_counter() - t0
+    return {'value': n / dt, 'unit': 'impressions/s', 'cores': os.cpu_count(), 'kind': 'reference', 'ms_per_batch': dt * 1e3,
+            'sample': f'one batch of {n} impressions (H=200, ragged candidates) through the unmodified reference test.py:model_test on the host CPU, '
+                      '2-model ensemble'}
+
+
+def make_records(n, H, C, seed, user_num):
+    """Synthetic impressions in the reference's record-list layout (tool/process_data.py:252; what import_processed_data returns)."""
+    from news_recommendation_model_b200.synthetic import make_batch
+    b = make_batch(n, H, C, seed=seed, user_num=user_num, fp32_exact=True)
+    return [[b.impression_id[i].numpy(), b.user_id[i].numpy(), b.x_history[i].numpy(), b.x_target[i].numpy(), b.x_global[i].numpy(),
+             b.label[i].numpy(), b.label_id[i].numpy(), b.empty_num[i].numpy()] for i in range(n)]
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
@@ -346,53 +461,60 @@ def run_ours(args):
     launches = tr.launches_per_step                  # kernels of ours per step (counted while the step was recorded)
 
     # ---- per-kernel timing pass (CUDA events on the launch stream inside the library)
-    lib.nrm_timing_enable(1)
     kt_steps = min(K, 8)
-    for i in range(kt_steps):
-        step(pool[i % N_POOL])
-    torch.cuda.synchronize()
-    import ctypes
-    cbuf = ctypes.create_string_buffer(8192)
-    _lib.check(lib.nrm_timing_report(cbuf, 8192), 'nrm_timing_report')
-    lib.nrm_timing_enable(0)
-    kern = {}
-    for ln in cbuf.value.decode().strip().splitlines():
-        name, cnt, tot = ln.split()
-        kern[name] = {'launch_groups': int(cnt), 'ms_per_step': float(tot) / kt_steps}
+    kern = timed_kernels(lib, lambda i: step(pool[i % N_POOL]), kt_steps)
     pk = peaks()
-    # dominant SINGLE kernel (groups that are one launch each); algorithmic work per launch from SURVEY 8(d) / DESIGN 4
-    pairs = B * C * H
-    R = B * C
-    single = {
-        'attention_forward_label': ('tensor', 2.0 * pairs * D * D), 'attention_forward_textimg': ('tensor', 2.0 * pairs * D * D),
-        'attention_forward': ('tensor', 2 * 2.0 * pairs * D * D),            # both branches in one launch (tensor-core path)
-        'attention_backward_label': ('tensor', 3 * 2.0 * pairs * D * D), 'attention_backward_textimg': ('tensor', 2 * 2.0 * pairs * D * D),
-        'embed_rows': ('hbm', 8.0 * (80 * H + 81 * C) * B + 4.0 * (66 * H * B + 136 * R)),
-        'w1_forward': ('hbm', 4.0 * (66 + 64) * H * B),
-    }
-    cand = {k: v for k, v in kern.items() if k in single}
-    top = max(cand, key=lambda k: cand[k]['ms_per_step']) if cand else None
-    roofline = None
-    if top is not None:
-        bound, work = single[top]
-        dur = kern[top]['ms_per_step'] / 1e3
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    total_params = model.flat_parameters().total
+    work = algorithmic_work(B, H, C, total_params)
+    traffic_table = None
+    for tname in ('r02_traffic.json', 'r01_traffic.json'):
+        tpath = os.path.join(ROOT, 'profiles', tname)
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.precision, {}).get(top)
-        if bound == 'tensor':
-            ach = work / dur / 1e12
-            roofline = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
-                        'frac': ach / pk['tensor'], 'traffic': traffic, 'peak_source': pk['source'] + ' bf16 sustained (cuBLAS)',
-                        'algorithmic_flops_per_launch': work, 'launch_ms': dur * 1e3,
-                        'note': {'fp32': 'FFMA path: the pair products run on the CUDA cores',
-                                 'bf16': 'tcgen05 tiles, bf16 operands',
-                                 'bf16x3': 'tcgen05 tiles, 3 MMAs issued per algorithmic product (hi/lo split); the kernel is bound by its '
-                                           'GELU / operand-build epilogues on the CUDA cores, see DESIGN.md section 4'}[args.precision]}
-        else:
-            ach = work / dur / 1e9
-            roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
-                        'traffic': traffic, 'peak_source': pk['source'], 'algorithmic_bytes_per_launch': work, 'launch_ms': dur * 1e3}
+            traffic_table = json.load(open(tpath)).get(args.precision, {})
+            break
+    roofline = pick_roofline(kern, work, pk, args.precision, traffic_table)
+    roofline_all = all_fractions(kern, work, pk)
+
+    # ---- A2. loader leg: from the reference's record list to the loss.  wire.from_records converts the records once
+    #          (timed, reported), wire.PrefetchLoader's background thread gathers shuffled batches into its fixed pinned ring and
+    #          FusedTrainStep trains on them; the timed region is whole epochs of that loop, every loss read by the host.
+    loader_leg = None
+    if not args.no_loader:
+        n_rec = B * 8
+        t0 = time.perf_counter()
+        records = make_records(n_rec, H, C, 31337 + rank, args.user_num)
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ds = wire.from_records(records, pin=True)
+        t_conv = time.perf_counter() - t0
+        del records
+        tr_l = nrm.FusedTrainStep(model, B, H, C, lr=1e-3, weight_decay=1e-5, nslots=3, use_graph=not args.no_graph, articles=ds.table.to(dev))
+
+        loader = wire.PrefetchLoader(ds, B, shuffle=True, drop_last=True, depth=4)      # the pinned ring is allocated once
+
+        def epoch(seed):
+            prev, last = None, 0.0
+            for cb in loader.set_epoch(seed):
+                h = tr_l.step(cb)
+                if prev is not None:
+                    last = prev.item()
+                prev = h
+            return prev.item()
+        epoch(0)                                            # captures the graphs of the three slots
+        barrier()
+        n_ep = max(1, (K + 7) // 8)
+        e0.record()
+        for ep in range(n_ep):
+            epoch(1 + ep)
+        e1.record()
+        barrier()
+        l_ms = max_over_ranks(e0.elapsed_time(e1))
+        loader_leg = {'value': world * B * 8 * n_ep / (l_ms / 1e3), 'unit': 'impressions/s', 'ms_per_step': l_ms / (8 * n_ep), 'steps': 8 * n_ep,
+                      'records': n_rec, 'from_records_s': round(t_conv, 3), 'articles_in_table': ds.table.n,
+                      'h2d_bytes_per_step': next(iter(ds.batches(B, pin=False))).input_bytes(),
+                      'note': 'record list (process_data.py:252 layout) -> wire.from_records (once) -> PrefetchLoader thread + fixed pinned '
+                              'ring -> FusedTrainStep (compact wire format); shuffled epochs, drop_last, every loss read by the host'}
+        del tr_l, ds, loader
 
     # ---- D. scoring (BASELINE configs[2]; test.py:31-74 + 118-132): 2-model ensemble (train + validation checkpoints), eval mode,
     #         H = 200 (the ETL's pad length), ragged candidate lists padded to the batch maximum, pads trimmed per batch as
@@ -480,7 +602,72 @@ def run_ours(args):
                                       'e2e_compact': {'value': world * Bs / (ms_e2ec / 1e3), 'ms_per_batch': ms_e2ec,
                                                       'h2d_bytes_per_batch': hc[0].input_bytes()},
                                       'candidate_columns': hb[0].x_target.shape[1] - trims[0]}
+            if Bs == 80:
+                # roofline of the scoring leg: its dominant kernel (one launch per model and batch at batch 80), timed by the library's
+                # CUDA events, against the algorithmic FLOPs of the pair products of that batch
+                ks = timed_kernels(lib, lambda i: score(db[i % 2], trims[i % 2], False), 4)
+                keep = hb[0].x_target.shape[1] - trims[0]
+                pairs = 0.5 * sum(Bs * (b.x_target.shape[1] - t) * 200 for b, t in zip(hb, trims))     # mean of the two batches
+                if 'attention_forward' in ks:
+                    per_launch_ms = ks['attention_forward']['ms'] / len(ens)
+                    ach = 2 * 2.0 * pairs * D * D / (per_launch_ms / 1e3) / 1e12
+                    scoring['roofline'] = {'kernel': 'attention_forward (batch 80, per model)', 'bound': 'tensor', 'achieved': ach, 'peak': pk['tensor'],
+                                           'unit': 'TFLOP/s', 'frac': ach / pk['tensor'], 'launch_ms': per_launch_ms, 'traffic': None,
+                                           'algorithmic_flops_per_launch': 2 * 2.0 * pairs * D * D,
+                                           'kernels_ms_per_batch': {k: round(v['ms'], 4) for k, v in ks.items()}}
+                if world == 1 and rank == 0 and not args.no_cpu_baseline:
+                    scoring['cpu_baseline'] = scoring_cpu_baseline(hb[0], args.user_num)
         model.train()
+
+    # ---- E. long-history stress (BASELINE configs[4]): B = 4096 impressions, H = 256 with variable length (zero-padded rows, as the
+    #         ETL pads), C = 5; one resident batch: training step (FusedTrainStep, CUDA-graph replay) and eval forward; roofline of
+    #         its dominant kernel.  0.67 GB of float64 inputs per batch: resident only.
+    long_history = None
+    if not args.no_long_history:
+        Bl, Hl, Cl = 4096, 256, 5
+        hbl = make_batch(Bl, Hl, Cl, seed=555 + rank, user_num=args.user_num, variable_history=True)
+        dbl = hbl.to(dev)
+        trl = nrm.FusedTrainStep(model, Bl, Hl, Cl, lr=1e-3, weight_decay=1e-5, nslots=1, use_graph=not args.no_graph)
+        sl = trl.load(hbl)
+        torch.cuda.synchronize()
+        for i in range(3):
+            trl.run(sl)
+        barrier()
+        nl = 5
+        e0.record()
+        for i in range(nl):
+            trl.run(sl)
+        e1.record()
+        barrier()
+        ms_l = max_over_ranks(e0.elapsed_time(e1)) / nl
+        model.eval()
+        with torch.no_grad():
+            for i in range(2):
+                model(dbl.x_history, dbl.x_target, dbl.x_global)
+            barrier()
+            e0.record()
+            for i in range(nl):
+                model(dbl.x_history, dbl.x_target, dbl.x_global)
+            e1.record()
+            barrier()
+        ms_le = max_over_ranks(e0.elapsed_time(e1)) / nl
+        model.train()
+
+        def lstep(i):
+            out = model(dbl.x_history, dbl.x_target, dbl.x_global)
+            model.loss(dbl.user_id, out, dbl.label).backward()
+            model.zero_grad(set_to_none=True)
+        lstep(0)
+        kl = timed_kernels(lib, lstep, 3)
+        wl = algorithmic_work(Bl, Hl, Cl, total_params)
+        long_history = {'workload': f'B={Bl}/GPU, H={Hl} (variable length, zero-padded rows), C={Cl}, user_num={args.user_num}',
+                        'train': {'value': world * Bl / (ms_l / 1e3), 'unit': 'impressions/s', 'ms_per_step': ms_l},
+                        'eval_forward': {'value': world * Bl / (ms_le / 1e3), 'unit': 'impressions/s', 'ms_per_batch': ms_le},
+                        'roofline': pick_roofline(kl, wl, pk, args.precision), 'roofline_fraction_by_kernel': all_fractions(kl, wl, pk),
+                        'kernels_ms_per_step': {k: round(v['ms'], 4) for k, v in kl.items()},
+                        'l2_policy': 'one batch: 0.67 GB of inputs > 126 MB L2'}
+        del trl, sl, dbl, hbl
+        torch.cuda.empty_cache()
 
     # short resident runs of the other precisions (same step, same data), for context
     variants = {}
@@ -529,7 +716,9 @@ def run_ours(args):
         'module_path': {'value': world * B * K / (mod_ms / 1e3), 'unit': 'impressions/s', 'ms_per_step': mod_ms / K,
                         'note': 'drop-in nn.Module path driven like train.py:69-75 (autograd + FusedAdam), device-resident'},
         'api': 'FusedTrainStep (CUDA-graph replay of the 5 C-ABI calls)' if not args.no_graph else 'FusedTrainStep (eager C-ABI calls)',
-        'roofline': roofline, 'kernels_ms_per_step': {k: round(v['ms_per_step'], 4) for k, v in kern.items()},
+        'roofline': roofline, 'roofline_fraction_by_kernel': roofline_all,
+        'kernels_ms_per_step': {k: round(v['ms'], 4) for k, v in kern.items()},
+        'e2e_loader': loader_leg, 'long_history': long_history,
         'cpu_baseline': cpu, 'precision_variants': variants, 'scoring': scoring, 'dp_parity': dp_parity,
     }
     print(json.dumps(line), flush=True)

@@ -161,8 +161,8 @@ class PrefetchLoader:
     the training step itself) while the GPU trains on the current one.  Replaces `torch.utils.data.DataLoader(list, batch_size,
     shuffle=True)` + default collate of float64 `[B,200,80]` records (train.py:37-40).
 
-        loader = PrefetchLoader(ds, batch_size, shuffle=True, seed=epoch)
-        for cb in loader:                       # cb: pinned CompactBatch view of a ring slot (the last one may be shorter)
+        loader = PrefetchLoader(ds, batch_size, shuffle=True)      # once: the pinned ring is allocated here
+        for cb in loader.set_epoch(epoch):                       # cb: pinned CompactBatch view of a ring slot (the last one may be shorter)
             handle = step.step(cb)              # FusedTrainStep.load enqueues the H2D copies and releases the slot when they are done
 
     A slot is recycled once its consumer has released it: `FusedTrainStep.load` does so with the event of its copy stream;
@@ -182,12 +182,19 @@ class PrefetchLoader:
             t = torch.empty((batch_size,) + tuple(getattr(d, f).shape[1:]), dtype=getattr(d, f).dtype)
             return t.pin_memory() if pin else t
         self.ring = [CompactBatch(*[buf(f) for f in self.fields]) for _ in range(depth)]
+        self._src = {f: getattr(d, f).numpy() for f in self.fields}                       # numpy views (no copies)
+        self._dst = [{f: getattr(b, f).numpy() for f in self.fields} for b in self.ring]
         self._free: 'queue.Queue' = queue.Queue()
         self._full: 'queue.Queue' = queue.Queue()
         self._events = [None] * depth
         self._thread: Optional[threading.Thread] = None
         self._pending_slot: Optional[int] = None
         self._lock = threading.Lock()
+
+    def set_epoch(self, seed: int) -> 'PrefetchLoader':
+        """Shuffle seed of the next pass (the ring is allocated once; iterate the same loader every epoch)."""
+        self.seed = seed
+        return self
 
     def __len__(self) -> int:
         n = len(self.ds)
@@ -208,9 +215,9 @@ class PrefetchLoader:
                     ev.synchronize()                          # the consumer's H2D copies out of this slot have finished
                     self._events[slot] = None
                 rows = int(idx.numel())
-                buf = self.ring[slot]
-                for f in self.fields:                         # gathers release the GIL; they write straight into pinned memory
-                    torch.index_select(getattr(self.ds.data, f), 0, idx, out=getattr(buf, f)[:rows])
+                idx_np = idx.numpy()
+                for f in self.fields:                         # numpy gathers (GIL released) straight into the pinned slot
+                    np.take(self._src[f], idx_np, axis=0, out=self._dst[slot][f][:rows], mode='clip')
                 self._full.put((slot, rows))
         finally:
             self._full.put(None)
