@@ -97,6 +97,23 @@ int         nrm_debug_mma_microbench(long long* out, int variant, int reps, int 
 
 /* Phase cycle counters of the tensor-core attention forward (only in a -DNRM_TC_PROFILE build; otherwise returns
  * NRM_EUNSUPPORTED): 16 host int64 = clock64 cycles accumulated by CTA 0 per phase since the last call. */
+/* ---- data parallelism over peer memory (no counterpart in the single-process reference; north_star: gradient all-reduce) ----
+ * The gradient average over the ranks is fused into the optimizer: every rank's flat gradient buffer sits in symmetric (peer-mapped)
+ * memory and nrm_adam_step_allreduce reads all of them in rank order while it updates.  `peer_ctx` is a device struct
+ *     { int rank, world; long long n; const float* grad[8]; unsigned* pad[8]; double* stats[8]; }
+ * (nrm_peer_ctx_bytes() bytes) holding the peer-mapped pointers; the library uses the u32 words [64, nrm_peer_flag_words()) of every
+ * signal pad; `stats` buffers hold nrm_peer_stats_bytes() bytes.  Call order per step: ... forward, loss ..., nrm_peer_wait_consumed,
+ * backward ..., nrm_adam_step_allreduce.  nrm_peer_allsum_stats sums the BatchNorm statistics (which = 0 forward, 1 backward) over the
+ * ranks between the two halves of nrm_forward / nrm_backward (synchronised BatchNorm). */
+size_t      nrm_peer_ctx_bytes(void);
+size_t      nrm_peer_stats_bytes(void);
+int         nrm_peer_flag_words(void);
+int         nrm_peer_preload(void);
+int         nrm_adam_step_allreduce(float* param, float* exp_avg, float* exp_avg_sq, long long n, void* adam_state,
+                                    const void* peer_ctx, void* ticket, void* stream);
+int         nrm_peer_wait_consumed(const void* adam_state, const void* peer_ctx, void* stream);
+int         nrm_peer_allsum_stats(const double* local, int which, double* out, const void* adam_state, const void* peer_ctx, void* stream);
+
 int         nrm_debug_rsprof(long long* host_out64);   /* row-stacked attention kernels: per-role wait cycles (-DNRM_RS_PROFILE builds) */
 int         nrm_debug_tcprof(long long* host_out32);
 

@@ -48,6 +48,13 @@ SIGNATURES = {
     'nrm_loss_backward': (i32, [vp, i32, i32, vp, vp, vp, ll, vp, sz, vp]),
     'nrm_adam_step': (i32, [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, ll, f32, vp]),
     'nrm_adam_step_device': (i32, [vp, vp, vp, vp, ll, vp, vp]),
+    'nrm_peer_ctx_bytes': (sz, []),
+    'nrm_peer_stats_bytes': (sz, []),
+    'nrm_peer_flag_words': (i32, []),
+    'nrm_peer_preload': (i32, []),
+    'nrm_adam_step_allreduce': (i32, [vp, vp, vp, ll, vp, vp, vp, vp]),
+    'nrm_peer_wait_consumed': (i32, [vp, vp, vp]),
+    'nrm_peer_allsum_stats': (i32, [vp, i32, vp, vp, vp, vp]),
     'nrm_batch_metrics': (i32, [vp, ll, vp, ll, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     'nrm_score_epilogue': (i32, [vp, i32, ll, ll, i32, i32, vp, vp, vp, vp]),
     'nrm_rank_strings_capacity': (sz, [i32, i32]),

@@ -232,9 +232,195 @@ adam_device_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
     adam_one(p[i], g[i], m[i], v[i], a);
 }
 
+// ---------------------------------------------------------------------------------
+// Data parallelism over peer memory (NVLink / NVSwitch): the gradient all-reduce fused into the optimizer.
+//
+// Every rank's flat gradient buffer, a few flag words and its BatchNorm statistics live in SYMMETRIC memory (one allocation per
+// rank, mapped into every peer's address space; torch.distributed._symmetric_memory does the mapping, dp.PeerContext fills the
+// PeerCtx below).  One step of rank r:
+//     backward kernels write grads_r                                     (stream order)
+//     adam_allreduce_kernel:  flag "ready(step)" -> every peer;  wait for every peer's flag;
+//                             g = (g_0 + g_1 + ... + g_{N-1}) / N  read straight from the N buffers in RANK ORDER (every rank computes
+//                             the same bits: replicas cannot drift), Adam on the local weights / moments;
+//                             the last block flags "consumed(step)" -> every peer
+//     ... next forward ...
+//     peer_wait_consumed_kernel: before the next backward overwrites grads_r, every peer has flagged consumed(step)
+// No NCCL launch, no second graph, no collective channels competing with the backward kernels for SMs; the transfer (N-1 remote reads
+// of 0.9 MB per rank) overlaps the update element by element.  Flags are monotonic step numbers, so CUDA-graph replay is safe.
+// ---------------------------------------------------------------------------------
+constexpr int PEER_MAX = 8;
+constexpr int PEER_FLAG_BASE = 64;           // first u32 word of the signal pad this library uses (the words below belong to torch)
+enum { PEER_SLOT_READY = 0, PEER_SLOT_CONSUMED = 1, PEER_SLOT_STATS_FWD = 2, PEER_SLOT_STATS_BWD = 3 };
+constexpr int BN_STATS = 2 * E;              // doubles per BatchNorm statistics exchange
+struct PeerCtx {                             // mirrored by dp.PeerContext (python): part of the C ABI
+  int rank, world;
+  long long n;                               // floats of the flat buffers
+  const float* grad[PEER_MAX];               // flat gradient buffers, peer-mapped, indexed by rank
+  unsigned* pad[PEER_MAX];                   // signal pads (u32 words), peer-mapped
+  double* stats[PEER_MAX];                   // [2][BN_STATS]: forward | backward BatchNorm sums, peer-mapped
+};
+static_assert(sizeof(PeerCtx) == 16 + 3 * 8 * PEER_MAX, "PeerCtx layout is part of the C ABI");
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// peer data changes every step and is cached by the local L1 only (peer addresses bypass the local L2): read it uncached
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f(const float* p) { float v; asm volatile("ld.volatile.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ double ld_peer_d(const double* p) { double v; asm volatile("ld.volatile.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory"); return v; }
+
+// threads [0, world) of the calling block: flag `epoch` into slot `slot` of every peer's pad (word index = this rank)
+__device__ __forceinline__ void peer_signal(const PeerCtx* c, int slot, unsigned epoch) {
+  if ((int)threadIdx.x < c->world) {
+    __threadfence_system();
+    st_release_sys(c->pad[threadIdx.x] + PEER_FLAG_BASE + slot * PEER_MAX + c->rank, epoch);
+  }
+}
+// threads [0, world): wait until every peer has flagged at least `epoch` in this rank's own pad (local memory).  Bounded: a rank
+// that never arrives (a crashed peer) traps after ~10 s instead of wedging the GPU.
+__device__ __forceinline__ void peer_wait(const PeerCtx* c, int slot, unsigned epoch) {
+  if ((int)threadIdx.x < c->world) {
+    const unsigned* p = c->pad[c->rank] + PEER_FLAG_BASE + slot * PEER_MAX + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(p) - epoch) < 0) {
+      if (clock64() - t0 > 20000000000LL) asm volatile("trap;\n");
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_allreduce_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const AdamDeviceState* __restrict__ st,
+                      const PeerCtx* __restrict__ c, unsigned* __restrict__ ticket) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ int is_last;
+  const unsigned epoch = (unsigned)st->step;                 // adam_prepare_kernel has already counted this step
+  if (blockIdx.x == 0) peer_signal(c, PEER_SLOT_READY, epoch);      // my gradients are complete (stream order)
+  peer_wait(c, PEER_SLOT_READY, epoch);
+  __syncthreads();
+  AdamArgs a;
+  a.step_size = st->step_size; a.bc2_sqrt = st->bc2_sqrt; a.beta1 = st->beta1; a.beta2 = st->beta2;
+  a.eps = st->eps; a.wd = st->wd; a.grad_scale = st->grad_scale;
+  const int world = c->world;
+  const float inv = 1.0f / (float)world;
+  const long long n = c->n, n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+    float4 gg = ld_peer_f4(c->grad[0] + 4 * i);
+    for (int r = 1; r < world; ++r) {
+      const float4 x = ld_peer_f4(c->grad[r] + 4 * i);
+      gg.x += x.x; gg.y += x.y; gg.z += x.z; gg.w += x.w;
+    }
+    gg.x *= inv; gg.y *= inv; gg.z *= inv; gg.w *= inv;
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, a); adam_one(pp.y, gg.y, mm.y, vv.y, a);
+    adam_one(pp.z, gg.z, mm.z, vv.z, a); adam_one(pp.w, gg.w, mm.w, vv.w, a);
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+    float g = ld_peer_f(c->grad[0] + i);
+    for (int r = 1; r < world; ++r) g += ld_peer_f(c->grad[r] + i);
+    adam_one(p[i], g * inv, m[i], v[i], a);
+  }
+  // the block that finishes last tells every peer that this rank no longer reads their gradients of this step
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x == 0) *ticket = 0u;
+    peer_signal(c, PEER_SLOT_CONSUMED, epoch);
+  }
+}
+
+// one small block, in front of the next backward: every peer has consumed this rank's gradients of the previous step
+__global__ void peer_wait_consumed_kernel(const AdamDeviceState* __restrict__ st, const PeerCtx* __restrict__ c) {
+  pdl_wait();
+  pdl_trigger();
+  peer_wait(c, PEER_SLOT_CONSUMED, (unsigned)st->step);
+}
+
+// BatchNorm statistics (2 x 264 doubles) summed over the ranks in rank order: local -> this rank's symmetric slot -> flags -> sum.
+// which = 0: forward (column sums of e_concat), 1: backward.  One block of 544 threads.
+__global__ void __launch_bounds__(544)
+peer_allsum_stats_kernel(const double* __restrict__ local, int which, double* __restrict__ out, const AdamDeviceState* __restrict__ st,
+                         const PeerCtx* __restrict__ c) {
+  pdl_wait();
+  pdl_trigger();
+  const unsigned epoch = (unsigned)st->step + 1u;              // the step in flight (adam_prepare_kernel counts it at its end)
+  const int t = threadIdx.x;
+  double* mine = c->stats[c->rank] + which * BN_STATS;
+  if (t < BN_STATS) mine[t] = local[t];
+  __threadfence_system();
+  __syncthreads();
+  peer_signal(c, PEER_SLOT_STATS_FWD + which, epoch);
+  peer_wait(c, PEER_SLOT_STATS_FWD + which, epoch);
+  __syncthreads();
+  if (t < BN_STATS) {
+    double s = 0.0;
+    for (int r = 0; r < c->world; ++r) s += ld_peer_d(c->stats[r] + which * BN_STATS + t);
+    out[t] = s;
+  }
+}
+
 }  // namespace nrm
 
 using namespace nrm;
+
+extern "C" size_t nrm_peer_ctx_bytes(void) { return sizeof(PeerCtx); }
+extern "C" size_t nrm_peer_stats_bytes(void) { return sizeof(double) * 2 * BN_STATS; }
+extern "C" int nrm_peer_flag_words(void) { return PEER_FLAG_BASE + 4 * PEER_MAX; }
+// Loads the peer kernels' code (CUDA loads kernels lazily on first use; a first use inside a stream capture is best avoided).
+extern "C" int nrm_peer_preload(void) {
+  cudaFuncAttributes a;
+  NRM_CUDA(cudaFuncGetAttributes(&a, adam_allreduce_kernel));
+  NRM_CUDA(cudaFuncGetAttributes(&a, peer_wait_consumed_kernel));
+  NRM_CUDA(cudaFuncGetAttributes(&a, peer_allsum_stats_kernel));
+  return NRM_OK;
+}
+
+// Adam with the gradient average over the ranks fused in (see the block comment above).  `peer_ctx`: device PeerCtx;
+// `ticket`: one zeroed u32 of device scratch.  The caller's own gradient buffer is peer_ctx->grad[rank].
+extern "C" int nrm_adam_step_allreduce(float* param, float* exp_avg, float* exp_avg_sq, long long n, void* adam_state,
+                                       const void* peer_ctx, void* ticket, void* stream) {
+  if (!param || !exp_avg || !exp_avg_sq || !adam_state || !peer_ctx || !ticket || n <= 0) { set_error("nrm_adam_step_allreduce: bad argument"); return NRM_EINVAL; }
+  if ((((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) { set_error("nrm_adam_step_allreduce: buffers must be 16-byte aligned"); return NRM_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream;
+  AdamDeviceState* st = (AdamDeviceState*)adam_state;
+  launch_pdl(adam_prepare_kernel, dim3(1), dim3(32), 0, s, st);
+  NRM_LAUNCH_CHECK("adam_prepare_kernel");
+  long long blocks = ((n + 3) / 4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 4;             // every block is resident: each one waits for the peers' flags
+  if (blocks > cap) blocks = cap;
+  KernelTimer t("adam", s);
+  launch_pdl(adam_allreduce_kernel, dim3((int)blocks), dim3(256), 0, s, param, exp_avg, exp_avg_sq, st, (const PeerCtx*)peer_ctx, (unsigned*)ticket);
+  NRM_LAUNCH_CHECK("adam_allreduce_kernel");
+  return NRM_OK;
+}
+extern "C" int nrm_peer_wait_consumed(const void* adam_state, const void* peer_ctx, void* stream) {
+  if (!adam_state || !peer_ctx) { set_error("nrm_peer_wait_consumed: bad argument"); return NRM_EINVAL; }
+  launch_pdl(peer_wait_consumed_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (const AdamDeviceState*)adam_state, (const PeerCtx*)peer_ctx);
+  NRM_LAUNCH_CHECK("peer_wait_consumed_kernel");
+  return NRM_OK;
+}
+extern "C" int nrm_peer_allsum_stats(const double* local, int which, double* out, const void* adam_state, const void* peer_ctx, void* stream) {
+  if (!local || !out || !adam_state || !peer_ctx || which < 0 || which > 1) { set_error("nrm_peer_allsum_stats: bad argument"); return NRM_EINVAL; }
+  launch_pdl(peer_allsum_stats_kernel, dim3(1), dim3(544), 0, (cudaStream_t)stream, local, which, out, (const AdamDeviceState*)adam_state,
+             (const PeerCtx*)peer_ctx);
+  NRM_LAUNCH_CHECK("peer_allsum_stats_kernel");
+  return NRM_OK;
+}
 
 extern "C" int nrm_adam_step_device(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                                     void* adam_state, void* stream) {

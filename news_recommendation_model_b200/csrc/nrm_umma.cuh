@@ -182,10 +182,10 @@ __device__ __forceinline__ void store_bf16x8_split(void* dst_hi, void* dst_lo, c
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+    // the two hi values come back as floats with one shift and one mask of the packed word (6 instructions per pair)
     const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
     hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - __uint_as_float(hi[i] << 16), v[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
     lo[i] = *reinterpret_cast<const uint32_t*>(&l);
   }
   *reinterpret_cast<uint4*>(dst_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

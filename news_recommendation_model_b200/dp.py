@@ -11,6 +11,7 @@ DDP behaviour, no collective in the forward).
 """
 from __future__ import annotations
 
+import struct
 from typing import Optional
 
 import torch
@@ -73,11 +74,51 @@ class GradientBuckets:
         self.handles = []
 
 
+class PeerContext:
+    """Symmetric (peer-mapped) memory of one rank for the fused data-parallel path (csrc/nrm_loss_adam.cu, "data parallelism over
+    peer memory"): the flat gradient buffer every peer reads while it runs Adam, and a control block [BatchNorm sums 2 x 528 doubles |
+    flag words].  `torch.distributed._symmetric_memory` allocates and maps the memory (CUDA VMM handles exchanged through the
+    process group's store); the kernels only ever see the raw pointers packed into `self.ctx` (the C ABI's PeerCtx struct).
+    Raises if the GPUs of the group cannot map each other's memory; callers fall back to NCCL."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        lib = _lib.load()
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError('PeerContext: at most 8 ranks (one NVSwitch domain)')
+        stats_bytes = int(lib.nrm_peer_stats_bytes())
+        flag_bytes = 4 * int(lib.nrm_peer_flag_words())
+        self.grads = symm.empty(n_floats, dtype=torch.float32, device=device)
+        self.control = symm.empty((stats_bytes + flag_bytes + 255) // 256 * 256, dtype=torch.uint8, device=device)
+        self.grads.zero_()
+        self.control.zero_()
+        torch.cuda.synchronize(device)
+        self._hg = symm.rendezvous(self.grads, group)
+        self._hc = symm.rendezvous(self.control, group)
+        gp = [int(x) for x in self._hg.buffer_ptrs]
+        cp = [int(x) for x in self._hc.buffer_ptrs]
+        pad8 = lambda xs: xs + [0] * (8 - len(xs))
+        raw = struct.pack('<iiq', self.rank, self.world, n_floats) + struct.pack('<8Q', *pad8(gp)) \
+            + struct.pack('<8Q', *pad8([c + stats_bytes for c in cp])) + struct.pack('<8Q', *pad8(cp))
+        assert len(raw) == int(lib.nrm_peer_ctx_bytes())
+        self.ctx = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=device)
+        self.stats_out = torch.zeros(2, stats_bytes // 16, dtype=torch.float64, device=device)     # [forward | backward] global sums
+        self.stats_local = torch.zeros(2, stats_bytes // 16, dtype=torch.float64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                  # every rank's flags are zero before anybody signals
+
+
 class DataParallel:
     """Attach to a UserModel: `DataParallel(model)`; afterwards model.forward / backward
     run the collectives described in the module docstring."""
 
-    def __init__(self, model, group=None, sync_bn: bool = False, broadcast: bool = True):
+    def __init__(self, model, group=None, sync_bn: bool = False, broadcast: bool = True, peer_memory: bool = True):
+        """peer_memory: let FusedTrainStep average the gradients inside its Adam kernel over peer-mapped memory (PeerContext) when
+        the backend is NCCL and the GPUs can map each other; otherwise (and on the module path) NCCL all-reduce buckets."""
         if not dist.is_initialized():
             raise RuntimeError('torch.distributed is not initialised')
         self.group = group
@@ -88,12 +129,34 @@ class DataParallel:
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self._head_begin = None
         self._rows_checked = None
+        self.peer_memory = bool(peer_memory) and dist.get_backend(group) == 'nccl'
+        self.peer: Optional[PeerContext] = None
+        self.peer_error: Optional[str] = None
         model._dp = self
         if broadcast:
             flat = model.flat_parameters()
             dist.broadcast(flat.buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             for b in (model.bn.running_mean, model.bn.running_var, model.bn.num_batches_tracked):
                 dist.broadcast(b, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+
+    def peer_context(self, n_floats: int, device) -> Optional[PeerContext]:
+        """Create (once) the symmetric-memory context for a flat buffer of `n_floats`; None when peer mapping is off or impossible.
+        Collective: every rank must call it at the same point."""
+        if not self.peer_memory:
+            return None
+        if self.peer is None and self.peer_error is None:
+            ok = 1
+            try:
+                self.peer = PeerContext(n_floats, device, self.group)
+            except Exception as ex:                          # no P2P / fabric handles, old driver ...: NCCL stays the transport
+                self.peer_error = f'{type(ex).__name__}: {ex}'
+                ok = 0
+            t = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            if int(t.item()) == 0:                           # all ranks or none
+                self.peer = None
+                self.peer_error = self.peer_error or 'a peer rank could not map symmetric memory'
+        return self.peer
 
     # ---- BatchNorm statistics -----------------------------------------------------------
     def all_reduce_stats(self, sums: torch.Tensor, local_rows: int) -> int:

@@ -60,6 +60,8 @@ class LossHandle:
 
 
 class FusedTrainStep:
+    SYNC_BN = True          # DataParallel(sync_bn=True) is supported on this path (tests/dp_check.py looks at this flag)
+
     def __init__(self, model, B: int, H: int, C: int, *, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5,
                  alpha=0.95, use_graph=True, ring=8, nslots=2, articles=None):
         """`articles`: a device `wire.ArticleTable`; with it `load()` also accepts `wire.CompactBatch`es (ids instead of
@@ -74,7 +76,10 @@ class FusedTrainStep:
         self.precision = model._precision_code()
         self.mode = engine.MODE_BN_BATCH_STATS | engine.MODE_KEEP_FOR_BWD
         n = self.flat.total
-        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        # data parallel: the flat gradient buffer in symmetric (peer-mapped) memory, so that the Adam kernel of every rank can read
+        # all of them (dp.PeerContext); None -> NCCL all-reduce between two graphs
+        self.peer = self.dp.peer_context(n, dev) if self.dp is not None else None
+        self.grads = self.peer.grads if self.peer is not None else torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         # AdamDeviceState: int64 step | lr, beta1, beta2, eps, wd, grad_scale, step_size, bc2_sqrt
@@ -93,7 +98,9 @@ class FusedTrainStep:
         self.slots: List[_Slot] = [_Slot(B, H, C, dev) for _ in range(nslots)]
         self.loaded = 0
         self.copy_stream = torch.cuda.Stream(dev)
-        self.use_graph = use_graph
+        # NCCL collectives between the halves of a synchronised-BatchNorm step are issued eagerly: no graph on that (fallback) path
+        self.use_graph = use_graph and not (self.dp is not None and self.dp.sync_bn and self.peer is None)
+        self.one_graph = self.dp is None or self.peer is not None
         self.world = world
         self._tail_scratch = {}
         self._warmup()
@@ -108,7 +115,11 @@ class FusedTrainStep:
         saved = (m.bn.running_mean.clone(), m.bn.running_var.clone(), m.bn.num_batches_tracked.clone())
         scratch_loss = self.loss_dev.new_zeros(())
         n0 = lib.nrm_launch_count()
+        self._warming = True                  # no cross-rank flags during the warm-up pass: their epochs belong to real steps
         self._forward_backward(s, scratch_loss)
+        self._warming = False
+        if self.peer is not None:
+            _lib.check(lib.nrm_peer_preload(), 'nrm_peer_preload')      # load the peer kernels outside any graph capture
         self.launches_per_step = int(lib.nrm_launch_count() - n0) + 2      # + Adam prepare / update
         with torch.no_grad():
             m.bn.running_mean.copy_(saved[0]); m.bn.running_var.copy_(saved[1]); m.bn.num_batches_tracked.copy_(saved[2])
@@ -127,22 +138,67 @@ class FusedTrainStep:
         H, C = self.H, self.C
         B = self.B if B is None else B
         loss_scratch = self.loss_scratch if loss_scratch is None else loss_scratch
-        if self.dp is not None and self.dp.sync_bn:
-            raise _lib.NrmError('FusedTrainStep: sync_bn needs the two-phase calls; use model.forward/backward')
-        _lib.check(lib.nrm_forward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf),
-                                   _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked), self.mode,
-                                   self.precision, _p(self.logits), _p(self.ws), self.ws.numel(), st), 'nrm_forward')
+        warming = getattr(self, '_warming', False)
+        sync_bn = self.dp is not None and self.dp.sync_bn and not warming
+        if not sync_bn:
+            _lib.check(lib.nrm_forward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf),
+                                       _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked), self.mode,
+                                       self.precision, _p(self.logits), _p(self.ws), self.ws.numel(), st), 'nrm_forward')
+        else:
+            # synchronised BatchNorm: the two halves of the forward around the exchange of the column sums (2 x 264 doubles);
+            # N ranks x B impressions then reproduce one process on N * B
+            sums = self._bn_sums(0)
+            _lib.check(lib.nrm_forward_encoder(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
+                                               self.precision, _p(sums), _p(self.ws), self.ws.numel(), st), 'nrm_forward_encoder')
+            gsums = self._exchange_stats(0, sums, B * C)
+            _lib.check(lib.nrm_forward_head(B, H, C, _p(f.buf), _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked),
+                                            self.mode, _p(gsums), B * C * self.world, _p(self.logits), _p(self.ws), self.ws.numel(), st),
+                       'nrm_forward_head')
         delta = f.buf[f.fixed:f.fixed + f.delta_numel]
         _lib.check(lib.nrm_loss_forward(_p(self.logits), _p(delta), f.delta_numel, _p(s.uid), _p(s.label), B, C, self.alpha, _p(loss_out),
                                         _p(loss_scratch), loss_scratch.numel(), st), 'nrm_loss_forward')
+        if self.peer is not None and not warming:
+            # before anything of this step is written into the gradient buffer: every peer has consumed the previous step's
+            _lib.check(lib.nrm_peer_wait_consumed(_p(self.adam_state), _p(self.peer.ctx), st), 'nrm_peer_wait_consumed')
         ddelta = self.grads[f.fixed:f.fixed + f.delta_numel]
         _lib.check(lib.nrm_loss_backward(_p(s.uid), B, C, _p(self.one), _p(self.dlogits), _p(ddelta), f.delta_numel,
                                          _p(loss_scratch), loss_scratch.numel(), st), 'nrm_loss_backward')
-        _lib.check(lib.nrm_backward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
-                                    self.precision, _p(self.dlogits), _p(self.grads), _p(self.ws), self.ws.numel(), st),
-                   'nrm_backward')
+        if not sync_bn:
+            _lib.check(lib.nrm_backward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
+                                        self.precision, _p(self.dlogits), _p(self.grads), _p(self.ws), self.ws.numel(), st),
+                       'nrm_backward')
+        else:
+            sums = self._bn_sums(1)
+            _lib.check(lib.nrm_backward_head(B, H, C, _p(f.buf), _p(self.dlogits), _p(self.grads), _p(sums), _p(self.ws), self.ws.numel(), st),
+                       'nrm_backward_head')
+            gsums = self._exchange_stats(1, sums, B * C)
+            _lib.check(lib.nrm_backward_encoder(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
+                                                self.precision, _p(gsums), B * C * self.world, _p(self.grads), _p(self.ws), self.ws.numel(), st),
+                       'nrm_backward_encoder')
+
+    def _bn_sums(self, which: int) -> torch.Tensor:
+        if self.peer is not None:
+            return self.peer.stats_local[which]
+        if not hasattr(self, '_sums_local'):
+            self._sums_local = torch.zeros(2, 528, dtype=torch.float64, device=self.dev)
+        return self._sums_local[which]
+
+    def _exchange_stats(self, which: int, sums: torch.Tensor, local_rows: int) -> torch.Tensor:
+        """Sum the BatchNorm statistics over the ranks: one small kernel over peer memory (graph-safe), else an NCCL all-reduce."""
+        if self.peer is not None:
+            out = self.peer.stats_out[which]
+            _lib.check(self.lib.nrm_peer_allsum_stats(_p(sums), which, _p(out), _p(self.adam_state), _p(self.peer.ctx),
+                                                      engine._stream(self.dev)), 'nrm_peer_allsum_stats')
+            return out
+        self.dp.all_reduce_stats(sums, local_rows)
+        return sums
 
     def _adam(self):
+        if self.peer is not None:            # gradient average over the ranks fused into the update (peer memory)
+            _lib.check(self.lib.nrm_adam_step_allreduce(_p(self.flat.buf), _p(self.exp_avg), _p(self.exp_avg_sq), self.flat.total,
+                                                        _p(self.adam_state), _p(self.peer.ctx), _p(self.peer.ticket), engine._stream(self.dev)),
+                       'nrm_adam_step_allreduce')
+            return
         _lib.check(self.lib.nrm_adam_step_device(_p(self.flat.buf), _p(self.grads), _p(self.exp_avg), _p(self.exp_avg_sq),
                                                  self.flat.total, _p(self.adam_state), engine._stream(self.dev)),
                    'nrm_adam_step_device')
@@ -267,15 +323,15 @@ class FusedTrainStep:
                     if s.wire == 'compact':
                         self._expand(s)
                     self._forward_backward(s, s.loss_slot)
-                    if self.dp is None:
-                        self._adam()                     # single process: the whole step is ONE graph
+                    if self.one_graph:
+                        self._adam()                     # single process or peer-memory data parallel: the whole step is ONE graph
                 s.graph_wire = s.wire
-                if self.dp is not None:                  # data parallel: the gradient all-reduce sits between two graphs
+                if not self.one_graph:                   # NCCL data parallel: the gradient all-reduce sits between two graphs
                     s.graph_adam = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(s.graph_adam):
                         self._adam()
             s.graph_fb.replay()
-            if self.dp is not None:
+            if not self.one_graph:
                 self.dp.buckets.reduce(self.grads, 0, self.grads.numel())
                 self.dp.buckets.wait()
                 s.graph_adam.replay()
@@ -284,7 +340,7 @@ class FusedTrainStep:
             if s.wire == 'compact':
                 self._expand(s)
             self._forward_backward(s, loss_out)
-            if self.dp is not None:
+            if self.dp is not None and self.peer is None:
                 self.dp.buckets.reduce(self.grads, 0, self.grads.numel())
                 self.dp.buckets.wait()
             self._adam()
