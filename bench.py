@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--cpu-steps', type=int, default=60, help='train steps of the CPU port timed for cpu_baseline (about 15 s on 16 cores)')
     ap.add_argument('--no-scoring', action='store_true', help='skip the scoring (configs[2]) leg')
     ap.add_argument('--no-loader', action='store_true', help='skip the record-list -> loader -> loss leg')
+    ap.add_argument('--no-large-users', action='store_true', help='skip the user_num = 2 000 000 leg')
     ap.add_argument('--no-long-history', action='store_true', help='skip the configs[4] leg (B=4096, H=256)')
     ap.add_argument('--no-dp-check', action='store_true', help='skip the N-rank vs single-process numerical pre-flight (world > 1)')
     ap.add_argument('--no-affinity', action='store_true', help='do not bind each rank to the CPU cores local to its GPU')
@@ -669,6 +670,43 @@ def run_ours(args):
         del trl, sl, dbl, hbl
         torch.cuda.empty_cache()
 
+    # ---- F. large user table (user_num = 2 000 000 -> delta holds 8 MB, its gradient <= B non-zeros per rank):
+    #         resident FusedTrainStep; under data parallelism the sparse (user id, value) exchange against the dense one
+    large_users = None
+    if not args.no_large_users:
+        UL = 2_000_000
+        large_users = {'user_num': UL}
+        hl = [make_batch(B, H, C, seed=4242 + 97 * rank + i, user_num=UL).pin() for i in range(2)]
+        for label_, smin in (('sparse_delta_exchange', nrm.FusedTrainStep.SPARSE_DELTA_MIN), ('dense_delta_exchange', 1 << 40)):
+            if world == 1 and label_ == 'sparse_delta_exchange':
+                continue                                    # one process: nothing to exchange, the dense Adam pass is all there is
+            mL = nrm.UserModel(UL)
+            mL.load_state_dict(load_weights(), strict=False)
+            mL.to(dev).train().set_precision(args.precision)
+            if world > 1:
+                DataParallel(mL, sync_bn=args.sync_bn)
+            old_min = nrm.FusedTrainStep.SPARSE_DELTA_MIN
+            nrm.FusedTrainStep.SPARSE_DELTA_MIN = smin
+            try:
+                trL = nrm.FusedTrainStep(mL, B, H, C, lr=1e-3, weight_decay=1e-5, nslots=2, use_graph=not args.no_graph)
+            finally:
+                nrm.FusedTrainStep.SPARSE_DELTA_MIN = old_min
+            sL = [trL.load(b) for b in hl]
+            torch.cuda.synchronize()
+            for i in range(4):
+                trL.run(sL[i % 2])
+            barrier()
+            e0.record()
+            for i in range(10):
+                trL.run(sL[i % 2])
+            e1.record()
+            barrier()
+            msL = max_over_ranks(e0.elapsed_time(e1)) / 10
+            large_users[label_ if world > 1 else 'single_process'] = {'value': world * B / (msL / 1e3), 'ms_per_step': msL,
+                                                                      'sparse': bool(trL.sparse_delta)}
+            del trL, sL, mL
+        torch.cuda.empty_cache()
+
     # short resident runs of the other precisions (same step, same data), for context
     variants = {}
     if not args.no_variants:
@@ -716,9 +754,11 @@ def run_ours(args):
         'module_path': {'value': world * B * K / (mod_ms / 1e3), 'unit': 'impressions/s', 'ms_per_step': mod_ms / K,
                         'note': 'drop-in nn.Module path driven like train.py:69-75 (autograd + FusedAdam), device-resident'},
         'api': 'FusedTrainStep (CUDA-graph replay of the 5 C-ABI calls)' if not args.no_graph else 'FusedTrainStep (eager C-ABI calls)',
+        'dp_transport': (None if world == 1 else ('peer memory: gradient average fused into the Adam kernel over NVLink (one CUDA graph per step)'
+                                                  if tr.peer is not None else f'NCCL all-reduce between two graphs ({model._dp.peer_error})')),
         'roofline': roofline, 'roofline_fraction_by_kernel': roofline_all,
         'kernels_ms_per_step': {k: round(v['ms'], 4) for k, v in kern.items()},
-        'e2e_loader': loader_leg, 'long_history': long_history,
+        'e2e_loader': loader_leg, 'long_history': long_history, 'large_user_table': large_users,
         'cpu_baseline': cpu, 'precision_variants': variants, 'scoring': scoring, 'dp_parity': dp_parity,
     }
     print(json.dumps(line), flush=True)

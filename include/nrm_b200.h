@@ -100,7 +100,8 @@ int         nrm_debug_mma_microbench(long long* out, int variant, int reps, int 
 /* ---- data parallelism over peer memory (no counterpart in the single-process reference; north_star: gradient all-reduce) ----
  * The gradient average over the ranks is fused into the optimizer: every rank's flat gradient buffer sits in symmetric (peer-mapped)
  * memory and nrm_adam_step_allreduce reads all of them in rank order while it updates.  `peer_ctx` is a device struct
- *     { int rank, world; long long n; const float* grad[8]; unsigned* pad[8]; double* stats[8]; }
+ *     { int rank, world; long long n; const float* grad[8]; unsigned* pad[8]; double* stats[8];
+ *       const long long* suid[8]; const float* sval[8]; long long* acc; unsigned* gridbar; long long delta_off, delta_n, rows; }
  * (nrm_peer_ctx_bytes() bytes) holding the peer-mapped pointers; the library uses the u32 words [64, nrm_peer_flag_words()) of every
  * signal pad; `stats` buffers hold nrm_peer_stats_bytes() bytes.  Call order per step: ... forward, loss ..., nrm_peer_wait_consumed,
  * backward ..., nrm_adam_step_allreduce.  nrm_peer_allsum_stats sums the BatchNorm statistics (which = 0 forward, 1 backward) over the
@@ -111,6 +112,11 @@ int         nrm_peer_flag_words(void);
 int         nrm_peer_preload(void);
 int         nrm_adam_step_allreduce(float* param, float* exp_avg, float* exp_avg_sq, long long n, void* adam_state,
                                     const void* peer_ctx, void* ticket, void* stream);
+/* Large user tables (user_num ~ 2 000 000): the per-user bias gradient travels as (user id, value) per impression instead of a dense
+ * [user_num + 1] buffer: nrm_loss_backward_sparse publishes the lists (symmetric memory), nrm_adam_step_allreduce sums all ranks' lists into
+ * peer_ctx->acc (fixed point, integer atomics: order independent) and runs the dense Adam pass over delta from it (delta_n > 0). */
+int         nrm_loss_backward_sparse(const long long* user_id, int B, int C, const float* grad_loss, float* dlogits, long long delta_numel,
+                                     long long* sparse_uid, float* sparse_val, const void* scratch, size_t scratch_bytes, void* stream);
 int         nrm_peer_wait_consumed(const void* adam_state, const void* peer_ctx, void* stream);
 int         nrm_peer_allsum_stats(const double* local, int which, double* out, const void* adam_state, const void* peer_ctx, void* stream);
 

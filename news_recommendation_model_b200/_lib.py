@@ -54,6 +54,7 @@ SIGNATURES = {
     'nrm_peer_preload': (i32, []),
     'nrm_adam_step_allreduce': (i32, [vp, vp, vp, ll, vp, vp, vp, vp]),
     'nrm_peer_wait_consumed': (i32, [vp, vp, vp]),
+    'nrm_loss_backward_sparse': (i32, [vp, i32, i32, vp, vp, ll, vp, vp, vp, sz, vp]),
     'nrm_peer_allsum_stats': (i32, [vp, i32, vp, vp, vp, vp]),
     'nrm_batch_metrics': (i32, [vp, ll, vp, ll, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     'nrm_score_epilogue': (i32, [vp, i32, ll, ll, i32, i32, vp, vp, vp, vp]),

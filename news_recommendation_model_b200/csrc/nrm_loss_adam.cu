@@ -148,6 +148,24 @@ loss_backward_kernel(const float* __restrict__ dlog, const float* __restrict__ g
   if (lane == 0) ddelta[id] = tot * __ldg(grad_loss);
 }
 
+// Sparse variant for large user tables: dlogits as above; instead of the dense [user_num + 1] gradient, impression b publishes
+// (uid[b], d loss / d delta[uid[b]] of that impression) -- duplicates are summed by the consumer (adam_allreduce_kernel).
+__global__ void __launch_bounds__(256)
+loss_backward_sparse_kernel(const float* __restrict__ dlog, const float* __restrict__ grad_loss, long long n, float* __restrict__ out,
+                            const long long* __restrict__ uid, const float* __restrict__ drow, int B, long long delta_numel,
+                            long long* __restrict__ suid, float* __restrict__ sval) {
+  pdl_wait();
+  pdl_trigger();
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const float gl = __ldg(grad_loss);
+  if (i < n) out[i] = dlog[i] * gl;
+  if (i < B) {
+    const long long id = uid[i];
+    suid[i] = (id >= 0 && id < delta_numel) ? id : -1;
+    sval[i] = drow[i] * gl;
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // Adam
 // ---------------------------------------------------------------------------------
@@ -258,8 +276,16 @@ struct PeerCtx {                             // mirrored by dp.PeerContext (pyth
   const float* grad[PEER_MAX];               // flat gradient buffers, peer-mapped, indexed by rank
   unsigned* pad[PEER_MAX];                   // signal pads (u32 words), peer-mapped
   double* stats[PEER_MAX];                   // [2][BN_STATS]: forward | backward BatchNorm sums, peer-mapped
+  // sparse exchange of the per-user bias gradient (delta, user_model.py:23: one float per user, <= B non-zeros per rank and step)
+  const long long* suid[PEER_MAX];           // [rows] user id of each impression of the rank (-1: out of range), peer-mapped
+  const float* sval[PEER_MAX];               // [rows] d loss / d delta[uid] contributed by that impression, peer-mapped
+  long long* acc;                            // [delta_n] local fixed-point accumulator, all zero between steps
+  unsigned* gridbar;                         // local: [0] arrival counter, [1] generation of the in-kernel grid barrier
+  long long delta_off, delta_n;              // delta's range in the flat buffers; delta_n = 0: no sparse part (delta is averaged densely)
+  long long rows;                            // impressions per rank
 };
-static_assert(sizeof(PeerCtx) == 16 + 3 * 8 * PEER_MAX, "PeerCtx layout is part of the C ABI");
+static_assert(sizeof(PeerCtx) == 16 + 5 * 8 * PEER_MAX + 5 * 8, "PeerCtx layout is part of the C ABI");
+constexpr double DELTA_FIXED_SCALE = 17592186044416.0;      // 2^44: |sum| < 2^19 fits 63 bits, resolution 5.7e-14
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -310,8 +336,22 @@ adam_allreduce_kernel(float* __restrict__ p, float* __restrict__ m, float* __res
   a.eps = st->eps; a.wd = st->wd; a.grad_scale = st->grad_scale;
   const int world = c->world;
   const float inv = 1.0f / (float)world;
-  const long long n = c->n, n4 = n >> 2;
+  const bool sparse = c->delta_n > 0;
+  const long long n = sparse ? c->delta_off : c->n, n4 = n >> 2;     // densely averaged range (delta_off is a multiple of 4)
   const long long stride = (long long)gridDim.x * 256;
+  if (sparse) {
+    // every rank's (user id, value) list -> local fixed-point accumulator.  Integer atomics: the sum does not depend on the order,
+    // so every rank ends up with the same bits.
+    const long long rows = c->rows, total = rows * world;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) {
+      const int r = (int)(e / rows);
+      const long long b = e - r * rows;
+      long long id; float val;
+      asm volatile("ld.volatile.global.s64 %0, [%1];\n" : "=l"(id) : "l"(c->suid[r] + b) : "memory");
+      val = ld_peer_f(c->sval[r] + b);
+      if (id >= 0 && id < c->delta_n) atomicAdd(reinterpret_cast<unsigned long long*>(c->acc + id), (unsigned long long)__double2ll_rn((double)val * DELTA_FIXED_SCALE));
+    }
+  }
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
     float4 gg = ld_peer_f4(c->grad[0] + 4 * i);
     for (int r = 1; r < world; ++r) {
@@ -330,6 +370,34 @@ adam_allreduce_kernel(float* __restrict__ p, float* __restrict__ m, float* __res
     float g = ld_peer_f(c->grad[0] + i);
     for (int r = 1; r < world; ++r) g += ld_peer_f(c->grad[r] + i);
     adam_one(p[i], g * inv, m[i], v[i], a);
+  }
+  if (sparse) {
+    // grid barrier (every block is resident: the launcher caps the grid), then the dense Adam pass over delta with the accumulated
+    // gradient; touched accumulator entries go back to zero
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned gen = *reinterpret_cast<volatile unsigned*>(c->gridbar + 1);
+      if (atomicAdd(c->gridbar, 1u) == gridDim.x - 1) {
+        *reinterpret_cast<volatile unsigned*>(c->gridbar) = 0u;
+        __threadfence();
+        atomicAdd(c->gridbar + 1, 1u);
+      } else {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned*>(c->gridbar + 1) == gen) {
+          if (clock64() - t0 > 20000000000LL) asm volatile("trap;\n");
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    const double unscale = 1.0 / DELTA_FIXED_SCALE;
+    float* dp = p + c->delta_off; float* dm = m + c->delta_off; float* dv = v + c->delta_off;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < c->delta_n; i += stride) {
+      const long long acc = c->acc[i];
+      if (acc != 0) c->acc[i] = 0;
+      adam_one(dp[i], (float)((double)acc * unscale) * inv, dm[i], dv[i], a);
+    }
   }
   // the block that finishes last tells every peer that this rank no longer reads their gradients of this step
   __syncthreads();
@@ -387,6 +455,7 @@ extern "C" int nrm_peer_preload(void) {
   NRM_CUDA(cudaFuncGetAttributes(&a, adam_allreduce_kernel));
   NRM_CUDA(cudaFuncGetAttributes(&a, peer_wait_consumed_kernel));
   NRM_CUDA(cudaFuncGetAttributes(&a, peer_allsum_stats_kernel));
+  NRM_CUDA(cudaFuncGetAttributes(&a, loss_backward_sparse_kernel));
   return NRM_OK;
 }
 
@@ -478,6 +547,20 @@ extern "C" int nrm_loss_backward(const long long* user_id, int B, int C, const f
   launch_pdl(loss_backward_kernel, dim3(nscale + (want_delta ? (B + 7) / 8 : 0)), dim3(256), 0, s, ls.dlog, grad_loss, n, nscale, dlogits,
              user_id, ls.drow, B, ddelta, delta_numel);
   NRM_LAUNCH_CHECK("loss_backward_kernel");
+  return NRM_OK;
+}
+
+extern "C" int nrm_loss_backward_sparse(const long long* user_id, int B, int C, const float* grad_loss, float* dlogits, long long delta_numel,
+                                        long long* sparse_uid, float* sparse_val, const void* scratch, size_t scratch_bytes, void* stream) {
+  if (!user_id || !grad_loss || !dlogits || !sparse_uid || !sparse_val || !scratch || B <= 0 || C <= 0) {
+    set_error("nrm_loss_backward_sparse: bad argument"); return NRM_EINVAL;
+  }
+  LossScratch ls;
+  if (carve_loss(ls, const_cast<void*>(scratch), B, C) > scratch_bytes) { set_error("nrm_loss_backward_sparse: scratch too small"); return NRM_EWORKSPACE; }
+  const long long n = (long long)B * C;
+  launch_pdl(loss_backward_sparse_kernel, dim3((int)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, ls.dlog, grad_loss, n, dlogits, user_id,
+             ls.drow, B, delta_numel, sparse_uid, sparse_val);
+  NRM_LAUNCH_CHECK("loss_backward_sparse_kernel");
   return NRM_OK;
 }
 

@@ -81,7 +81,9 @@ class PeerContext:
     process group's store); the kernels only ever see the raw pointers packed into `self.ctx` (the C ABI's PeerCtx struct).
     Raises if the GPUs of the group cannot map each other's memory; callers fall back to NCCL."""
 
-    def __init__(self, n_floats: int, device, group=None):
+    def __init__(self, n_floats: int, device, group=None, rows: int = 0, delta_off: int = 0, delta_n: int = 0):
+        """rows / delta_off / delta_n > 0: sparse exchange of the per-user bias gradient (`rows` (user id, value) entries per rank
+        instead of delta's dense range [delta_off, delta_off + delta_n) of the flat buffers)."""
         import torch.distributed._symmetric_memory as symm
         from . import _lib
         lib = _lib.load()
@@ -93,16 +95,28 @@ class PeerContext:
         flag_bytes = 4 * int(lib.nrm_peer_flag_words())
         self.grads = symm.empty(n_floats, dtype=torch.float32, device=device)
         self.control = symm.empty((stats_bytes + flag_bytes + 255) // 256 * 256, dtype=torch.uint8, device=device)
+        self.sparse_rows = int(rows) if delta_n > 0 else 0
+        srows = max(self.sparse_rows, 1)
+        self.sparse = symm.empty(srows * 12 + 16, dtype=torch.uint8, device=device)       # [rows] int64 user ids | [rows] float32 values
         self.grads.zero_()
         self.control.zero_()
+        self.sparse.zero_()
         torch.cuda.synchronize(device)
         self._hg = symm.rendezvous(self.grads, group)
         self._hc = symm.rendezvous(self.control, group)
+        self._hs = symm.rendezvous(self.sparse, group)
         gp = [int(x) for x in self._hg.buffer_ptrs]
         cp = [int(x) for x in self._hc.buffer_ptrs]
+        sp = [int(x) for x in self._hs.buffer_ptrs]
+        self.sparse_uid = self.sparse[:srows * 8].view(torch.int64)
+        self.sparse_val = self.sparse[srows * 8:srows * 12].view(torch.float32)
+        self.acc = torch.zeros(max(int(delta_n), 1), dtype=torch.int64, device=device)      # fixed-point accumulator, zero between steps
+        self.gridbar = torch.zeros(4, dtype=torch.int32, device=device)
         pad8 = lambda xs: xs + [0] * (8 - len(xs))
         raw = struct.pack('<iiq', self.rank, self.world, n_floats) + struct.pack('<8Q', *pad8(gp)) \
-            + struct.pack('<8Q', *pad8([c + stats_bytes for c in cp])) + struct.pack('<8Q', *pad8(cp))
+            + struct.pack('<8Q', *pad8([c + stats_bytes for c in cp])) + struct.pack('<8Q', *pad8(cp)) \
+            + struct.pack('<8Q', *pad8(sp)) + struct.pack('<8Q', *pad8([x + srows * 8 for x in sp])) \
+            + struct.pack('<QQqqq', self.acc.data_ptr(), self.gridbar.data_ptr(), int(delta_off), int(delta_n) if self.sparse_rows else 0, srows)
         assert len(raw) == int(lib.nrm_peer_ctx_bytes())
         self.ctx = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
         self.ticket = torch.zeros(4, dtype=torch.int32, device=device)
@@ -139,15 +153,19 @@ class DataParallel:
             for b in (model.bn.running_mean, model.bn.running_var, model.bn.num_batches_tracked):
                 dist.broadcast(b, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
 
-    def peer_context(self, n_floats: int, device) -> Optional[PeerContext]:
-        """Create (once) the symmetric-memory context for a flat buffer of `n_floats`; None when peer mapping is off or impossible.
-        Collective: every rank must call it at the same point."""
+    def peer_context(self, n_floats: int, device, rows: int = 0, delta_off: int = 0, delta_n: int = 0) -> Optional[PeerContext]:
+        """Create (once per shape) the symmetric-memory context for a flat buffer of `n_floats`; None when peer mapping is off or
+        impossible.  Collective: every rank must call it at the same point."""
         if not self.peer_memory:
             return None
+        key = (n_floats, rows, delta_off, delta_n)
+        if self.peer is not None and getattr(self, '_peer_key', None) != key:
+            self.peer = None                                 # another step shape: a new context (the old one stays alive with its step)
         if self.peer is None and self.peer_error is None:
             ok = 1
             try:
-                self.peer = PeerContext(n_floats, device, self.group)
+                self.peer = PeerContext(n_floats, device, self.group, rows, delta_off, delta_n)
+                self._peer_key = key
             except Exception as ex:                          # no P2P / fabric handles, old driver ...: NCCL stays the transport
                 self.peer_error = f'{type(ex).__name__}: {ex}'
                 ok = 0

@@ -61,6 +61,7 @@ class LossHandle:
 
 class FusedTrainStep:
     SYNC_BN = True          # DataParallel(sync_bn=True) is supported on this path (tests/dp_check.py looks at this flag)
+    SPARSE_DELTA_MIN = 65536
 
     def __init__(self, model, B: int, H: int, C: int, *, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5,
                  alpha=0.95, use_graph=True, ring=8, nslots=2, articles=None):
@@ -78,7 +79,12 @@ class FusedTrainStep:
         n = self.flat.total
         # data parallel: the flat gradient buffer in symmetric (peer-mapped) memory, so that the Adam kernel of every rank can read
         # all of them (dp.PeerContext); None -> NCCL all-reduce between two graphs
-        self.peer = self.dp.peer_context(n, dev) if self.dp is not None else None
+        # user tables beyond SPARSE_DELTA_MIN entries: delta's gradient (<= B non-zeros per rank) travels as (user id, value) lists
+        self.sparse_delta = self.dp is not None and self.flat.delta_numel >= self.SPARSE_DELTA_MIN
+        self.peer = None
+        if self.dp is not None:
+            self.peer = self.dp.peer_context(n, dev, B, self.flat.fixed, self.flat.delta_numel if self.sparse_delta else 0)
+        self.sparse_delta = self.sparse_delta and self.peer is not None
         self.grads = self.peer.grads if self.peer is not None else torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -160,9 +166,13 @@ class FusedTrainStep:
         if self.peer is not None and not warming:
             # before anything of this step is written into the gradient buffer: every peer has consumed the previous step's
             _lib.check(lib.nrm_peer_wait_consumed(_p(self.adam_state), _p(self.peer.ctx), st), 'nrm_peer_wait_consumed')
-        ddelta = self.grads[f.fixed:f.fixed + f.delta_numel]
-        _lib.check(lib.nrm_loss_backward(_p(s.uid), B, C, _p(self.one), _p(self.dlogits), _p(ddelta), f.delta_numel,
-                                         _p(loss_scratch), loss_scratch.numel(), st), 'nrm_loss_backward')
+        if self.sparse_delta and not warming:
+            _lib.check(lib.nrm_loss_backward_sparse(_p(s.uid), B, C, _p(self.one), _p(self.dlogits), f.delta_numel, _p(self.peer.sparse_uid),
+                                                    _p(self.peer.sparse_val), _p(loss_scratch), loss_scratch.numel(), st), 'nrm_loss_backward_sparse')
+        else:
+            ddelta = self.grads[f.fixed:f.fixed + f.delta_numel]
+            _lib.check(lib.nrm_loss_backward(_p(s.uid), B, C, _p(self.one), _p(self.dlogits), _p(ddelta), f.delta_numel,
+                                             _p(loss_scratch), loss_scratch.numel(), st), 'nrm_loss_backward')
         if not sync_bn:
             _lib.check(lib.nrm_backward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
                                         self.precision, _p(self.dlogits), _p(self.grads), _p(self.ws), self.ws.numel(), st),
