@@ -154,27 +154,23 @@ class DataParallel:
                 dist.broadcast(b, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
 
     def peer_context(self, n_floats: int, device, rows: int = 0, delta_off: int = 0, delta_n: int = 0) -> Optional[PeerContext]:
-        """Create (once per shape) the symmetric-memory context for a flat buffer of `n_floats`; None when peer mapping is off or
-        impossible.  Collective: every rank must call it at the same point."""
-        if not self.peer_memory:
+        """A NEW symmetric-memory context for one FusedTrainStep (its flags count that step object's optimizer steps, so contexts
+        are never shared); None when peer mapping is off or impossible.  Collective: every rank must call it at the same point."""
+        if not self.peer_memory or self.peer_error is not None:
             return None
-        key = (n_floats, rows, delta_off, delta_n)
-        if self.peer is not None and getattr(self, '_peer_key', None) != key:
-            self.peer = None                                 # another step shape: a new context (the old one stays alive with its step)
-        if self.peer is None and self.peer_error is None:
-            ok = 1
-            try:
-                self.peer = PeerContext(n_floats, device, self.group, rows, delta_off, delta_n)
-                self._peer_key = key
-            except Exception as ex:                          # no P2P / fabric handles, old driver ...: NCCL stays the transport
-                self.peer_error = f'{type(ex).__name__}: {ex}'
-                ok = 0
-            t = torch.tensor([ok], dtype=torch.int32, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
-            if int(t.item()) == 0:                           # all ranks or none
-                self.peer = None
-                self.peer_error = self.peer_error or 'a peer rank could not map symmetric memory'
-        return self.peer
+        ok, ctx = 1, None
+        try:
+            ctx = PeerContext(n_floats, device, self.group, rows, delta_off, delta_n)
+        except Exception as ex:                              # no P2P / fabric handles, old driver ...: NCCL stays the transport
+            self.peer_error = f'{type(ex).__name__}: {ex}'
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        if int(t.item()) == 0:                               # all ranks or none
+            ctx = None
+            self.peer_error = self.peer_error or 'a peer rank could not map symmetric memory'
+        self.peer = ctx
+        return ctx
 
     # ---- BatchNorm statistics -----------------------------------------------------------
     def all_reduce_stats(self, sums: torch.Tensor, local_rows: int) -> int:
