@@ -222,7 +222,7 @@ def timed_kernels(lib, fn, n):
     lib.nrm_timing_enable(0)
     kern = {}
     for ln in cbuf.value.decode().strip().splitlines():
-        name, cnt, tot = ln.split()
+        name, cnt, tot = ln.split()[:3]
         kern[name] = {'launch_groups': int(cnt), 'ms': float(tot) / n}
     return kern
 

@@ -108,6 +108,13 @@ bool use_rowstacked() {
   return on;
 }
 
+// The FFMA forward of w1 streams at ~35 % of the HBM roofline once there are several tiles per SM; the tensor-core version only
+// pays when NRM_W1_FWD_TC=1 asks for it (kept for A/B runs): with <= 3 tiles per SM its per-CTA prologue is not amortised.
+bool w1_forward_on_tensor_cores(const Workspace&) {
+  static const bool on = getenv("NRM_W1_FWD_TC") != nullptr;
+  return on;
+}
+
 bool pdl_enabled() {
   static const bool on = getenv("NRM_NO_PDL") == nullptr;
   return on;
@@ -258,7 +265,8 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   }
   // xh = w1(xin_h)   (user_invariant_interest_model.py:78)
   NRM_CUDA(cudaStreamWaitEvent(s, ss->join0, 0));            // w1^T ready
-  { KernelTimer t("w1_forward", s); NRM_TRY(launch_w1_forward(P, w, s)); }
+  { KernelTimer t("w1_forward", s);
+    if (tc && use_rowstacked() && w1_forward_on_tensor_cores(w)) NRM_TRY(launch_w1_forward_tc(P, w, precision, s)); else NRM_TRY(launch_w1_forward(P, w, s)); }
   NRM_CUDA(cudaStreamWaitEvent(s, ss->join_tp, 0));          // join: derived weights, transposed head matrices, tp
   if (!tc) {
     { KernelTimer t("attention_forward_label", s); NRM_TRY(launch_attention_forward(in, P, w, 0, precision, s)); }
@@ -289,7 +297,9 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
   NRM_CUDA(cudaEventRecord(ss->fork2, s));
   NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork2, 0));
   // w1: dxin_h = dxh W1, dW1 = dxh^T xin_h, db1 = colsum(dxh)
-  { KernelTimer t("w1_backward", ss->stream); NRM_TRY(launch_w1_backward(P, w, G, ss->stream)); }
+  { KernelTimer t("w1_backward", ss->stream);
+    if (precision != NRM_PRECISION_FP32 && use_rowstacked()) NRM_TRY(launch_w1_backward_tc(P, w, G, precision, ss->stream));
+    else NRM_TRY(launch_w1_backward(P, w, G, ss->stream)); }
   NRM_CUDA(cudaEventRecord(ss->join2, ss->stream));
   { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
   { KernelTimer t("attention_finish", s);
@@ -334,7 +344,14 @@ extern "C" int nrm_timing_report(char* buf, size_t buf_bytes) {
       NRM_CUDA(cudaEventElapsedTime(&ms, t.beg[k], t.end[k]));
       total += ms;
     }
-    const int n = snprintf(buf + off, buf_bytes - off, "%s %d %.6f\n", t.name, t.used, total);
+    // optional 4th / 5th columns: start and end of the group's LAST recorded launch relative to the first event of the first group
+    // (a timeline: gaps and overlaps between groups, tools/step_timeline.py)
+    float t_beg = 0.f, t_end = 0.f;
+    if (t.used > 0 && g_ntimers > 0 && g_timers[0].used > 0) {
+      cudaEventElapsedTime(&t_beg, g_timers[0].beg[g_timers[0].used - 1], t.beg[t.used - 1]);
+      cudaEventElapsedTime(&t_end, g_timers[0].beg[g_timers[0].used - 1], t.end[t.used - 1]);
+    }
+    const int n = snprintf(buf + off, buf_bytes - off, "%s %d %.6f %.6f %.6f\n", t.name, t.used, total, t_beg, t_end);
     if (n < 0 || (size_t)n >= buf_bytes - off) break;
     off += (size_t)n;
   }

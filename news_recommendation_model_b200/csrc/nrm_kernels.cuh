@@ -20,6 +20,10 @@ int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, c
 int launch_w1_forward(const float* P, Workspace& w, cudaStream_t s);             // w.xin_h -> w.xh
 int launch_w1_backward(const float* P, Workspace& w, float* grads, cudaStream_t s);  // w.dxh -> w.dxin_h, w1 gradients
 
+// nrm_w1_tc.cu  (tensor-core tiles; precision = bf16 / bf16x3)
+int launch_w1_forward_tc(const float* P, Workspace& w, int precision, cudaStream_t s);
+int launch_w1_backward_tc(const float* P, Workspace& w, float* grads, int precision, cudaStream_t s);
+
 // nrm_attention.cu  (branch 0 = label attention on w1-projected features, 1 = text/img PCA)
 int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);
 int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s);

@@ -193,6 +193,12 @@ int launch_w1_forward(const float* P, Workspace& w, cudaStream_t s) {
   return NRM_OK;
 }
 
+int launch_w1_finish(Workspace& w, int nparts, float* G, cudaStream_t s) {
+  launch_pdl(w1_finish_kernel, dim3((W1_PART + 63) / 64), dim3(256), 0, s, w.splitk, nparts, G);
+  NRM_LAUNCH_CHECK("w1_finish_kernel");
+  return NRM_OK;
+}
+
 int launch_w1_backward(const float* P, Workspace& w, float* G, cudaStream_t s) {
   static DeviceOnce configured;                          // function attributes are per device
   if (configured.first_time()) {

@@ -71,7 +71,22 @@ buf = ctypes.create_string_buffer(8192)
 lib.nrm_timing_report(buf, 8192)
 lib.nrm_timing_enable(0)
 for ln in buf.value.decode().strip().splitlines():
-    name, cnt, tot = ln.split()
+    name, cnt, tot = ln.split()[:3]
     print(f'  {name:32s} {float(tot) / 8 * 1e3:8.1f} us')
+# whole step: FusedTrainStep, CUDA-graph replay, resident inputs (what bench.py reports as `value`)
+host = [make_batch(B, H, C, seed=99 + i, user_num=1000).pin() for i in range(4)]
+tr = nrm.FusedTrainStep(model, B, H, C, lr=1e-3, weight_decay=1e-5, nslots=4)
+slots = [tr.load(hb) for hb in host]
+torch.cuda.synchronize()
+for i in range(8):
+    tr.run(slots[i % 4])
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record()
+for i in range(40):
+    tr.run(slots[i % 4])
+e1.record()
+torch.cuda.synchronize()
+print(f'STEP {e0.elapsed_time(e1) / 40 * 1e3:.1f} us per step (graph replay, resident), {tr.launches_per_step} launches')
 print('ALL OK' if ok else 'SOME FAILED')
 sys.exit(0 if ok else 1)
