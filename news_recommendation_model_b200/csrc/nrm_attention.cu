@@ -511,7 +511,11 @@ int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, 
 }
 
 int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s) {
-  if (precision == NRM_PRECISION_BF16 || precision == NRM_PRECISION_BF16X3) return launch_attention_backward_tc(in, P, w, branch, precision, s);
+  if (precision == NRM_PRECISION_BF16 || precision == NRM_PRECISION_BF16X3) {
+    // text/img branch (no input gradients): the row-stacked kernel; label branch: item tiles (input gradients) for now
+    if (branch == 1 && use_rowstacked()) return launch_attention_backward_rs(w, branch, precision, false, s);
+    return launch_attention_backward_tc(in, P, w, branch, precision, s);
+  }
   if (precision != NRM_PRECISION_FP32) { set_error("attention: precision %d not built", precision); return NRM_EUNSUPPORTED; }
   const size_t smem = sizeof(AttSmemBwd);
   const int grid = att_bwd_grid(w.B);

@@ -25,39 +25,15 @@
 // pooled^T[k][c] = sum_h H[h][k] s[c][h] per chunk (M = 64, N = 16, accumulated over the chunks in TMEM), as in nrm_attention_tc.cu.
 //
 // SPLIT = 1: bf16 operands.  SPLIT = 3: hi + lo bf16 parts, A_hi W_hi + A_hi W_lo + A_lo W_hi (fp32-grade, "bf16x3").
-#include "nrm_kernels.cuh"
-#include <cstddef>
 
-#include "nrm_umma.cuh"
+#include "nrm_attention_rs.cuh"
 
 namespace nrm {
 namespace rs {
 
-// Optional per-role wait accounting (make EXTRA=-DNRM_RS_PROFILE; tools/rs_roleprof.py): in CTA 0, lane 0 of one warp per role
-// adds the clock64 cycles it spends inside each kind of mbarrier wait to g_rsprof[role * 8 + kind]; slot 7 = the role's total.
 #ifdef NRM_RS_PROFILE
 __device__ long long g_rsprof[64];
-#define RSPROF_WAIT(role, kind, stmt) do { const long long t__ = clock64(); stmt; if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_rsprof[(role) * 8 + (kind)] += clock64() - t__; } while (0)
-#define RSPROF_TOTAL_BEGIN const long long rsprof_t0 = clock64();
-#define RSPROF_TOTAL_END(role) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_rsprof[(role) * 8 + 7] += clock64() - rsprof_t0; } while (0)
-#else
-#define RSPROF_WAIT(role, kind, stmt) do { stmt; } while (0)
-#define RSPROF_TOTAL_BEGIN
-#define RSPROF_TOTAL_END(role) do { } while (0)
 #endif
-
-constexpr int THREADS = 832;                 // 26 warps
-constexpr int N_PROD = 8, N_EPI = 16;        // producer warps (sub-partition x K half), epilogue warps (sub-partition x column quarter)
-constexpr int W_PROD = 0, W_EPI = 8, W_MMA = 24, W_LOAD = 25;   // first warp of each role; warp % 4 = TMEM sub-partition for producers and epilogue
-constexpr int CG = 8;                        // candidates per unit
-constexpr int HCH = 64;                      // history rows per chunk
-constexpr int NSTAGE = 3;                    // history-chunk stages (the loader runs two chunks ahead)
-constexpr int HF_STRIDE = 68;                // floats per staged fp32 history row (272 B: conflict-free 16-byte reads across rows)
-constexpr uint32_t W_TILE = 16384;           // [64 j][128 k'] bf16, K-major, un-swizzled: (j, 8 kb) at kb*1024 + (j/8)*128 + (j%8)*16
-
-// weight image in global memory (att_prep_rs_kernel): per branch  W hi | W lo | w2[64] | b2 (+3 pad)
-constexpr int IMG_BRANCH_BYTES = 2 * (int)W_TILE + 64 * 4 + 16;
-__host__ __device__ constexpr int img_bytes() { return 2 * IMG_BRANCH_BYTES; }
 
 __global__ void __launch_bounds__(256)
 att_prep_rs_kernel(const float* __restrict__ P, unsigned char* __restrict__ img_all) {
@@ -82,41 +58,6 @@ att_prep_rs_kernel(const float* __restrict__ P, unsigned char* __restrict__ img_
   }
 }
 
-// ---- inline PTX not in nrm_umma.cuh ------------------------------------------------------------------------------------------
-// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 16 slice; A: 128 lanes x 8 columns (two bf16 per 32-bit column, even k in the low half)
-__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// this thread's lane, 8 consecutive 32-bit columns
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {       // a -> low half
-  const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&p);
-}
-// hi / lo split of two floats -> packed bf16 pairs: hi = bf16_rn(v), lo = bf16_rn(v - hi).  The two hi values come back as floats
-// with one shift and one mask of the packed word (6 instructions per pair).
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  hi = pack_bf16(a, b);
-  lo = pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
-}
-
-// ---- packed fp32 pairs (Blackwell fma.rn.f32x2 / mul / add): one issue slot for two lanes' worth of FP32 work -----------------------
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 struct Stage {
   float hf[HCH * HF_STRIDE];                       // fp32 history rows of the chunk (producers)
@@ -144,37 +85,7 @@ constexpr uint32_t COL_A = 128;        // 2 x (64 hi + 64 lo)   operand rows, K 
 constexpr uint32_t COL_POOL = 384;     // 2 x 32   pooled^T partials (candidate + 8 * column quarter)
 constexpr uint32_t TMEM_COLS = 512;
 
-struct Geo {
-  int B, H, C, G, nchunks;
-  __device__ __forceinline__ void unit(int u, int& branch, int& b, int& c0, int& ncg) const {
-    const int per_branch = B * G;
-    branch = u >= per_branch ? 1 : 0;
-    const int r = u - branch * per_branch;
-    b = r / G;
-    c0 = (r - b * G) * CG;
-    ncg = min(CG, C - c0);
-  }
-  __device__ __forceinline__ void chunk(int ci, int ncg, int& h0, int& hl, int& rows, int& ntiles) const {
-    h0 = ci * HCH;
-    hl = min(HCH, H - h0);
-    rows = ncg * hl;
-    ntiles = (rows + 127) >> 7;
-  }
-};
 
-__device__ __forceinline__ void arrive_warp(uint64_t* bar) {       // one arrival per warp, after all its lanes are done
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar);
-}
-
-// ---- loader: one history chunk + the unit's candidate vectors -> stage ---------------------------------------------------------
-// Both branches read fp32 rows [NH, 64] (label: the w1 projection xh; text/img: the PCA slice embed_rows_kernel wrote as fp32).
-// The copies are 16-byte cp.async (no registers, any number in flight): the loader issues chunk n + 2 before it finishes chunk n.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(umma::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void issue_stage(Stage& st, const float* __restrict__ rows, const float* __restrict__ e, int toff,
                                             const float* __restrict__ tpg, int H, int C, int b, int c0, int ncg, int h0, int hl) {
@@ -189,18 +100,6 @@ __device__ __forceinline__ void issue_stage(Stage& st, const float* __restrict__
   }
   cp_async_commit();
 }
-// flattened (unit, chunk) sequence of a CTA
-struct ChunkIter {
-  int u, ci, branch, b, c0, ncg, h0, hl, rows, ntiles;
-  __device__ __forceinline__ void set(const Geo& g, int u_, int ci_) {
-    u = u_; ci = ci_;
-    g.unit(u, branch, b, c0, ncg);
-    g.chunk(ci, ncg, h0, hl, rows, ntiles);
-  }
-  __device__ __forceinline__ void next(const Geo& g) {
-    if (ci + 1 < g.nchunks) set(g, u, ci + 1); else set(g, u + 1, 0);
-  }
-};
 
 template <int SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)

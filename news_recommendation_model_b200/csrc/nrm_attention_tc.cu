@@ -651,21 +651,27 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
             umma::tmem_ld32(my_tmem + BWD_COL_HID + cb * 32, v);
             if (act) {
               const float* tp = tt + half * 128 + 64 + cb * 32;
+              // packed pairs (fma.rn.f32x2): the epilogue is bound by issue slots
+              const f32x2 ds2 = pk(dsr, dsr);
+              f32x2 sacc2 = pk(0.f, 0.f);
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 float dh[8];
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
+                for (int jj = 0; jj < 8; jj += 2) {
                   const int j = j8 * 8 + jj;
-                  float gp;
-                  const float g = gelu_both(v[j] + tp[j], gp);
-                  const float w = sm.w2[cb * 32 + j];
-                  if (INPUT_GRADS) sacc = fmaf(g, w, sacc);
-                  dw2_acc[j] = fmaf(dsr, g, dw2_acc[j]);
-                  dh[jj] = dsr * w * gp;
+                  const float2 tpp = *reinterpret_cast<const float2*>(tp + j);
+                  const float2 wp = *reinterpret_cast<const float2*>(&sm.w2[cb * 32 + j]);
+                  f32x2 g, gp;
+                  gelu_both2(add2(pk(v[j], v[j + 1]), pk(tpp.x, tpp.y)), g, gp);
+                  const f32x2 w = pk(wp.x, wp.y);
+                  if (INPUT_GRADS) sacc2 = fma2(g, w, sacc2);
+                  upk(fma2(ds2, g, pk(dw2_acc[j], dw2_acc[j + 1])), dw2_acc[j], dw2_acc[j + 1]);
+                  upk(mul2(mul2(ds2, w), gp), dh[jj], dh[jj + 1]);
                 }
                 umma::store_operand8<NP>(sm.opBD[DH][half], umma::tile64_offset(row, cb * 4 + j8), umma::TILE64_BYTES, dh);
               }
+              if (INPUT_GRADS) { float s0, s1; upk(sacc2, s0, s1); sacc += s0 + s1; }
               if (ch == 0) db2_acc += dsr;
               if (INPUT_GRADS) sm.sc[((ch * 2 + half) * TC_MAXC + c) * 64 + row] = sacc;
             }
@@ -720,11 +726,16 @@ attention_backward_tc_kernel(const double* __restrict__ xh, const float* __restr
             float v[32];
             umma::tmem_ld32(my_tmem + BWD_COL_S + cb * 32, v);
             if (act) {
+              const f32x2 tk2 = pk(tk, tk);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                dwd_acc[j] = fmaf(tk, v[j], dwd_acc[j]);
-                if (DA_IN_REGS) da_acc[j] += v[j];
-                if (INPUT_GRADS) dt = fmaf(v[j], __ldg(Wd_rm + (cb * 32 + j) * 256 + row), dt);
+              for (int j = 0; j < 32; j += 2) {
+                const f32x2 v2 = pk(v[j], v[j + 1]);
+                upk(fma2(tk2, v2, pk(dwd_acc[j], dwd_acc[j + 1])), dwd_acc[j], dwd_acc[j + 1]);
+                if (DA_IN_REGS) upk(add2(pk(da_acc[j], da_acc[j + 1]), v2), da_acc[j], da_acc[j + 1]);
+                if (INPUT_GRADS) {
+                  dt = fmaf(v[j], __ldg(Wd_rm + (cb * 32 + j) * 256 + row), dt);
+                  dt = fmaf(v[j + 1], __ldg(Wd_rm + (cb * 32 + j + 1) * 256 + row), dt);
+                }
               }
             }
             if (INPUT_GRADS) {

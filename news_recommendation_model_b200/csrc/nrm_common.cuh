@@ -189,6 +189,8 @@ struct Workspace {
   float* head_part_w;  // [5][chunks][66*264+264] weight-gradient partials
   float* att_derived;  // [2][12420] derived attention weights (tensor-core paths)
   float* tp;           // [2][R,64]  tp = (Wb + Wc) t + b1 per candidate row and branch (tensor-core paths)
+  unsigned char* att_dhid;  // label branch, training: dhid tile images (hi | lo) exported by the row-stacked backward for the input-gradient kernel
+  float* att_sc;       // label branch, training: partial scores [tiles][4][128]
   float* att_rs_img;   // weight image of the row-stacked attention kernels (nrm_attention_rs.cu): bf16 operand tiles, hi | lo
   // backward (training only)
   float* da3; float* da2; float* da1;   // [R,66]
@@ -261,6 +263,37 @@ __device__ __forceinline__ float gelu_both(float x, float& grad) {
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float g; (void)gelu_both(x, g); return g;
 }
+// ---- packed fp32 pairs (Blackwell fma.rn.f32x2 / mul / add): one issue slot for two FP32 operations.  The attention kernels are
+// bound by issue slots on the CUDA cores (GELU, operand splits), so their element-wise math runs on pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// gelu(x) and d gelu / dx of a pair (same formulas as gelu_both):  q = 1/2 - 0.5 erfc(|x| / sqrt 2);  cdf = 1/2 + copysign(q, x);
+// gelu = x cdf;  gelu' = cdf + x pdf,  pdf = exp(-x^2 / 2) / sqrt(2 pi)
+__device__ __forceinline__ void gelu_both2(f32x2 x, f32x2& g, f32x2& gp) {
+  float a, b, ta, tb, ea, eb;
+  upk(x, a, b);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ta) : "f"(fmaf(fabsf(a), 0.23164189f, 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tb) : "f"(fmaf(fabsf(b), 0.23164189f, 1.0f)));
+  upk(mul2(mul2(x, x), pk(-0.72134752044448170368f, -0.72134752044448170368f)), ea, eb);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(ea));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(eb));
+  const f32x2 t2 = pk(ta, tb), e2 = pk(ea, eb);
+  f32x2 poly = fma2(t2, pk(0.5f * 1.061405429f, 0.5f * 1.061405429f), pk(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  poly = fma2(t2, poly, pk(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  poly = fma2(t2, poly, pk(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  poly = fma2(t2, poly, pk(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  poly = mul2(poly, t2);
+  float qa, qb;
+  upk(fma2(poly, mul2(e2, pk(-1.f, -1.f)), pk(0.5f, 0.5f)), qa, qb);            // 1/2 - half >= 0
+  const f32x2 cdf = add2(pk(copysignf(qa, a), copysignf(qb, b)), pk(0.5f, 0.5f));
+  g = mul2(x, cdf);
+  gp = fma2(mul2(x, pk(0.39894228040143267794f, 0.39894228040143267794f)), e2, cdf);
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 }  // namespace nrm
