@@ -210,6 +210,11 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
       w.att_part = (float*)take(f * 2 * (ffma > tc ? ffma : tc));
     }
     w.dtp = (float*)take(f * 2 * R * 64);
+    {
+      const size_t tiles = (size_t)attention_rs_tiles(B, H, C);
+      w.att_dhid = (unsigned char*)take(tiles * 2 * 16384);       // dhid tile images of the label branch (hi | lo)
+      w.att_sc = (float*)take(f * tiles * 512);
+    }
     w.att_dA = (float*)take(f * 2 * 4096);
     w.tp_part = (float*)take(f * 2 * ((R + 31) / 32) * (4096 + 64));
     w.splitk = (float*)take(f * (size_t)(64 * XIN + 64) * W1_SPLITS);   // per-CTA partials of the w1 weight / bias gradient

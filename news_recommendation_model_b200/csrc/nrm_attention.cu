@@ -512,8 +512,11 @@ int launch_attention_forward(const BatchPtrs& in, const float* P, Workspace& w, 
 
 int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w, int branch, int precision, cudaStream_t s) {
   if (precision == NRM_PRECISION_BF16 || precision == NRM_PRECISION_BF16X3) {
-    // text/img branch (no input gradients): the row-stacked kernel; label branch: item tiles (input gradients) for now
-    if (branch == 1 && use_rowstacked()) return launch_attention_backward_rs(w, branch, precision, false, s);
+    if (use_rowstacked()) {
+      // row-stacked kernels: sums over rows (weight gradients, dtp); the label branch exports dhid for its input-gradient kernel
+      NRM_TRY(launch_attention_backward_rs(w, branch, precision, branch == 0, s));
+      return branch == 0 ? launch_attention_input_grad_rs(w, precision, s) : NRM_OK;
+    }
     return launch_attention_backward_tc(in, P, w, branch, precision, s);
   }
   if (precision != NRM_PRECISION_FP32) { set_error("attention: precision %d not built", precision); return NRM_EUNSUPPORTED; }

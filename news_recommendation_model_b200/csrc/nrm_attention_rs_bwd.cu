@@ -492,6 +492,263 @@ attention_backward_rs_kernel(const float* __restrict__ rows_g, int branch, int B
   if (warp == 0) umma::tmem_dealloc(tmem, B_TMEM_COLS);
 }
 
+// =====================================================================================================
+// input gradients of the label branch from the exported dhid tiles
+// =====================================================================================================
+constexpr int IG_THREADS = 608;                  // 19 warps: 16 epilogue (warp % 4 = TMEM sub-partition, warp / 4 = column quarter), MMA, 2 loaders
+constexpr int IG_W_MMA = 16, IG_W_LOAD = 17, IG_W_TILES = 18;
+constexpr int ZS = 68;                           // floats per row of the exchange tiles
+
+struct StageI {
+  float hf[HCH * HF_STRIDE];
+  __align__(16) float tv[CG][64];
+  __align__(16) float dpv[CG][64];
+};
+template <int NP>
+struct SmemI {
+  __align__(128) unsigned char W[2][W_TILE];
+  __align__(128) unsigned char dhid[2][NP * DHID_PART];   // two tile stages, each hi | lo (the exported image, copied by the TMA engine)
+  __align__(16) float sc[2][4][128];                      // partial scores of the tile
+  StageI st[NST];
+  __align__(16) float Z[128 * ZS];                        // per row: t (.) X + Y + s dP   (what the row adds to dh of its history row)
+  __align__(16) float Uu[128 * ZS];                       // per row: h (.) X              (what the row adds to dt of its candidate)
+  float b2;
+  __align__(16) float zrow[64];
+  uint64_t stage_full[NST], stage_empty[NST], tile_full[2], tile_empty[2], xy_full[2], xy_empty[2], wbar;
+  uint32_t tmem_base;
+};
+
+template <int SPLIT>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+attention_input_grad_rs_kernel(const float* __restrict__ rows_g, int B, int H, int C, const unsigned char* __restrict__ img,
+                               const float* __restrict__ e, const float* __restrict__ de, const unsigned char* __restrict__ dhid_g,
+                               const float* __restrict__ sc_g, float* __restrict__ dxh, float* __restrict__ dxt) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int NP = SPLIT == 3 ? 2 : 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemI<NP>& sm = *reinterpret_cast<SmemI<NP>*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t TILE_BYTES = NP * DHID_PART;
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { umma::mbar_init(&sm.stage_full[i], 1); umma::mbar_init(&sm.stage_empty[i], 16); }
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(&sm.tile_full[i], 1); umma::mbar_init(&sm.tile_empty[i], 1 + 16);     // product's commit + 16 epilogue warps (scores)
+      umma::mbar_init(&sm.xy_full[i], 1); umma::mbar_init(&sm.xy_empty[i], 16);
+    }
+    umma::mbar_init(&sm.wbar, 1);
+    const uint32_t bar = umma::smem_u32(&sm.wbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2u * W_TILE) : "memory");
+    for (int p = 0; p < 2; ++p)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(umma::smem_u32(sm.W[p])),
+                   "l"(img + (size_t)p * W_TILE), "r"(W_TILE), "r"(bar) : "memory");
+  }
+  if (tid < 64) {
+    sm.zrow[tid] = 0.f;
+    if (tid == 0) sm.b2 = 0.f;
+  }
+  if (warp == 0) umma::tmem_alloc(&sm.tmem_base, 256);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  GeoB g;
+  g.B = B; g.H = H; g.C = C; g.G = (C + CG - 1) / CG; g.nchunks = (H + HCH - 1) / HCH;
+  // more than two candidate groups per impression: whole impressions per CTA, so that dxh is accumulated group after group by ONE
+  // CTA (plain read-modify-write, fixed order); exactly two groups: each adds once into a zeroed buffer (commutative); one: plain store
+  int u0, u1;
+  if (g.G > 2) {
+    u0 = (int)((long long)B * blockIdx.x / gridDim.x) * g.G;
+    u1 = (int)((long long)B * (blockIdx.x + 1) / gridDim.x) * g.G;
+  } else {
+    const long long U = (long long)B * g.G;
+    u0 = (int)(U * blockIdx.x / gridDim.x); u1 = (int)(U * (blockIdx.x + 1) / gridDim.x);
+  }
+  const long long tile0 = g.tile_base(u0);
+
+  if (warp == IG_W_LOAD) {
+    // =========================================== loader ===========================================
+    const int total = (u1 - u0) * g.nchunks;
+    ChunkIterB it_issue, it_fin;
+    int n_issued = 0;
+    auto issue = [&]() {
+      const int s = n_issued % NST;
+      umma::mbar_wait(&sm.stage_empty[s], ((n_issued / NST) & 1) ^ 1);
+      StageI& st = sm.st[s];
+      const float* src = rows_g + ((long long)it_issue.b * H + it_issue.h0) * 64;
+      for (int i = lane; i < it_issue.hl * 16; i += 32) cp_async16(&st.hf[(i >> 4) * HF_STRIDE + 4 * (i & 15)], src + 4 * i);
+      for (int i = lane; i < it_issue.ncg * 16; i += 32) {
+        const int c = i >> 4, q = i & 15;
+        const long long rc = (long long)it_issue.b * C + it_issue.c0 + c;
+        cp_async16(&st.tv[c][4 * q], e + rc * E + E_XT + 4 * q);
+        cp_async16(&st.dpv[c][4 * q], de + rc * E + E_LAB + 4 * q);
+      }
+      cp_async_commit();
+      ++n_issued;
+      if (n_issued < total) it_issue.next(g);
+    };
+    if (total > 0) { it_issue.set(g, u0, 0); it_fin.set(g, u0, 0); }
+    while (n_issued < total && n_issued < NST - 1) issue();
+    for (int k = 0; k < total; ++k) {
+      if (n_issued - k - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
+      arrive_warp(&sm.stage_full[k % NST]);
+      if (k + 1 < total) it_fin.next(g);
+      if (n_issued < total) issue();
+    }
+  } else if (warp == IG_W_TILES) {
+    // =========================================== tile loader: dhid images + scores, bulk copies by the TMA engine ===========================================
+    if (lane == 0) {
+      uint32_t tile_seq = 0;
+      for (int u = u0; u < u1; ++u) {
+        int b, c0, ncg; g.unit(u, b, c0, ncg);
+        for (int ci = 0; ci < g.nchunks; ++ci) {
+          int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
+          for (int ti = 0; ti < ntiles; ++ti, ++tile_seq) {
+            const uint32_t ts = tile_seq & 1;
+            umma::mbar_wait(&sm.tile_empty[ts], ((tile_seq >> 1) & 1) ^ 1);
+            const uint32_t bar = umma::smem_u32(&sm.tile_full[ts]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(TILE_BYTES + 2048u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(umma::smem_u32(sm.dhid[ts])),
+                         "l"(dhid_g + (size_t)(tile0 + tile_seq) * TILE_BYTES), "r"(TILE_BYTES), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(umma::smem_u32(sm.sc[ts])),
+                         "l"(sc_g + (size_t)(tile0 + tile_seq) * 512), "r"(2048u), "r"(bar) : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp == IG_W_MMA) {
+    // =========================================== MMA issuer ===========================================
+    if (umma::elect_one()) {
+      umma::mbar_wait(&sm.wbar, 0);
+      constexpr uint32_t IDESC_XY = umma::make_idesc_bf16(128, 128, false, true);     // dhid (K-major) x W read MN-major: da[r][k'] = sum_j dhid[r][j] W[j][k']
+      const umma::Operand w_mn = umma::make_operand(umma::smem_u32(sm.W[0]), 128, 1024, 256, W_TILE);
+      uint32_t tile_seq = 0;
+      for (int u = u0; u < u1; ++u) {
+        int b, c0, ncg; g.unit(u, b, c0, ncg);
+        for (int ci = 0; ci < g.nchunks; ++ci) {
+          int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
+          for (int ti = 0; ti < ntiles; ++ti, ++tile_seq) {
+            const uint32_t ts = tile_seq & 1, ph = (tile_seq >> 1) & 1;
+            umma::mbar_wait(&sm.tile_full[ts], ph);
+            umma::mbar_wait(&sm.xy_empty[ts], ph ^ 1);
+            umma::fence_after_sync();
+            umma::mma_product<SPLIT, 4>(tmem + 128 * ts, umma::make_operand(umma::smem_u32(sm.dhid[ts]), LBO128, 128, 2 * LBO128, DHID_PART), w_mn,
+                                        IDESC_XY, false);
+            umma::mma_commit(&sm.tile_empty[ts]);
+            umma::mma_commit(&sm.xy_full[ts]);
+          }
+        }
+      }
+    }
+  } else if (warp < 16) {
+    // =========================================== epilogue ===========================================
+    const int sp = warp & 3, cq = warp >> 2;
+    const uint32_t lane_sel = (uint32_t)(32 * sp) << 16;
+    const int et = tid;                                     // 0 .. 511
+    const int rh = et >> 3, rk8 = et & 7;                   // dh reduction: history row, 8-column block
+    const int tslot = et >> 6, tk = et & 63;                // dt reduction: candidate slot, column
+    uint32_t chunk_seq = 0, tile_seq = 0;
+    for (int u = u0; u < u1; ++u) {
+      int b, c0, ncg; g.unit(u, b, c0, ncg);
+      const int gidx = u - (u / g.G) * g.G;
+      float dt_acc = 0.f;
+      for (int ci = 0; ci < g.nchunks; ++ci, ++chunk_seq) {
+        int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
+        const uint32_t s = chunk_seq % NST, ph = (chunk_seq / NST) & 1;
+        const StageI& st = sm.st[s];
+        const float inv_hl = 1.0f / (float)hl;
+        umma::mbar_wait(&sm.stage_full[s], ph);
+        float dh_acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dh_acc[i] = 0.f;
+        for (int ti = 0; ti < ntiles; ++ti, ++tile_seq) {
+          const uint32_t ts = tile_seq & 1, tph = (tile_seq >> 1) & 1;
+          umma::mbar_wait(&sm.xy_full[ts], tph);
+          umma::fence_after_sync();
+          float X[16], Y[16];
+          umma::tmem_ld16(tmem + 128 * ts + 16 * cq + lane_sel, X);
+          umma::tmem_ld16(tmem + 128 * ts + 64 + 16 * cq + lane_sel, Y);
+          umma::fence_before_sync();
+          arrive_warp(&sm.xy_empty[ts]);
+          const int r = 32 * sp + lane, rg = ti * 128 + r;
+          const bool valid = rg < rows;
+          const int cl = valid ? __float2int_rz(((float)rg + 0.5f) * inv_hl) : 0, hloc = valid ? rg - cl * hl : 0;
+          // tile_full completed before xy_full (the product waited for it): the scores are visible
+          const float srow = valid ? ((sm.sc[ts][0][r] + sm.sc[ts][1][r]) + sm.sc[ts][2][r]) + sm.sc[ts][3][r] : 0.f;
+          arrive_warp(&sm.tile_empty[ts]);
+          const float* hrow = valid ? &st.hf[hloc * HF_STRIDE + 16 * cq] : sm.zrow;
+          const float* trow = &st.tv[cl][16 * cq];
+          const float* dprow = &st.dpv[cl][16 * cq];
+          float* zr = &sm.Z[r * ZS + 16 * cq];
+          float* ur = &sm.Uu[r * ZS + 16 * cq];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(trow + 4 * q), p4 = *reinterpret_cast<const float4*>(dprow + 4 * q);
+            const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * q);
+            float4 z, uu;
+            z.x = fmaf(t4.x, X[4 * q], fmaf(srow, p4.x, Y[4 * q]));         uu.x = h4.x * X[4 * q];
+            z.y = fmaf(t4.y, X[4 * q + 1], fmaf(srow, p4.y, Y[4 * q + 1])); uu.y = h4.y * X[4 * q + 1];
+            z.z = fmaf(t4.z, X[4 * q + 2], fmaf(srow, p4.z, Y[4 * q + 2])); uu.z = h4.z * X[4 * q + 2];
+            z.w = fmaf(t4.w, X[4 * q + 3], fmaf(srow, p4.w, Y[4 * q + 3])); uu.w = h4.w * X[4 * q + 3];
+            if (!valid) { z = make_float4(0.f, 0.f, 0.f, 0.f); uu = z; }
+            *reinterpret_cast<float4*>(zr + 4 * q) = z;
+            *reinterpret_cast<float4*>(ur + 4 * q) = uu;
+          }
+          asm volatile("bar.sync 1, 512;\n" ::: "memory");              // Z / U of the tile complete
+          // dh[h][8 k8 ..]: the rows (c, h) of this tile, candidates in order
+          if (rh < hl) {
+#pragma unroll 1
+            for (int c = 0; c < ncg; ++c) {
+              const int rr = c * hl + rh - ti * 128;
+              if (rr >= 0 && rr < 128) {
+                const float4 a = *reinterpret_cast<const float4*>(&sm.Z[rr * ZS + 8 * rk8]), bq = *reinterpret_cast<const float4*>(&sm.Z[rr * ZS + 8 * rk8 + 4]);
+                dh_acc[0] += a.x; dh_acc[1] += a.y; dh_acc[2] += a.z; dh_acc[3] += a.w;
+                dh_acc[4] += bq.x; dh_acc[5] += bq.y; dh_acc[6] += bq.z; dh_acc[7] += bq.w;
+              }
+            }
+          }
+          // dt[slot][k]: the rows of candidate `slot` inside this tile, in row order
+          if (tslot < ncg) {
+            const int lo = max(tslot * hl - ti * 128, 0), hi = min(min((tslot + 1) * hl - ti * 128, 128), rows - ti * 128);
+            for (int rr = lo; rr < hi; ++rr) dt_acc += sm.Uu[rr * ZS + tk];
+          }
+          asm volatile("bar.sync 2, 512;\n" ::: "memory");              // exchange tiles free for the next tile
+        }
+        // dh of this chunk's history rows
+        if (rh < hl) {
+          float* dst = dxh + ((long long)b * H + h0 + rh) * 64 + 8 * rk8;
+          if (g.G == 1 || (g.G > 2 && gidx == 0)) {
+            *reinterpret_cast<float4*>(dst) = make_float4(dh_acc[0], dh_acc[1], dh_acc[2], dh_acc[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(dh_acc[4], dh_acc[5], dh_acc[6], dh_acc[7]);
+          } else if (g.G == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(dst + i, dh_acc[i]);
+          } else {
+            float4 a = *reinterpret_cast<float4*>(dst), bq = *reinterpret_cast<float4*>(dst + 4);
+            a.x += dh_acc[0]; a.y += dh_acc[1]; a.z += dh_acc[2]; a.w += dh_acc[3];
+            bq.x += dh_acc[4]; bq.y += dh_acc[5]; bq.z += dh_acc[6]; bq.w += dh_acc[7];
+            *reinterpret_cast<float4*>(dst) = a; *reinterpret_cast<float4*>(dst + 4) = bq;
+          }
+        }
+        arrive_warp(&sm.stage_empty[s]);
+      }
+      // dt of the unit's candidates + the direct ec path (user_model.py:31: e_concat holds the candidate's own features)
+      if (tslot < ncg) {
+        const long long rc = (long long)b * C + c0 + tslot;
+        dxt[rc * 64 + tk] = dt_acc + __ldg(de + rc * E + E_XT + tk);
+      }
+      if (g.G > 2) __threadfence();                          // the next group of this impression (same CTA) reads dxh back
+    }
+  }
+
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
 }  // namespace rsb
 
 static int rs_bwd_grid(const Workspace& w) {
@@ -524,8 +781,26 @@ static int launch_bwd_rs(Workspace& w, int branch, cudaStream_t s) {
   return NRM_OK;
 }
 
-// weights-side backward of one branch (0 = label, 1 = text/img).  The label branch also needs the input gradients: they still come
-// from the item-tile kernel (nrm_attention_tc.cu) until attention_input_grad_rs_kernel replaces it.
+template <int SPLIT>
+static int launch_ig_rs(Workspace& w, cudaStream_t s) {
+  constexpr int NP = SPLIT == 3 ? 2 : 1;
+  const size_t smem = sizeof(rsb::SmemI<NP>);
+  const int G = (w.C + rs::CG - 1) / rs::CG;
+  const int grid = (int)std::min<long long>(G > 2 ? (long long)w.B : (long long)w.B * G, (long long)sm_count());
+  if (G == 2) NRM_CUDA(cudaMemsetAsync(w.dxh, 0, sizeof(float) * (size_t)w.NH * 64, s));     // the two groups of an impression add into it
+  NRM_CUDA(cudaFuncSetAttribute(rsb::attention_input_grad_rs_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  launch_pdl(rsb::attention_input_grad_rs_kernel<SPLIT>, dim3(grid), dim3(rsb::IG_THREADS), smem, s, w.xh, w.B, w.H, w.C,
+             reinterpret_cast<const unsigned char*>(w.att_rs_img), w.e, w.de, reinterpret_cast<const unsigned char*>(w.att_dhid), w.att_sc, w.dxh, w.dxt);
+  NRM_LAUNCH_CHECK("attention_input_grad_rs_kernel");
+  return NRM_OK;
+}
+// label branch: dh (-> w.dxh) and dt (-> w.dxt) from the tiles exported by launch_attention_backward_rs(..., export_dhid = true)
+int launch_attention_input_grad_rs(Workspace& w, int precision, cudaStream_t s) {
+  return precision == NRM_PRECISION_BF16 ? launch_ig_rs<1>(w, s) : launch_ig_rs<3>(w, s);
+}
+
+// weights-side backward of one branch (0 = label, 1 = text/img).  The label branch exports its dhid tiles for
+// launch_attention_input_grad_rs.
 int launch_attention_backward_rs(Workspace& w, int branch, int precision, bool export_dhid, cudaStream_t s) {
   if (precision == NRM_PRECISION_BF16) return export_dhid ? launch_bwd_rs<1, true>(w, branch, s) : launch_bwd_rs<1, false>(w, branch, s);
   return export_dhid ? launch_bwd_rs<3, true>(w, branch, s) : launch_bwd_rs<3, false>(w, branch, s);

@@ -43,6 +43,7 @@ int launch_attention_prep_rs(const float* P, Workspace& w, cudaStream_t s);     
 int launch_attention_forward_rs(const BatchPtrs& in, Workspace& w, int precision, cudaStream_t s);   // both branches, one launch
 // nrm_attention_rs_bwd.cu: sums over rows (weight gradients, dtp) of one branch; export_dhid also writes the dhid tiles / scores
 int launch_attention_backward_rs(Workspace& w, int branch, int precision, bool export_dhid, cudaStream_t s);
+int launch_attention_input_grad_rs(Workspace& w, int precision, cudaStream_t s);   // label branch: dxh, dxt from the exported tiles
 long long attention_rs_tiles(int B, int H, int C);
 bool use_rowstacked();
 
