@@ -57,20 +57,20 @@ struct SmemB {
   __align__(128) unsigned char dhid[2][DHID_PART]; // dhid of the tile, hi | lo
   __align__(128) unsigned char sel[SEL_BYTES];     // row -> candidate slot selection (0 / 1)
   StageB st[NST];
-  float ds_part[2][2][128];                        // [tile parity][K half][row]  partial dP . h
+  float ds_part[4][2][128];                        // [tile % 4][K half][row]  partial dP . h
   float red[16][17];                               // final reduction of dw2 / db2
   float w2[64];
   float b2;
   __align__(16) float zrow[64];
-  uint64_t stage_full[NST], stage_empty[NST], a_full, a_empty, d_full[2], d_empty[2], as_full, e1_done, dw_done, dtp_full[2], dtp_empty[2], wbar, fin;
+  uint64_t stage_full[NST], stage_empty[NST], a_full[2], a_empty[2], d_full[2], d_empty[2], as_full, e1_done, dw_done, dtp_full[2], dtp_empty[2], wbar, fin;
   uint32_t tmem_base;
 };
 
 // TMEM columns
 constexpr uint32_t C_D = 0;            // 2 x 64   hid accumulators
-constexpr uint32_t C_A = 128;          // 64 hi + 64 lo   operand rows (K = 128 bf16 = 64 columns per part)
-constexpr uint32_t C_DW = 256;         // 64   dW^T accumulator [128 k'][64 j], whole CTA
-constexpr uint32_t C_DTP = 320;        // 2 x 8   dtp^T [64 j][8 slots] per unit
+constexpr uint32_t C_A = 128;          // 2 x (64 hi + 64 lo)   operand rows (K = 128 bf16 = 64 columns per part), double-buffered
+constexpr uint32_t C_DW = 384;         // 64   dW^T accumulator [128 k'][64 j], whole CTA
+constexpr uint32_t C_DTP = 448;        // 2 x 8   dtp^T [64 j][8 slots] per unit
 constexpr uint32_t B_TMEM_COLS = 512;
 
 struct GeoB {
@@ -113,6 +113,27 @@ struct ChunkIterB {
   }
 };
 
+// flattened (unit, chunk, tile) sequence of a CTA
+struct TileIterB {
+  int u, ci, ti, b, c0, ncg, h0, hl, rows, ntiles;
+  uint32_t chunk_seq, tile_seq;
+  bool live;
+  __device__ __forceinline__ void load(const GeoB& g) { g.unit(u, b, c0, ncg); g.chunk(ci, ncg, h0, hl, rows, ntiles); }
+  __device__ __forceinline__ void init(const GeoB& g, int u0, int u1) {
+    u = u0; ci = 0; ti = 0; chunk_seq = 0; tile_seq = 0;
+    live = u0 < u1;
+    if (live) load(g);
+  }
+  __device__ __forceinline__ void next(const GeoB& g, int u1) {
+    ++tile_seq;
+    if (++ti < ntiles) return;
+    ti = 0; ++chunk_seq;
+    if (++ci == g.nchunks) { ci = 0; ++u; }
+    live = u < u1;
+    if (live) load(g);
+  }
+};
+
 __device__ __forceinline__ void issue_stage_b(StageB& st, const float* __restrict__ rows, const float* __restrict__ e, const float* __restrict__ de,
                                               int toff, int poff, const float* __restrict__ tpg, int H, int C, int b, int c0, int ncg, int h0, int hl) {
   const int lane = threadIdx.x & 31;
@@ -149,8 +170,8 @@ attention_backward_rs_kernel(const float* __restrict__ rows_g, int branch, int B
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(&sm.d_full[i], 1); umma::mbar_init(&sm.d_empty[i], N_EPI);
       umma::mbar_init(&sm.dtp_full[i], 1); umma::mbar_init(&sm.dtp_empty[i], 4);
+      umma::mbar_init(&sm.a_full[i], N_PROD); umma::mbar_init(&sm.a_empty[i], 1);
     }
-    umma::mbar_init(&sm.a_full, N_PROD); umma::mbar_init(&sm.a_empty, 1);
     umma::mbar_init(&sm.as_full, N_PROD); umma::mbar_init(&sm.e1_done, N_EPI); umma::mbar_init(&sm.dw_done, 1);
     umma::mbar_init(&sm.wbar, 1); umma::mbar_init(&sm.fin, 1);
     const uint32_t bar = umma::smem_u32(&sm.wbar);
@@ -236,10 +257,10 @@ attention_backward_rs_kernel(const float* __restrict__ rows_g, int branch, int B
           int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
           for (int ti = 0; ti < ntiles; ++ti, ++tile_seq) {
             const uint32_t ds = tile_seq & 1, dph = (tile_seq >> 1) & 1;
-            umma::mbar_wait(&sm.a_full, tile_seq & 1);
+            umma::mbar_wait(&sm.a_full[ds], dph);
             umma::mbar_wait(&sm.d_empty[ds], dph ^ 1);
             umma::fence_after_sync();
-            const uint32_t d = tmem + C_D + 64 * ds, a = tmem + C_A;
+            const uint32_t d = tmem + C_D + 64 * ds, a = tmem + C_A + 128 * ds;
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
               const uint32_t ap = (t == 2) ? 64u : 0u;
@@ -247,7 +268,7 @@ attention_backward_rs_kernel(const float* __restrict__ rows_g, int branch, int B
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks) mma_bf16_ts(d, a + ap + 8 * ks, wd + (uint64_t)(ks * 128), IDESC_HID, (t > 0 || ks > 0) ? 1u : 0u);
             }
-            umma::mma_commit(&sm.a_empty);
+            umma::mma_commit(&sm.a_empty[ds]);
             umma::mma_commit(&sm.d_full[ds]);
             if (pend) second_group();
             pend = true; p_seq = tile_seq; p_ps = unit_seq & 1; p_pph = (unit_seq >> 1) & 1;
@@ -261,92 +282,104 @@ attention_backward_rs_kernel(const float* __restrict__ rows_g, int branch, int B
     }
   } else if (warp < W_EPI) {
     // =========================================== producers ===========================================
+    // Software-pipelined over the flattened tile sequence: phase 1 (operand row -> tensor memory, partial ds) of tile t + 1 runs BEFORE
+    // phase 2 (shared-memory copies for the weight-gradient product) of tile t, which has to wait for the previous tile's second
+    // product group; the operand rows are double-buffered in tensor memory, so the next hid product never waits for that chain.
     const int sp = warp & 3, khalf = warp >> 2;
     const uint32_t lane_sel = (uint32_t)(32 * sp) << 16;
-    uint32_t chunk_seq = 0, tile_seq = 0;
-    for (int u = u0; u < u1; ++u) {
-      int b, c0, ncg; g.unit(u, b, c0, ncg);
-      for (int ci = 0; ci < g.nchunks; ++ci, ++chunk_seq) {
-        int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
-        const uint32_t s = chunk_seq % NST, ph = (chunk_seq / NST) & 1;
-        const StageB& st = sm.st[s];
-        const float inv_hl = 1.0f / (float)hl;
-        umma::mbar_wait(&sm.stage_full[s], ph);
-        for (int ti = 0; ti < ntiles; ++ti, ++tile_seq) {
-          // ---- phase 1: operand row -> tensor memory, partial ds
-          umma::mbar_wait(&sm.a_empty, (tile_seq & 1) ^ 1);
-          umma::fence_after_sync();
-          const int r = 32 * sp + lane, rg = ti * 128 + r;
-          const bool valid = rg < rows;
-          const int cl = valid ? __float2int_rz(((float)rg + 0.5f) * inv_hl) : 0, hloc = valid ? rg - cl * hl : 0;
-          const uint32_t a_hi = tmem + C_A + lane_sel, a_lo = a_hi + 64;
-          const float* hrow = valid ? &st.hf[hloc * HF_STRIDE] : sm.zrow;
-          const float* trow = &st.tv[cl][0];
-          const float* dprow = &st.dpv[cl][0];
-          float dsp = 0.f;
+    const int r = 32 * sp + lane;
+    TileIterB p1, p2;
+    p1.init(g, u0, u1);
+    p2 = p1;
+    auto phase1 = [&](const TileIterB& it) {
+      const uint32_t s = it.chunk_seq % NST;
+      const StageB& st = sm.st[s];
+      if (it.ti == 0) umma::mbar_wait(&sm.stage_full[s], (it.chunk_seq / NST) & 1);
+      const uint32_t as = it.tile_seq & 1;
+      umma::mbar_wait(&sm.a_empty[as], ((it.tile_seq >> 1) & 1) ^ 1);
+      umma::fence_after_sync();
+      const int rg = it.ti * 128 + r;
+      const bool valid = rg < it.rows;
+      const int cl = valid ? __float2int_rz(((float)rg + 0.5f) * (1.0f / (float)it.hl)) : 0, hloc = valid ? rg - cl * it.hl : 0;
+      const uint32_t a_hi = tmem + C_A + 128 * as + lane_sel, a_lo = a_hi + 64;
+      const float* hrow = valid ? &st.hf[hloc * HF_STRIDE] : sm.zrow;
+      const float* trow = &st.tv[cl][0];
+      const float* dprow = &st.dpv[cl][0];
+      float dsp = 0.f;
 #pragma unroll
-          for (int kq = 0; kq < 2; ++kq) {
-            const int kp = 2 * khalf + kq;
-            uint32_t ph_hi[8], ph_lo[8], hh[8], hl_[8];
+      for (int kq = 0; kq < 2; ++kq) {
+        const int kp = 2 * khalf + kq;
+        uint32_t ph_hi[8], ph_lo[8], hh[8], hl_[8];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int kb = 2 * kp + q;
-              const float4 h0v = *reinterpret_cast<const float4*>(hrow + 8 * kb), h1v = *reinterpret_cast<const float4*>(hrow + 8 * kb + 4);
-              const float4 t0v = *reinterpret_cast<const float4*>(trow + 8 * kb), t1v = *reinterpret_cast<const float4*>(trow + 8 * kb + 4);
-              const float4 p0v = *reinterpret_cast<const float4*>(dprow + 8 * kb), p1v = *reinterpret_cast<const float4*>(dprow + 8 * kb + 4);
-              const float hv[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
-              const float tv8[8] = {t0v.x, t0v.y, t0v.z, t0v.w, t1v.x, t1v.y, t1v.z, t1v.w};
-              const float pv8[8] = {p0v.x, p0v.y, p0v.z, p0v.w, p1v.x, p1v.y, p1v.z, p1v.w};
+        for (int q = 0; q < 2; ++q) {
+          const int kb = 2 * kp + q;
+          const float4 h0v = *reinterpret_cast<const float4*>(hrow + 8 * kb), h1v = *reinterpret_cast<const float4*>(hrow + 8 * kb + 4);
+          const float4 t0v = *reinterpret_cast<const float4*>(trow + 8 * kb), t1v = *reinterpret_cast<const float4*>(trow + 8 * kb + 4);
+          const float4 p0v = *reinterpret_cast<const float4*>(dprow + 8 * kb), p1v = *reinterpret_cast<const float4*>(dprow + 8 * kb + 4);
+          const float hv[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+          const float tv8[8] = {t0v.x, t0v.y, t0v.z, t0v.w, t1v.x, t1v.y, t1v.z, t1v.w};
+          const float pv8[8] = {p0v.x, p0v.y, p0v.z, p0v.w, p1v.x, p1v.y, p1v.z, p1v.w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) dsp = fmaf(hv[i], pv8[i], dsp);
+          for (int i = 0; i < 8; ++i) dsp = fmaf(hv[i], pv8[i], dsp);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (NP == 2) {
-                  split2(hv[2 * i] * tv8[2 * i], hv[2 * i + 1] * tv8[2 * i + 1], ph_hi[4 * q + i], ph_lo[4 * q + i]);
-                  split2(hv[2 * i], hv[2 * i + 1], hh[4 * q + i], hl_[4 * q + i]);
-                } else {
-                  ph_hi[4 * q + i] = pack_bf16(hv[2 * i] * tv8[2 * i], hv[2 * i + 1] * tv8[2 * i + 1]);
-                  hh[4 * q + i] = pack_bf16(hv[2 * i], hv[2 * i + 1]);
-                }
-              }
-            }
-            tmem_st8(a_hi + 8 * kp, ph_hi);
-            tmem_st8(a_hi + 32 + 8 * kp, hh);
-            if (NP == 2) { tmem_st8(a_lo + 8 * kp, ph_lo); tmem_st8(a_lo + 32 + 8 * kp, hl_); }
-          }
-          sm.ds_part[tile_seq & 1][khalf][r] = dsp;          // rows past the end read the zero row: 0
-          tmem_st_wait();
-          umma::fence_before_sync();
-          arrive_warp(&sm.a_full);
-          // ---- phase 2: once the previous tile's weight-gradient product has read them, refill the shared-memory copies: this thread's
-          // operand row (read back from tensor memory: no recomputation) and the row -> candidate selection entries
-          umma::mbar_wait(&sm.dw_done, (tile_seq & 1) ^ 1);
-          umma::fence_after_sync();
-#pragma unroll
-          for (int kq = 0; kq < 2; ++kq) {
-            const int kp = 2 * khalf + kq;
-#pragma unroll
-            for (int pt = 0; pt < NP; ++pt) {
-              uint32_t w8[8];
-              tmem_ld8u(a_hi + 64 * pt + 8 * kp, w8);                          // t (.) h half: k' blocks 2 kp, 2 kp + 1
-              *reinterpret_cast<uint4*>(sm.arow[pt] + tile_off(r, 2 * kp)) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-              *reinterpret_cast<uint4*>(sm.arow[pt] + tile_off(r, 2 * kp + 1)) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
-              tmem_ld8u(a_hi + 64 * pt + 32 + 8 * kp, w8);                     // h half: k' blocks 8 + 2 kp, 9 + 2 kp
-              *reinterpret_cast<uint4*>(sm.arow[pt] + tile_off(r, 8 + 2 * kp)) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-              *reinterpret_cast<uint4*>(sm.arow[pt] + tile_off(r, 9 + 2 * kp)) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+          for (int i = 0; i < 4; ++i) {
+            if (NP == 2) {
+              split2(hv[2 * i] * tv8[2 * i], hv[2 * i + 1] * tv8[2 * i + 1], ph_hi[4 * q + i], ph_lo[4 * q + i]);
+              split2(hv[2 * i], hv[2 * i + 1], hh[4 * q + i], hl_[4 * q + i]);
+            } else {
+              ph_hi[4 * q + i] = pack_bf16(hv[2 * i] * tv8[2 * i], hv[2 * i + 1] * tv8[2 * i + 1]);
+              hh[4 * q + i] = pack_bf16(hv[2 * i], hv[2 * i + 1]);
             }
           }
-          if (khalf == 0) {
-            unsigned char* sp_ = sm.sel + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 2u;
-#pragma unroll
-            for (int c = 0; c < CG; ++c) *reinterpret_cast<unsigned short*>(sp_ + c * 16) = (valid && cl == c) ? (unsigned short)0x3f80 : (unsigned short)0;
-          }
-          umma::fence_before_sync();
-          umma::fence_async_smem();
-          arrive_warp(&sm.as_full);
         }
-        arrive_warp(&sm.stage_empty[s]);
+        tmem_st8(a_hi + 8 * kp, ph_hi);
+        tmem_st8(a_hi + 32 + 8 * kp, hh);
+        if (NP == 2) { tmem_st8(a_lo + 8 * kp, ph_lo); tmem_st8(a_lo + 32 + 8 * kp, hl_); }
       }
+      sm.ds_part[it.tile_seq & 3][khalf][r] = dsp;          // rows past the end read the zero row: 0
+      tmem_st_wait();
+      umma::fence_before_sync();
+      arrive_warp(&sm.a_full[as]);
+      if (it.ti == it.ntiles - 1) arrive_warp(&sm.stage_empty[s]);      // last read of this chunk's stage by this warp
+    };
+    auto phase2 = [&](const TileIterB& it) {
+      // once the previous tile's weight-gradient product has read them, refill the shared-memory copies: this thread's operand row
+      // (read back from tensor memory: no recomputation) and the row -> candidate selection entries
+      const uint32_t as = it.tile_seq & 1;
+      const int rg = it.ti * 128 + r;
+      const bool valid = rg < it.rows;
+      const int cl = valid ? __float2int_rz(((float)rg + 0.5f) * (1.0f / (float)it.hl)) : 0;
+      const uint32_t a_hi = tmem + C_A + 128 * as + lane_sel;
+      umma::mbar_wait(&sm.dw_done, (it.tile_seq & 1) ^ 1);
+      umma::fence_after_sync();
+#pragma unroll
+      for (int kq = 0; kq < 2; ++kq) {
+        const int kp = 2 * khalf + kq;
+#pragma unroll
+        for (int pt = 0; pt < NP; ++pt) {
+          uint32_t w8[8];
+          tmem_ld8u(a_hi + 64 * pt + 8 * kp, w8);                          // t (.) h half: k' blocks 2 kp, 2 kp + 1
+          *reinterpret_cast<uint4*>(sm.arow[pt] + tile_off(r, 2 * kp)) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+          *reinterpret_cast<uint4*>(sm.arow[pt] + tile_off(r, 2 * kp + 1)) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+          tmem_ld8u(a_hi + 64 * pt + 32 + 8 * kp, w8);                     // h half: k' blocks 8 + 2 kp, 9 + 2 kp
+          *reinterpret_cast<uint4*>(sm.arow[pt] + tile_off(r, 8 + 2 * kp)) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+          *reinterpret_cast<uint4*>(sm.arow[pt] + tile_off(r, 9 + 2 * kp)) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+        }
+      }
+      if (khalf == 0) {
+        unsigned char* sp_ = sm.sel + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 2u;
+#pragma unroll
+        for (int c = 0; c < CG; ++c) *reinterpret_cast<unsigned short*>(sp_ + c * 16) = (valid && cl == c) ? (unsigned short)0x3f80 : (unsigned short)0;
+      }
+      umma::fence_before_sync();
+      umma::fence_async_smem();
+      arrive_warp(&sm.as_full);
+    };
+    if (p1.live) { phase1(p1); p1.next(g, u1); }
+    while (p2.live) {
+      if (p1.live) { phase1(p1); p1.next(g, u1); }
+      phase2(p2);
+      p2.next(g, u1);
     }
   } else {
     // =========================================== epilogue ===========================================
@@ -400,7 +433,7 @@ attention_backward_rs_kernel(const float* __restrict__ rows_g, int branch, int B
           const bool valid = rg < rows;
           const int cl = valid ? __float2int_rz(((float)rg + 0.5f) * inv_hl) : 0;
           const float* tp = &st.tpv[cl][16 * cq];
-          const float dsr = valid ? sm.ds_part[ds][0][r] + sm.ds_part[ds][1][r] : 0.f;
+          const float dsr = valid ? sm.ds_part[tile_seq & 3][0][r] + sm.ds_part[tile_seq & 3][1][r] : 0.f;
           const f32x2 ds2 = pk(dsr, dsr);
           uint32_t dh_hi[8], dh_lo[8];
           f32x2 sacc2 = pk(0.f, 0.f);
@@ -649,12 +682,14 @@ attention_input_grad_rs_kernel(const float* __restrict__ rows_g, int B, int H, i
     const uint32_t lane_sel = (uint32_t)(32 * sp) << 16;
     const int et = tid;                                     // 0 .. 511
     const int rh = et >> 3, rk8 = et & 7;                   // dh reduction: history row, 8-column block
-    const int tslot = et >> 6, tk = et & 63;                // dt reduction: candidate slot, column
+    // dt reduction: (candidate slot, 4-column block, quarter of the slot's rows); the four quarters (adjacent lanes) are combined with
+    // shuffles in a fixed order, so that no thread walks more than 16 rows
+    const int tslot = et >> 6, tk4 = (et >> 2) & 15, tq = et & 3;
     uint32_t chunk_seq = 0, tile_seq = 0;
     for (int u = u0; u < u1; ++u) {
       int b, c0, ncg; g.unit(u, b, c0, ncg);
       const int gidx = u - (u / g.G) * g.G;
-      float dt_acc = 0.f;
+      float4 dt_acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int ci = 0; ci < g.nchunks; ++ci, ++chunk_seq) {
         int h0, hl, rows, ntiles; g.chunk(ci, ncg, h0, hl, rows, ntiles);
         const uint32_t s = chunk_seq % NST, ph = (chunk_seq / NST) & 1;
@@ -713,7 +748,11 @@ attention_input_grad_rs_kernel(const float* __restrict__ rows_g, int B, int H, i
           // dt[slot][k]: the rows of candidate `slot` inside this tile, in row order
           if (tslot < ncg) {
             const int lo = max(tslot * hl - ti * 128, 0), hi = min(min((tslot + 1) * hl - ti * 128, 128), rows - ti * 128);
-            for (int rr = lo; rr < hi; ++rr) dt_acc += sm.Uu[rr * ZS + tk];
+#pragma unroll 4
+            for (int rr = lo + tq; rr < hi; rr += 4) {
+              const float4 v = *reinterpret_cast<const float4*>(&sm.Uu[rr * ZS + 4 * tk4]);
+              dt_acc.x += v.x; dt_acc.y += v.y; dt_acc.z += v.z; dt_acc.w += v.w;
+            }
           }
           asm volatile("bar.sync 2, 512;\n" ::: "memory");              // exchange tiles free for the next tile
         }
@@ -736,9 +775,17 @@ attention_input_grad_rs_kernel(const float* __restrict__ rows_g, int B, int H, i
         arrive_warp(&sm.stage_empty[s]);
       }
       // dt of the unit's candidates + the direct ec path (user_model.py:31: e_concat holds the candidate's own features)
-      if (tslot < ncg) {
-        const long long rc = (long long)b * C + c0 + tslot;
-        dxt[rc * 64 + tk] = dt_acc + __ldg(de + rc * E + E_XT + tk);
+      {
+        float4 t = dt_acc;                                  // quarters 0..3 of the rows: (q0 + q1) + (q2 + q3)
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, 1); t.y += __shfl_xor_sync(0xffffffffu, t.y, 1);
+        t.z += __shfl_xor_sync(0xffffffffu, t.z, 1); t.w += __shfl_xor_sync(0xffffffffu, t.w, 1);
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, 2); t.y += __shfl_xor_sync(0xffffffffu, t.y, 2);
+        t.z += __shfl_xor_sync(0xffffffffu, t.z, 2); t.w += __shfl_xor_sync(0xffffffffu, t.w, 2);
+        if (tslot < ncg && tq == 0) {
+          const long long rc = (long long)b * C + c0 + tslot;
+          const float4 d = __ldg(reinterpret_cast<const float4*>(de + rc * E + E_XT) + tk4);
+          *reinterpret_cast<float4*>(dxt + rc * 64 + 4 * tk4) = make_float4(t.x + d.x, t.y + d.y, t.z + d.z, t.w + d.w);
+        }
       }
       if (g.G > 2) __threadfence();                          // the next group of this impression (same CTA) reads dxh back
     }
