@@ -227,6 +227,9 @@ def timed_kernels(lib, fn, n):
     return kern
 
 
+ROWSTACKED = set() if os.environ.get('NRM_ATT_ITEM_TILES') else {'attention_input_grad_label'}
+
+
 def algorithmic_work(B, H, C, total_params):
     """Algorithmic FLOPs / bytes of every timed kernel group of one training step (SURVEY 8d per-impression figures x B;
     DESIGN.md section 4).  EVERY group is a roofline candidate: the dominant one is whichever takes longest."""
@@ -236,7 +239,11 @@ def algorithmic_work(B, H, C, total_params):
     return {
         'attention_forward_label': ('tensor', 2.0 * P * D * D), 'attention_forward_textimg': ('tensor', 2.0 * P * D * D),
         'attention_forward': ('tensor', 2 * 2.0 * P * D * D),    # both branches in one launch (tensor-core paths)
-        'attention_backward_label': ('tensor', 3 * 2.0 * P * D * D), 'attention_backward_textimg': ('tensor', 2 * 2.0 * P * D * D),
+        # backward products per pair: hid recompute + weight gradient (both branches); + input gradient (label branch: its own
+        # kernel on the row-stacked path, inside attention_backward_label on the item-tile path)
+        'attention_backward_label': ('tensor', (2 if 'attention_input_grad_label' in ROWSTACKED else 3) * 2.0 * P * D * D),
+        'attention_input_grad_label': ('tensor', 2.0 * P * D * D),
+        'attention_backward_textimg': ('tensor', 2 * 2.0 * P * D * D),
         'head_forward': ('tensor', head), 'head_backward': ('tensor', 2 * head),
         'w1_backward': ('tensor', 2 * 2.0 * 66 * 64 * NH),
         'embed_rows': ('hbm', 8.0 * (80 * NH + 81 * R) + 4.0 * (66 * NH + 64 * NH + 136 * R)),

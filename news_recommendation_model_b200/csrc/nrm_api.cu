@@ -297,6 +297,11 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
   SideStream* ss = side_stream(s);
   if (ss == nullptr) { set_error("encoder_backward: cannot create the side stream"); return NRM_ECUDA; }
   { KernelTimer t("attention_backward_label", s); NRM_TRY(launch_attention_backward(in, P, w, 0, precision, s)); }
+  if (precision != NRM_PRECISION_FP32 && use_rowstacked()) {
+    // row-stacked kernels: the label branch's input gradients (dxh, dxt) come from the dhid tiles the kernel above exported
+    KernelTimer t("attention_input_grad_label", s);
+    NRM_TRY(launch_attention_input_grad_rs(w, precision, s));
+  }
   // fork: the w1 backward only needs dxh (label attention); it runs on the side stream under the text/img attention
   // backward and the reductions of the attention weight gradients
   NRM_CUDA(cudaEventRecord(ss->fork2, s));

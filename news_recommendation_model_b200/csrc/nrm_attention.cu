@@ -514,8 +514,7 @@ int launch_attention_backward(const BatchPtrs& in, const float* P, Workspace& w,
   if (precision == NRM_PRECISION_BF16 || precision == NRM_PRECISION_BF16X3) {
     if (use_rowstacked()) {
       // row-stacked kernels: sums over rows (weight gradients, dtp); the label branch exports dhid for its input-gradient kernel
-      NRM_TRY(launch_attention_backward_rs(w, branch, precision, branch == 0, s));
-      return branch == 0 ? launch_attention_input_grad_rs(w, precision, s) : NRM_OK;
+      return launch_attention_backward_rs(w, branch, precision, branch == 0, s);
     }
     return launch_attention_backward_tc(in, P, w, branch, precision, s);
   }

@@ -94,7 +94,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   int spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 4000) asm volatile("trap;\n");        // 4000 x <= 1 ms
+#ifdef NRM_WAIT_NANOSLEEP
+    asm volatile("nanosleep.u32 %0;\n" ::"n"(NRM_WAIT_NANOSLEEP));      // experiment: fewer wake-ups of a waiting warp
+#endif
+    if (++spins > 40000000) asm volatile("trap;\n");     // a protocol error must not wedge the GPU
   }
 }
 

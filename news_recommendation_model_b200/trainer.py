@@ -262,6 +262,8 @@ class FusedTrainStep:
             s.compact = wire.CompactBatch(*[torch.zeros((self.B,) + tuple(getattr(batch, f).shape[1:]), dtype=getattr(batch, f).dtype, device=self.dev)
                                             for f in batch.__dataclass_fields__])
             self._expand(s)                                  # first launch of the kernel outside any graph capture
+            # the zero fills / the expansion above run on the compute stream: the H2D copies below must not overtake them
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(self.copy_stream):
             if s.used:
                 self.copy_stream.wait_event(s.consumed)
