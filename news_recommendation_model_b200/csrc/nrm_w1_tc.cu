@@ -139,8 +139,40 @@ w1_forward_tc_kernel(const float* __restrict__ xin, const float* __restrict__ P,
   if (warp == 0) umma::tmem_dealloc(tmem, 64);
 }
 
+// fp32 rows already staged in shared memory (row-major, `cols` floats per row, cp.async) -> K-major bf16 tile(s)
+template <int NP, int KB>
+__device__ __forceinline__ void convert_staged(const float* __restrict__ stg, int cols, int nr, unsigned char* tile, uint32_t part, int one_col) {
+  for (int it = threadIdx.x; it < ROWS * KB; it += THREADS) {
+    const int r = it & (ROWS - 1), kb = it >> 7;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (r < nr) {
+      const float* p = stg + r * cols + kb * 8;
+      if (kb * 8 + 8 <= cols) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 x = *reinterpret_cast<const float2*>(p + 2 * i); v[2 * i] = x.x; v[2 * i + 1] = x.y; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (kb * 8 + i < cols) v[i] = p[i];
+      }
+      if (one_col >= 0 && (one_col >> 3) == kb) v[one_col & 7] = 1.0f;
+    }
+    umma::store_operand8<NP>(tile, tile_off(r, kb), part, v);
+  }
+}
+// a tile of rows is one contiguous block of global memory: 16-byte cp.async, every request in flight at once
+__device__ __forceinline__ void stage_rows(float* stg, const float* __restrict__ src, int nfloats) {
+  const int n4 = nfloats >> 2;                            // tile starts are multiples of 128 rows: 16-byte aligned; nfloats is even
+  for (int i = threadIdx.x; i < n4; i += THREADS)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(umma::smem_u32(stg + 4 * i)), "l"(src + 4 * i) : "memory");
+  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += THREADS) stg[i] = __ldg(src + i);
+}
+
 template <int NP>
 struct SmemBwd {
+  __align__(16) float stg_d[ROWS * 64];                 // fp32 staging of the NEXT tile (cp.async), filled while the products of the current one run
+  __align__(16) float stg_x[ROWS * XIN];
   __align__(128) unsigned char ds[NP * D_TILE];         // dxh tile  [128 r][64 j]
   __align__(128) unsigned char xs[NP * X_TILE];         // xin tile  [128 r][80 k], column 66 = 1
   __align__(128) unsigned char wt[NP * KX * 64 * 2];    // W1^T      [80 k][64 j]
@@ -173,14 +205,30 @@ w1_backward_tc_kernel(const float* __restrict__ xin, const float* __restrict__ d
   uint32_t phase = 0;
   bool started = false;
   const long long ntiles = (NH + ROWS - 1) / ROWS;
+  if ((long long)blockIdx.x < ntiles) {
+    const long long r0 = (long long)blockIdx.x * ROWS;
+    const int nr = (int)min((long long)ROWS, NH - r0);
+    stage_rows(sm.stg_d, dxh + r0 * 64, nr * 64);
+    stage_rows(sm.stg_x, xin + r0 * XIN, nr * XIN);
+  }
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long r0 = tile * ROWS;
     const int nr = (int)min((long long)ROWS, NH - r0);
-    convert_rows<NP, 8>(dxh, 64, r0, nr, sm.ds, D_TILE, -1);
-    convert_rows<NP, KX / 8>(xin, XIN, r0, nr, sm.xs, X_TILE, XIN);            // column 66 := 1 -> db1 comes out of the weight product
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();                                   // staged rows visible; the previous tile's products have completed (waited below)
+    convert_staged<NP, 8>(sm.stg_d, 64, nr, sm.ds, D_TILE, -1);
+    convert_staged<NP, KX / 8>(sm.stg_x, XIN, nr, sm.xs, X_TILE, XIN);         // column 66 := 1 -> db1 comes out of the weight product
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
+    {                                                  // the next tile travels while this one is multiplied and written out
+      const long long nt = tile + gridDim.x;
+      if (nt < ntiles) {
+        const int nnr = (int)min((long long)ROWS, NH - nt * ROWS);
+        stage_rows(sm.stg_d, dxh + nt * ROWS * 64, nnr * 64);
+        stage_rows(sm.stg_x, xin + nt * ROWS * XIN, nnr * XIN);
+      }
+    }
     if (warp == 0 && umma::elect_one()) {
       umma::fence_after_sync();
       umma::mma_product<SPLIT, 4>(tmem + COL_DX, op_k(umma::smem_u32(sm.ds), D_TILE),
@@ -253,7 +301,7 @@ static int launch_bwd(const float* P, Workspace& w, float* G, cudaStream_t s) {
   constexpr int NP = SPLIT == 3 ? 2 : 1;
   const size_t smem = sizeof(w1tc::SmemBwd<NP>);
   const long long ntiles = (w.NH + w1tc::ROWS - 1) / w1tc::ROWS;
-  const int grid = (int)min(ntiles, (long long)min(2 * sm_count(), W1_SPLITS));
+  const int grid = (int)min(ntiles, (long long)min(sm_count(), W1_SPLITS));      // one CTA per SM (157 KB of shared memory), tiles in a grid-stride loop
   NRM_CUDA(cudaFuncSetAttribute(w1tc::w1_backward_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   launch_pdl(w1tc::w1_backward_tc_kernel<SPLIT>, dim3(grid), dim3(w1tc::THREADS), smem, s, w.xin_h, w.dxh, P, w.dxin_h, w.NH, w.splitk);
   NRM_LAUNCH_CHECK("w1_backward_tc_kernel");
