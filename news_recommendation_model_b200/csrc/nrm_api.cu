@@ -255,7 +255,9 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork0, 0));
   NRM_TRY(launch_head_transpose(P, w, ss->stream));          // includes w1^T for the history projection below
   NRM_CUDA(cudaEventRecord(ss->join0, ss->stream));
-  if (tc) { NRM_TRY(launch_attention_prep(P, w, ss->stream)); NRM_TRY(launch_attention_prep_rs(P, w, ss->stream)); }
+  if (tc) {                                                  // derived weights of the path in use (weights only)
+    if (use_rowstacked()) NRM_TRY(launch_attention_prep_rs(P, w, ss->stream)); else NRM_TRY(launch_attention_prep(P, w, ss->stream));
+  }
   { KernelTimer t("embed_rows", s);
     NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
   // fork: the per-candidate vectors tp (they need the candidate rows of e) run under the w1 projection; then, for the
