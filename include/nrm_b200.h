@@ -121,6 +121,7 @@ int         nrm_peer_wait_consumed(const void* adam_state, const void* peer_ctx,
 int         nrm_peer_allsum_stats(const double* local, int which, double* out, const void* adam_state, const void* peer_ctx, void* stream);
 
 int         nrm_debug_rsprof(long long* host_out64);   /* row-stacked attention kernels: per-role wait cycles (-DNRM_RS_PROFILE builds) */
+int         nrm_debug_headprof(long long* host_out32); /* tensor-core head kernels: the same (-DNRM_RS_PROFILE builds) */
 int         nrm_debug_tcprof(long long* host_out32);
 
 /* ---- flat parameter layout (reference state_dict order) ---- */
@@ -157,13 +158,14 @@ int nrm_forward(const double* x_history, const double* x_target, long long x_tar
  * nrm_forward_encoder writes e_concat and bn_sums[2][264] (double: column sums and sums
  * of squares over this rank's B*C rows, may be null to keep them in the workspace only);
  * the caller all-reduces bn_sums and calls nrm_forward_head with the GLOBAL row count
- * (bn_sums null / bn_global_rows 0 = use this rank's own statistics). */
+ * (bn_sums null / bn_global_rows 0 = use this rank's own statistics).  `precision` is the one given to
+ * nrm_forward_encoder (it selects the tensor-core head, whose weight images that call prepares). */
 int nrm_forward_encoder(const double* x_history, const double* x_target, long long x_target_batch_stride,
                         const double* x_global, long long x_global_batch_stride,
                         int B, int H, int C, const float* params, int mode, int precision,
                         double* bn_sums, void* workspace, size_t workspace_bytes, void* stream);
 int nrm_forward_head(int B, int H, int C, const float* params, float* bn_running_mean, float* bn_running_var,
-                     long long* bn_num_batches_tracked, int mode,
+                     long long* bn_num_batches_tracked, int mode, int precision,
                      const double* bn_sums, long long bn_global_rows,
                      float* logits, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -179,8 +181,15 @@ int nrm_backward(const double* x_history, const double* x_target, long long x_ta
                  int B, int H, int C, const float* params, int mode, int precision,
                  const float* dlogits, float* grads,
                  void* workspace, size_t workspace_bytes, void* stream);
-int nrm_backward_head(int B, int H, int C, const float* params, const float* dlogits, float* grads,
+int nrm_backward_head(int B, int H, int C, const float* params, int precision, const float* dlogits, float* grads,
                       double* bn_bwd_sums, void* workspace, size_t workspace_bytes, void* stream);
+/* As nrm_backward_head, but the head's five weight gradients (needed by the optimizer only) are left running on the
+ * library's side stream of `stream`; the NEXT nrm_backward_encoder on the same stream joins them before it returns, so
+ * `grads` is complete after that call as usual.  For callers that put a cross-rank exchange of the BatchNorm sums
+ * between the two calls (FusedTrainStep with synchronised BatchNorm); a caller that reads the head's weight gradients
+ * between the calls (bucketed all-reduce, engine.backward_params) uses nrm_backward_head. */
+int nrm_backward_head_deferred(int B, int H, int C, const float* params, int precision, const float* dlogits, float* grads,
+                               double* bn_bwd_sums, void* workspace, size_t workspace_bytes, void* stream);
 int nrm_backward_encoder(const double* x_history, const double* x_target, long long x_target_batch_stride,
                          const double* x_global, long long x_global_batch_stride,
                          int B, int H, int C, const float* params, int mode, int precision,

@@ -30,6 +30,7 @@ SIGNATURES = {
     'nrm_debug_mma_microbench': (i32, [vp, i32, i32, i32, vp]),
     'nrm_debug_tcprof': (i32, [vp]),
     'nrm_debug_rsprof': (i32, [vp]),
+    'nrm_debug_headprof': (i32, [vp]),
     'nrm_layout_entries': (i32, []),
     'nrm_layout_name': (C.c_char_p, [i32]),
     'nrm_layout_offset': (ll, [i32]),
@@ -39,9 +40,10 @@ SIGNATURES = {
     'nrm_workspace_e_offset': (sz, [i32, i32, i32, i32]),
     'nrm_forward': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp]),
     'nrm_forward_encoder': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, vp, sz, vp]),
-    'nrm_forward_head': (i32, [i32, i32, i32, vp, vp, vp, vp, i32, vp, ll, vp, vp, sz, vp]),
+    'nrm_forward_head': (i32, [i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, ll, vp, vp, sz, vp]),
     'nrm_backward': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, vp, vp, sz, vp]),
-    'nrm_backward_head': (i32, [i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
+    'nrm_backward_head': (i32, [i32, i32, i32, vp, i32, vp, vp, vp, vp, sz, vp]),
+    'nrm_backward_head_deferred': (i32, [i32, i32, i32, vp, i32, vp, vp, vp, vp, sz, vp]),
     'nrm_backward_encoder': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, ll, vp, vp, sz, vp]),
     'nrm_loss_scratch_bytes': (sz, [i32, i32]),
     'nrm_loss_forward': (i32, [vp, vp, ll, vp, vp, i32, i32, f32, vp, vp, sz, vp]),

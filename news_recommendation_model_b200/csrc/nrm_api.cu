@@ -79,6 +79,7 @@ KernelTimer::~KernelTimer() {
 struct SideStream {
   int dev; cudaStream_t caller;
   cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp, fork3, join3, fork4, join4;
+  bool head_wgrad_pending = false;     // nrm_backward_head_deferred ran on `caller`; the next nrm_backward_encoder joins join4
 };
 // One side stream + event set per (device, caller stream): two models / threads that drive different streams of one device
 // never share fork / join events (a wait can only ever bind to its own caller's record).  Created under a mutex on first use
@@ -192,6 +193,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   w.att_derived = (float*)take(f * 2 * 12420);
   w.tp = (float*)take(f * 2 * R * 64);
   w.att_rs_img = (float*)take(attention_rs_image_bytes());
+  w.head_img = (float*)take(head_tc_image_bytes());
   if (training) {
     w.da3 = (float*)take(f * R * HID); w.da2 = (float*)take(f * R * HID); w.da1 = (float*)take(f * R * HID);
     w.dy = (float*)take(f * R * E);
@@ -233,6 +235,12 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   return off;
 }
 
+// NRM_HEAD_FFMA=1 keeps the scoring head on the FFMA kernels (nrm_head_fused.cu) in the tensor-core precisions too
+static bool head_on_tensor_cores(int precision) {
+  static const bool ffma = [] { const char* e = getenv("NRM_HEAD_FFMA"); return e != nullptr && e[0] == '1'; }();
+  return precision != NRM_PRECISION_FP32 && use_rowstacked() && !ffma;
+}
+
 static int check_shape(const char* fn, int B, int H, int C) {
   if (B <= 0 || H <= 0 || C <= 0) { set_error("%s: B, H, C must be positive (got %d, %d, %d)", fn, B, H, C); return NRM_EINVAL; }
   if (((long long)B * H + (long long)B * C) * 6 >= (1LL << 31)) { set_error("%s: batch too large for 32-bit entry ids", fn); return NRM_EINVAL; }
@@ -257,6 +265,7 @@ static int encoder_forward(const BatchPtrs& in, const float* P, Workspace& w, in
   NRM_CUDA(cudaEventRecord(ss->join0, ss->stream));
   if (tc) {                                                  // derived weights of the path in use (weights only)
     if (use_rowstacked()) NRM_TRY(launch_attention_prep_rs(P, w, ss->stream)); else NRM_TRY(launch_attention_prep(P, w, ss->stream));
+    if (head_on_tensor_cores(precision)) NRM_TRY(launch_head_images_tc(P, w, precision, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, ss->stream));
   }
   { KernelTimer t("embed_rows", s);
     NRM_TRY(launch_embed_rows(in, P, w, (mode & NRM_MODE_KEEP_FOR_BWD) != 0, s)); }
@@ -371,6 +380,7 @@ extern "C" int nrm_timing_report(char* buf, size_t buf_bytes) {
 }
 // per-role wait cycles of the row-stacked attention kernels (development builds with -DNRM_RS_PROFILE); reads and clears
 extern "C" int nrm_debug_rsprof(long long* host_out64) { return rsprof_read(host_out64); }
+extern "C" int nrm_debug_headprof(long long* host_out32) { return headprof_read(host_out32); }
 extern "C" const char* nrm_last_error(void) { return g_err; }
 extern "C" int nrm_layout_entries(void) { return kLayoutEntries; }
 extern "C" const char* nrm_layout_name(int i) { return (i >= 0 && i < kLayoutEntries) ? kLayout[i].name : nullptr; }
@@ -414,7 +424,7 @@ extern "C" int nrm_forward_encoder(const double* x_history, const double* x_targ
 }
 
 extern "C" int nrm_forward_head(int B, int H, int C, const float* params, float* bn_running_mean, float* bn_running_var,
-                                  long long* bn_num_batches_tracked, int mode, const double* bn_sums,
+                                  long long* bn_num_batches_tracked, int mode, int precision, const double* bn_sums,
                                   long long bn_global_rows, float* logits, void* workspace, size_t workspace_bytes,
                                   void* stream) {
   const int training = mode & NRM_MODE_BN_BATCH_STATS;
@@ -426,6 +436,9 @@ extern "C" int nrm_forward_head(int B, int H, int C, const float* params, float*
   const double* sums = bn_sums ? bn_sums : w.bn_sums;
   const long long rows = bn_global_rows > 0 ? bn_global_rows : w.R;
   KernelTimer t("head_forward", (cudaStream_t)stream);
+  if (head_on_tensor_cores(precision))
+    return launch_head_forward_tc(params, w, precision, bn_running_mean, bn_running_var, bn_num_batches_tracked, training,
+                                  (mode & NRM_MODE_KEEP_FOR_BWD) != 0, sums, rows, logits, (cudaStream_t)stream);
   return launch_head_forward(params, w, bn_running_mean, bn_running_var, bn_num_batches_tracked, training,
                              (mode & NRM_MODE_KEEP_FOR_BWD) != 0, sums, rows,
                              logits, (cudaStream_t)stream);
@@ -437,21 +450,49 @@ extern "C" int nrm_forward(const double* x_history, const double* x_target, long
                            float* logits, void* workspace, size_t workspace_bytes, void* stream) {
   NRM_TRY(nrm_forward_encoder(x_history, x_target, xt_bs, x_global, xg_bs, B, H, C, params, mode, precision, nullptr,
                               workspace, workspace_bytes, stream));
-  return nrm_forward_head(B, H, C, params, bn_running_mean, bn_running_var, bn_num_batches_tracked, mode, nullptr, 0,
+  return nrm_forward_head(B, H, C, params, bn_running_mean, bn_running_var, bn_num_batches_tracked, mode, precision, nullptr, 0,
                             logits, workspace, workspace_bytes, stream);
 }
 
-extern "C" int nrm_backward_head(int B, int H, int C, const float* params, const float* dlogits, float* grads,
-                                   double* bn_bwd_sums, void* workspace, size_t workspace_bytes, void* stream) {
-  NRM_TRY(check_shape("nrm_backward_head", B, H, C));
-  if (!params || !dlogits || !grads) { set_error("nrm_backward_head: null pointer"); return NRM_EINVAL; }
+static int backward_head(const char* fn, bool defer_wgrad, int B, int H, int C, const float* params, int precision, const float* dlogits, float* grads,
+                         double* bn_bwd_sums, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape(fn, B, H, C));
+  if (!params || !dlogits || !grads) { set_error("%s: null pointer", fn); return NRM_EINVAL; }
   Workspace w;
-  NRM_TRY(get_workspace("nrm_backward_head", w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
+  NRM_TRY(get_workspace(fn, w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
   cudaStream_t s = (cudaStream_t)stream;
-  { KernelTimer t("head_backward", s); NRM_TRY(launch_head_backward(params, w, dlogits, grads, s)); }
+  const bool tc = head_on_tensor_cores(precision);
+  const int tiles = tc ? head_tc_tiles(w.R) : 0;
+  if (!defer_wgrad) {
+    KernelTimer t("head_backward", s);
+    if (tc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
+    NRM_TRY(launch_head_backward_bn(w, grads, s, tiles));
+    NRM_TRY(launch_head_backward_wgrad(params, w, grads, s, tiles));
+  } else {
+    SideStream* ss = side_stream(s);
+    if (ss == nullptr) { set_error("%s: cannot create the side stream", fn); return NRM_ECUDA; }
+    KernelTimer t("head_backward", s);
+    if (tc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
+    NRM_CUDA(cudaEventRecord(ss->fork4, s));
+    NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork4, 0));
+    NRM_TRY(launch_head_backward_wgrad(params, w, grads, ss->stream, tiles));
+    NRM_CUDA(cudaEventRecord(ss->join4, ss->stream));
+    ss->head_wgrad_pending = true;
+    NRM_TRY(launch_head_backward_bn(w, grads, s, tiles));
+  }
   if (bn_bwd_sums != nullptr && bn_bwd_sums != w.bn_bwd_sums)
     NRM_CUDA(cudaMemcpyAsync(bn_bwd_sums, w.bn_bwd_sums, sizeof(double) * 2 * E, cudaMemcpyDeviceToDevice, s));
   return NRM_OK;
+}
+
+extern "C" int nrm_backward_head(int B, int H, int C, const float* params, int precision, const float* dlogits, float* grads,
+                                 double* bn_bwd_sums, void* workspace, size_t workspace_bytes, void* stream) {
+  return backward_head("nrm_backward_head", false, B, H, C, params, precision, dlogits, grads, bn_bwd_sums, workspace, workspace_bytes, stream);
+}
+
+extern "C" int nrm_backward_head_deferred(int B, int H, int C, const float* params, int precision, const float* dlogits, float* grads,
+                                          double* bn_bwd_sums, void* workspace, size_t workspace_bytes, void* stream) {
+  return backward_head("nrm_backward_head_deferred", true, B, H, C, params, precision, dlogits, grads, bn_bwd_sums, workspace, workspace_bytes, stream);
 }
 
 extern "C" int nrm_backward_encoder(const double* x_history, const double* x_target, long long xt_bs,
@@ -468,7 +509,13 @@ extern "C" int nrm_backward_encoder(const double* x_history, const double* x_tar
   const double* sums = bn_bwd_sums ? bn_bwd_sums : w.bn_bwd_sums;
   const long long rows = bn_global_rows > 0 ? bn_global_rows : w.R;
   NRM_TRY(launch_bn_backward_combine(params, w, training, sums, rows, s));
-  return encoder_backward(in, params, w, precision, grads, s);
+  NRM_TRY(encoder_backward(in, params, w, precision, grads, s));
+  SideStream* ss = side_stream(s);
+  if (ss != nullptr && ss->head_wgrad_pending) {             // nrm_backward_head_deferred on this stream: join its weight gradients
+    NRM_CUDA(cudaStreamWaitEvent(s, ss->join4, 0));
+    ss->head_wgrad_pending = false;
+  }
+  return NRM_OK;
 }
 
 extern "C" int nrm_backward(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
@@ -485,13 +532,15 @@ extern "C" int nrm_backward(const double* x_history, const double* x_target, lon
   SideStream* ss = side_stream(s);
   if (ss == nullptr) { set_error("nrm_backward: cannot create the side stream"); return NRM_ECUDA; }
   const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
+  const bool htc = head_on_tensor_cores(precision);
+  const int tiles = htc ? head_tc_tiles(w.R) : 0;
   { KernelTimer t("head_backward", s);
-    NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
+    if (htc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
     NRM_CUDA(cudaEventRecord(ss->fork4, s));
     NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork4, 0));
-    NRM_TRY(launch_head_backward_wgrad(params, w, grads, ss->stream));
+    NRM_TRY(launch_head_backward_wgrad(params, w, grads, ss->stream, tiles));
     NRM_CUDA(cudaEventRecord(ss->join4, ss->stream));
-    NRM_TRY(launch_head_backward_bn(w, grads, s)); }
+    NRM_TRY(launch_head_backward_bn(w, grads, s, tiles)); }
   NRM_TRY(launch_bn_backward_combine(params, w, training, w.bn_bwd_sums, w.R, s));
   NRM_TRY(encoder_backward(in, params, w, precision, grads, s));
   NRM_CUDA(cudaStreamWaitEvent(s, ss->join4, 0));          // join: head weight gradients written

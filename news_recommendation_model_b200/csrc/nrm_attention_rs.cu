@@ -31,9 +31,6 @@
 namespace nrm {
 namespace rs {
 
-#ifdef NRM_RS_PROFILE
-__device__ long long g_rsprof[64];
-#endif
 
 __global__ void __launch_bounds__(256)
 att_prep_rs_kernel(const float* __restrict__ P, unsigned char* __restrict__ img_all) {

@@ -13,7 +13,7 @@ namespace rs {
 // Optional per-role wait accounting (make EXTRA=-DNRM_RS_PROFILE; tools/rs_roleprof.py): in CTA 0, lane 0 of one warp per role
 // adds the clock64 cycles it spends inside each kind of mbarrier wait to g_rsprof[role * 8 + kind]; slot 7 = the role's total.
 #ifdef NRM_RS_PROFILE
-extern __device__ long long g_rsprof[64];
+static __device__ long long g_rsprof[64];      // one copy per translation unit; rsprof_read returns the forward kernels' copy
 #define RSPROF_WAIT(role, kind, stmt) do { const long long t__ = clock64(); stmt; if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_rsprof[(role) * 8 + (kind)] += clock64() - t__; } while (0)
 #define RSPROF_TOTAL_BEGIN const long long rsprof_t0 = clock64();
 #define RSPROF_TOTAL_END(role) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_rsprof[(role) * 8 + 7] += clock64() - rsprof_t0; } while (0)

@@ -714,28 +714,30 @@ int launch_head_backward_dgrad(const float* P, Workspace& w, const float* dlogit
   return NRM_OK;
 }
 
-int launch_head_backward_bn(Workspace& w, float* G, cudaStream_t s) {
+int launch_head_backward_bn(Workspace& w, float* G, cudaStream_t s, int dgrad_tiles) {
   int rpc, nchunks;
   head_wgrad_shape(w, rpc, nchunks);
-  launch_pdl(head_grad_finish_kernel, dim3((2 * E + GF_ENT - 1) / GF_ENT, 1), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, head_tiles(w.R), w.head_part_bn, G, w.bn_bwd_sums, 6);
+  const int ntiles = dgrad_tiles > 0 ? dgrad_tiles : head_tiles(w.R);      // row tiles of the data-gradient kernel that wrote the partials
+  launch_pdl(head_grad_finish_kernel, dim3((2 * E + GF_ENT - 1) / GF_ENT, 1), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums, 6);
   NRM_LAUNCH_CHECK("head_grad_finish_kernel");
   return NRM_OK;
 }
 
-int launch_head_backward_wgrad(const float* P, Workspace& w, float* G, cudaStream_t s) {
+int launch_head_backward_wgrad(const float* P, Workspace& w, float* G, cudaStream_t s, int dgrad_tiles) {
   int rpc, nchunks;
   head_wgrad_shape(w, rpc, nchunks);
+  const int ntiles = dgrad_tiles > 0 ? dgrad_tiles : head_tiles(w.R);
   launch_pdl(head_wgrad_kernel, dim3(nchunks, 5), dim3(WG_THREADS), 0, s, w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2, w.dgate, w.da1, w.head_part_w);
   NRM_LAUNCH_CHECK("head_wgrad_kernel");
-  launch_pdl(head_grad_finish_kernel, dim3((WG_PART + GF_ENT - 1) / GF_ENT, 6), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, head_tiles(w.R), w.head_part_bn, G, w.bn_bwd_sums, 0);
+  launch_pdl(head_grad_finish_kernel, dim3((WG_PART + GF_ENT - 1) / GF_ENT, 6), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums, 0);
   NRM_LAUNCH_CHECK("head_grad_finish_kernel");
   return NRM_OK;
 }
 
 int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogits, float* G, cudaStream_t s) {
   NRM_TRY(launch_head_backward_dgrad(P, w, dlogits, s));
-  NRM_TRY(launch_head_backward_bn(w, G, s));
-  return launch_head_backward_wgrad(P, w, G, s);
+  NRM_TRY(launch_head_backward_bn(w, G, s, 0));
+  return launch_head_backward_wgrad(P, w, G, s, 0);
 }
 
 }  // namespace nrm

@@ -92,12 +92,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, ui
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  int spins = 0;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
   while (!mbar_try_wait(bar, parity)) {
 #ifdef NRM_WAIT_NANOSLEEP
     asm volatile("nanosleep.u32 %0;\n" ::"n"(NRM_WAIT_NANOSLEEP));      // experiment: fewer wake-ups of a waiting warp
 #endif
-    if (++spins > 40000000) asm volatile("trap;\n");     // a protocol error must not wedge the GPU
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) asm volatile("trap;\n");     // 4 s: a protocol error must not wedge the GPU
   }
 }
 

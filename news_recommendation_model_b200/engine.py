@@ -203,7 +203,7 @@ def forward_logits(rt: Runtime, flat: FlatParams, bn_mean, bn_var, bn_nbt, x_his
         _lib.check(lib.nrm_forward_encoder(_ptr(xh), _ptr(xt), xt_bs, _ptr(xg), xg_bs, B, H, C, _ptr(flat.buf), mode,
                                            precision, _ptr(sums), _ptr(ws), ws.numel(), st), 'nrm_forward_encoder')
         rows = dp.all_reduce_stats(sums, B * C)
-        _lib.check(lib.nrm_forward_head(B, H, C, _ptr(flat.buf), _ptr(bn_mean), _ptr(bn_var), _ptr(bn_nbt), mode,
+        _lib.check(lib.nrm_forward_head(B, H, C, _ptr(flat.buf), _ptr(bn_mean), _ptr(bn_var), _ptr(bn_nbt), mode, precision,
                                         _ptr(sums), rows, _ptr(logits), _ptr(ws), ws.numel(), st), 'nrm_forward_head')
     else:
         _lib.check(lib.nrm_forward(_ptr(xh), _ptr(xt), xt_bs, _ptr(xg), xg_bs, B, H, C, _ptr(flat.buf), _ptr(bn_mean),
@@ -235,7 +235,7 @@ def backward_params(flat: FlatParams, token: StepToken, dlogits: torch.Tensor, p
     else:
         sync = dp.sync_bn and (token.mode & MODE_BN_BATCH_STATS)
         sums = torch.empty(2 * E_DIM, dtype=torch.float64, device=dev) if sync else None
-        _lib.check(lib.nrm_backward_head(B, H, C, _ptr(flat.buf), _ptr(dl), _ptr(g), _ptr(sums), _ptr(ws), ws.numel(), st),
+        _lib.check(lib.nrm_backward_head(B, H, C, _ptr(flat.buf), precision, _ptr(dl), _ptr(g), _ptr(sums), _ptr(ws), ws.numel(), st),
                    'nrm_backward_head')
         rows = 0
         if sync:

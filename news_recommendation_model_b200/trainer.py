@@ -158,7 +158,7 @@ class FusedTrainStep:
                                                self.precision, _p(sums), _p(self.ws), self.ws.numel(), st), 'nrm_forward_encoder')
             gsums = self._exchange_stats(0, sums, B * C)
             _lib.check(lib.nrm_forward_head(B, H, C, _p(f.buf), _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked),
-                                            self.mode, _p(gsums), B * C * self.world, _p(self.logits), _p(self.ws), self.ws.numel(), st),
+                                            self.mode, self.precision, _p(gsums), B * C * self.world, _p(self.logits), _p(self.ws), self.ws.numel(), st),
                        'nrm_forward_head')
         delta = f.buf[f.fixed:f.fixed + f.delta_numel]
         _lib.check(lib.nrm_loss_forward(_p(self.logits), _p(delta), f.delta_numel, _p(s.uid), _p(s.label), B, C, self.alpha, _p(loss_out),
@@ -179,8 +179,9 @@ class FusedTrainStep:
                        'nrm_backward')
         else:
             sums = self._bn_sums(1)
-            _lib.check(lib.nrm_backward_head(B, H, C, _p(f.buf), _p(self.dlogits), _p(self.grads), _p(sums), _p(self.ws), self.ws.numel(), st),
-                       'nrm_backward_head')
+            # head weight gradients stay on the library's side stream until the encoder backward has been enqueued
+            _lib.check(lib.nrm_backward_head_deferred(B, H, C, _p(f.buf), self.precision, _p(self.dlogits), _p(self.grads), _p(sums), _p(self.ws),
+                                                      self.ws.numel(), st), 'nrm_backward_head_deferred')
             gsums = self._exchange_stats(1, sums, B * C)
             _lib.check(lib.nrm_backward_encoder(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
                                                 self.precision, _p(gsums), B * C * self.world, _p(self.grads), _p(self.ws), self.ws.numel(), st),
