@@ -244,7 +244,7 @@ def algorithmic_work(B, H, C, total_params):
         'attention_backward_label': ('tensor', (2 if 'attention_input_grad_label' in ROWSTACKED else 3) * 2.0 * P * D * D),
         'attention_input_grad_label': ('tensor', 2.0 * P * D * D),
         'attention_backward_textimg': ('tensor', 2 * 2.0 * P * D * D),
-        'head_forward': ('tensor', head), 'head_backward': ('tensor', 2 * head),
+        'head_forward': ('tensor', head), 'head_backward': ('tensor', head), 'head_wgrad': ('tensor', head),   # dgrad chain | weight gradients
         'w1_backward': ('tensor', 2 * 2.0 * 66 * 64 * NH),
         'embed_rows': ('hbm', 8.0 * (80 * NH + 81 * R) + 4.0 * (66 * NH + 64 * NH + 136 * R)),
         'w1_forward': ('hbm', 4.0 * (66 + 64) * NH),
@@ -259,7 +259,7 @@ def algorithmic_work(B, H, C, total_params):
 # Groups the library launches on its side stream, concurrently with main-stream kernels that fill the SMs (the text/img attention
 # backward, the table gradients): their event-to-event time is mostly waiting for SMs, so they are reported (kernels_ms_per_step,
 # roofline_fraction_by_kernel) but are not candidates for the DOMINANT kernel; profiles/ holds their stand-alone ncu durations.
-SIDE_STREAM_GROUPS = {'w1_backward', 'small_linear_grads'}
+SIDE_STREAM_GROUPS = {'w1_backward', 'small_linear_grads', 'head_wgrad'}
 
 
 def pick_roofline(kern, work, pk, precision, traffic_table=None):
@@ -278,7 +278,8 @@ def pick_roofline(kern, work, pk, precision, traffic_table=None):
                 'note': {'fp32': 'FFMA path: the products run on the CUDA cores',
                          'bf16': 'tcgen05 tiles, bf16 operands',
                          'bf16x3': 'attention: tcgen05 tiles, 3 MMAs issued per algorithmic product (hi/lo split); bound by the GELU / '
-                                   'operand-build work on the CUDA cores (issue slots), see DESIGN.md section 4.  head / w1: FFMA'}[precision]}
+                                   'operand-build work on the CUDA cores (issue slots), see DESIGN.md section 4.  head forward / dgrad: tcgen05 M = 64 tiles, '
+                                   'six part products (three-part bf16 split, fp32-grade); w1 backward: tcgen05; head weight gradients: FFMA'}[precision]}
     ach = w / dur / 1e9
     return {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'], 'traffic': traffic,
             'peak_source': pk['source'], 'algorithmic_bytes_per_launch': w, 'launch_ms': dur * 1e3}

@@ -31,6 +31,7 @@ SIGNATURES = {
     'nrm_debug_tcprof': (i32, [vp]),
     'nrm_debug_rsprof': (i32, [vp]),
     'nrm_debug_headprof': (i32, [vp]),
+    'nrm_debug_ws_field': (ll, [i32, i32, i32, i32, C.c_char_p, vp]),
     'nrm_layout_entries': (i32, []),
     'nrm_layout_name': (C.c_char_p, [i32]),
     'nrm_layout_offset': (ll, [i32]),

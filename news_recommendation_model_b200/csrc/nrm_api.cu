@@ -79,7 +79,9 @@ KernelTimer::~KernelTimer() {
 struct SideStream {
   int dev; cudaStream_t caller;
   cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp, fork3, join3, fork4, join4;
-  bool head_wgrad_pending = false;     // nrm_backward_head_deferred ran on `caller`; the next nrm_backward_encoder joins join4
+  // head weight gradients left for encoder_backward to enqueue on the side stream behind the w1 backward, i.e. beside the latency-bound
+  // tail of the step (attention_finish, table gradients) instead of beside the attention backward kernels, which need whole SMs
+  bool head_wgrad_pending = false; const float* wg_params = nullptr; float* wg_grads = nullptr; int wg_tiles = 0;
 };
 // One side stream + event set per (device, caller stream): two models / threads that drive different streams of one device
 // never share fork / join events (a wait can only ever bind to its own caller's record).  Created under a mutex on first use
@@ -194,6 +196,7 @@ size_t carve_workspace(Workspace& w, void* base, int B, int H, int C, int mode) 
   w.tp = (float*)take(f * 2 * R * 64);
   w.att_rs_img = (float*)take(attention_rs_image_bytes());
   w.head_img = (float*)take(head_tc_image_bytes());
+  w.head_arrive = (unsigned int*)take(256);          // arrival counter of the tensor-core head backward (zeroed by the image kernel)
   if (training) {
     w.da3 = (float*)take(f * R * HID); w.da2 = (float*)take(f * R * HID); w.da1 = (float*)take(f * R * HID);
     w.dy = (float*)take(f * R * E);
@@ -322,6 +325,11 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
     if (precision != NRM_PRECISION_FP32 && use_rowstacked()) NRM_TRY(launch_w1_backward_tc(P, w, G, precision, ss->stream));
     else NRM_TRY(launch_w1_backward(P, w, G, ss->stream)); }
   NRM_CUDA(cudaEventRecord(ss->join2, ss->stream));
+  if (ss->head_wgrad_pending) {                              // behind the w1 backward on the side stream; covered by join3 below
+    ss->head_wgrad_pending = false;
+    KernelTimer t("head_wgrad", ss->stream);
+    NRM_TRY(launch_head_backward_wgrad(ss->wg_params, w, ss->wg_grads, ss->stream, ss->wg_tiles));
+  }
   { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
   { KernelTimer t("attention_finish", s);
     NRM_TRY(launch_attention_finish(P, w, 0, precision, G, s));
@@ -380,6 +388,21 @@ extern "C" int nrm_timing_report(char* buf, size_t buf_bytes) {
 }
 // per-role wait cycles of the row-stacked attention kernels (development builds with -DNRM_RS_PROFILE); reads and clears
 extern "C" int nrm_debug_rsprof(long long* host_out64) { return rsprof_read(host_out64); }
+// Byte offset / size of a named workspace buffer (debugging aid: lets a script compare intermediate buffers between runs)
+extern "C" long long nrm_debug_ws_field(int B, int H, int C, int mode, const char* name, long long* bytes) {
+  if (B <= 0 || H <= 0 || C <= 0 || !name || !bytes) return -1;
+  Workspace w;
+  carve_workspace(w, reinterpret_cast<void*>(uintptr_t(256)), B, H, C, mode);
+  const size_t R = (size_t)w.R, NH = (size_t)w.NH;
+  struct F { const char* n; const void* p; size_t b; };
+  const F fields[] = {{"e", w.e, R * E * 4}, {"de", w.de, R * E * 4}, {"dz", w.dz, R * E * 4}, {"dxh", w.dxh, NH * 64 * 4}, {"dxt", w.dxt, R * 64 * 4},
+                      {"dxin_h", w.dxin_h, NH * XIN * 4}, {"att_dhid", w.att_dhid, (size_t)attention_rs_tiles(B, H, C) * 2 * 16384},
+                      {"att_sc", w.att_sc, (size_t)attention_rs_tiles(B, H, C) * 512 * 4}, {"xh", w.xh, NH * 64 * 4}, {"dtp", w.dtp, 2 * R * 64 * 4},
+                      {"tp", w.tp, 2 * R * 64 * 4}};
+  for (const F& f : fields)
+    if (strcmp(f.n, name) == 0 && f.p != nullptr) { *bytes = (long long)f.b; return (long long)(reinterpret_cast<uintptr_t>(f.p) - 256); }
+  return -1;
+}
 extern "C" int nrm_debug_headprof(long long* host_out32) { return headprof_read(host_out32); }
 extern "C" const char* nrm_last_error(void) { return g_err; }
 extern "C" int nrm_layout_entries(void) { return kLayoutEntries; }
@@ -465,20 +488,16 @@ static int backward_head(const char* fn, bool defer_wgrad, int B, int H, int C, 
   const int tiles = tc ? head_tc_tiles(w.R) : 0;
   if (!defer_wgrad) {
     KernelTimer t("head_backward", s);
-    if (tc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
-    NRM_TRY(launch_head_backward_bn(w, grads, s, tiles));
+    if (tc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, grads, s));
+    else { NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s)); NRM_TRY(launch_head_backward_bn(w, grads, s, 0)); }
     NRM_TRY(launch_head_backward_wgrad(params, w, grads, s, tiles));
   } else {
     SideStream* ss = side_stream(s);
     if (ss == nullptr) { set_error("%s: cannot create the side stream", fn); return NRM_ECUDA; }
     KernelTimer t("head_backward", s);
-    if (tc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
-    NRM_CUDA(cudaEventRecord(ss->fork4, s));
-    NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork4, 0));
-    NRM_TRY(launch_head_backward_wgrad(params, w, grads, ss->stream, tiles));
-    NRM_CUDA(cudaEventRecord(ss->join4, ss->stream));
-    ss->head_wgrad_pending = true;
-    NRM_TRY(launch_head_backward_bn(w, grads, s, tiles));
+    if (tc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, grads, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
+    ss->head_wgrad_pending = true; ss->wg_params = params; ss->wg_grads = grads; ss->wg_tiles = tiles;
+    if (!tc) NRM_TRY(launch_head_backward_bn(w, grads, s, 0));
   }
   if (bn_bwd_sums != nullptr && bn_bwd_sums != w.bn_bwd_sums)
     NRM_CUDA(cudaMemcpyAsync(bn_bwd_sums, w.bn_bwd_sums, sizeof(double) * 2 * E, cudaMemcpyDeviceToDevice, s));
@@ -508,14 +527,8 @@ extern "C" int nrm_backward_encoder(const double* x_history, const double* x_tar
   const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
   const double* sums = bn_bwd_sums ? bn_bwd_sums : w.bn_bwd_sums;
   const long long rows = bn_global_rows > 0 ? bn_global_rows : w.R;
-  NRM_TRY(launch_bn_backward_combine(params, w, training, sums, rows, s));
-  NRM_TRY(encoder_backward(in, params, w, precision, grads, s));
-  SideStream* ss = side_stream(s);
-  if (ss != nullptr && ss->head_wgrad_pending) {             // nrm_backward_head_deferred on this stream: join its weight gradients
-    NRM_CUDA(cudaStreamWaitEvent(s, ss->join4, 0));
-    ss->head_wgrad_pending = false;
-  }
-  return NRM_OK;
+  NRM_TRY(launch_bn_backward_combine(params, w, training, sums, rows, head_on_tensor_cores(precision), s));
+  return encoder_backward(in, params, w, precision, grads, s);   // also enqueues and joins the weight gradients nrm_backward_head_deferred left
 }
 
 extern "C" int nrm_backward(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
@@ -535,14 +548,9 @@ extern "C" int nrm_backward(const double* x_history, const double* x_target, lon
   const bool htc = head_on_tensor_cores(precision);
   const int tiles = htc ? head_tc_tiles(w.R) : 0;
   { KernelTimer t("head_backward", s);
-    if (htc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
-    NRM_CUDA(cudaEventRecord(ss->fork4, s));
-    NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork4, 0));
-    NRM_TRY(launch_head_backward_wgrad(params, w, grads, ss->stream, tiles));
-    NRM_CUDA(cudaEventRecord(ss->join4, ss->stream));
-    NRM_TRY(launch_head_backward_bn(w, grads, s, tiles)); }
-  NRM_TRY(launch_bn_backward_combine(params, w, training, w.bn_bwd_sums, w.R, s));
-  NRM_TRY(encoder_backward(in, params, w, precision, grads, s));
-  NRM_CUDA(cudaStreamWaitEvent(s, ss->join4, 0));          // join: head weight gradients written
-  return NRM_OK;
+    if (htc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, grads, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
+    ss->head_wgrad_pending = true; ss->wg_params = params; ss->wg_grads = grads; ss->wg_tiles = tiles;
+    if (!htc) NRM_TRY(launch_head_backward_bn(w, grads, s, 0)); }
+  NRM_TRY(launch_bn_backward_combine(params, w, training, w.bn_bwd_sums, w.R, htc, s));
+  return encoder_backward(in, params, w, precision, grads, s);     // enqueues the head weight gradients on the side stream and joins them
 }

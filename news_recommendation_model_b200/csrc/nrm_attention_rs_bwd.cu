@@ -509,6 +509,7 @@ attention_backward_rs_kernel(const float* __restrict__ rows_g, int branch, int B
         for (int i = 0; i < 16; ++i) sm.red[warp - W_EPI][i] = a[i];
         sm.red[warp - W_EPI][16] = db2a;
       }
+      __syncwarp();
       asm volatile("bar.sync 1, 512;\n" ::: "memory");     // the 16 epilogue warps
       const int et = tid - W_EPI * 32;
       if (et < 64) {                                       // column j = 16 cq' + i: the four sub-partition warps of quarter cq', in order
@@ -711,7 +712,9 @@ attention_input_grad_rs_kernel(const float* __restrict__ rows_g, int B, int H, i
           const int r = 32 * sp + lane, rg = ti * 128 + r;
           const bool valid = rg < rows;
           const int cl = valid ? __float2int_rz(((float)rg + 0.5f) * inv_hl) : 0, hloc = valid ? rg - cl * hl : 0;
-          // tile_full completed before xy_full (the product waited for it): the scores are visible
+          // the scores were written by the TMA engine (async proxy): every reading thread acquires the tile's own barrier -- its phase
+          // completed long ago (the product waited for it), but observing xy_full alone does not order these reads behind the copy
+          umma::mbar_wait(&sm.tile_full[ts], tph);
           const float srow = valid ? ((sm.sc[ts][0][r] + sm.sc[ts][1][r]) + sm.sc[ts][2][r]) + sm.sc[ts][3][r] : 0.f;
           arrive_warp(&sm.tile_empty[ts]);
           const float* hrow = valid ? &st.hf[hloc * HF_STRIDE + 16 * cq] : sm.zrow;
@@ -732,6 +735,7 @@ attention_input_grad_rs_kernel(const float* __restrict__ rows_g, int B, int H, i
             *reinterpret_cast<float4*>(zr + 4 * q) = z;
             *reinterpret_cast<float4*>(ur + 4 * q) = uu;
           }
+          __syncwarp();                                                  // bar.sync is the ALIGNED barrier: the warp must arrive converged
           asm volatile("bar.sync 1, 512;\n" ::: "memory");              // Z / U of the tile complete
           // dh[h][8 k8 ..]: the rows (c, h) of this tile, candidates in order
           if (rh < hl) {
@@ -754,6 +758,7 @@ attention_input_grad_rs_kernel(const float* __restrict__ rows_g, int B, int H, i
               dt_acc.x += v.x; dt_acc.y += v.y; dt_acc.z += v.z; dt_acc.w += v.w;
             }
           }
+          __syncwarp();                                                  // (the dt loop above has lane-dependent trip counts)
           asm volatile("bar.sync 2, 512;\n" ::: "memory");              // exchange tiles free for the next tile
         }
         // dh of this chunk's history rows

@@ -191,6 +191,7 @@ struct Workspace {
   float* tp;           // [2][R,64]  tp = (Wb + Wc) t + b1 per candidate row and branch (tensor-core paths)
   unsigned char* att_dhid;  // label branch, training: dhid tile images (hi | lo) exported by the row-stacked backward for the input-gradient kernel
   float* att_sc;       // label branch, training: partial scores [tiles][4][128]
+  unsigned int* head_arrive;   // arrival counter: the last CTA of the tensor-core head backward sums the BatchNorm partials
   float* head_img;     // operand images of the ten head products (nrm_head_tc.cu): bf16 parts, chunked in ring order
   float* att_rs_img;   // weight image of the row-stacked attention kernels (nrm_attention_rs.cu): bf16 operand tiles, hi | lo
   // backward (training only)

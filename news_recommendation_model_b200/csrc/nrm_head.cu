@@ -41,10 +41,11 @@ bn_partial_reduce_kernel(const double* __restrict__ part, int nparts, double* __
 
 // de += rstd * gamma * (dz - mean_r(dz) - xhat * mean_r(dz * xhat))      (training)
 // de += rstd * gamma * dz                                                 (eval)
+// gate != null: `de` holds dx = dL/d(gate * e) as the tensor-core head backward leaves it; the direct path dx * gate is formed here
 __global__ void __launch_bounds__(256)
 bn_bwd_combine_kernel(const float* __restrict__ dz, const float* __restrict__ e, const float* __restrict__ mean,
                       const float* __restrict__ rstd, const float* __restrict__ gamma, const double* __restrict__ sums,
-                      long long rows, int training, long long total4, float* __restrict__ de) {
+                      long long rows, int training, long long total4, const float* __restrict__ gate, float* __restrict__ de) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
   // four consecutive columns per thread (264 = 66 x 4: a float4 never straddles a row)
@@ -64,6 +65,10 @@ bn_bwd_combine_kernel(const float* __restrict__ dz, const float* __restrict__ e,
       v.w = v.w - m1[3] - (x.w - mu.w) * rs.w * m2[3];
     }
     float4 d = reinterpret_cast<float4*>(de)[i];
+    if (gate != nullptr) {
+      const float4 gt = __ldg(reinterpret_cast<const float4*>(gate) + i);
+      d.x *= gt.x; d.y *= gt.y; d.z *= gt.z; d.w *= gt.w;
+    }
     d.x += rs.x * g.x * v.x; d.y += rs.y * g.y * v.y; d.z += rs.z * g.z * v.z; d.w += rs.w * g.w * v.w;
     reinterpret_cast<float4*>(de)[i] = d;
   }
@@ -95,10 +100,10 @@ int launch_head_backward(const float* P, Workspace& w, const float* dlogits, flo
 }
 
 int launch_bn_backward_combine(const float* P, Workspace& w, int training, const double* bn_bwd_sums,
-                               long long global_rows, cudaStream_t s) {
+                               long long global_rows, bool de_holds_dx, cudaStream_t s) {
   const long long total4 = w.R * (E / 4);
   const long long blocks = min((total4 + 255) / 256, (long long)sm_count() * 8);
-  launch_pdl(bn_bwd_combine_kernel, dim3((int)blocks), dim3(256), 0, s, w.dz, w.e, w.mean, w.rstd, P + P_BN_W, bn_bwd_sums, global_rows, training, total4, w.de);
+  launch_pdl(bn_bwd_combine_kernel, dim3((int)blocks), dim3(256), 0, s, w.dz, w.e, w.mean, w.rstd, P + P_BN_W, bn_bwd_sums, global_rows, training, total4, de_holds_dx ? w.gate : nullptr, w.de);
   NRM_LAUNCH_CHECK("bn_bwd_combine_kernel");
   return NRM_OK;
 }

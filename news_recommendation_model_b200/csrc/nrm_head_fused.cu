@@ -63,7 +63,8 @@ head_transpose_kernel(const float* __restrict__ P, float* __restrict__ wt) {
 // per chunk: the consumer warps drift apart by up to the ring depth.
 struct HeadLayerDesc { const float* W; int K; int nout; };
 
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(HT_CONSUMERS) : "memory"); }
+// bar.sync is the ALIGNED barrier: a warp must arrive converged (a diverged warp arriving in two groups releases it early)
+__device__ __forceinline__ void consumer_sync() { __syncwarp(); asm volatile("bar.sync 1, %0;\n" ::"n"(HT_CONSUMERS) : "memory"); }
 
 __device__ __forceinline__ void weight_producer(HeadSmem& sm, const HeadLayerDesc (&layers)[5]) {
   for (int g = 0; g < W_CHUNKS; ++g) {

@@ -102,9 +102,10 @@ __constant__ ImgDesc c_img[10] = {
 
 template <int NP>
 __global__ void __launch_bounds__(256)
-head_image_kernel(const float* __restrict__ P, unsigned char* __restrict__ img, int first_layer) {
+head_image_kernel(const float* __restrict__ P, unsigned char* __restrict__ img, int first_layer, unsigned int* __restrict__ arrive) {
   pdl_wait();
   pdl_trigger();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *arrive = 0u;
   const int layer = first_layer + blockIdx.y;
   const ImgDesc d = c_img[layer];
   const float* src = P + d.src;
@@ -148,7 +149,8 @@ struct Smem {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_THREADS) : "memory"); }
+// bar.sync is the ALIGNED barrier: a warp must arrive converged (a diverged warp arriving in two groups releases it early)
+__device__ __forceinline__ void epi_sync() { __syncwarp(); asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_THREADS) : "memory"); }
 // the calling epilogue warp has written its share of the next operand: make it visible to the tensor core, one arrival per warp
 __device__ __forceinline__ void operand_written(uint64_t* bar) {
   umma::fence_async_smem();
@@ -513,7 +515,8 @@ head_backward_tc_kernel(const float* __restrict__ e, const float* __restrict__ m
                         const float* __restrict__ a1g, const float* __restrict__ gateg, const float* __restrict__ a2g,
                         const float* __restrict__ a3g, float* __restrict__ da3g, float* __restrict__ dyg, float* __restrict__ da2g,
                         float* __restrict__ dgateg, float* __restrict__ da1g, float* __restrict__ dzg, float* __restrict__ deg,
-                        float* __restrict__ part_f, double* __restrict__ part_bn) {
+                        float* __restrict__ part_f, double* __restrict__ part_bn, unsigned int* __restrict__ arrive,
+                        float* __restrict__ grads, double* __restrict__ bn_bwd_sums) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -698,7 +701,7 @@ head_backward_tc_kernel(const float* __restrict__ e, const float* __restrict__ m
       // da2 = (dy M2) gelu'(a2)
       narrow_layer(a2g, da2g);
       operand_written(&sm.a_ready);
-      // dx = da2 M1;  dgate = dx e -> global, aw;  de (direct path) = dx gate -> global
+      // dx = da2 M1 -> global (the BatchNorm combine kernel forms the direct path de = dx gate);  dgate = dx e -> global, aw
       {
         float4 ev[5][2];
         wide_layer(
@@ -710,12 +713,7 @@ head_backward_tc_kernel(const float* __restrict__ e, const float* __restrict__ m
               }
             },
             [&](int j, int c0, float* o) {
-              if (live) {
-                float4 gv[2];
-                load8(gateg, c0, gv);
-                const float dd[8] = {o[0] * gv[0].x, o[1] * gv[0].y, o[2] * gv[0].z, o[3] * gv[0].w, o[4] * gv[1].x, o[5] * gv[1].y, o[6] * gv[1].z, o[7] * gv[1].w};
-                store8(deg, c0, dd);
-              }
+              if (live) store8(deg, c0, o);
               o[0] *= ev[j][0].x; o[1] *= ev[j][0].y; o[2] *= ev[j][0].z; o[3] *= ev[j][0].w;
               o[4] *= ev[j][1].x; o[5] *= ev[j][1].y; o[6] *= ev[j][1].z; o[7] *= ev[j][1].w;
               if (live) store8(dgateg, c0, o);
@@ -762,6 +760,26 @@ head_backward_tc_kernel(const float* __restrict__ e, const float* __restrict__ m
         part_bn[tile * 2 * E + i] = ((double)sm.par[i] + (double)sm.par[2 * E + i]) + ((double)sm.par[4 * E + i] + (double)sm.par[6 * E + i]);
       epi_sync();
     }
+    // the last CTA to arrive adds the tiles' BatchNorm partials in tile order: column sums of dz and dz * xhat over this rank's
+    // rows (-> bn_bwd_sums for the encoder backward) = the gradients of bn.bias / bn.weight
+    __threadfence();
+    epi_sync();
+    if (tid == 0) {
+      const unsigned int prev = atomicAdd(arrive, 1u);
+      sm.tmem_base = (prev == gridDim.x - 1) ? 1u : 0u;         // (the allocation address has been read into `tmem` by everyone)
+    }
+    epi_sync();
+    if (sm.tmem_base != 0u) {
+      __threadfence();
+      for (int i = tid; i < 2 * E; i += EPI_THREADS) {
+        double acc = 0.0;
+#pragma unroll 8
+        for (long long tl = 0; tl < ntiles; ++tl) acc += __ldcg(part_bn + tl * 2 * E + i);
+        bn_bwd_sums[i] = acc;
+        if (i < E) grads[P_BN_B + i] = (float)acc; else grads[P_BN_W + (i - E)] = (float)acc;
+      }
+      if (tid == 0) *arrive = 0u;
+    }
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -792,8 +810,8 @@ static int head_np(int precision) { return precision == NRM_PRECISION_BF16 ? 2 :
 int launch_head_images_tc(const float* P, Workspace& w, int precision, bool with_backward, cudaStream_t s) {
   unsigned char* img = reinterpret_cast<unsigned char*>(w.head_img);
   const dim3 grid(10, with_backward ? 10 : 5);
-  if (head_np(precision) == 2) launch_pdl(htc::head_image_kernel<2>, grid, dim3(256), 0, s, P, img, 0);
-  else launch_pdl(htc::head_image_kernel<3>, grid, dim3(256), 0, s, P, img, 0);
+  if (head_np(precision) == 2) launch_pdl(htc::head_image_kernel<2>, grid, dim3(256), 0, s, P, img, 0, w.head_arrive);
+  else launch_pdl(htc::head_image_kernel<3>, grid, dim3(256), 0, s, P, img, 0, w.head_arrive);
   NRM_LAUNCH_CHECK("head_image_kernel");
   return NRM_OK;
 }
@@ -820,7 +838,7 @@ int launch_head_forward_tc(const float* P, Workspace& w, int precision, float* r
 
 
 template <int NP>
-static int launch_bwd(const float* P, Workspace& w, const float* dlogits, cudaStream_t s) {
+static int launch_bwd(const float* P, Workspace& w, const float* dlogits, float* G, cudaStream_t s) {
   static DeviceOnce configured;
   if (configured.first_time())
     NRM_CUDA(cudaFuncSetAttribute(htc::head_backward_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(htc::Smem)));
@@ -828,15 +846,15 @@ static int launch_bwd(const float* P, Workspace& w, const float* dlogits, cudaSt
   const int grid = (int)min(ntiles, (long long)sm_count());
   launch_pdl(htc::head_backward_tc_kernel<NP>, dim3(grid), dim3(htc::THREADS), sizeof(htc::Smem), s, w.e, w.mean, w.rstd, P,
              reinterpret_cast<const unsigned char*>(w.head_img), w.R, dlogits, w.a1, w.gate, w.a2, w.a3, w.da3, w.dy, w.da2, w.dgate, w.da1, w.dz,
-             w.de, w.head_part_f, w.head_part_bn);
+             w.de, w.head_part_f, w.head_part_bn, w.head_arrive, G, w.bn_bwd_sums);
   NRM_LAUNCH_CHECK("head_backward_tc_kernel");
   return NRM_OK;
 }
 
 // data-gradient chain; per-tile partials for head_tc_tiles(R) tiles (head_grad_finish_kernel sums them)
 int head_tc_tiles(long long R) { return (int)((R + htc::ROWS - 1) / htc::ROWS); }
-int launch_head_backward_dgrad_tc(const float* P, Workspace& w, int precision, const float* dlogits, cudaStream_t s) {
-  return head_np(precision) == 2 ? launch_bwd<2>(P, w, dlogits, s) : launch_bwd<3>(P, w, dlogits, s);
+int launch_head_backward_dgrad_tc(const float* P, Workspace& w, int precision, const float* dlogits, float* G, cudaStream_t s) {
+  return head_np(precision) == 2 ? launch_bwd<2>(P, w, dlogits, G, s) : launch_bwd<3>(P, w, dlogits, G, s);
 }
 
 }  // namespace nrm

@@ -61,7 +61,8 @@ size_t head_tc_image_bytes();
 int headprof_read(long long* host_out32);                                       // -DNRM_RS_PROFILE builds only
 int launch_head_images_tc(const float* P, Workspace& w, int precision, bool with_backward, cudaStream_t s);   // weights only -> w.head_img
 int head_tc_tiles(long long R);
-int launch_head_backward_dgrad_tc(const float* P, Workspace& w, int precision, const float* dlogits, cudaStream_t s);   // same outputs as launch_head_backward_dgrad
+// tensor-core data-gradient chain: as launch_head_backward_dgrad + launch_head_backward_bn, except that w.de holds dx (not dx * gate)
+int launch_head_backward_dgrad_tc(const float* P, Workspace& w, int precision, const float* dlogits, float* grads, cudaStream_t s);
 int launch_head_forward_tc(const float* P, Workspace& w, int precision, float* run_mean, float* run_var, long long* nbt, int training, int keep,
                            const double* bn_sums, long long bn_rows, float* logits, cudaStream_t s);
 
@@ -71,6 +72,6 @@ int launch_head_forward(const float* P, Workspace& w, float* run_mean, float* ru
                         int training, int keep, const double* bn_sums, long long global_rows, float* logits, cudaStream_t s);
 int launch_head_backward(const float* P, Workspace& w, const float* dlogits, float* grads, cudaStream_t s);  // -> w.bn_bwd_sums
 int launch_bn_backward_combine(const float* P, Workspace& w, int training, const double* bn_bwd_sums,
-                               long long global_rows, cudaStream_t s);  // w.de += BN path
+                               long long global_rows, bool de_holds_dx, cudaStream_t s);  // w.de += BN path
 
 }  // namespace nrm

@@ -133,13 +133,9 @@ def test_config2_full_size_train_step_matches_the_oracle(precision):
         scale = go.abs().max().item()
         tol = P.TOL_GRAD_ABS if k in P.NOISE_KEYS else P.TOL_GRAD_REL * scale + P.TOL_GRAD_ABS
         assert (g_c[k] - go).abs().max().item() <= tol, (k, (g_c[k] - go).abs().max().item(), scale)
-    for k, v in model.named_parameters():
-        if k in P.NOISE_KEYS:                               # pure-noise gradients: Adam turns their sign into +-lr
-            continue
-        ref = leaves[k].detach()
-        moved = (ref - before[k]).abs().max().item()
-        err = (v.detach().cpu() - ref).abs().max().item()
-        assert err <= 0.05 * max(moved, 1e-3) + 1e-7, (k, err, moved)
+    # weights after the Adam step: quantile + max bound (an element whose gradient is ~1e-6 turns a 5e-8 rounding difference into a
+    # 5 % different step; see parity.assert_weights_follow)
+    P.assert_weights_follow(model.named_parameters(), {k: v.detach() for k, v in leaves.items()}, steps=1, lr=1e-3)
     for k in ('bn.running_mean', 'bn.running_var'):
         ref = p[k]
         assert (model.state_dict()[k].cpu() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), k
