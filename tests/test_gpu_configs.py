@@ -217,6 +217,19 @@ def test_config2_full_size_two_implementations_agree_and_are_deterministic():
         assert (g32[k] - g3[k]).abs().max().item() <= tol, (k, (g32[k] - g3[k]).abs().max().item(), scale)
 
 
+def test_config2_full_size_training_step_is_bitwise_reproducible_over_repeats():
+    """Six eager training steps on the same inputs at B=1024 (about 7 work units per CTA in the warp-specialised attention kernels:
+    long barrier / pipeline sequences, which two runs of a short sequence do not exercise): every gradient bit-identical every time."""
+    b = make_batch(1024, 50, 5, seed=2024, user_num=1000).to('cuda')
+    m = _model('train', 1000, 'bf16x3', train=True)
+    first = _train_step(m, b)
+    for rep in range(5):
+        again = _train_step(m, b)
+        assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1]), rep
+        for k in first[2]:
+            assert torch.equal(first[2][k], again[2][k]), (rep, k)
+
+
 def test_config2_subset_matches_oracle_eval():
     full = make_batch(1024, 50, 5, seed=77, user_num=1000)
     idx = torch.tensor([0, 1, 2, 511, 512, 1021, 1022, 1023])
