@@ -332,7 +332,7 @@ class FusedTrainStep:
                 # eager warm-up pass is NOT wanted (it would be an extra optimizer step): capture directly
                 s.graph_fb = torch.cuda.CUDAGraph()
                 s.loss_slot = self.loss_dev.new_zeros(())
-                with torch.cuda.graph(s.graph_fb):
+                with torch.cuda.graph(s.graph_fb, capture_error_mode='thread_local'):       # other threads (a loader) may call CUDA meanwhile
                     if s.wire == 'compact':
                         self._expand(s)
                     self._forward_backward(s, s.loss_slot)
@@ -341,7 +341,7 @@ class FusedTrainStep:
                 s.graph_wire = s.wire
                 if not self.one_graph:                   # NCCL data parallel: the gradient all-reduce sits between two graphs
                     s.graph_adam = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(s.graph_adam):
+                    with torch.cuda.graph(s.graph_adam, capture_error_mode='thread_local'):
                         self._adam()
             s.graph_fb.replay()
             if not self.one_graph:

@@ -23,6 +23,7 @@ from __future__ import annotations
 import ctypes
 import queue
 import threading
+import time
 from dataclasses import dataclass
 from typing import Iterator, List, Optional, Sequence
 
@@ -212,7 +213,10 @@ class PrefetchLoader:
                     return
                 ev = self._events[slot]
                 if ev is not None:
-                    ev.synchronize()                          # the consumer's H2D copies out of this slot have finished
+                    # the consumer's H2D copies out of this slot have finished.  Polling, not cudaEventSynchronize: another thread may
+                    # be capturing a CUDA graph, during which synchronising calls are not permitted
+                    while not ev.query():
+                        time.sleep(20e-6)
                     self._events[slot] = None
                 rows = int(idx.numel())
                 idx_np = idx.numpy()
