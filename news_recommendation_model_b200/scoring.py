@@ -154,6 +154,73 @@ def submission_text(impression_id, ranks, empty_num=None) -> bytes:
     return submission_lines(impression_id, ranks, empty_num)[0]
 
 
+class SubmissionRing:
+    """Pinned result ring for the submission text (`test.py:118-132`) of a scoring loop.  `push` formats one batch on the GPU and
+    enqueues the device-to-host copies of the text and its line offsets into the next pinned slot WITHOUT synchronising, so the
+    host goes straight on to the next batch; the (text, offsets) of an older batch comes back from `push` once the ring wraps
+    (`depth - 1` batches late), the rest from `drain()` — always in push order.  `submission_lines` is the blocking one-batch form."""
+
+    def __init__(self, max_batch: int, max_candidates: int, depth: int = 4, device='cuda'):
+        if depth < 2:
+            raise ValueError('SubmissionRing needs at least 2 slots')
+        self.lib = _lib.load()
+        self.dev = torch.device(device)
+        self.depth, self.max_batch, self.max_candidates = depth, max_batch, max_candidates
+        cap = int(self.lib.nrm_rank_strings_capacity(max_batch, max_candidates))
+        self._dtext = [torch.empty(cap, dtype=torch.uint8, device=self.dev) for _ in range(depth)]
+        self._doff = [torch.empty(max_batch + 1, dtype=torch.int64, device=self.dev) for _ in range(depth)]
+        self._htext = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self._hoff = [torch.empty(max_batch + 1, dtype=torch.int64).pin_memory() for _ in range(depth)]
+        self._event = [torch.cuda.Event() for _ in range(depth)]
+        self._rows = [0] * depth                      # 0 = slot free
+        self._caps = [0] * depth
+        self._head = 0                                # next slot to fill
+        self._tail = 0                                # oldest slot not yet collected
+
+    def _collect(self) -> Tuple[bytes, np.ndarray]:
+        slot = self._tail % self.depth
+        self._event[slot].synchronize()
+        B = self._rows[slot]
+        off = self._hoff[slot][:B + 1].numpy().copy()
+        total = int(off[-1])
+        if total > self._caps[slot]:
+            raise _lib.NrmError('nrm_rank_strings: text does not fit the buffer')
+        text = self._htext[slot][:total].numpy().tobytes()
+        self._rows[slot] = 0
+        self._tail += 1
+        return text, off
+
+    def push(self, impression_id: torch.Tensor, ranks: torch.Tensor, empty_num: Optional[torch.Tensor] = None
+             ) -> Optional[Tuple[bytes, np.ndarray]]:
+        if not ranks.is_cuda:
+            raise _lib.NrmError('SubmissionRing runs on CUDA tensors only (no CPU fallback)')
+        rk = ranks.detach().to(torch.int32).contiguous()
+        B, C = rk.shape
+        if B == 0 or C == 0 or B > self.max_batch or C > self.max_candidates:
+            raise ValueError(f'ranks [{B},{C}] outside the ring\'s [1..{self.max_batch}, 1..{self.max_candidates}]')
+        done = self._collect() if self._head - self._tail == self.depth else None
+        slot = self._head % self.depth
+        ids = impression_id.detach().to(device=self.dev, dtype=torch.int64, non_blocking=True).contiguous()
+        if ids.shape != (B,):
+            raise ValueError('impression_id must be [B]')
+        en = None if empty_num is None else empty_num.detach().to(device=self.dev, dtype=torch.int64, non_blocking=True).contiguous()
+        cap = int(self.lib.nrm_rank_strings_capacity(B, C))
+        _lib.check(self.lib.nrm_rank_strings(_ptr(ids), _ptr(rk), _ptr(en), B, C, _ptr(self._doff[slot]), _ptr(self._dtext[slot]), cap,
+                                             _stream(self.dev)), 'nrm_rank_strings')
+        self._hoff[slot][:B + 1].copy_(self._doff[slot][:B + 1], non_blocking=True)
+        self._htext[slot][:cap].copy_(self._dtext[slot][:cap], non_blocking=True)      # the whole capacity: its length is not known on the host yet
+        self._event[slot].record(torch.cuda.current_stream(self.dev))
+        self._rows[slot], self._caps[slot] = B, cap
+        self._head += 1
+        return done
+
+    def drain(self) -> List[Tuple[bytes, np.ndarray]]:
+        out = []
+        while self._tail < self._head:
+            out.append(self._collect())
+        return out
+
+
 @torch.no_grad()
 def model_test(model_list, test_data, device='cuda', prediction_queue=None, id_list=None, batch_size=1, text_sink: Optional[List[bytes]] = None):
     """Mirror of `test.py:model_test` (`test.py:31-74`): same arguments, the same records
@@ -169,6 +236,7 @@ def model_test(model_list, test_data, device='cuda', prediction_queue=None, id_l
         prediction_queue = _queue.Queue()
     if id_list is None:
         id_list = []
+    ring = None
     for data in loader:
         impression_id, user_id, x_history, x_inview, x_global, _, label_id, empty_num = data
         trim = int(torch.min(empty_num))
@@ -181,13 +249,21 @@ def model_test(model_list, test_data, device='cuda', prediction_queue=None, id_l
             label_id = label_id[:, 0:-trim]
             empty_num = empty_num - trim
         scores, ranks = ensemble_scores(model_list, x_history, x_inview, x_global, empty_num, want_ranks=text_sink is not None)
-        if text_sink is not None:
-            text_sink.append(submission_text(impression_id, ranks, empty_num))
+        if text_sink is not None:                                  # the text comes back through a pinned ring, a few batches late
+            if ring is None or ranks.shape[0] > ring.max_batch or ranks.shape[1] > ring.max_candidates:
+                if ring is not None:
+                    text_sink.extend(t for t, _ in ring.drain())
+                ring = SubmissionRing(max(ranks.shape[0], batch_size), max(ranks.shape[1], 64), device=ranks.device)
+            done = ring.push(impression_id, ranks, empty_num)
+            if done is not None:
+                text_sink.append(done[0])
         host = scores.cpu().numpy()
         for d_i in range(host.shape[0]):
             n = host.shape[1] - int(empty_num[d_i])
             prediction_queue.put([impression_id[d_i], user_id[d_i], host[d_i, :n].copy(), label_id[d_i, :n].numpy()])
             id_list.append('{}_{}'.format(int(impression_id[d_i]), int(user_id[d_i])))
+    if ring is not None:
+        text_sink.extend(t for t, _ in ring.drain())
     return prediction_queue, id_list
 
 
