@@ -81,7 +81,7 @@ struct SideStream {
   cudaStream_t stream; cudaEvent_t fork, join, fork2, join2, fork0, join0, join_tp, fork3, join3, fork4, join4;
   // head weight gradients left for encoder_backward to enqueue on the side stream behind the w1 backward, i.e. beside the latency-bound
   // tail of the step (attention_finish, table gradients) instead of beside the attention backward kernels, which need whole SMs
-  bool head_wgrad_pending = false; const float* wg_params = nullptr; float* wg_grads = nullptr; int wg_tiles = 0;
+  bool head_wgrad_pending = false; const float* wg_params = nullptr; float* wg_grads = nullptr; int wg_tiles = 0, wg_precision = 0;
 };
 // One side stream + event set per (device, caller stream): two models / threads that drive different streams of one device
 // never share fork / join events (a wait can only ever bind to its own caller's record).  Created under a mutex on first use
@@ -328,7 +328,7 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
   if (ss->head_wgrad_pending) {                              // behind the w1 backward on the side stream; covered by join3 below
     ss->head_wgrad_pending = false;
     KernelTimer t("head_wgrad", ss->stream);
-    NRM_TRY(launch_head_backward_wgrad(ss->wg_params, w, ss->wg_grads, ss->stream, ss->wg_tiles));
+    NRM_TRY(launch_head_backward_wgrad(ss->wg_params, w, ss->wg_grads, ss->stream, ss->wg_tiles, ss->wg_precision));
   }
   { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
   { KernelTimer t("attention_finish", s);
@@ -490,13 +490,13 @@ static int backward_head(const char* fn, bool defer_wgrad, int B, int H, int C, 
     KernelTimer t("head_backward", s);
     if (tc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, grads, s));
     else { NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s)); NRM_TRY(launch_head_backward_bn(w, grads, s, 0)); }
-    NRM_TRY(launch_head_backward_wgrad(params, w, grads, s, tiles));
+    NRM_TRY(launch_head_backward_wgrad(params, w, grads, s, tiles, tc ? precision : 0));
   } else {
     SideStream* ss = side_stream(s);
     if (ss == nullptr) { set_error("%s: cannot create the side stream", fn); return NRM_ECUDA; }
     KernelTimer t("head_backward", s);
     if (tc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, grads, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
-    ss->head_wgrad_pending = true; ss->wg_params = params; ss->wg_grads = grads; ss->wg_tiles = tiles;
+    ss->head_wgrad_pending = true; ss->wg_params = params; ss->wg_grads = grads; ss->wg_tiles = tiles; ss->wg_precision = tc ? precision : 0;
     if (!tc) NRM_TRY(launch_head_backward_bn(w, grads, s, 0));
   }
   if (bn_bwd_sums != nullptr && bn_bwd_sums != w.bn_bwd_sums)
@@ -549,7 +549,7 @@ extern "C" int nrm_backward(const double* x_history, const double* x_target, lon
   const int tiles = htc ? head_tc_tiles(w.R) : 0;
   { KernelTimer t("head_backward", s);
     if (htc) NRM_TRY(launch_head_backward_dgrad_tc(params, w, precision, dlogits, grads, s)); else NRM_TRY(launch_head_backward_dgrad(params, w, dlogits, s));
-    ss->head_wgrad_pending = true; ss->wg_params = params; ss->wg_grads = grads; ss->wg_tiles = tiles;
+    ss->head_wgrad_pending = true; ss->wg_params = params; ss->wg_grads = grads; ss->wg_tiles = tiles; ss->wg_precision = htc ? precision : 0;
     if (!htc) NRM_TRY(launch_head_backward_bn(w, grads, s, 0)); }
   NRM_TRY(launch_bn_backward_combine(params, w, training, w.bn_bwd_sums, w.R, htc, s));
   return encoder_backward(in, params, w, precision, grads, s);     // enqueues the head weight gradients on the side stream and joins them

@@ -724,10 +724,20 @@ int launch_head_backward_bn(Workspace& w, float* G, cudaStream_t s, int dgrad_ti
   return NRM_OK;
 }
 
-int launch_head_backward_wgrad(const float* P, Workspace& w, float* G, cudaStream_t s, int dgrad_tiles) {
+int launch_head_backward_wgrad(const float* P, Workspace& w, float* G, cudaStream_t s, int dgrad_tiles, int tc_precision) {
   int rpc, nchunks;
   head_wgrad_shape(w, rpc, nchunks);
   const int ntiles = dgrad_tiles > 0 ? dgrad_tiles : head_tiles(w.R);
+  if (tc_precision != 0) {
+    // tensor-core products: chunks of whole 64-row tiles, about one wave of 5-layer CTAs
+    int nch = (sm_count() + 4) / 5;
+    const int maxn = (int)((w.R + 63) / 64);
+    if (nch > maxn) nch = maxn;
+    if (nch > HEAD_WG_CHUNKS_MAX) nch = HEAD_WG_CHUNKS_MAX;
+    rpc = (int)(((w.R + nch - 1) / nch + 63) / 64 * 64);
+    nchunks = (int)((w.R + rpc - 1) / rpc);
+    NRM_TRY(launch_head_wgrad_tc(P, w, tc_precision, rpc, nchunks, s));
+  } else
   launch_pdl(head_wgrad_kernel, dim3(nchunks, 5), dim3(WG_THREADS), 0, s, w.e, w.mean, w.rstd, P, w.R, rpc, w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2, w.dgate, w.da1, w.head_part_w);
   NRM_LAUNCH_CHECK("head_wgrad_kernel");
   launch_pdl(head_grad_finish_kernel, dim3((WG_PART + GF_ENT - 1) / GF_ENT, 6), dim3(256), 0, s, w.head_part_w, nchunks, w.head_part_f, ntiles, w.head_part_bn, G, w.bn_bwd_sums, 0);

@@ -786,6 +786,158 @@ head_backward_tc_kernel(const float* __restrict__ e, const float* __restrict__ m
   if (warp == W_MMA) umma::tmem_dealloc(tmem, TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight gradients of the five Linear layers: dW_l [66][264] = Pn^T Qw over the candidate rows (same operands, partial layout and
+// finishing kernel as head_wgrad_kernel in nrm_head_fused.cu).  blockIdx.y = layer, blockIdx.x = row chunk.
+//   layer 0 out_mlp.fc1: Pn = da3,      Qw = y         | 1 mlp.fc2: Pn = gelu(a2), Qw = dy     | 2 mlp.fc1: Pn = da2, Qw = gate * e
+//   layer 3 gate.fc2   : Pn = gelu(a1), Qw = dgate     | 4 gate.fc1: Pn = da1,     Qw = BN(e)
+// The contraction runs over the ROWS: a tile of 64 rows is written once as two K-major bf16 tiles (Qw: 64 x 272, Pn: 64 x 80, hi | lo)
+// and both are read MN-major through the descriptor, D[feature][n] += Qw^T Pn, three M blocks (features 0-127, 128-255, 208-271),
+// accumulated in tensor memory over all tiles of the CTA.  Column 264 of Qw and column 66 of Pn are ones: row 264 / column 66 of D are
+// the column sums, i.e. the bias gradients.  hi / lo split (three products) as in the attention kernels.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 256;
+constexpr uint32_t WG_QPART = (KE / 8) * A_LBO, WG_PPART = (KH / 8) * A_LBO;
+constexpr uint32_t WG_COLS = 256;                     // three accumulator blocks of 72 columns
+constexpr int WG_PART = HID * E + E;                  // partial per (layer, chunk): [66][264] in (n, feature) order | bias [264]
+struct WgSmem {
+  __align__(128) unsigned char q[2 * WG_QPART];
+  __align__(128) unsigned char p[2 * WG_PPART];
+  uint64_t mbar;
+  uint32_t tmem_base;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+head_wgrad_tc_kernel(const float* __restrict__ e, const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ P,
+                     long long R, int rows_per_chunk, const float* __restrict__ a1g, const float* __restrict__ gateg,
+                     const float* __restrict__ a2g, const float* __restrict__ yg, const float* __restrict__ da3g, const float* __restrict__ dyg,
+                     const float* __restrict__ da2g, const float* __restrict__ dgateg, const float* __restrict__ da1g, float* __restrict__ part) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw);
+  const int layer = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long rbeg = (long long)blockIdx.x * rows_per_chunk, rend = min(R, rbeg + rows_per_chunk);
+  const float* Psrc = layer == 0 ? da3g : layer == 1 ? a2g : layer == 2 ? da2g : layer == 3 ? a1g : da1g;
+  const float* Qsrc = layer == 0 ? yg : layer == 1 ? dyg : layer == 2 ? gateg : layer == 3 ? dgateg : e;
+  const bool p_gelu = layer == 1 || layer == 3, wide_bias = p_gelu;
+  if (tid == 0) umma::mbar_init(&sm.mbar, 1);
+  if (warp == 0) umma::tmem_alloc(&sm.tmem_base, WG_COLS);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  constexpr uint32_t ID128 = umma::make_idesc_bf16(128, NN, true, true), ID64 = umma::make_idesc_bf16(64, NN, true, true);
+  uint32_t phase = 0;
+  bool started = false;
+  for (long long t0 = rbeg; t0 < rend; t0 += ROWS) {
+    const int nr = (int)min((long long)ROWS, rend - t0);
+    // ---- operand tiles of rows [t0, t0 + 64): items (row, 8-column block), consecutive lanes take consecutive rows
+    for (int it = tid; it < ROWS * (KE / 8); it += WG_THREADS) {
+      const int r = it & (ROWS - 1), kb = it >> 6;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      if (r < nr) {
+        if (kb < E / 8) {
+          const long long gi = (t0 + r) * E + 8 * kb;
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(Qsrc + gi)), x1 = __ldg(reinterpret_cast<const float4*>(Qsrc + gi) + 1);
+          v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+          if (layer == 2) {
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(e + gi)), e1 = __ldg(reinterpret_cast<const float4*>(e + gi) + 1);
+            v[0] *= e0.x; v[1] *= e0.y; v[2] *= e0.z; v[3] *= e0.w; v[4] *= e1.x; v[5] *= e1.y; v[6] *= e1.z; v[7] *= e1.w;
+          } else if (layer == 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = 8 * kb + i;
+              v[i] = (v[i] - __ldg(mean + c)) * __ldg(rstd + c) * __ldg(P + P_BN_W + c) + __ldg(P + P_BN_B + c);
+            }
+          }
+        } else {
+          v[0] = 1.0f;                                 // column 264: ones -> row 264 of D = column sums of Pn
+        }
+      }
+      split_store8<NP>(sm.q + a_off(r, kb), WG_QPART, v);
+    }
+    for (int it = tid; it < ROWS * (KH / 8); it += WG_THREADS) {
+      const int r = it & (ROWS - 1), kb = it >> 6;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      if (r < nr) {
+        const float* ap = Psrc + (t0 + r) * HID + 8 * kb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (8 * kb + 2 * i < HID) {
+            const float2 x = __ldg(reinterpret_cast<const float2*>(ap) + i);
+            v[2 * i] = p_gelu ? gelu_f(x.x) : x.x; v[2 * i + 1] = p_gelu ? gelu_f(x.y) : x.y;
+          }
+        if (kb == HID / 8) v[HID & 7] = 1.0f;          // column 66: ones -> column 66 of D = column sums of Qw
+      }
+      split_store8<NP>(sm.p + a_off(r, kb), WG_PPART, v);
+    }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0 && umma::elect_one()) {
+      umma::fence_after_sync();
+      const uint32_t qa = umma::smem_u32(sm.q), pa = umma::smem_u32(sm.p);
+#pragma unroll
+      for (int pr = 0; pr < n_products(NP); ++pr) {
+        const uint32_t qo = prod_a(NP, pr) * WG_QPART, po = prod_b(NP, pr) * WG_PPART;
+        // MN-major views of the K-major tiles: LBO (between K = row groups of 8) = 128, SBO (between 8-feature groups) = A_LBO
+        const uint64_t db = umma::make_desc(pa + po, 128, A_LBO);
+#pragma unroll
+        for (int blk = 0; blk < 3; ++blk) {
+          const uint32_t f0 = blk == 0 ? 0 : blk == 1 ? 128 : 208;
+          const uint64_t da = umma::make_desc(qa + qo + (f0 / 8) * A_LBO, 128, A_LBO);
+#pragma unroll
+          for (int ks = 0; ks < ROWS / 16; ++ks)       // 16 rows per K step: two row groups of 8 = 256 bytes
+            umma::mma_bf16(tmem + NN * blk, da + (uint64_t)(ks * (256 >> 4)), db + (uint64_t)(ks * (256 >> 4)), blk == 2 ? ID64 : ID128,
+                           (started || pr > 0 || ks > 0) ? 1u : 0u);
+        }
+      }
+      umma::mma_commit(&sm.mbar);
+    }
+    started = true;
+    umma::mbar_wait(&sm.mbar, phase);                  // the tiles are rewritten by the next iteration
+    phase ^= 1;
+  }
+  // ---- per-CTA partial: out[n][feature] = D[feature][n]; bias = column sums
+  umma::fence_after_sync();
+  float* out = part + ((long long)layer * gridDim.x + blockIdx.x) * WG_PART;
+  const int sp = warp & 3, half = warp >> 2;           // 8 warps: sub-partition, half of the 72 columns
+  float v[40];
+#pragma unroll 1
+  for (int blk = 0; blk < 3; ++blk) {
+    const uint32_t a = tmem + NN * blk + 36 * half + ((uint32_t)(32 * sp) << 16);
+    umma::tmem_ld32(a, v);
+    umma::tmem_ld8(a + 32, v + 32);                    // (4 columns more than this half needs)
+    int f;
+    bool ok;
+    if (blk < 2) { f = 128 * blk + 32 * sp + lane; ok = true; }
+    else { f = 208 + 16 * sp + lane; ok = lane < 16 && f >= 256; }       // M = 64: lanes 0-15 of each sub-partition; features 256-264 are new
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < 36; ++j) {
+        const int n = 36 * half + j;
+        const float x = started ? v[j] : 0.f;
+        if (f < E) {
+          if (n < HID) out[n * E + f] = x;
+          else if (n == HID && wide_bias) out[HID * E + f] = x;
+        } else if (f == E && !wide_bias && n < HID) {
+          out[HID * E + n] = x;
+        }
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, WG_COLS);
+}
+
 }  // namespace htc
 
 int headprof_read(long long* host_out32) {
@@ -848,6 +1000,24 @@ static int launch_bwd(const float* P, Workspace& w, const float* dlogits, float*
              reinterpret_cast<const unsigned char*>(w.head_img), w.R, dlogits, w.a1, w.gate, w.a2, w.a3, w.da3, w.dy, w.da2, w.dgate, w.da1, w.dz,
              w.de, w.head_part_f, w.head_part_bn, w.head_arrive, G, w.bn_bwd_sums);
   NRM_LAUNCH_CHECK("head_backward_tc_kernel");
+  return NRM_OK;
+}
+
+
+// weight gradients on the tensor cores: partials in head_wgrad_kernel's layout; returns the number of row chunks
+int launch_head_wgrad_tc(const float* P, Workspace& w, int precision, int rows_per_chunk, int nchunks, cudaStream_t s) {
+  static DeviceOnce configured;
+  if (configured.first_time()) {
+    NRM_CUDA(cudaFuncSetAttribute(htc::head_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(htc::WgSmem)));
+    NRM_CUDA(cudaFuncSetAttribute(htc::head_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(htc::WgSmem)));
+  }
+  if (precision == NRM_PRECISION_BF16)
+    launch_pdl(htc::head_wgrad_tc_kernel<1>, dim3(nchunks, 5), dim3(htc::WG_THREADS), sizeof(htc::WgSmem), s, w.e, w.mean, w.rstd, P, w.R, rows_per_chunk,
+               w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2, w.dgate, w.da1, w.head_part_w);
+  else
+    launch_pdl(htc::head_wgrad_tc_kernel<2>, dim3(nchunks, 5), dim3(htc::WG_THREADS), sizeof(htc::WgSmem), s, w.e, w.mean, w.rstd, P, w.R, rows_per_chunk,
+               w.a1, w.gate, w.a2, w.y, w.da3, w.dy, w.da2, w.dgate, w.da1, w.head_part_w);
+  NRM_LAUNCH_CHECK("head_wgrad_tc_kernel");
   return NRM_OK;
 }
 

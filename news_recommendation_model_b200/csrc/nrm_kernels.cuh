@@ -53,7 +53,7 @@ int launch_head_forward_fused(const float* P, Workspace& w, float* run_mean, flo
                               const double* bn_sums, long long bn_rows, float* logits, cudaStream_t s);
 int launch_head_backward_dgrad(const float* P, Workspace& w, const float* dlogits, cudaStream_t s);
 int launch_head_backward_bn(Workspace& w, float* grads, cudaStream_t s, int dgrad_tiles);   // dgrad_tiles: row tiles of the dgrad kernel (0 = FFMA kernel's)                   // -> w.bn_bwd_sums, bn.weight / bn.bias gradients
-int launch_head_backward_wgrad(const float* P, Workspace& w, float* grads, cudaStream_t s, int dgrad_tiles);   // weight gradients of the five Linear layers + out_mlp.fc2
+int launch_head_backward_wgrad(const float* P, Workspace& w, float* grads, cudaStream_t s, int dgrad_tiles, int tc_precision = 0);   // tc_precision != 0: products on tcgen05   // weight gradients of the five Linear layers + out_mlp.fc2
 int launch_head_backward_fused(const float* P, Workspace& w, const float* dlogits, float* grads, cudaStream_t s);   // -> w.bn_bwd_sums, w.dz, w.de
 
 // nrm_head_tc.cu  (tensor-core head; precision = bf16 / bf16x3)
@@ -61,6 +61,7 @@ size_t head_tc_image_bytes();
 int headprof_read(long long* host_out32);                                       // -DNRM_RS_PROFILE builds only
 int launch_head_images_tc(const float* P, Workspace& w, int precision, bool with_backward, cudaStream_t s);   // weights only -> w.head_img
 int head_tc_tiles(long long R);
+int launch_head_wgrad_tc(const float* P, Workspace& w, int precision, int rows_per_chunk, int nchunks, cudaStream_t s);   // partials in head_wgrad_kernel's layout
 // tensor-core data-gradient chain: as launch_head_backward_dgrad + launch_head_backward_bn, except that w.de holds dx (not dx * gate)
 int launch_head_backward_dgrad_tc(const float* P, Workspace& w, int precision, const float* dlogits, float* grads, cudaStream_t s);
 int launch_head_forward_tc(const float* P, Workspace& w, int precision, float* run_mean, float* run_var, long long* nbt, int training, int keep,
