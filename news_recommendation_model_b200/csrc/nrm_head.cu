@@ -48,6 +48,15 @@ bn_bwd_combine_kernel(const float* __restrict__ dz, const float* __restrict__ e,
                       long long rows, int training, long long total4, const float* __restrict__ gate, float* __restrict__ de) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
+  // per-column means of dz and dz * xhat once per block (two double divisions per column instead of eight per element)
+  __shared__ __align__(16) float s_m1[E], s_m2[E];
+  if (training) {
+    for (int n = threadIdx.x; n < E; n += 256) {
+      s_m1[n] = (float)(sums[n] / (double)rows);
+      s_m2[n] = (float)(sums[E + n] / (double)rows);
+    }
+    __syncthreads();
+  }
   // four consecutive columns per thread (264 = 66 x 4: a float4 never straddles a row)
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total4; i += (long long)gridDim.x * 256) {
     const int n = (int)(i % (E / 4)) * 4;
@@ -55,14 +64,11 @@ bn_bwd_combine_kernel(const float* __restrict__ dz, const float* __restrict__ e,
     float4 v = __ldg(reinterpret_cast<const float4*>(dz) + i);
     if (training) {
       const float4 x = __ldg(reinterpret_cast<const float4*>(e) + i), mu = *reinterpret_cast<const float4*>(mean + n);
-      const float m1[4] = {(float)(sums[n] / (double)rows), (float)(sums[n + 1] / (double)rows), (float)(sums[n + 2] / (double)rows),
-                           (float)(sums[n + 3] / (double)rows)};
-      const float m2[4] = {(float)(sums[E + n] / (double)rows), (float)(sums[E + n + 1] / (double)rows),
-                           (float)(sums[E + n + 2] / (double)rows), (float)(sums[E + n + 3] / (double)rows)};
-      v.x = v.x - m1[0] - (x.x - mu.x) * rs.x * m2[0];
-      v.y = v.y - m1[1] - (x.y - mu.y) * rs.y * m2[1];
-      v.z = v.z - m1[2] - (x.z - mu.z) * rs.z * m2[2];
-      v.w = v.w - m1[3] - (x.w - mu.w) * rs.w * m2[3];
+      const float4 m1 = *reinterpret_cast<const float4*>(s_m1 + n), m2 = *reinterpret_cast<const float4*>(s_m2 + n);
+      v.x = v.x - m1.x - (x.x - mu.x) * rs.x * m2.x;
+      v.y = v.y - m1.y - (x.y - mu.y) * rs.y * m2.y;
+      v.z = v.z - m1.z - (x.z - mu.z) * rs.z * m2.z;
+      v.w = v.w - m1.w - (x.w - mu.w) * rs.w * m2.w;
     }
     float4 d = reinterpret_cast<float4*>(de)[i];
     if (gate != nullptr) {

@@ -98,18 +98,26 @@ loss_forward_kernel(const float* __restrict__ logits, const float* __restrict__ 
   }
   if (lane == 0) { red[warp][0] = l1; red[warp][1] = l2; }
   __syncthreads();
+  __shared__ unsigned last_block;
   if (threadIdx.x == 0) {
     double s1 = 0.0, s2 = 0.0;
     for (int i = 0; i < 8; ++i) { s1 += red[i][0]; s2 += red[i][1]; }
     lpart[blockIdx.x * 2 + 0] = s1; lpart[blockIdx.x * 2 + 1] = s2;
-    // the block that arrives last adds the block sums in block order (deterministic) and leaves the counter at zero
     __threadfence();
-    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
-      __threadfence();
-      s1 = 0.0; s2 = 0.0;
-      for (unsigned i = 0; i < gridDim.x; ++i) { s1 += __ldcg(lpart + i * 2); s2 += __ldcg(lpart + i * 2 + 1); }
+    last_block = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  // the block that arrives last adds the block sums (deterministic: lane l takes blocks l, l + 32, ... in order, the lanes are
+  // combined in lane order; every load is in flight at once) and leaves the counter at zero
+  if (last_block != 0u && warp == 0) {
+    __threadfence();
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned i = lane; i < gridDim.x; i += 32) { s1 += __ldcg(lpart + i * 2); s2 += __ldcg(lpart + i * 2 + 1); }
+    double t1 = 0.0, t2 = 0.0;
+    for (int l = 0; l < 32; ++l) { t1 += __shfl_sync(0xffffffffu, s1, l); t2 += __shfl_sync(0xffffffffu, s2, l); }
+    if (lane == 0) {
       const double n = (double)B * (double)C;
-      const float a = (float)(s1 / n), c = (float)(s2 / n);
+      const float a = (float)(t1 / n), c = (float)(t2 / n);
       *loss = (1.f - alpha) * a + alpha * c;
       *ticket = 0u;
     }
