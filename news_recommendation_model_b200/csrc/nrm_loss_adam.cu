@@ -371,11 +371,15 @@ adam_allreduce_kernel(float* __restrict__ p, float* __restrict__ m, float* __res
     }
   }
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
-    float4 gg = ld_peer_f4(c->grad[0] + 4 * i);
-    for (int r = 1; r < world; ++r) {
-      const float4 x = ld_peer_f4(c->grad[r] + 4 * i);
-      gg.x += x.x; gg.y += x.y; gg.z += x.z; gg.w += x.w;
-    }
+    // all ranks' loads in flight at once (a load-add loop serialises one NVLink round trip per rank), summed in rank order
+    float4 x[PEER_MAX];
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; ++r)
+      if (r < world) x[r] = ld_peer_f4(c->grad[r] + 4 * i);
+    float4 gg = x[0];
+#pragma unroll
+    for (int r = 1; r < PEER_MAX; ++r)
+      if (r < world) { gg.x += x[r].x; gg.y += x[r].y; gg.z += x[r].z; gg.w += x[r].w; }
     gg.x *= inv; gg.y *= inv; gg.z *= inv; gg.w *= inv;
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -454,8 +458,14 @@ peer_allsum_stats_kernel(const double* __restrict__ local, int which, double* __
   peer_wait(c, PEER_SLOT_STATS_FWD + which, epoch);
   __syncthreads();
   if (t < BN_STATS) {
+    double x[PEER_MAX];
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; ++r)
+      if (r < c->world) x[r] = ld_peer_d(c->stats[r] + which * BN_STATS + t);      // every rank's value in flight at once
     double s = 0.0;
-    for (int r = 0; r < c->world; ++r) s += ld_peer_d(c->stats[r] + which * BN_STATS + t);
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; ++r)
+      if (r < c->world) s += x[r];
     out[t] = s;
   }
 }
@@ -488,7 +498,17 @@ extern "C" int nrm_adam_step_allreduce(float* param, float* exp_avg, float* exp_
   launch_pdl(adam_prepare_kernel, dim3(1), dim3(32), 0, s, st);
   NRM_LAUNCH_CHECK("adam_prepare_kernel");
   long long blocks = ((n + 3) / 4 + 255) / 256;
-  const long long cap = (long long)sm_count() * 4;             // every block is resident: each one waits for the peers' flags
+  // every block must be resident (each one waits for the peers' flags, and the sparse path has a grid barrier): the cap comes from
+  // the occupancy the driver reports for this kernel, not from an assumed register count
+  static DeviceOnce configured;
+  static int per_sm[64];
+  const int dev = current_device();
+  if (configured.first_time() || per_sm[dev & 63] == 0) {
+    int nb = 0;
+    NRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, adam_allreduce_kernel, 256, 0));
+    per_sm[dev & 63] = nb > 0 ? nb : 1;
+  }
+  const long long cap = (long long)sm_count() * per_sm[dev & 63];
   if (blocks > cap) blocks = cap;
   KernelTimer t("adam", s);
   launch_pdl(adam_allreduce_kernel, dim3((int)blocks), dim3(256), 0, s, param, exp_avg, exp_avg_sq, st, (const PeerCtx*)peer_ctx, (unsigned*)ticket);
