@@ -958,13 +958,14 @@ attention_tp_grad_block(int block, TpgSmem& sm, const float* __restrict__ dtp_al
   const int toff = branch == 0 ? E_XT : E_PCAT;
   const float* W = P + (branch == 0 ? ATT_LABEL.fc1_w : ATT_TI.fc1_w);     // fc1.weight [64,256]
   const int input_grads = branch == 0;
-  float* part = part_all + (long long)branch * nparts * TPG_PART;
+  const int nblocks = (nparts + TPG_SUB - 1) / TPG_SUB;                    // one partial per BLOCK: its four tiles are added in tile order
+  float* part = part_all + (long long)branch * nblocks * TPG_PART;
   const int sub = threadIdx.x >> 8, tid = threadIdx.x & 255;
   const int tile = block * TPG_SUB + sub;
   float (*sd)[65] = sm.sd[sub];
   float (*st)[64] = sm.st[sub];
   const long long r0 = (long long)tile * TPG_ROWS;
-  const int nr = (int)max(0LL, min((long long)TPG_ROWS, R - r0));
+  const int nr = (int)max(0LL, min((long long)TPG_ROWS, R - r0));          // 0 for a tile past the end: it contributes zeros
   for (int i = tid; i < TPG_ROWS * 64; i += 256) {
     const int r = i >> 6, k = i & 63;
     sd[r][k] = r < nr ? __ldg(dtp + (r0 + r) * 64 + k) : 0.f;
@@ -976,33 +977,24 @@ attention_tp_grad_block(int block, TpgSmem& sm, const float* __restrict__ dtp_al
       sm.sB[j][k] = __ldg(W + j * 256 + 64 + k) + __ldg(W + j * 256 + 128 + k);
     }
   __syncthreads();
-  if (tile >= nparts) return;
-  {
-    // dBm partial: thread (tj, tk) owns a 4 x 4 block of [j][k]
-    const int tj = tid >> 4, tk = tid & 15;
-    float acc[4][4];
+  // dBm partial: thread (tj, tk) owns a 4 x 4 block of [j][k]
+  const int tj = tid >> 4, tk = tid & 15;
+  float acc[4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    float b1[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float b1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-    for (int r = 0; r < TPG_ROWS; ++r) {
-      const float dv[4] = {sd[r][4 * tj], sd[r][4 * tj + 1], sd[r][4 * tj + 2], sd[r][4 * tj + 3]};
-      const float4 tk4 = *reinterpret_cast<const float4*>(&st[r][4 * tk]);
-      const float tv[4] = {tk4.x, tk4.y, tk4.z, tk4.w};
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        b1[a] += dv[a];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], tv[b], acc[a][b]);
-      }
-    }
-    float* out = part + (long long)tile * TPG_PART;
+  for (int r = 0; r < TPG_ROWS; ++r) {
+    const float dv[4] = {sd[r][4 * tj], sd[r][4 * tj + 1], sd[r][4 * tj + 2], sd[r][4 * tj + 3]};
+    const float4 tk4 = *reinterpret_cast<const float4*>(&st[r][4 * tk]);
+    const float tv[4] = {tk4.x, tk4.y, tk4.z, tk4.w};
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      *reinterpret_cast<float4*>(out + (4 * tj + a) * 64 + 4 * tk) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-      if (tk == 0) out[4096 + 4 * tj + a] = b1[a];
+      b1[a] += dv[a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], tv[b], acc[a][b]);
     }
   }
   if (input_grads) {
@@ -1018,6 +1010,36 @@ attention_tp_grad_block(int block, TpgSmem& sm, const float* __restrict__ dtp_al
     if (r < nr) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) dxt[(r0 + r) * 64 + kq + 8 * i] += v[i];
+    }
+  }
+  // the four tiles of the block: tiles 1-3 hand their sums over through shared memory (the row buffers are free now), tile 0 adds
+  // them in tile order and writes the block's partial
+  __syncthreads();
+  float* xch = &sm.sd[0][0][0];                                             // >= 3 * TPG_PART floats (sd and st are contiguous)
+  static_assert(sizeof(TpgSmem::sd) + sizeof(TpgSmem::st) >= 3 * TPG_PART * sizeof(float), "exchange area");
+  if (sub > 0) {
+    float* o = xch + (sub - 1) * TPG_PART;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      *reinterpret_cast<float4*>(o + (4 * tj + a) * 64 + 4 * tk) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+      if (tk == 0) o[4096 + 4 * tj + a] = b1[a];
+    }
+  }
+  __syncthreads();
+  if (sub == 0) {
+    float* out = part + (long long)block * TPG_PART;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float4 v = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+      float bb = b1[a];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const float4 x = *reinterpret_cast<const float4*>(xch + t * TPG_PART + (4 * tj + a) * 64 + 4 * tk);
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+        bb += xch[t * TPG_PART + 4096 + 4 * tj + a];
+      }
+      *reinterpret_cast<float4*>(out + (4 * tj + a) * 64 + 4 * tk) = v;
+      if (tk == 0) out[4096 + 4 * tj + a] = bb;
     }
   }
 }
@@ -1211,7 +1233,7 @@ int launch_attention_finish_tc(const float* P, Workspace& w, float* grads, cudaS
   }
   launch_pdl(attention_finish_kernel, dim3(COMPOSE_BLOCKS + (nparts + TPG_SUB - 1) / TPG_SUB, 2), dim3(1024), sizeof(TpgSmem), s, w.att_part, w.att_tc_parts[0], w.att_tc_parts[1], grads, w.att_dA, w.dtp, w.e, w.R, P, w.dxt, w.tp_part, nparts);
   NRM_LAUNCH_CHECK("attention_finish_kernel");
-  launch_pdl(attention_tp_finish_kernel, dim3(dim3(TPG_PART / 64, 2)), dim3(256), 0, s, w.tp_part, nparts, w.att_dA, grads);
+  launch_pdl(attention_tp_finish_kernel, dim3(dim3(TPG_PART / 64, 2)), dim3(256), 0, s, w.tp_part, (nparts + TPG_SUB - 1) / TPG_SUB, w.att_dA, grads);
   NRM_LAUNCH_CHECK("attention_tp_finish_kernel");
   return NRM_OK;
 }
