@@ -834,32 +834,46 @@ head_wgrad_tc_kernel(const float* __restrict__ e, const float* __restrict__ mean
   bool started = false;
   for (long long t0 = rbeg; t0 < rend; t0 += ROWS) {
     const int nr = (int)min((long long)ROWS, rend - t0);
-    // ---- operand tiles of rows [t0, t0 + 64): items (row, 8-column block), consecutive lanes take consecutive rows
-    for (int it = tid; it < ROWS * (KE / 8); it += WG_THREADS) {
-      const int r = it & (ROWS - 1), kb = it >> 6;
-      float v[8];
+    // ---- operand tiles of rows [t0, t0 + 64): items (row, 8-column block), consecutive lanes take consecutive rows.  The loads of
+    // a batch of items are all issued before the first one is used (a load -> convert -> store loop pays one memory round trip per item)
+    constexpr int QITEMS = ROWS * (KE / 8), QIT = (QITEMS + WG_THREADS - 1) / WG_THREADS;      // 9 items per thread
+    constexpr int QBATCH = 5;
+#pragma unroll 1
+    for (int u0 = 0; u0 < QIT; u0 += QBATCH) {
+      float4 qv[QBATCH][2], ev[QBATCH][2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (r < nr) {
-        if (kb < E / 8) {
+      for (int u = 0; u < QBATCH; ++u) {
+        const int it = tid + (u0 + u) * WG_THREADS, r = it & (ROWS - 1), kb = it >> 6;
+        qv[u][0] = qv[u][1] = ev[u][0] = ev[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u0 + u < QIT && it < QITEMS && r < nr && kb < E / 8) {
           const long long gi = (t0 + r) * E + 8 * kb;
-          const float4 x0 = __ldg(reinterpret_cast<const float4*>(Qsrc + gi)), x1 = __ldg(reinterpret_cast<const float4*>(Qsrc + gi) + 1);
-          v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-          if (layer == 2) {
-            const float4 e0 = __ldg(reinterpret_cast<const float4*>(e + gi)), e1 = __ldg(reinterpret_cast<const float4*>(e + gi) + 1);
-            v[0] *= e0.x; v[1] *= e0.y; v[2] *= e0.z; v[3] *= e0.w; v[4] *= e1.x; v[5] *= e1.y; v[6] *= e1.z; v[7] *= e1.w;
-          } else if (layer == 4) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int c = 8 * kb + i;
-              v[i] = (v[i] - __ldg(mean + c)) * __ldg(rstd + c) * __ldg(P + P_BN_W + c) + __ldg(P + P_BN_B + c);
-            }
-          }
-        } else {
-          v[0] = 1.0f;                                 // column 264: ones -> row 264 of D = column sums of Pn
+          qv[u][0] = __ldg(reinterpret_cast<const float4*>(Qsrc + gi)); qv[u][1] = __ldg(reinterpret_cast<const float4*>(Qsrc + gi) + 1);
+          if (layer == 2) { ev[u][0] = __ldg(reinterpret_cast<const float4*>(e + gi)); ev[u][1] = __ldg(reinterpret_cast<const float4*>(e + gi) + 1); }
         }
       }
-      split_store8<NP>(sm.q + a_off(r, kb), WG_QPART, v);
+#pragma unroll
+      for (int u = 0; u < QBATCH; ++u) {
+        const int it = tid + (u0 + u) * WG_THREADS, r = it & (ROWS - 1), kb = it >> 6;
+        if (u0 + u >= QIT || it >= QITEMS) break;
+        float v[8] = {qv[u][0].x, qv[u][0].y, qv[u][0].z, qv[u][0].w, qv[u][1].x, qv[u][1].y, qv[u][1].z, qv[u][1].w};
+        if (r < nr) {
+          if (kb < E / 8) {
+            if (layer == 2) {
+              v[0] *= ev[u][0].x; v[1] *= ev[u][0].y; v[2] *= ev[u][0].z; v[3] *= ev[u][0].w;
+              v[4] *= ev[u][1].x; v[5] *= ev[u][1].y; v[6] *= ev[u][1].z; v[7] *= ev[u][1].w;
+            } else if (layer == 4) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int c = 8 * kb + i;
+                v[i] = (v[i] - __ldg(mean + c)) * __ldg(rstd + c) * __ldg(P + P_BN_W + c) + __ldg(P + P_BN_B + c);
+              }
+            }
+          } else {
+            v[0] = 1.0f;                               // column 264: ones -> row 264 of D = column sums of Pn
+          }
+        }
+        split_store8<NP>(sm.q + a_off(r, kb), WG_QPART, v);
+      }
     }
     for (int it = tid; it < ROWS * (KH / 8); it += WG_THREADS) {
       const int r = it & (ROWS - 1), kb = it >> 6;

@@ -67,7 +67,7 @@ __device__ __forceinline__ void build_w_jk(const float* __restrict__ W, unsigned
 // W1^T as a K-major tile [80 rows k][64 j] (LBO = 80 rows * 16 B = 1280): B operand of the dxin product
 template <int NP>
 __device__ __forceinline__ void build_w_kj(const float* __restrict__ W, unsigned char* tile, uint32_t part) {
-  for (int it = threadIdx.x; it < KX * 8; it += THREADS) {
+  for (int it = threadIdx.x; it < KX * 8; it += (int)blockDim.x) {
     const int k = it % KX, jb = it / KX;
     float v[8];
 #pragma unroll
@@ -142,7 +142,7 @@ w1_forward_tc_kernel(const float* __restrict__ xin, const float* __restrict__ P,
 // fp32 rows already staged in shared memory (row-major, `cols` floats per row, cp.async) -> K-major bf16 tile(s)
 template <int NP, int KB>
 __device__ __forceinline__ void convert_staged(const float* __restrict__ stg, int cols, int nr, unsigned char* tile, uint32_t part, int one_col) {
-  for (int it = threadIdx.x; it < ROWS * KB; it += THREADS) {
+  for (int it = threadIdx.x; it < ROWS * KB; it += (int)blockDim.x) {
     const int r = it & (ROWS - 1), kb = it >> 7;
     float v[8];
 #pragma unroll
@@ -164,9 +164,9 @@ __device__ __forceinline__ void convert_staged(const float* __restrict__ stg, in
 // a tile of rows is one contiguous block of global memory: 16-byte cp.async, every request in flight at once
 __device__ __forceinline__ void stage_rows(float* stg, const float* __restrict__ src, int nfloats) {
   const int n4 = nfloats >> 2;                            // tile starts are multiples of 128 rows: 16-byte aligned; nfloats is even
-  for (int i = threadIdx.x; i < n4; i += THREADS)
+  for (int i = threadIdx.x; i < n4; i += (int)blockDim.x)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(umma::smem_u32(stg + 4 * i)), "l"(src + 4 * i) : "memory");
-  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += THREADS) stg[i] = __ldg(src + i);
+  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += (int)blockDim.x) stg[i] = __ldg(src + i);
 }
 
 template <int NP>
@@ -181,8 +181,9 @@ struct SmemBwd {
 };
 constexpr uint32_t COL_DX = 0, COL_DW = 128, BWD_COLS = 256;   // dxin accumulator [128][80]; dW1^T-side accumulator [64 j][80 k]
 
+constexpr int BWD_THREADS = 512;              // 16 warps stage and convert the tiles; warps 0-7 read the accumulators back
 template <int SPLIT>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(BWD_THREADS)
 w1_backward_tc_kernel(const float* __restrict__ xin, const float* __restrict__ dxh, const float* __restrict__ P, float* __restrict__ dxin,
                       long long NH, float* __restrict__ part) {
   pdl_wait();
@@ -241,6 +242,7 @@ w1_backward_tc_kernel(const float* __restrict__ xin, const float* __restrict__ d
     phase ^= 1;
     umma::fence_after_sync();
     // dxin rows: thread = (row, column half of 40)
+    if (warp < 8) {
     float v[40];
     umma::tmem_ld32(tmem + COL_DX + 40 * half + ((uint32_t)(32 * sp) << 16), v);
     umma::tmem_ld8(tmem + COL_DX + 40 * half + 32 + ((uint32_t)(32 * sp) << 16), v + 32);
@@ -253,11 +255,12 @@ w1_backward_tc_kernel(const float* __restrict__ xin, const float* __restrict__ d
       for (int q = 0; q < 20; ++q)
         if (2 * q < ncol) dst[q] = make_float2(v[2 * q], v[2 * q + 1]);
     }
+    }
   }
   // per-CTA partial of dW1 / db1: an M = 64 accumulator occupies lanes 0-15 of every sub-partition (j = 16 sp + lane)
   umma::fence_after_sync();
   float* out = part + (long long)blockIdx.x * W1_PART;
-  {
+  if (warp < 8) {
     float v[40];
     umma::tmem_ld32(tmem + COL_DW + 40 * half + ((uint32_t)(32 * sp) << 16), v);
     umma::tmem_ld8(tmem + COL_DW + 40 * half + 32 + ((uint32_t)(32 * sp) << 16), v + 32);
@@ -303,7 +306,7 @@ static int launch_bwd(const float* P, Workspace& w, float* G, cudaStream_t s) {
   const long long ntiles = (w.NH + w1tc::ROWS - 1) / w1tc::ROWS;
   const int grid = (int)min(ntiles, (long long)min(sm_count(), W1_SPLITS));      // one CTA per SM (157 KB of shared memory), tiles in a grid-stride loop
   NRM_CUDA(cudaFuncSetAttribute(w1tc::w1_backward_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  launch_pdl(w1tc::w1_backward_tc_kernel<SPLIT>, dim3(grid), dim3(w1tc::THREADS), smem, s, w.xin_h, w.dxh, P, w.dxin_h, w.NH, w.splitk);
+  launch_pdl(w1tc::w1_backward_tc_kernel<SPLIT>, dim3(grid), dim3(w1tc::BWD_THREADS), smem, s, w.xin_h, w.dxh, P, w.dxin_h, w.NH, w.splitk);
   NRM_LAUNCH_CHECK("w1_backward_tc_kernel");
   return launch_w1_finish(w, grid, G, s);
 }
