@@ -268,9 +268,14 @@ class FusedTrainStep:
         with torch.cuda.stream(self.copy_stream):
             if s.used:
                 self.copy_stream.wait_event(s.consumed)
-            for f in ('hist_article', 'hist_time', 'hist_click', 'cand_article', 'cand_time', 'label'):
-                getattr(s.compact, f)[:b].copy_(getattr(batch, f), non_blocking=True)
-            s.uid[:b].copy_(batch.user_id, non_blocking=True)
+            fields = ('hist_article', 'hist_time', 'hist_click', 'cand_article', 'cand_time', 'label')
+            if b == self.B:                                  # full batch: one multi-tensor copy call (host time, not bytes, is what counts here)
+                torch._foreach_copy_([getattr(s.compact, f) for f in fields] + [s.uid], [getattr(batch, f) for f in fields] + [batch.user_id],
+                                     non_blocking=True)
+            else:
+                for f in fields:
+                    getattr(s.compact, f)[:b].copy_(getattr(batch, f), non_blocking=True)
+                s.uid[:b].copy_(batch.user_id, non_blocking=True)
             s.ready.record(self.copy_stream)
         loader = getattr(batch, '_loader', None)
         if loader is not None:                               # wire.PrefetchLoader: its pinned ring slot is free once these copies are done
@@ -301,11 +306,15 @@ class FusedTrainStep:
         with torch.cuda.stream(self.copy_stream):
             if s.used:
                 self.copy_stream.wait_event(s.consumed)      # do not overwrite a slot still being read
-            s.xh[:b].copy_(batch.x_history, non_blocking=True)
-            s.xt[:b].copy_(batch.x_target, non_blocking=True)
-            s.xg[:b].copy_(batch.x_global, non_blocking=True)
-            s.label[:b].copy_(batch.label, non_blocking=True)
-            s.uid[:b].copy_(batch.user_id, non_blocking=True)
+            if b == self.B:
+                torch._foreach_copy_([s.xh, s.xt, s.xg, s.label, s.uid], [batch.x_history, batch.x_target, batch.x_global, batch.label, batch.user_id],
+                                     non_blocking=True)
+            else:
+                s.xh[:b].copy_(batch.x_history, non_blocking=True)
+                s.xt[:b].copy_(batch.x_target, non_blocking=True)
+                s.xg[:b].copy_(batch.x_global, non_blocking=True)
+                s.label[:b].copy_(batch.label, non_blocking=True)
+                s.uid[:b].copy_(batch.user_id, non_blocking=True)
             s.ready.record(self.copy_stream)
         return s
 
