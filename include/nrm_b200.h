@@ -197,6 +197,31 @@ int nrm_backward_encoder(const double* x_history, const double* x_target, long l
                          const double* bn_bwd_sums, long long bn_global_rows, float* grads,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the compact wire format as a direct input (no expansion to the packed float64 tensors) ----------------------------
+ * nrm_expand_compact (below) rebuilds the reference's packed tensors for the entry points above.  These variants hand the
+ * article table + per-impression ids / time buckets / click features straight to the row kernels instead: the 36 MB of
+ * float64 rows are neither written nor read.  Same results, bit for bit.  Tensor-core precisions only (the FFMA attention
+ * kernels of precision fp32 read the packed rows): NRM_EUNSUPPORTED otherwise.  label32 / label64 are optional (both null):
+ * when given, the float32 labels are converted to the float64 labels nrm_loss_forward reads. */
+typedef struct {
+  const float* articles; int n_articles;      /* [n,80] float32, row 0 = the all-zero pad article                 */
+  const int* hist_article; const unsigned* hist_time; const float* hist_click;   /* [B,H], [B,H] packed buckets, [B,H,2] */
+  const int* cand_article; const unsigned* cand_time;                            /* [B,C], [B,C]                          */
+  const float* label32; double* label64;      /* [B,C] each, optional                                              */
+} nrm_compact_batch;
+int nrm_forward_compact(const nrm_compact_batch* batch, int B, int H, int C, const float* params, float* bn_running_mean,
+                        float* bn_running_var, long long* bn_num_batches_tracked, int mode, int precision,
+                        float* logits, void* workspace, size_t workspace_bytes, void* stream);
+int nrm_forward_encoder_compact(const nrm_compact_batch* batch, int B, int H, int C, const float* params, int mode, int precision,
+                                double* bn_sums, void* workspace, size_t workspace_bytes, void* stream);
+int nrm_backward_compact(const nrm_compact_batch* batch, int B, int H, int C, const float* params, int mode, int precision,
+                         const float* dlogits, float* grads, void* workspace, size_t workspace_bytes, void* stream);
+int nrm_backward_encoder_compact(const nrm_compact_batch* batch, int B, int H, int C, const float* params, int mode, int precision,
+                                 const double* bn_bwd_sums, long long bn_global_rows, float* grads, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
+
+
 /* ---- UserModel.loss (user_model.py:37-43) ---------------------------------------- */
 /* loss = (1-alpha) BCE(softmax(out), y) + alpha BCE(softmax(out + delta[id]), y), mean
  * over B*C, log clamped at -100 (nn.BCELoss).  Writes *loss (float32) and keeps the unit

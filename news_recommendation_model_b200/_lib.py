@@ -43,6 +43,10 @@ SIGNATURES = {
     'nrm_forward_encoder': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, vp, sz, vp]),
     'nrm_forward_head': (i32, [i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, ll, vp, vp, sz, vp]),
     'nrm_backward': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, vp, vp, sz, vp]),
+    'nrm_forward_compact': (i32, [vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp]),
+    'nrm_forward_encoder_compact': (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp, sz, vp]),
+    'nrm_backward_compact': (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, sz, vp]),
+    'nrm_backward_encoder_compact': (i32, [vp, i32, i32, i32, vp, i32, i32, vp, ll, vp, vp, sz, vp]),
     'nrm_backward_head': (i32, [i32, i32, i32, vp, i32, vp, vp, vp, vp, sz, vp]),
     'nrm_backward_head_deferred': (i32, [i32, i32, i32, vp, i32, vp, vp, vp, vp, sz, vp]),
     'nrm_backward_encoder': (i32, [vp, vp, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, ll, vp, vp, sz, vp]),
@@ -113,3 +117,10 @@ def layout():
     entries = [(lib.nrm_layout_name(i).decode(), int(lib.nrm_layout_offset(i)), int(lib.nrm_layout_numel(i)))
                for i in range(lib.nrm_layout_entries())]
     return entries, int(lib.nrm_layout_fixed_floats())
+
+
+class CompactBatchStruct(C.Structure):
+    """`nrm_compact_batch` of include/nrm_b200.h: the compact wire format as a direct input of the row kernels."""
+    _fields_ = [('articles', C.c_void_p), ('n_articles', C.c_int), ('hist_article', C.c_void_p), ('hist_time', C.c_void_p),
+                ('hist_click', C.c_void_p), ('cand_article', C.c_void_p), ('cand_time', C.c_void_p), ('label32', C.c_void_p),
+                ('label64', C.c_void_p)]

@@ -426,16 +426,11 @@ extern "C" size_t nrm_workspace_e_offset(int B, int H, int C, int mode) {
   return (size_t)(reinterpret_cast<uintptr_t>(w.e) - 256);
 }
 
-extern "C" int nrm_forward_encoder(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
-                                   long long xg_bs, int B, int H, int C, const float* params, int mode, int precision,
-                                   double* bn_sums, void* workspace, size_t workspace_bytes, void* stream) {
-  NRM_TRY(check_shape("nrm_forward_encoder", B, H, C));
-  if (!x_history || !x_target || !x_global || !params) { set_error("nrm_forward_encoder: null pointer"); return NRM_EINVAL; }
-  if (xt_bs < (long long)C * TC || xg_bs < (long long)C * GC) { set_error("nrm_forward_encoder: batch stride smaller than one impression"); return NRM_EINVAL; }
+static int forward_encoder_impl(const char* fn, const BatchPtrs& in, int B, int H, int C, const float* params, int mode, int precision,
+                                double* bn_sums, void* workspace, size_t workspace_bytes, void* stream) {
   Workspace w;
-  NRM_TRY(get_workspace("nrm_forward_encoder", w, workspace, workspace_bytes, B, H, C, mode));
+  NRM_TRY(get_workspace(fn, w, workspace, workspace_bytes, B, H, C, mode));
   cudaStream_t s = (cudaStream_t)stream;
-  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
   NRM_TRY(encoder_forward(in, params, w, mode, precision, s));
   if (mode & NRM_MODE_BN_BATCH_STATS) {
     KernelTimer t("bn_statistics", s);
@@ -444,6 +439,44 @@ extern "C" int nrm_forward_encoder(const double* x_history, const double* x_targ
       NRM_CUDA(cudaMemcpyAsync(bn_sums, w.bn_sums, sizeof(double) * 2 * E, cudaMemcpyDeviceToDevice, s));
   }
   return NRM_OK;
+}
+
+// compact wire format as the input of the row kernels (no expansion to the packed float64 tensors): needs the kernels that never
+// touch the packed rows again, i.e. the row-stacked tensor-core path
+static int compact_batch(const char* fn, const nrm_compact_batch* cb, int precision, CompactPtrs& cp) {
+  if (!cb || !cb->articles || cb->n_articles <= 0 || !cb->hist_article || !cb->hist_time || !cb->hist_click || !cb->cand_article || !cb->cand_time ||
+      (cb->label32 && !cb->label64)) {
+    set_error("%s: bad compact batch", fn); return NRM_EINVAL;
+  }
+  if ((reinterpret_cast<uintptr_t>(cb->articles) & 15) != 0) { set_error("%s: the article table must be 16-byte aligned", fn); return NRM_EINVAL; }
+  if (precision == NRM_PRECISION_FP32 || !use_rowstacked()) {
+    set_error("%s: the compact wire format is read directly by the tensor-core precisions only (use nrm_expand_compact otherwise)", fn);
+    return NRM_EUNSUPPORTED;
+  }
+  cp = CompactPtrs{cb->articles, cb->n_articles, cb->hist_article, cb->hist_time, cb->hist_click, cb->cand_article, cb->cand_time,
+                   cb->label32, cb->label64};
+  return NRM_OK;
+}
+
+extern "C" int nrm_forward_encoder(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
+                                   long long xg_bs, int B, int H, int C, const float* params, int mode, int precision,
+                                   double* bn_sums, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape("nrm_forward_encoder", B, H, C));
+  if (!x_history || !x_target || !x_global || !params) { set_error("nrm_forward_encoder: null pointer"); return NRM_EINVAL; }
+  if (xt_bs < (long long)C * TC || xg_bs < (long long)C * GC) { set_error("nrm_forward_encoder: batch stride smaller than one impression"); return NRM_EINVAL; }
+  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
+  return forward_encoder_impl("nrm_forward_encoder", in, B, H, C, params, mode, precision, bn_sums, workspace, workspace_bytes, stream);
+}
+
+extern "C" int nrm_forward_encoder_compact(const nrm_compact_batch* batch, int B, int H, int C, const float* params, int mode, int precision,
+                                           double* bn_sums, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape("nrm_forward_encoder_compact", B, H, C));
+  if (!params) { set_error("nrm_forward_encoder_compact: null pointer"); return NRM_EINVAL; }
+  CompactPtrs cp;
+  NRM_TRY(compact_batch("nrm_forward_encoder_compact", batch, precision, cp));
+  BatchPtrs in{nullptr, nullptr, 0, nullptr, 0};
+  in.compact = &cp;
+  return forward_encoder_impl("nrm_forward_encoder_compact", in, B, H, C, params, mode, precision, bn_sums, workspace, workspace_bytes, stream);
 }
 
 extern "C" int nrm_forward_head(int B, int H, int C, const float* params, float* bn_running_mean, float* bn_running_var,
@@ -473,6 +506,14 @@ extern "C" int nrm_forward(const double* x_history, const double* x_target, long
                            float* logits, void* workspace, size_t workspace_bytes, void* stream) {
   NRM_TRY(nrm_forward_encoder(x_history, x_target, xt_bs, x_global, xg_bs, B, H, C, params, mode, precision, nullptr,
                               workspace, workspace_bytes, stream));
+  return nrm_forward_head(B, H, C, params, bn_running_mean, bn_running_var, bn_num_batches_tracked, mode, precision, nullptr, 0,
+                            logits, workspace, workspace_bytes, stream);
+}
+
+extern "C" int nrm_forward_compact(const nrm_compact_batch* batch, int B, int H, int C, const float* params, float* bn_running_mean,
+                                   float* bn_running_var, long long* bn_num_batches_tracked, int mode, int precision,
+                                   float* logits, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(nrm_forward_encoder_compact(batch, B, H, C, params, mode, precision, nullptr, workspace, workspace_bytes, stream));
   return nrm_forward_head(B, H, C, params, bn_running_mean, bn_running_var, bn_num_batches_tracked, mode, precision, nullptr, 0,
                             logits, workspace, workspace_bytes, stream);
 }
@@ -514,37 +555,53 @@ extern "C" int nrm_backward_head_deferred(int B, int H, int C, const float* para
   return backward_head("nrm_backward_head_deferred", true, B, H, C, params, precision, dlogits, grads, bn_bwd_sums, workspace, workspace_bytes, stream);
 }
 
-extern "C" int nrm_backward_encoder(const double* x_history, const double* x_target, long long xt_bs,
-                                    const double* x_global, long long xg_bs, int B, int H, int C, const float* params,
-                                    int mode, int precision, const double* bn_bwd_sums, long long bn_global_rows,
-                                    float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+static int backward_encoder_impl(const char* fn, const BatchPtrs& in, int B, int H, int C, const float* params, int mode, int precision,
+                                 const double* bn_bwd_sums, long long bn_global_rows, float* grads, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
   const int training = mode & NRM_MODE_BN_BATCH_STATS;
-  NRM_TRY(check_shape("nrm_backward_encoder", B, H, C));
-  if (!x_history || !x_target || !x_global || !params || !grads) { set_error("nrm_backward_encoder: null pointer"); return NRM_EINVAL; }
   Workspace w;
-  NRM_TRY(get_workspace("nrm_backward_encoder", w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
+  NRM_TRY(get_workspace(fn, w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
   cudaStream_t s = (cudaStream_t)stream;
-  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
   const double* sums = bn_bwd_sums ? bn_bwd_sums : w.bn_bwd_sums;
   const long long rows = bn_global_rows > 0 ? bn_global_rows : w.R;
   NRM_TRY(launch_bn_backward_combine(params, w, training, sums, rows, head_on_tensor_cores(precision), s));
   return encoder_backward(in, params, w, precision, grads, s);   // also enqueues and joins the weight gradients nrm_backward_head_deferred left
 }
 
-extern "C" int nrm_backward(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
-                            long long xg_bs, int B, int H, int C, const float* params, int mode, int precision,
-                            const float* dlogits, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int nrm_backward_encoder(const double* x_history, const double* x_target, long long xt_bs,
+                                    const double* x_global, long long xg_bs, int B, int H, int C, const float* params,
+                                    int mode, int precision, const double* bn_bwd_sums, long long bn_global_rows,
+                                    float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape("nrm_backward_encoder", B, H, C));
+  if (!x_history || !x_target || !x_global || !params || !grads) { set_error("nrm_backward_encoder: null pointer"); return NRM_EINVAL; }
+  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
+  return backward_encoder_impl("nrm_backward_encoder", in, B, H, C, params, mode, precision, bn_bwd_sums, bn_global_rows, grads, workspace,
+                               workspace_bytes, stream);
+}
+
+extern "C" int nrm_backward_encoder_compact(const nrm_compact_batch* batch, int B, int H, int C, const float* params, int mode, int precision,
+                                            const double* bn_bwd_sums, long long bn_global_rows, float* grads, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape("nrm_backward_encoder_compact", B, H, C));
+  if (!params || !grads) { set_error("nrm_backward_encoder_compact: null pointer"); return NRM_EINVAL; }
+  CompactPtrs cp;
+  NRM_TRY(compact_batch("nrm_backward_encoder_compact", batch, precision, cp));
+  BatchPtrs in{nullptr, nullptr, 0, nullptr, 0};
+  in.compact = &cp;
+  return backward_encoder_impl("nrm_backward_encoder_compact", in, B, H, C, params, mode, precision, bn_bwd_sums, bn_global_rows, grads, workspace,
+                               workspace_bytes, stream);
+}
+
+static int backward_impl(const char* fn, const BatchPtrs& in, int B, int H, int C, const float* params, int mode, int precision,
+                         const float* dlogits, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
   // Head and encoder backward in one call: the head's weight gradients (only the optimizer needs them) run on the side
-  // stream beside the BatchNorm path and the start of the encoder backward instead of in front of them.
+  // stream behind the w1 backward, beside the tail of the encoder backward, instead of in front of it.
   const int training = mode & NRM_MODE_BN_BATCH_STATS;
-  NRM_TRY(check_shape("nrm_backward", B, H, C));
-  if (!x_history || !x_target || !x_global || !params || !dlogits || !grads) { set_error("nrm_backward: null pointer"); return NRM_EINVAL; }
   Workspace w;
-  NRM_TRY(get_workspace("nrm_backward", w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
+  NRM_TRY(get_workspace(fn, w, workspace, workspace_bytes, B, H, C, NRM_MODE_KEEP_FOR_BWD));
   cudaStream_t s = (cudaStream_t)stream;
   SideStream* ss = side_stream(s);
-  if (ss == nullptr) { set_error("nrm_backward: cannot create the side stream"); return NRM_ECUDA; }
-  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
+  if (ss == nullptr) { set_error("%s: cannot create the side stream", fn); return NRM_ECUDA; }
   const bool htc = head_on_tensor_cores(precision);
   const int tiles = htc ? head_tc_tiles(w.R) : 0;
   { KernelTimer t("head_backward", s);
@@ -553,4 +610,24 @@ extern "C" int nrm_backward(const double* x_history, const double* x_target, lon
     if (!htc) NRM_TRY(launch_head_backward_bn(w, grads, s, 0)); }
   NRM_TRY(launch_bn_backward_combine(params, w, training, w.bn_bwd_sums, w.R, htc, s));
   return encoder_backward(in, params, w, precision, grads, s);     // enqueues the head weight gradients on the side stream and joins them
+}
+
+extern "C" int nrm_backward(const double* x_history, const double* x_target, long long xt_bs, const double* x_global,
+                            long long xg_bs, int B, int H, int C, const float* params, int mode, int precision,
+                            const float* dlogits, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape("nrm_backward", B, H, C));
+  if (!x_history || !x_target || !x_global || !params || !dlogits || !grads) { set_error("nrm_backward: null pointer"); return NRM_EINVAL; }
+  const BatchPtrs in{x_history, x_target, xt_bs, x_global, xg_bs};
+  return backward_impl("nrm_backward", in, B, H, C, params, mode, precision, dlogits, grads, workspace, workspace_bytes, stream);
+}
+
+extern "C" int nrm_backward_compact(const nrm_compact_batch* batch, int B, int H, int C, const float* params, int mode, int precision,
+                                    const float* dlogits, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  NRM_TRY(check_shape("nrm_backward_compact", B, H, C));
+  if (!params || !dlogits || !grads) { set_error("nrm_backward_compact: null pointer"); return NRM_EINVAL; }
+  CompactPtrs cp;
+  NRM_TRY(compact_batch("nrm_backward_compact", batch, precision, cp));
+  BatchPtrs in{nullptr, nullptr, 0, nullptr, 0};
+  in.compact = &cp;
+  return backward_impl("nrm_backward_compact", in, B, H, C, params, mode, precision, dlogits, grads, workspace, workspace_bytes, stream);
 }

@@ -14,36 +14,77 @@ namespace nrm {
 // Rows are addressed as one list: [0, NH) history, [NH, NH+R) targets.
 // When keys32/keys8 are non-null the decoded table ids are also written as sort keys.
 // ---------------------------------------------------------------------------------
+// One row's decoded fields, from either wire format (the compact one: nrm_wire.cu; float32 article rows hold exactly the
+// values `x.to(float32)` gives the reference, so both formats produce the same bits)
+struct RowFields {
+  int tix[4], cat, sub[5], typ;
+  float s0, s1, s2;
+};
+struct CompactArgs {
+  const float* articles; int n_articles;
+  const int* hist_article; const unsigned* hist_time; const float* hist_click;
+  const int* cand_article; const unsigned* cand_time;
+  const float* label32; double* label64;
+};
+__device__ __forceinline__ const float* compact_article(const CompactArgs& ca, bool is_hist, long long r) {
+  int art = is_hist ? ca.hist_article[r] : ca.cand_article[r];
+  art = (art < 0 || art >= ca.n_articles) ? 0 : art;         // out-of-range ids read the pad article (as nrm_expand_compact does)
+  return ca.articles + (long long)art * 80;
+}
+
+template <bool COMPACT>
 __global__ void __launch_bounds__(256)
 embed_rows_kernel(const double* __restrict__ xh, const double* __restrict__ xt, long long xt_bs,
-                  const double* __restrict__ xg, long long xg_bs, int H, int C, long long NH, long long N,
+                  const double* __restrict__ xg, long long xg_bs, const CompactArgs ca, int H, int C, long long NH, long long N,
                   const float* __restrict__ P, float* __restrict__ xin_h, float* __restrict__ e, float* __restrict__ pca_h,
                   int* __restrict__ keys32, int* __restrict__ keys8) {
   pdl_wait();                                          // programmatic dependent launch: see nrm_common.cuh
   pdl_trigger();
+  if (COMPACT && (long long)blockIdx.x * 32 >= N) {    // tail blocks: float32 labels -> float64
+    const long long i = ((long long)blockIdx.x - (N + 31) / 32) * 256 + threadIdx.x;
+    if (ca.label32 != nullptr && i < (N - NH)) ca.label64[i] = (double)ca.label32[i];
+    return;
+  }
   const long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
   const int q = threadIdx.x & 7;
   if (row >= N) return;
   const bool is_hist = row < NH;
-  const double* src;
-  if (is_hist) {
-    src = xh + row * HC;
+  const double* src = nullptr;
+  const float* art = nullptr;
+  RowFields f;
+  if (COMPACT) {
+    const long long r = is_hist ? row : row - NH;
+    art = compact_article(ca, is_hist, r);
+    const unsigned t = is_hist ? ca.hist_time[r] : ca.cand_time[r];
+    f.tix[0] = (int)(t & 0xfffu); f.tix[1] = (int)((t >> 12) & 0xfu); f.tix[2] = (int)((t >> 16) & 0x1fu); f.tix[3] = (int)((t >> 21) & 0x1fu);
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(art + 64)), c1 = __ldg(reinterpret_cast<const float4*>(art + 68));
+    const float2 c2 = __ldg(reinterpret_cast<const float2*>(art + 72));
+    f.cat = (int)c0.x; f.sub[0] = (int)c0.y; f.sub[1] = (int)c0.z; f.sub[2] = (int)c0.w; f.sub[3] = (int)c1.x; f.sub[4] = (int)c1.y;
+    f.s0 = c1.z; f.s1 = c1.w; f.s2 = c2.x; f.typ = (int)c2.y;
   } else {
-    const long long r = row - NH;
-    src = xt + (r / C) * xt_bs + (r % C) * TC;
-  }
-  // ids are exact integers stored as doubles; float32 -> int64 truncation in the reference
-  int tix[4];
+    if (is_hist) {
+      src = xh + row * HC;
+    } else {
+      const long long r = row - NH;
+      src = xt + (r / C) * xt_bs + (r % C) * TC;
+    }
+    // ids are exact integers stored as doubles; float32 -> int64 truncation in the reference
 #pragma unroll
-  for (int i = 0; i < 4; ++i) tix[i] = (int)(float)src[i];
-  const int cat = clampi((int)(float)src[68], 0, NCAT - 1);
+    for (int i = 0; i < 4; ++i) f.tix[i] = (int)(float)src[i];
+    f.cat = (int)(float)src[68];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) f.sub[i] = (int)(float)src[69 + i];
+    f.s0 = (float)src[74]; f.s1 = (float)src[75]; f.s2 = (float)src[76];
+    f.typ = (int)(float)src[77];
+  }
+  const int cat = clampi(f.cat, 0, NCAT - 1);
   int sub[5];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) sub[i] = clampi((int)(float)src[69 + i], 0, NCAT - 1);
-  const float s0 = (float)src[74], s1 = (float)src[75], s2 = (float)src[76];
-  const int typ = clampi((int)(float)src[77], 0, NTYPE - 1);
-  const int iy = clampi(tix[0], 0, NYEAR - 1), im = clampi(tix[1], 0, NMONTH - 1);
-  const int id = clampi(tix[2], 0, NDAY - 1), ih = clampi(tix[3], 0, NHOUR - 1);
+  for (int i = 0; i < 5; ++i) sub[i] = clampi(f.sub[i], 0, NCAT - 1);
+  const float s0 = f.s0, s1 = f.s1, s2 = f.s2;
+  const int typ = clampi(f.typ, 0, NTYPE - 1);
+  const int iy = clampi(f.tix[0], 0, NYEAR - 1), im = clampi(f.tix[1], 0, NMONTH - 1);
+  const int id = clampi(f.tix[2], 0, NDAY - 1), ih = clampi(f.tix[3], 0, NHOUR - 1);
 
   // category + mean of the 5 sub-categories, columns 4q..4q+3
   const float4* tab = reinterpret_cast<const float4*>(P + P_CAT);
@@ -81,25 +122,37 @@ embed_rows_kernel(const double* __restrict__ xh, const double* __restrict__ xt, 
   dst[48 + q] = ty;
   dst[56 + q] = tm;
   if (is_hist) {
-    if (q < 2) dst[64 + q] = (float)src[78 + q];
+    if (q < 2) dst[64 + q] = COMPACT ? __ldg(ca.hist_click + row * 2 + q) : (float)src[78 + q];
     if (pca_h != nullptr) {
       // text/img PCA slice as fp32 [NH, 64] (what `x_history.to(float32)` gives the reference, user_invariant_interest_model.py:74):
-      // the attention kernels of both branches then stage plain fp32 rows, and the float64 rows are read exactly once per step
-      const double2* ps = reinterpret_cast<const double2*>(src + 4 + q * 8);
-      const double2 a = ps[0], b = ps[1], c2 = ps[2], d = ps[3];
+      // the attention kernels of both branches then stage plain fp32 rows, and the input rows are read exactly once per step
       float4* pd = reinterpret_cast<float4*>(pca_h + row * 64 + q * 8);
-      pd[0] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
-      pd[1] = make_float4((float)c2.x, (float)c2.y, (float)d.x, (float)d.y);
+      if (COMPACT) {
+        pd[0] = __ldg(reinterpret_cast<const float4*>(art + q * 8));
+        pd[1] = __ldg(reinterpret_cast<const float4*>(art + q * 8) + 1);
+      } else {
+        const double2* ps = reinterpret_cast<const double2*>(src + 4 + q * 8);
+        const double2 a = ps[0], b = ps[1], c2 = ps[2], d = ps[3];
+        pd[0] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+        pd[1] = make_float4((float)c2.x, (float)c2.y, (float)d.x, (float)d.y);
+      }
     }
   } else {
     const long long r = row - NH;
     float* er = e + r * E;
     // pca columns 4..67 -> e[200:264]; 8 threads x 8 values
+    float g0, g1, g2;
+    if (COMPACT) {
+      reinterpret_cast<float4*>(er + E_PCAT + q * 8)[0] = __ldg(reinterpret_cast<const float4*>(art + q * 8));
+      reinterpret_cast<float4*>(er + E_PCAT + q * 8)[1] = __ldg(reinterpret_cast<const float4*>(art + q * 8) + 1);
+      g0 = __ldg(art + 74); g1 = __ldg(art + 75); g2 = __ldg(art + 76);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) er[E_PCAT + q * 8 + i] = (float)src[4 + q * 8 + i];
+      for (int i = 0; i < 8; ++i) er[E_PCAT + q * 8 + i] = (float)src[4 + q * 8 + i];
+      const double* gsrc = xg + (r / C) * xg_bs + (r % C) * GC;
+      g0 = (float)gsrc[0]; g1 = (float)gsrc[1]; g2 = (float)gsrc[2];
+    }
     // instant-interest: relu(W g + b), output q
-    const double* gsrc = xg + (r / C) * xg_bs + (r % C) * GC;
-    const float g0 = (float)gsrc[0], g1 = (float)gsrc[1], g2 = (float)gsrc[2];
     const float* w = P + P_INST_W + q * 3;
     float v = __ldg(P + P_INST_B + q);
     v = fmaf(g0, __ldg(w + 0), v); v = fmaf(g1, __ldg(w + 1), v); v = fmaf(g2, __ldg(w + 2), v);
@@ -441,9 +494,10 @@ table_grad_l2_kernel(const SortPair sp, const float* __restrict__ gpart32, const
 // of the instant-interest layer.
 // part[blockIdx.x][0:64]  = sentiment (o*4 + i), part[..][64:96] = instant (o*4 + i)
 // ---------------------------------------------------------------------------------
+template <bool COMPACT>
 __global__ void __launch_bounds__(256)
 small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict__ xt, long long xt_bs,
-                         const double* __restrict__ xg, long long xg_bs, int C, long long NH, long long N,
+                         const double* __restrict__ xg, long long xg_bs, const CompactArgs ca, int C, long long NH, long long N,
                          const float* __restrict__ xin_h, const float* __restrict__ e,
                          const float* __restrict__ dxin_h, const float* __restrict__ dxt, const float* __restrict__ de,
                          float* __restrict__ part) {
@@ -464,11 +518,23 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
   for (long long row = (long long)blockIdx.x * 256 + threadIdx.x; row < N; row += stride) {
     const bool is_hist = row < NH;
     const long long r = row - NH;
-    const double* src = is_hist ? (xh + row * HC) : (xt + (r / C) * xt_bs + (r % C) * TC);
     const float* actp = is_hist ? (xin_h + row * XIN + 32) : (e + r * E + E_XT + 32);
     const float* dvp = is_hist ? (dxin_h + row * XIN + 32) : (dxt + r * D + 32);
-    const double2 s01 = __ldg(reinterpret_cast<const double2*>(src + 74));     // columns 74, 75 (16-byte aligned: rows are 640 / 624 B)
-    const double s2 = __ldg(src + 76);
+    float in[3], gl[3] = {0.f, 0.f, 0.f};
+    if (COMPACT) {
+      const float* art = compact_article(ca, is_hist, is_hist ? row : r);
+      const float2 a = __ldg(reinterpret_cast<const float2*>(art + 70));      // sentiment 70-72
+      in[0] = a.x; in[1] = a.y; in[2] = __ldg(art + 72);
+      if (!is_hist) { gl[0] = __ldg(art + 74); gl[1] = __ldg(art + 75); gl[2] = __ldg(art + 76); }
+    } else {
+      const double* src = is_hist ? (xh + row * HC) : (xt + (r / C) * xt_bs + (r % C) * TC);
+      const double2 s01 = __ldg(reinterpret_cast<const double2*>(src + 74));     // columns 74, 75 (16-byte aligned: rows are 640 / 624 B)
+      in[0] = (float)s01.x; in[1] = (float)s01.y; in[2] = (float)__ldg(src + 76);
+      if (!is_hist) {
+        const double* gsrc = xg + (r / C) * xg_bs + (r % C) * GC;
+        gl[0] = (float)__ldg(gsrc); gl[1] = (float)__ldg(gsrc + 1); gl[2] = (float)__ldg(gsrc + 2);
+      }
+    }
     float act[16], dv[16];
     if (is_hist) {                                   // 66-float rows: 8-byte aligned
 #pragma unroll
@@ -484,7 +550,6 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
         dv[4 * q] = d.x; dv[4 * q + 1] = d.y; dv[4 * q + 2] = d.z; dv[4 * q + 3] = d.w;
       }
     }
-    const float in[3] = {(float)s01.x, (float)s01.y, (float)s2};
 #pragma unroll
     for (int o = 0; o < 16; ++o) {
       const float dpre = act[o] > 0.f ? dv[o] : 0.f;
@@ -492,8 +557,7 @@ small_linear_grad_kernel(const double* __restrict__ xh, const double* __restrict
       as[o][2] = fmaf(dpre, in[2], as[o][2]); as[o][3] += dpre;
     }
     if (!is_hist) {
-      const double* gsrc = xg + (r / C) * xg_bs + (r % C) * GC;
-      const float g0 = (float)__ldg(gsrc), g1 = (float)__ldg(gsrc + 1), g2 = (float)__ldg(gsrc + 2);
+      const float g0 = gl[0], g1 = gl[1], g2 = gl[2];
       const float4 ia0 = __ldg(reinterpret_cast<const float4*>(e + r * E + E_INST)), ia1 = __ldg(reinterpret_cast<const float4*>(e + r * E + E_INST) + 1);
       const float4 di0 = __ldg(reinterpret_cast<const float4*>(de + r * E + E_INST)), di1 = __ldg(reinterpret_cast<const float4*>(de + r * E + E_INST) + 1);
       const float iav[8] = {ia0.x, ia0.y, ia0.z, ia0.w, ia1.x, ia1.y, ia1.z, ia1.w};
@@ -567,9 +631,24 @@ small_linear_grad_finish_kernel(const float* __restrict__ part, int nparts, floa
 // ---------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------
+static CompactArgs compact_args(const BatchPtrs& in) {
+  CompactArgs ca{};
+  if (in.compact != nullptr) {
+    const CompactPtrs& c = *in.compact;
+    ca = CompactArgs{c.articles, c.n_articles, c.hist_article, c.hist_time, c.hist_click, c.cand_article, c.cand_time, c.label32, c.label64};
+  }
+  return ca;
+}
+
 int launch_embed_rows(const BatchPtrs& in, const float* P, Workspace& w, bool with_keys, cudaStream_t s) {
   const int grid = (int)((w.N + 31) / 32);
-  launch_pdl(embed_rows_kernel, dim3(grid), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.H, w.C, w.NH, w.N, P, w.xin_h, w.e, w.pca_h, with_keys ? w.keys32 : nullptr, with_keys ? w.keys8 : nullptr);
+  const CompactArgs ca = compact_args(in);
+  if (in.compact != nullptr) {
+    const int tail = ca.label32 != nullptr ? (int)((w.R + 255) / 256) : 0;       // label conversion blocks
+    launch_pdl(embed_rows_kernel<true>, dim3(grid + tail), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, ca, w.H, w.C, w.NH, w.N, P, w.xin_h, w.e, w.pca_h, with_keys ? w.keys32 : nullptr, with_keys ? w.keys8 : nullptr);
+  } else {
+    launch_pdl(embed_rows_kernel<false>, dim3(grid), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, ca, w.H, w.C, w.NH, w.N, P, w.xin_h, w.e, w.pca_h, with_keys ? w.keys32 : nullptr, with_keys ? w.keys8 : nullptr);
+  }
   NRM_LAUNCH_CHECK("embed_rows_kernel");
   return NRM_OK;
 }
@@ -617,7 +696,11 @@ int launch_small_linear_grads(const BatchPtrs& in, Workspace& w, float* grads, c
   // one row per lane and pass: enough CTAs to cover the rows once, at most one wave of 2 CTAs per SM
   int nparts = (int)((w.N + 255) / 256);
   nparts = max(1, min(nparts, min(1024, 2 * sm_count())));
-  launch_pdl(small_linear_grad_kernel, dim3(nparts), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, w.C, w.NH, w.N, w.xin_h, w.e, w.dxin_h, w.dxt, w.de, w.small_part);
+  const CompactArgs ca = compact_args(in);
+  if (in.compact != nullptr)
+    launch_pdl(small_linear_grad_kernel<true>, dim3(nparts), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, ca, w.C, w.NH, w.N, w.xin_h, w.e, w.dxin_h, w.dxt, w.de, w.small_part);
+  else
+    launch_pdl(small_linear_grad_kernel<false>, dim3(nparts), dim3(256), 0, s, in.xh, in.xt, in.xt_bs, in.xg, in.xg_bs, ca, w.C, w.NH, w.N, w.xin_h, w.e, w.dxin_h, w.dxt, w.de, w.small_part);
   NRM_LAUNCH_CHECK("small_linear_grad_kernel");
   launch_pdl(small_linear_grad_finish_kernel, dim3(96), dim3(256), 0, s, w.small_part, nparts, grads);
   NRM_LAUNCH_CHECK("small_linear_grad_finish_kernel");

@@ -4,10 +4,18 @@
 
 namespace nrm {
 
+// compact wire format (nrm_wire.cu): the article table resident in HBM + per-impression ids / time buckets / click features
+struct CompactPtrs {
+  const float* articles; int n_articles;     // [n,80] float32: pca 64 | category | sub-category 5 | sentiment 3 | type | 3 global statistics | pad
+  const int* hist_article; const unsigned* hist_time; const float* hist_click;   // [B,H], [B,H], [B,H,2]
+  const int* cand_article; const unsigned* cand_time;                            // [B,C], [B,C]
+  const float* label32; double* label64;     // optional: float32 labels -> the float64 labels the loss kernels read
+};
 struct BatchPtrs {
   const double* xh;               // [B,H,80]
   const double* xt; long long xt_bs;   // [B,C,78], batch stride in doubles
   const double* xg; long long xg_bs;   // [B,C,3]
+  const CompactPtrs* compact = nullptr;   // non-null: the packed pointers above are unused, the row kernels read the compact format
 };
 
 // nrm_embed.cu

@@ -18,6 +18,7 @@ Under data parallelism the graph is split around the gradient all-reduce.
 from __future__ import annotations
 
 import ctypes
+import os
 import struct
 from typing import List, Optional
 
@@ -76,6 +77,9 @@ class FusedTrainStep:
         world = self.dp.world if self.dp is not None else 1
         self.precision = model._precision_code()
         self.mode = engine.MODE_BN_BATCH_STATS | engine.MODE_KEEP_FOR_BWD
+        # compact batches go straight into the row kernels (no expansion to the packed float64 tensors) on the row-stacked tensor-core
+        # path; precision fp32 and the item-tile kernels read the packed rows, so they get nrm_expand_compact in front
+        self.compact_direct = self.precision != 0 and os.environ.get('NRM_ATT_ITEM_TILES') is None
         n = self.flat.total
         # data parallel: the flat gradient buffer in symmetric (peer-mapped) memory, so that the Adam kernel of every rank can read
         # all of them (dp.PeerContext); None -> NCCL all-reduce between two graphs
@@ -146,16 +150,27 @@ class FusedTrainStep:
         loss_scratch = self.loss_scratch if loss_scratch is None else loss_scratch
         warming = getattr(self, '_warming', False)
         sync_bn = self.dp is not None and self.dp.sync_bn and not warming
+        direct = s.wire == 'compact' and self.compact_direct          # the slot's compact batch is the input itself
+        cb = ctypes.byref(s.cstruct) if direct else None
         if not sync_bn:
-            _lib.check(lib.nrm_forward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf),
-                                       _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked), self.mode,
-                                       self.precision, _p(self.logits), _p(self.ws), self.ws.numel(), st), 'nrm_forward')
+            if direct:
+                _lib.check(lib.nrm_forward_compact(cb, B, H, C, _p(f.buf), _p(m.bn.running_mean), _p(m.bn.running_var),
+                                                   _p(m.bn.num_batches_tracked), self.mode, self.precision, _p(self.logits), _p(self.ws),
+                                                   self.ws.numel(), st), 'nrm_forward_compact')
+            else:
+                _lib.check(lib.nrm_forward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf),
+                                           _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked), self.mode,
+                                           self.precision, _p(self.logits), _p(self.ws), self.ws.numel(), st), 'nrm_forward')
         else:
             # synchronised BatchNorm: the two halves of the forward around the exchange of the column sums (2 x 264 doubles);
             # N ranks x B impressions then reproduce one process on N * B
             sums = self._bn_sums(0)
-            _lib.check(lib.nrm_forward_encoder(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
-                                               self.precision, _p(sums), _p(self.ws), self.ws.numel(), st), 'nrm_forward_encoder')
+            if direct:
+                _lib.check(lib.nrm_forward_encoder_compact(cb, B, H, C, _p(f.buf), self.mode, self.precision, _p(sums), _p(self.ws),
+                                                           self.ws.numel(), st), 'nrm_forward_encoder_compact')
+            else:
+                _lib.check(lib.nrm_forward_encoder(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
+                                                   self.precision, _p(sums), _p(self.ws), self.ws.numel(), st), 'nrm_forward_encoder')
             gsums = self._exchange_stats(0, sums, B * C)
             _lib.check(lib.nrm_forward_head(B, H, C, _p(f.buf), _p(m.bn.running_mean), _p(m.bn.running_var), _p(m.bn.num_batches_tracked),
                                             self.mode, self.precision, _p(gsums), B * C * self.world, _p(self.logits), _p(self.ws), self.ws.numel(), st),
@@ -174,18 +189,26 @@ class FusedTrainStep:
             _lib.check(lib.nrm_loss_backward(_p(s.uid), B, C, _p(self.one), _p(self.dlogits), _p(ddelta), f.delta_numel,
                                              _p(loss_scratch), loss_scratch.numel(), st), 'nrm_loss_backward')
         if not sync_bn:
-            _lib.check(lib.nrm_backward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
-                                        self.precision, _p(self.dlogits), _p(self.grads), _p(self.ws), self.ws.numel(), st),
-                       'nrm_backward')
+            if direct:
+                _lib.check(lib.nrm_backward_compact(cb, B, H, C, _p(f.buf), self.mode, self.precision, _p(self.dlogits), _p(self.grads),
+                                                    _p(self.ws), self.ws.numel(), st), 'nrm_backward_compact')
+            else:
+                _lib.check(lib.nrm_backward(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
+                                            self.precision, _p(self.dlogits), _p(self.grads), _p(self.ws), self.ws.numel(), st),
+                           'nrm_backward')
         else:
             sums = self._bn_sums(1)
             # head weight gradients stay on the library's side stream until the encoder backward has been enqueued
             _lib.check(lib.nrm_backward_head_deferred(B, H, C, _p(f.buf), self.precision, _p(self.dlogits), _p(self.grads), _p(sums), _p(self.ws),
                                                       self.ws.numel(), st), 'nrm_backward_head_deferred')
             gsums = self._exchange_stats(1, sums, B * C)
-            _lib.check(lib.nrm_backward_encoder(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
-                                                self.precision, _p(gsums), B * C * self.world, _p(self.grads), _p(self.ws), self.ws.numel(), st),
-                       'nrm_backward_encoder')
+            if direct:
+                _lib.check(lib.nrm_backward_encoder_compact(cb, B, H, C, _p(f.buf), self.mode, self.precision, _p(gsums), B * C * self.world,
+                                                            _p(self.grads), _p(self.ws), self.ws.numel(), st), 'nrm_backward_encoder_compact')
+            else:
+                _lib.check(lib.nrm_backward_encoder(_p(s.xh), _p(s.xt), C * TGT_COLS, _p(s.xg), C * GLOBAL_COLS, B, H, C, _p(f.buf), self.mode,
+                                                    self.precision, _p(gsums), B * C * self.world, _p(self.grads), _p(self.ws), self.ws.numel(), st),
+                           'nrm_backward_encoder')
 
     def _bn_sums(self, which: int) -> torch.Tensor:
         if self.peer is not None:
@@ -262,6 +285,10 @@ class FusedTrainStep:
         if s.compact is None:
             s.compact = wire.CompactBatch(*[torch.zeros((self.B,) + tuple(getattr(batch, f).shape[1:]), dtype=getattr(batch, f).dtype, device=self.dev)
                                             for f in batch.__dataclass_fields__])
+            c = s.compact
+            s.cstruct = _lib.CompactBatchStruct(self.articles.rows.data_ptr(), int(self.articles.n), c.hist_article.data_ptr(),
+                                                c.hist_time.data_ptr(), c.hist_click.data_ptr(), c.cand_article.data_ptr(),
+                                                c.cand_time.data_ptr(), c.label.data_ptr(), s.label.data_ptr())
             self._expand(s)                                  # first launch of the kernel outside any graph capture
             # the zero fills / the expansion above run on the compute stream: the H2D copies below must not overtake them
             self.copy_stream.wait_stream(torch.cuda.current_stream(self.dev))
@@ -287,7 +314,11 @@ class FusedTrainStep:
         return s
 
     def _expand(self, s: _Slot):
+        """Compact slot -> what the forward reads: nothing to do on the direct path (the row kernels read the compact batch; the
+        labels are converted by the first of them), the packed float64 tensors otherwise."""
         from . import wire
+        if self.compact_direct:
+            return
         wire.expand_into(self.articles, s.compact, s.xh, s.xt, s.xg, s.label)
 
     def load(self, batch) -> _Slot:

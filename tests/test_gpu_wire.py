@@ -54,7 +54,11 @@ def test_scoring_forward_is_identical_for_both_wire_formats():
     assert torch.equal(out, ref)
 
 
-def test_fused_train_step_is_identical_for_both_wire_formats():
+@pytest.mark.parametrize('precision', ['bf16x3', 'fp32'])
+def test_fused_train_step_is_identical_for_both_wire_formats(precision):
+    """bf16x3: the compact batch is the direct input of the row kernels (nrm_forward_compact / nrm_backward_compact, no packed tensors);
+    fp32: it is expanded on the GPU first (the FFMA attention kernels read the packed rows).  Either way three training steps end
+    with the same bits as feeding the reference's packed float64 tensors."""
     B, H, C = 64, 50, 5
     table = wire.make_article_table(2000, seed=5)
     batches = [wire.make_compact_batch(table, B, H, C, seed=20 + i, user_num=100) for i in range(3)]
@@ -62,8 +66,9 @@ def test_fused_train_step_is_identical_for_both_wire_formats():
     for fmt in ('packed', 'compact'):
         m = nrm.UserModel(100)
         m.load_state_dict(load_weights('train'), strict=False)
-        m.to('cuda').train().set_precision('bf16x3')
+        m.to('cuda').train().set_precision(precision)
         tr = nrm.FusedTrainStep(m, B, H, C, lr=1e-3, weight_decay=1e-5, articles=table.to('cuda'))
+        assert tr.compact_direct == (precision != 'fp32')
         losses = []
         for cb in batches:
             if fmt == 'packed':
