@@ -612,10 +612,34 @@ def run_ours(args):
                                           variable_candidates=True).pin() for i in range(2)]
             trims_c = [int(b.empty_num.min()) for b in hc]
 
+            cstage = [hc[0].to(dev) for _ in range(NSLOT)]                # fixed device slots: compact batch + its expansion
+            xstage = [wire.expand(table, c) for c in cstage]
+            cdone = [None] * NSLOT
+
+            def fetch_c(i):
+                k = i % NSLOT
+                with torch.cuda.stream(cs):
+                    if cdone[k] is not None:
+                        cs.wait_event(cdone[k])
+                    src, dst = hc[i % 2], cstage[k]
+                    for f in src.__dataclass_fields__:
+                        getattr(dst, f).copy_(getattr(src, f), non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(cs)
+                return ev, k
+
             def e2e_scoring_compact(n):
                 total = 0
+                nxt = fetch_c(0)
                 for i in range(n):
-                    total += len(score(wire.expand(table, hc[i % 2].to(dev, non_blocking=True)), trims_c[i % 2], True))
+                    ev, k = nxt
+                    if i + 1 < n:
+                        nxt = fetch_c(i + 1)
+                    torch.cuda.current_stream(dev).wait_event(ev)
+                    x = xstage[k]
+                    wire.expand_into(table, cstage[k], x.x_history, x.x_target, x.x_global, x.label)
+                    x.impression_id, x.empty_num = cstage[k].impression_id, cstage[k].empty_num
+                    total += len(score(x, trims_c[i % 2], True))
+                    cdone[k] = torch.cuda.Event(); cdone[k].record(torch.cuda.current_stream(dev))
                 return total + sum(len(t) for t, _ in ring.drain())
             e2e_scoring_compact(2)
             barrier()
