@@ -15,8 +15,10 @@ from news_recommendation_model_b200.synthetic import make_batch
 from oracle import reference_port as O
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+C = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 U = 1000
-b = make_batch(B, 50, 5, seed=2024, user_num=U)
+b = make_batch(B, H, C, seed=2024, user_num=U)
 delta0 = torch.from_numpy(np.random.default_rng(11).normal(0, 0.3, U + 1).astype(np.float32))
 model, p = P.build_models(load_weights('train'), U, delta0)
 model.train().set_precision('bf16x3')
@@ -30,7 +32,7 @@ out = model(d.x_history, d.x_target, d.x_global)
 loss = model.loss(d.user_id, out, d.label)
 loss.backward()
 g_c = {k: v.grad.detach().cpu().clone() for k, v in model.named_parameters()}
-print('head FFMA' if os.environ.get('NRM_HEAD_FFMA') == '1' else 'head TC', 'B', B,
+print('head FFMA' if os.environ.get('NRM_HEAD_FFMA') == '1' else 'head TC', 'B', B, 'H', H, 'C', C,
       'logits err %.2e' % (out.detach().cpu() - out_o.detach()).abs().max().item(), 'loss err %.2e' % abs(float(loss) - float(loss_o)))
 for k, go in g_o.items():
     scale = go.abs().max().item()

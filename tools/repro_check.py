@@ -15,10 +15,12 @@ from news_recommendation_model_b200.synthetic import make_batch
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+H = int(sys.argv[3]) if len(sys.argv) > 3 else 50
+C = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 model = nrm.UserModel(1000)
 model.load_state_dict(load_weights('train'), strict=False)
 model.to('cuda').train().set_precision('bf16x3')
-d = make_batch(B, 50, 5, seed=2024, user_num=1000).to('cuda')
+d = make_batch(B, H, C, seed=2024, user_num=1000, variable_history=H > 50).to('cuda')
 import ctypes
 from news_recommendation_model_b200 import _lib
 lib = _lib.load()
@@ -28,7 +30,7 @@ def snapshot():
     out = {}
     for f in FIELDS:
         nb = ctypes.c_longlong()
-        off = lib.nrm_debug_ws_field(B, 50, 5, 3, f.encode(), ctypes.byref(nb))
+        off = lib.nrm_debug_ws_field(B, H, C, 3, f.encode(), ctypes.byref(nb))
         out[f] = ws[off:off + nb.value].clone()
     return out
 snaps = []
@@ -45,7 +47,7 @@ print('w1.weight equal to previous run:', [bool((runs[i][k0] == runs[i - 1][k0])
       'max|w1.weight| per run', ['%.6e' % runs[i][k0].abs().max().item() for i in range(N)])
 for f in FIELDS:
     print(f'  workspace {f:9s} bytes differing from run 0:', [int((snaps[i][f] != snaps[0][f]).sum().item()) for i in range(1, N)])
-d0 = snaps[0]['dxh'].view(torch.float32).view(B, 50, 64); d1 = snaps[1]['dxh'].view(torch.float32).view(B, 50, 64)
+d0 = snaps[0]['dxh'].view(torch.float32).view(B, H, 64); d1 = snaps[1]['dxh'].view(torch.float32).view(B, H, 64)
 idx = (d0 != d1).nonzero()
 if idx.numel():
     bs = idx[:, 0].unique(); hs = idx[:, 1].unique(); cs = idx[:, 2].unique()
@@ -59,5 +61,5 @@ for i in range(1, N):
         dlt = (runs[i][k] - runs[0][k]).abs().max().item()
         if dlt != 0.0:
             bad[k] = max(bad.get(k, 0.0), dlt / max(runs[0][k].abs().max().item(), 1e-30))
-print(' '.join(f'{k}={os.environ[k]}' for k in os.environ if k.startswith('NRM_')) or 'default', '->',
+print(f'B={B} H={H} C={C}', ' '.join(f'{k}={os.environ[k]}' for k in os.environ if k.startswith('NRM_')) or 'default', '->',
       'bitwise reproducible' if not bad else 'DIFFERS: ' + ', '.join(f'{k.split(".")[-2]}.{k.split(".")[-1]} {v:.1e}' for k, v in sorted(bad.items())))
