@@ -316,10 +316,12 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
     KernelTimer t("attention_input_grad_label", s);
     NRM_TRY(launch_attention_input_grad_rs(w, precision, s));
   }
-  // fork: the w1 backward only needs dxh (label attention); it runs on the side stream under the text/img attention
-  // backward and the reductions of the attention weight gradients
+  // fork: the w1 backward only needs dxh (label attention).  The text/img attention backward is launched FIRST: both become ready
+  // when the input-gradient kernel ends, both want every SM (one CTA of 150-200 KB each), and the one launched first gets them -- the
+  // attention kernel is on the critical path, the w1 backward then runs beside attention_finish in the latency-bound tail
   NRM_CUDA(cudaEventRecord(ss->fork2, s));
   NRM_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork2, 0));
+  { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
   // w1: dxin_h = dxh W1, dW1 = dxh^T xin_h, db1 = colsum(dxh)
   { KernelTimer t("w1_backward", ss->stream);
     if (precision != NRM_PRECISION_FP32 && use_rowstacked()) NRM_TRY(launch_w1_backward_tc(P, w, G, precision, ss->stream));
@@ -330,7 +332,6 @@ static int encoder_backward(const BatchPtrs& in, const float* P, Workspace& w, i
     KernelTimer t("head_wgrad", ss->stream);
     NRM_TRY(launch_head_backward_wgrad(ss->wg_params, w, ss->wg_grads, ss->stream, ss->wg_tiles, ss->wg_precision));
   }
-  { KernelTimer t("attention_backward_textimg", s); NRM_TRY(launch_attention_backward(in, P, w, 1, precision, s)); }
   { KernelTimer t("attention_finish", s);
     NRM_TRY(launch_attention_finish(P, w, 0, precision, G, s));
     NRM_TRY(launch_attention_finish(P, w, 1, precision, G, s)); }
