@@ -278,6 +278,54 @@ class PrefetchLoader:
             self.release(cb)
 
 
+def _zstd_decompress(buf: bytes) -> bytes:
+    """One zstd frame -> bytes, with whichever codec this environment has: `zstandard` (what the reference imports,
+    tool/process_data.py:16) or the zstd codec bundled with pyarrow."""
+    try:
+        import zstandard
+        return zstandard.ZstdDecompressor().decompress(buf)
+    except ImportError:
+        pass
+    try:
+        import pyarrow as pa
+    except ImportError as exc:
+        raise ImportError('reading a processed-data volume needs `zstandard` or `pyarrow` (zstd codec)') from exc
+    with pa.CompressedInputStream(pa.BufferReader(buf), 'zstd') as stream:
+        return stream.read()
+
+
+def _zstd_compress(buf: bytes, level: int = 11) -> bytes:
+    try:
+        import zstandard
+        return zstandard.ZstdCompressor(level=level).compress(buf)
+    except ImportError:
+        import pyarrow as pa
+        return pa.Codec('zstd', compression_level=level).compress(buf, asbytes=True)
+
+
+def load_processed_volume(path: str) -> list:
+    """`tool/process_data.py:import_processed_data` (lines 449-453): one zstd frame holding the pickled record list of a volume
+    (`process_data.py:252` layout).  Pickle executes code: only open volumes you produced yourself, as with the reference."""
+    import pickle
+    with open(path, 'rb') as f:
+        return pickle.loads(_zstd_decompress(f.read()))
+
+
+def save_processed_volume(records, path: str) -> None:
+    """`tool/process_data.py:export_processed_data` (lines 455-462): the inverse of `load_processed_volume`, readable by the reference."""
+    import pickle
+    with open(path, 'wb') as f:
+        f.write(_zstd_compress(pickle.dumps(list(records))))
+
+
+def from_volumes(paths: Sequence[str], pin: bool = False) -> CompactDataset:
+    """All impressions of the given processed-data volumes as one compact dataset (one article table over all of them)."""
+    records = []
+    for p in paths:
+        records.extend(load_processed_volume(p))
+    return from_records(records, pin=pin)
+
+
 def from_records(records: Sequence[Sequence], pin: bool = False) -> CompactDataset:
     """`records`: the list `tool/process_data.py:252` builds and `import_processed_data` returns —
     [impression_id, user_id, history [H,80], inview [C,78], global [C,3], label [C], label_id [C], empty_num] per impression,

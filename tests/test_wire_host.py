@@ -102,3 +102,38 @@ def test_prefetch_loader_yields_the_same_batches_as_the_synchronous_generator():
         assert got[-1].shape[0] == 53 % 8
     # a second pass over the same loader object works (one pass at a time)
     assert sum(cb.shape[0] for cb in wire.PrefetchLoader(ds, 16, drop_last=True, depth=2)) == 48
+
+
+def test_processed_data_volumes_round_trip_through_the_zstd_pickle_format(tmp_path):
+    """The reference stores a volume as ONE zstd frame of the pickled record list (tool/process_data.py:449-462).  Write two volumes,
+    read them back (with `zstandard` if present, else pyarrow's zstd codec), and build the compact dataset over both: same records,
+    same dataset as converting the concatenated list directly."""
+    import os
+    rng = np.random.default_rng(7)
+    H, C = 6, 4
+    arts = rng.normal(size=(9, 74)).astype(np.float32).astype(np.float64)
+
+    def record(i):
+        hist = np.zeros((H, 80)); cand = np.zeros((C, 78)); glob = np.zeros((C, 3))
+        nh, nc = int(rng.integers(1, H + 1)), int(rng.integers(1, C + 1))
+        for h in range(nh):
+            hist[h, 4:78] = arts[rng.integers(0, 9)]; hist[h, 0:4] = [3, 5, 17, 9]; hist[h, 78:80] = rng.random(2)
+        for c in range(nc):
+            cand[c, 4:78] = arts[rng.integers(0, 9)]; cand[c, 0:4] = [3, 5, 18, 11]; glob[c] = rng.random(3).astype(np.float32)
+        label = np.zeros(C); label[0] = 1
+        return [np.int64(1000 + i), np.int64(i % 5), hist, cand, glob, label, np.arange(C, dtype=np.float64), np.int64(C - nc)]
+
+    recs = [record(i) for i in range(10)]
+    p0, p1 = os.path.join(tmp_path, 'vol0.zst'), os.path.join(tmp_path, 'vol1.zst')
+    wire.save_processed_volume(recs[:6], p0)
+    wire.save_processed_volume(recs[6:], p1)
+    with open(p0, 'rb') as f:
+        assert f.read(4) == b'\x28\xb5\x2f\xfd'                      # zstd frame magic: what zstandard.ZstdDecompressor expects
+    back = wire.load_processed_volume(p0) + wire.load_processed_volume(p1)
+    assert len(back) == 10
+    for a, b in zip(recs, back):
+        assert all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(a, b))
+    ds0, ds1 = wire.from_records(recs), wire.from_volumes([p0, p1])
+    assert torch.equal(ds0.table.rows, ds1.table.rows)
+    for f in ds0.data.__dataclass_fields__:
+        assert torch.equal(getattr(ds0.data, f), getattr(ds1.data, f)), f
