@@ -92,6 +92,19 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().nrm_version() >= 100
 
 
+def test_ctypes_bindings_have_the_parameter_count_of_the_header():
+    """Every prototype of include/nrm_b200.h against the ctypes signature `_lib` binds: same number of parameters (a drifted
+    binding passes garbage instead of failing)."""
+    header = open(os.path.join(ROOT, 'include', 'nrm_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    protos = re.findall(r'\b(nrm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', header)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ('', 'void') else len(params.split(','))
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+
+
 def test_flat_layout_matches_reference_keys():
     entries, fixed = engine.layout()
     names = [n for n, _, _ in entries]
